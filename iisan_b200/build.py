@@ -1,0 +1,74 @@
+"""Build recipe for libiisan_b200.so (hand-written CUDA for sm_100a behind a C ABI).
+
+    python -m iisan_b200.build            # incremental
+    python -m iisan_b200.build --force
+
+nvcc cross-compiles without a GPU.  The shared object is written in-tree (iisan_b200/lib/) so that it
+travels to the GPU box with the repo snapshot; it is git-ignored.
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIBDIR = os.path.join(HERE, "lib")
+OBJDIR = os.path.join(HERE, "build")
+LIB = os.path.join(LIBDIR, "libiisan_b200.so")
+INCLUDE = os.path.join(os.path.dirname(HERE), "include")
+
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+         "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--expt-relaxed-constexpr", "-I", INCLUDE]
+
+
+def sources():
+    return sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
+
+
+def headers_mtime():
+    m = os.path.getmtime(os.path.join(INCLUDE, "iisan_b200.h"))
+    for f in os.listdir(CSRC):
+        if f.endswith(".cuh"):
+            m = max(m, os.path.getmtime(os.path.join(CSRC, f)))
+    return m
+
+
+def compile_one(src, force, hm, log):
+    obj = os.path.join(OBJDIR, src[:-3] + ".o")
+    spath = os.path.join(CSRC, src)
+    if not force and os.path.exists(obj) and os.path.getmtime(obj) >= max(os.path.getmtime(spath), hm):
+        return obj, False
+    cmd = [NVCC, *FLAGS, "-c", spath, "-o", obj]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    with open(os.path.join(OBJDIR, src[:-3] + ".ptxas.log"), "w") as f:
+        f.write(r.stderr)
+    if r.returncode != 0:
+        raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
+    if log:
+        print(f"[iisan_b200.build] compiled {src}")
+    return obj, True
+
+
+def build(force: bool = False, verbose: bool = True) -> str:
+    os.makedirs(LIBDIR, exist_ok=True)
+    os.makedirs(OBJDIR, exist_ok=True)
+    hm = headers_mtime()
+    with ThreadPoolExecutor(max_workers=8) as ex:
+        res = list(ex.map(lambda s: compile_one(s, force, hm, verbose), sources()))
+    objs = [o for o, _ in res]
+    if force or any(c for _, c in res) or not os.path.exists(LIB):
+        cmd = [NVCC, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcuda"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+        if verbose:
+            print(f"[iisan_b200.build] linked {LIB}")
+    return LIB
+
+
+if __name__ == "__main__":
+    build(force="--force" in sys.argv)

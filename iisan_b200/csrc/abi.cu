@@ -1,0 +1,111 @@
+// C-ABI plumbing: version/status/error reporting, the dense layer (com_dense) and the cached-state gather.
+#include "common.cuh"
+#include "gemm_simt.cuh"
+
+namespace iisan {
+thread_local cudaError_t g_last_cuda_error = cudaSuccess;
+
+// ---- cached-state gather -----------------------------------------------------------------------------
+// out[i, a, :] = table[ids[i], sel[a], :]  (zeros when ids[i] == 0).  One CTA handles a group of
+// (row, selected layer) pairs; every 2*d-byte (or 4*d-byte) layer row is moved with 128-bit loads and
+// stores, fully coalesced.  The table may live in HBM or in mapped pinned host memory (zero-copy
+// over the host link): the access pattern is identical.
+//   restates Build_MM_Dataset.__getitem__ (CC/data_utils/dataset.py:65-92): per-item load of the
+//   cached [layers, d] tensor, left padding with zeros, stacking into the batch.
+template <int BYTES_PER_ELT>
+__global__ void __launch_bounds__(256) gather_states_kernel(const uint4* __restrict__ table, int64_t n_table_items, int layers, int d,
+                                                            const int64_t* __restrict__ ids, int n, const int* __restrict__ sel, int n_sel,
+                                                            uint4* __restrict__ out) {
+  const int vec_per_row = d * BYTES_PER_ELT / 16;
+  const int64_t total = (int64_t)n * n_sel * vec_per_row;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int v = (int)(i % vec_per_row);
+    const int64_t ra = i / vec_per_row;
+    const int a = (int)(ra % n_sel);
+    const int64_t r = ra / n_sel;
+    const int64_t id = ids[r];
+    uint4 val = make_uint4(0u, 0u, 0u, 0u);
+    if (id > 0 && id < n_table_items) val = ld_stream_128(table + ((id * layers + sel[a]) * (int64_t)vec_per_row + v));
+    out[i] = val;
+  }
+}
+}  // namespace iisan
+
+using namespace iisan;
+
+extern "C" int iisan_abi_version(void) { return IISAN_ABI_VERSION; }
+
+extern "C" const char* iisan_status_string(int s) {
+  switch (s) {
+    case IISAN_OK: return "ok";
+    case IISAN_EINVAL: return "invalid argument (descriptor, pointer or unsupported shape)";
+    case IISAN_ECUDA: return "CUDA runtime error (see iisan_last_cuda_error_string)";
+    case IISAN_EWORKSPACE: return "workspace too small";
+    case IISAN_EUNSUPPORTED: return "configuration valid in the reference but not built here";
+  }
+  return "unknown status";
+}
+
+extern "C" size_t iisan_sizeof(int which) {
+  switch (which) {
+    case 0: return sizeof(iisan_san_desc);
+    case 1: return sizeof(iisan_san_params);
+    case 2: return sizeof(iisan_ue_desc);
+    case 3: return sizeof(iisan_ue_params);
+    case 4: return sizeof(iisan_ce_desc);
+  }
+  return 0;
+}
+
+extern "C" int iisan_last_cuda_error(void) { return (int)g_last_cuda_error; }
+extern "C" const char* iisan_last_cuda_error_string(void) { return cudaGetErrorString(g_last_cuda_error); }
+
+extern "C" int iisan_linear_forward(int32_t rows, int32_t out_features, int32_t in_features, const float* x, int64_t ldx,
+                                    const float* w, const float* b, float* y, int64_t ldy, int32_t compute, iisan_stream_t stream) {
+  (void)compute;
+  if (!x || !w || !y || rows <= 0 || out_features <= 0 || in_features <= 0) return IISAN_EINVAL;
+  GemmBatch g{}; g.n = 1;
+  g.p[0] = prob_linear(x, ldx, w, b, y, ldy, rows, out_features, in_features);
+  return launch_gemm(g, as_stream(stream));
+}
+
+extern "C" int iisan_linear_backward(int32_t rows, int32_t out_features, int32_t in_features, const float* x, int64_t ldx,
+                                     const float* w, const float* dy, int64_t lddy, float* dx, int64_t lddx, float* dw, float* db,
+                                     int32_t compute, iisan_stream_t stream) {
+  (void)compute;
+  if (!x || !w || !dy || rows <= 0 || out_features <= 0 || in_features <= 0) return IISAN_EINVAL;
+  cudaStream_t st = as_stream(stream);
+  if (dx) {
+    GemmBatch g{}; g.n = 1;
+    g.p[0] = prob_dgrad(dy, lddy, w, dx, lddx, rows, out_features, in_features);
+    IISAN_TRY(launch_gemm(g, st));
+  }
+  if (dw) {
+    GemmBatch g{}; g.n = 1;
+    g.p[0] = prob_wgrad(dy, lddy, x, ldx, dw, rows, out_features, in_features);
+    IISAN_TRY(launch_gemm(g, st));
+  }
+  if (db) {
+    ColsumBatch c{}; c.n = 1;
+    c.p[0] = {dy, lddy, rows, out_features, db};
+    IISAN_TRY(launch_colsum(c, st));
+  }
+  return IISAN_OK;
+}
+
+extern "C" int iisan_gather_states(const void* table, int32_t dtype, int64_t n_table_items, int32_t layers, int32_t d,
+                                   const int64_t* ids, int32_t n, const int32_t* sel, int32_t n_sel, void* out,
+                                   iisan_stream_t stream) {
+  if (!table || !ids || !sel || !out || n <= 0 || n_sel <= 0 || layers <= 0 || d <= 0 || n_table_items <= 0) return IISAN_EINVAL;
+  const int bpe = (int)dtype_size(dtype);
+  if ((d * bpe) % 16) return IISAN_EINVAL;
+  const int64_t total = (int64_t)n * n_sel * (d * bpe / 16);
+  const int blocks = (int)imin64((total + 255) / 256, 148 * 16);
+  cudaStream_t st = as_stream(stream);
+  if (bpe == 4)
+    gather_states_kernel<4><<<blocks, 256, 0, st>>>((const uint4*)table, n_table_items, layers, d, ids, n, sel, n_sel, (uint4*)out);
+  else
+    gather_states_kernel<2><<<blocks, 256, 0, st>>>((const uint4*)table, n_table_items, layers, d, ids, n, sel, n_sel, (uint4*)out);
+  IISAN_LAUNCH_OK();
+  return IISAN_OK;
+}

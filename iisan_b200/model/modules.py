@@ -1,0 +1,112 @@
+"""Parameter containers of the reference `model.modules` (Code_Cached/model/modules.py), same class names,
+constructor arguments, parameter names and initialisation -- the compute lives in libiisan_b200.so.
+
+The SASRec sub-blocks (PositionwiseFeedForward, MultiHeadedAttention, TransformerBlock) only own
+parameters: their arithmetic is executed by the fused user-encoder entry points, driven from
+TransformerEncoder.forward.
+"""
+from __future__ import annotations
+
+import torch
+from torch import nn
+
+from .. import _lib as L
+from ..ops import LinearFn, UserEncoderFn
+from ..plan import UserEncoderBinder
+from ..precision import compute_mode
+
+
+class PositionwiseFeedForward(nn.Module):
+    """Code_Cached/model/modules.py:6-18 (parameters only)."""
+
+    def __init__(self, d_model, d_inner, dropout):
+        super().__init__()
+        self.w_1 = nn.Linear(d_model, d_inner)
+        self.w_2 = nn.Linear(d_inner, d_model)
+        self.layer_norm = nn.LayerNorm(d_model, eps=1e-6)
+        self.dropout = nn.Dropout(dropout)
+        self.activate = nn.ReLU()
+
+
+class MultiHeadedAttention(nn.Module):
+    """Code_Cached/model/modules.py:35-64 (parameters only; Q/K/V/fc are bias-free)."""
+
+    def __init__(self, n_heads, d_model, dropout):
+        super().__init__()
+        if d_model % n_heads:
+            raise ValueError("d_model must be divisible by n_heads")
+        self.d_model, self.n_heads = d_model, n_heads
+        self.d_k = self.d_v = d_model // n_heads
+        for name in ("w_Q", "w_K", "w_V", "fc"):
+            setattr(self, name, nn.Linear(d_model, d_model, bias=False))
+        self.dropout = nn.Dropout(p=dropout)
+        self.layer_norm = nn.LayerNorm(d_model, eps=1e-6)
+
+
+class TransformerBlock(nn.Module):
+    """Code_Cached/model/modules.py:67-76 (parameters only)."""
+
+    def __init__(self, d_model, n_heads, d_inner, dropout):
+        super().__init__()
+        self.multi_head_attention = MultiHeadedAttention(n_heads=n_heads, d_model=d_model, dropout=dropout)
+        self.feed_forward = PositionwiseFeedForward(d_model=d_model, d_inner=d_inner, dropout=dropout)
+
+
+class TransformerEncoder(nn.Module):
+    """Code_Cached/model/modules.py:79-96.  forward() runs the whole encoder in the CUDA library."""
+
+    def __init__(self, n_vocab, n_position, d_model, n_heads, dropout, n_layers):
+        super().__init__()
+        self.position_embedding = nn.Embedding(n_position, d_model)
+        self.dropout = nn.Dropout(p=dropout)
+        self.layer_norm = nn.LayerNorm(d_model, eps=1e-6)
+        self.transformer_blocks = nn.ModuleList(
+            TransformerBlock(d_model=d_model, n_heads=n_heads, d_inner=d_model * 4, dropout=dropout) for _ in range(n_layers))
+        self._cfg = (d_model, n_heads, n_layers, float(dropout))
+        self._binder = None
+        self._step = 0
+        self.dropout_seed = 0x5EED1154
+
+    def _bind(self):
+        if self._binder is None:
+            names = ["transformer_encoder." + n for n, _ in self.named_parameters()]
+            d_model, n_heads, n_layers, p = self._cfg
+            self._binder = UserEncoderBinder(names, d_model, n_heads, n_layers, p)
+        return self._binder
+
+    def forward(self, input_embs, log_mask, att_mask=None):
+        # att_mask is implied by log_mask (causal + key padding, encoders.py:54-57) and rebuilt in-kernel.
+        params = tuple(self.parameters())
+        self._step += 1
+        return UserEncoderFn.apply(self._bind(), input_embs, log_mask, self.training, self.dropout_seed, self._step,
+                                   compute_mode(), *params)
+
+
+class AdapterBlock(nn.Module):
+    """Code_Cached/model/modules.py:98-116: fc_up(act(fc_down(x))) + x.  The Dropout is constructed but,
+    as in the reference forward, never applied.  Inside IISANAdaptedMModel the whole stage chain is
+    fused; this standalone forward exists for API parity and runs on the same dense-layer kernels."""
+
+    def __init__(self, args, input_size, down_size, dropout=0.1):
+        super().__init__()
+        if getattr(args, "adapter_activation", "RELU") == "GELU":
+            raise NotImplementedError("GELU adapters are not built")
+        self.fc_down = nn.Linear(input_size, down_size)
+        self.fc_up = nn.Linear(down_size, input_size)
+        for lin in (self.fc_down, self.fc_up):
+            nn.init.normal_(lin.weight, std=1e-2)
+            nn.init.zeros_(lin.bias)
+        self.activate = nn.ReLU()
+        self.dropout = nn.Dropout(dropout)
+
+    def forward(self, input_embs):
+        c = compute_mode()
+        z = self.activate(LinearFn.apply(input_embs, self.fc_down.weight, self.fc_down.bias, c))
+        return LinearFn.apply(z, self.fc_up.weight, self.fc_up.bias, c) + input_embs
+
+
+class FusedLinear(nn.Linear):
+    """nn.Linear whose forward/backward run through iisan_linear_* (used for com_dense)."""
+
+    def forward(self, x):
+        return LinearFn.apply(x, self.weight, self.bias, compute_mode())

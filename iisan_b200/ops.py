@@ -1,0 +1,236 @@
+"""torch.autograd glue over the C ABI (include/iisan_b200.h).
+
+PyTorch is only plumbing here: it owns device memory, the current stream and the autograd graph;
+every FLOP of the hot path happens inside libiisan_b200.so.  Nothing in this file computes on tensors
+with torch ops, and there is no fallback: tensors that are not on a CUDA device raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _workspace(nbytes: int, device):
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+# --------------------------------------------------------------------------------------------------
+# dense layer (com_dense)
+# --------------------------------------------------------------------------------------------------
+class LinearFn(torch.autograd.Function):
+    """y = x W^T + b through iisan_linear_forward / iisan_linear_backward."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, compute):
+        L.require_cuda(x, "linear input")
+        lib = L.load()
+        lead = x.shape[:-1]
+        x2 = x.reshape(-1, x.shape[-1])
+        if x2.stride(-1) != 1:
+            x2 = x2.contiguous()
+        x2 = x2.float()
+        rows, k = x2.shape
+        n = weight.shape[0]
+        y = torch.empty(rows, n, dtype=torch.float32, device=x.device)
+        L.check(lib.iisan_linear_forward(rows, n, k, _p(x2), x2.stride(0), _p(weight), _p(bias), _p(y), n, compute, _stream()),
+                "iisan_linear_forward")
+        ctx.save_for_backward(x2, weight)
+        ctx.has_bias = bias is not None
+        ctx.compute = compute
+        ctx.lead = lead
+        return y.view(*lead, n)
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = L.load()
+        x2, weight = ctx.saved_tensors
+        rows, k = x2.shape
+        n = weight.shape[0]
+        dy2 = dy.reshape(rows, n)
+        if dy2.stride(-1) != 1 or dy2.dtype != torch.float32:
+            dy2 = dy2.contiguous().float()
+        dx = torch.empty(rows, k, dtype=torch.float32, device=dy.device) if ctx.needs_input_grad[0] else None
+        dw = torch.zeros_like(weight) if ctx.needs_input_grad[1] else None
+        db = torch.zeros(n, dtype=torch.float32, device=dy.device) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+        L.check(lib.iisan_linear_backward(rows, n, k, _p(x2), x2.stride(0), _p(weight), _p(dy2), dy2.stride(0), _p(dx), k,
+                                          _p(dw), _p(db), ctx.compute, _stream()), "iisan_linear_backward")
+        return (None if dx is None else dx.view(*ctx.lead, k)), dw, db, None
+
+
+# --------------------------------------------------------------------------------------------------
+# side-adapter network
+# --------------------------------------------------------------------------------------------------
+class SanFn(torch.autograd.Function):
+    """out[N, 3E] = (cv | text | mm) embeddings.  `binder` builds descriptors and pointer tables."""
+
+    @staticmethod
+    def forward(ctx, binder, image, text, compute, *params):
+        L.require_cuda(image, "image hidden states")
+        L.require_cuda(text, "text hidden states")
+        lib = L.load()
+        image = image.contiguous()
+        text = text.contiguous()
+        desc = binder.desc(image, text, compute)
+        ptrs = binder.param_table(params)
+        n, e = desc.n_items, desc.emb
+        out = torch.empty(n, 3 * e, dtype=torch.float32, device=image.device)
+        nbytes = lib.iisan_san_workspace_bytes(C.byref(desc))
+        if nbytes == 0:
+            raise L.IisanLibraryError("iisan_san_workspace_bytes rejected the descriptor")
+        ws = _workspace(nbytes, image.device)
+        L.check(lib.iisan_san_forward(C.byref(desc), C.byref(ptrs), _p(image), _p(text), _p(ws), ws.numel(), _p(out), _stream()),
+                "iisan_san_forward")
+        ctx.binder, ctx.desc, ctx.ptrs, ctx.ws = binder, desc, ptrs, ws
+        ctx.image, ctx.text = image, text
+        ctx.params = params
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        lib = L.load()
+        d_out = d_out.contiguous().float()
+        flat, views, gptrs = ctx.binder.grad_table(ctx.params, d_out.device)
+        L.check(lib.iisan_san_backward(C.byref(ctx.desc), C.byref(ctx.ptrs), C.byref(gptrs), _p(ctx.image), _p(ctx.text),
+                                       _p(ctx.ws), ctx.ws.numel(), _p(d_out), _stream()), "iisan_san_backward")
+        ctx.ws = None
+        return (None, None, None, None, *views)
+
+
+# --------------------------------------------------------------------------------------------------
+# SASRec user encoder
+# --------------------------------------------------------------------------------------------------
+class UserEncoderFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, binder, embs, log_mask, training, seed, offset, compute, *params):
+        L.require_cuda(embs, "user-encoder input")
+        lib = L.load()
+        if embs.dtype != torch.float32 or embs.stride(-1) != 1 or embs.stride(1) != embs.shape[2]:
+            embs = embs.float().contiguous()
+        b, l, e = embs.shape
+        log_mask = log_mask.to(device=embs.device, dtype=torch.float32).contiguous()
+        desc = binder.desc(b, l, training, seed, offset, compute)
+        ptrs = binder.param_table(params)
+        nbytes = lib.iisan_user_encoder_workspace_bytes(C.byref(desc))
+        if nbytes == 0:
+            raise L.IisanLibraryError("iisan_user_encoder_workspace_bytes rejected the descriptor")
+        ws = _workspace(nbytes, embs.device)
+        out = torch.empty(b, l, e, dtype=torch.float32, device=embs.device)
+        L.check(lib.iisan_user_encoder_forward(C.byref(desc), C.byref(ptrs), _p(embs), embs.stride(0), _p(log_mask), _p(ws),
+                                               ws.numel(), _p(out), _stream()), "iisan_user_encoder_forward")
+        ctx.binder, ctx.desc, ctx.ptrs, ctx.ws = binder, desc, ptrs, ws
+        ctx.embs, ctx.log_mask, ctx.params = embs, log_mask, params
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        lib = L.load()
+        d_out = d_out.contiguous().float()
+        b, l, e = d_out.shape
+        flat, views, gptrs = ctx.binder.grad_table(ctx.params, d_out.device)
+        ld_user = ctx.embs.stride(0)                      # d_embs shares the input's user stride
+        d_full = torch.zeros(b, ld_user // e, e, dtype=torch.float32, device=d_out.device)
+        d_embs = d_full[:, :l]
+        L.check(lib.iisan_user_encoder_backward(C.byref(ctx.desc), C.byref(ctx.ptrs), C.byref(gptrs), _p(ctx.embs),
+                                                ctx.embs.stride(0), _p(ctx.log_mask), _p(ctx.ws), ctx.ws.numel(), _p(d_out),
+                                                _p(d_embs), _stream()), "iisan_user_encoder_backward")
+        ctx.ws = None
+        return (None, d_embs, None, None, None, None, None, *views)
+
+
+# --------------------------------------------------------------------------------------------------
+# in-batch cross-entropy
+# --------------------------------------------------------------------------------------------------
+def make_ce_desc(row_users, col_users, seq_len, emb, user_offset, compute):
+    d = L.CeDesc()
+    d.row_users, d.col_users, d.seq_len, d.emb = row_users, col_users, seq_len, emb
+    d.user_offset, d.compute = user_offset, compute
+    return d
+
+
+class InBatchCeFn(torch.autograd.Function):
+    """(loss_sum, n_valid, loss) of the local rows against the column pool.
+
+    prec [B*L, E]; score [C_users*(L+1), E]; ids int64; log_mask fp32 [.., L]; pop_prob fp32 table.
+    ``loss`` = loss_sum / n_valid is the reference's per-rank mean (CC/model/model.py:104); ``loss_sum``
+    and ``n_valid`` feed the global-negative normalisation.
+    """
+
+    @staticmethod
+    def forward(ctx, prec, score, ids_rows, ids_cols, lm_rows, lm_cols, pop_prob, user_offset, compute):
+        L.require_cuda(prec, "prec_vec")
+        lib = L.load()
+        prec = prec.contiguous().float()
+        score = score.contiguous().float()
+        ids_rows = ids_rows.contiguous().view(-1)
+        ids_cols = ids_cols.contiguous().view(-1)
+        lm_rows = lm_rows.contiguous().float()
+        lm_cols = lm_cols.contiguous().float()
+        b, l = lm_rows.shape
+        bc = lm_cols.shape[0]
+        e = prec.shape[1]
+        desc = make_ce_desc(b, bc, l, e, user_offset, compute)
+        nbytes = lib.iisan_inbatch_ce_workspace_bytes(C.byref(desc))
+        if nbytes == 0:
+            raise L.IisanLibraryError("iisan_inbatch_ce_workspace_bytes rejected the descriptor")
+        ws = _workspace(nbytes, prec.device)
+        res = torch.empty(2, dtype=torch.float32, device=prec.device)       # loss_sum, loss
+        n_valid = torch.empty(1, dtype=torch.int32, device=prec.device)
+        L.check(lib.iisan_inbatch_ce_forward(C.byref(desc), _p(prec), _p(score), _p(ids_rows), _p(ids_cols), _p(lm_rows),
+                                             _p(lm_cols), _p(pop_prob), _p(ws), ws.numel(), _p(res[0:1]), _p(n_valid),
+                                             _p(res[1:2]), _stream()), "iisan_inbatch_ce_forward")
+        ctx.desc, ctx.ws = desc, ws
+        ctx.tensors = (prec, score, ids_rows, ids_cols, lm_rows, lm_cols, pop_prob)
+        ctx.n_valid = n_valid
+        ctx.mark_non_differentiable(n_valid)
+        return res[0], n_valid, res[1]
+
+    @staticmethod
+    def backward(ctx, g_sum, _g_n, g_loss):
+        lib = L.load()
+        prec, score, ids_rows, ids_cols, lm_rows, lm_cols, pop_prob = ctx.tensors
+        g_sum = None if g_sum is None else g_sum.reshape(1).float().contiguous()
+        g_loss = None if g_loss is None else g_loss.reshape(1).float().contiguous()
+        d_prec = torch.empty_like(prec)
+        d_score = torch.empty_like(score)
+        L.check(lib.iisan_inbatch_ce_backward(C.byref(ctx.desc), _p(prec), _p(score), _p(ids_rows), _p(ids_cols), _p(lm_rows),
+                                              _p(lm_cols), _p(pop_prob), _p(ctx.ws), ctx.ws.numel(), _p(g_sum), _p(g_loss),
+                                              _p(ctx.n_valid), _p(d_prec), _p(d_score), _stream()), "iisan_inbatch_ce_backward")
+        return d_prec, d_score, None, None, None, None, None, None, None
+
+
+def inbatch_ce_masks(ids_rows, ids_cols, lm_rows, lm_cols, user_offset=0):
+    """uint8 [B*L, C] mask bits straight from the CUDA path (parity probe)."""
+    lib = L.load()
+    L.require_cuda(ids_rows, "ids")
+    b, l = lm_rows.shape
+    bc = lm_cols.shape[0]
+    desc = make_ce_desc(b, bc, l, 32, user_offset, 0)
+    out = torch.empty(b * l, bc * (l + 1), dtype=torch.uint8, device=ids_rows.device)
+    L.check(lib.iisan_inbatch_ce_masks(C.byref(desc), _p(ids_rows.contiguous().view(-1)), _p(ids_cols.contiguous().view(-1)),
+                                       _p(lm_rows.contiguous().float()), _p(lm_cols.contiguous().float()), _p(out), _stream()),
+            "iisan_inbatch_ce_masks")
+    return out
+
+
+def gather_states(table, ids, sel):
+    """out[n, len(sel), d] = table[ids, sel, :] (zeros for id 0) through iisan_gather_states."""
+    lib = L.load()
+    L.require_cuda(ids, "ids")
+    n_items, layers, d = table.shape
+    ids = ids.contiguous().view(-1)
+    sel_t = torch.as_tensor(sel, dtype=torch.int32, device=ids.device)
+    out = torch.empty(ids.numel(), len(sel), d, dtype=table.dtype, device=ids.device)
+    L.check(lib.iisan_gather_states(_p(table), L.torch_dtype_code(table.dtype), n_items, layers, d, _p(ids), ids.numel(),
+                                    _p(sel_t), len(sel), _p(out), _stream()), "iisan_gather_states")
+    return out

@@ -1,0 +1,111 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads without a GPU, exports every symbol
+include/iisan_b200.h declares, struct layouts agree, and the Python mirror has the reference's parameter ABI."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+from torch import nn
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, "include", "iisan_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(iisan_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    from iisan_b200 import _lib
+    lib = _lib.load()
+    declared = header_functions()
+    assert len(declared) >= 15
+    raw = ctypes.CDLL(_lib.lib_path())
+    for name in declared:
+        assert hasattr(raw, name), f"{name} declared in include/iisan_b200.h but not exported"
+    assert set(declared) == set(_lib.EXPORTED_SYMBOLS)
+    assert lib.iisan_abi_version() == _lib.ABI_VERSION
+    assert lib.iisan_status_string(3).decode() == "workspace too small"
+
+
+def test_struct_layouts_match():
+    from iisan_b200 import _lib
+    lib = _lib.load()
+    for which, st in enumerate((_lib.SanDesc, _lib.SanParams, _lib.UeDesc, _lib.UeParams, _lib.CeDesc)):
+        assert lib.iisan_sizeof(which) == ctypes.sizeof(st)
+
+
+def test_descriptor_validation_without_gpu():
+    """Pure host-side argument checks (no kernel is launched)."""
+    from iisan_b200 import _lib
+    lib = _lib.load()
+    d = _lib.SanDesc()
+    assert lib.iisan_san_workspace_bytes(ctypes.byref(d)) == 0            # empty descriptor rejected
+    ce = _lib.CeDesc()
+    ce.row_users, ce.col_users, ce.seq_len, ce.emb, ce.user_offset = 4, 2, 10, 64, 0     # rows outside the pool
+    assert lib.iisan_inbatch_ce_workspace_bytes(ctypes.byref(ce)) == 0
+    ce.col_users = 8
+    assert lib.iisan_inbatch_ce_workspace_bytes(ctypes.byref(ce)) > 0
+    assert lib.iisan_linear_forward(0, 1, 1, None, 0, None, None, None, 0, 0, None) == 1  # IISAN_EINVAL
+
+
+@pytest.mark.parametrize("asym", [False, True])
+def test_parameter_abi_matches_reference(asym):
+    """names, order and shapes == the reference's named_parameters() (tests/golden were generated after asserting
+    that oracle.synthetic.param_shapes equals the reference's own list)."""
+    from oracle.synthetic import PathConfig, make_args, param_shapes
+    if asym:
+        from iisan_b200 import model_asym as pkg
+        cfg = PathConfig(asym=True, d_text=96, d_img=64, layers_text=9, layers_img=5, bert_list="1,3,5,7", vit_list="1,3",
+                         r_cv=16, r_bert=24, embedding_dim=32, item_num=500)
+    else:
+        from iisan_b200 import model as pkg
+        cfg = PathConfig()
+    args = make_args(cfg)
+
+    class Img(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.classifier = nn.Linear(cfg.d_img, cfg.embedding_dim)
+
+    m = pkg.ModelMM(args, cfg.item_num, True, Img(), nn.Identity(), [1.0] * (cfg.item_num + 1))
+    m.mm_encoder = pkg.IISANAdaptedMModel(m.mm_encoder, args)
+    got = [(n, tuple(p.shape)) for n, p in m.named_parameters()]
+    assert got == list(param_shapes(cfg).items())
+    if not asym:
+        assert len(got) == 146 and sum(p.numel() for p in m.parameters()) == 4113877
+
+
+def test_product_refuses_cpu_tensors():
+    """No CPU fallback: the hot path raises instead of computing on the host."""
+    from iisan_b200 import _lib
+    from iisan_b200.model.modules import FusedLinear
+    lin = FusedLinear(8, 4)
+    with pytest.raises(_lib.IisanLibraryError):
+        lin(torch.zeros(2, 8))
+
+
+def test_unsupported_configs_rejected_at_construction():
+    from oracle.synthetic import PathConfig, make_args
+    from iisan_b200.plan import make_plan
+    a = make_args(PathConfig()); a.fusion_method = "sum"
+    with pytest.raises(NotImplementedError):
+        make_plan(a, False)
+    a = make_args(PathConfig()); a.modality = "intra"
+    with pytest.raises(NotImplementedError):
+        make_plan(a, False)
+
+
+def test_stage_plan_matches_oracle_plan():
+    from oracle.iisan_oracle import stage_plan
+    from oracle.synthetic import PathConfig, make_args
+    from iisan_b200.plan import make_plan
+    cfgs = [PathConfig(), PathConfig(remove_first="TRUE", bert_list="0,2,4,6,8,10"),
+            PathConfig(asym=True, d_text=96, d_img=64, layers_text=9, layers_img=5, bert_list="1,3,5,7", vit_list="1,3"),
+            PathConfig(asym=True, d_text=64, d_img=128, layers_text=5, layers_img=7, bert_list="1,3", vit_list="0,2,3,5")]
+    for cfg in cfgs:
+        plan = make_plan(make_args(cfg), cfg.asym)
+        exp = [tuple(-1 if v is None else v for v in st) for st in stage_plan(cfg)]
+        assert plan.stages == exp
