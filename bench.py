@@ -1,0 +1,361 @@
+#!/usr/bin/env python
+"""IISAN(Cached) training hot path benchmark (BASELINE.json metric: train samples/s, 1 sample = 1 user = 11 slots).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One step = one pass of the hot path over one synthetic batch: SAN forward -> fusion -> SASRec -> in-batch CE
+-> backward -> Adam.  Workload at N=1 is BASELINE configs[1] (Instrument shape: item_num 19,246, B=512 users,
+BERT-base + ViT-B/16 cached states [13, 768] stored bf16, random-init adapters).  For N>1 every rank gets its own
+B=512 users (weak scaling, BASELINE configs[2]) with the global in-batch negative pool (item-embedding all-gather).
+
+Prints ONE JSON line (see the keys at the bottom).  `--impl reference` times the reference algorithm's CPU path
+(the oracle port -- /root/reference is not present on the GPU box) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "iisan_cached_train_samples_per_s"
+UNIT = "samples/s"
+ITEM_NUM = 19246          # Instrument catalogue
+SEED = 12345              # reference seed (Code_Cached/scripts/run_IISAN.py:44)
+LRS = dict(lr=2e-4, adapter_cv_lr=1e-4, adapter_bert_lr=1e-4, fine_tune_lr_image=1e-4, fine_tune_lr_text=5e-5)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=512)
+    ap.add_argument("--compute", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--cpu-batch", type=int, default=512)
+    ap.add_argument("--cpu-steps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# CPU arm: the reference algorithm (oracle port) on the host cores
+# ----------------------------------------------------------------------------------------------------------------
+def cpu_reference_steps(batch, steps, warmup):
+    """fwd + bwd + Adam of the oracle restatement (fp32, all host threads).  Returns (samples/s, s/step, cores)."""
+    import numpy as np
+    import torch
+    from oracle import iisan_oracle as O
+    from oracle.synthetic import PathConfig, make_ids, make_params, make_pop_prob
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = PathConfig(item_num=ITEM_NUM)
+    ids, lm = make_ids(batch, cfg, SEED, "dense")
+    g = torch.Generator().manual_seed(SEED)
+    image = torch.randn(batch, 11, 13, 768, generator=g).numpy()
+    text = torch.randn(batch, 11, 13, 768, generator=g).numpy()
+    b = {"ids": ids, "log_mask": lm, "image": image, "text": text}
+    pop = make_pop_prob(cfg, SEED)
+    P = O.params_to_torch(make_params(cfg, SEED, perturb=False))
+    opt = torch.optim.Adam(list(P.values()), lr=LRS["lr"])
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        opt.zero_grad(set_to_none=True)
+        out = O.model_forward(P, b, pop, cfg)
+        out["loss"].backward()
+        opt.step()
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    sps = batch * len(times) / sum(times)
+    return sps, sum(times) / len(times), cores, float(out["loss"].item())
+
+
+def run_reference_arm(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sps, sec, cores, loss = cpu_reference_steps(a.cpu_batch, a.steps, a.warmup)
+    sample = f"{a.steps} full train steps (fwd+bwd+Adam) of B={a.cpu_batch} dense users, fp32, torch CPU, oracle port of the reference algorithm"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": sps, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": f"IISAN(Cached) Instrument shape, B={a.cpu_batch}, 13x768 BERT-base+ViT-B/16 cached states, CPU"},
+        "cpu_baseline": {"value": sps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": sps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "loss": loss,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self, t0, t1):
+        sm, mx, reasons = [], [], set()
+        for t, line in self.rows:
+            if t < t0 - 0.05 or t > t1 + 0.15:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_model(device, compute):
+    import torch
+    from torch import nn
+    from iisan_b200 import model as pkg
+    from iisan_b200.config import default_args
+    from iisan_b200.precision import set_compute_mode
+    args = default_args(**LRS)
+    cfg = args
+    torch.manual_seed(SEED)
+
+    class ImgStub(nn.Module):                                  # ViTForImageClassification head stand-in (run.py:44-49)
+        def __init__(self):
+            super().__init__()
+            self.classifier = nn.Linear(768, args.embedding_dim)
+
+    import numpy as np
+    rng = np.random.default_rng(SEED)
+    counts = np.floor(1.0 + rng.pareto(1.2, size=ITEM_NUM) * 3.0)
+    pop = np.concatenate([[1.0], counts / counts.sum()]).astype("float32")
+    m = pkg.ModelMM(args, ITEM_NUM, True, ImgStub(), nn.Identity(), pop)
+    m.mm_encoder = pkg.IISANAdaptedMModel(m.mm_encoder, args)          # Code_Cached/run.py:182-183
+    set_compute_mode(compute)
+    return m.to(device), args, cfg
+
+
+def make_device_batches(n, B, device, dtype, gen):
+    import torch
+    out = []
+    for _ in range(n):
+        ids = torch.randint(1, ITEM_NUM + 1, (B * 11,), device=device, generator=gen, dtype=torch.int64)
+        image = torch.randn(B, 11, 13, 768, device=device, generator=gen, dtype=torch.float32).to(dtype)
+        text = torch.randn(B, 11, 13, 768, device=device, generator=gen, dtype=torch.float32).to(dtype)
+        lm = torch.ones(B, 10, device=device, dtype=torch.float32)
+        out.append((ids, image, text, lm))
+    return out
+
+
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+    from iisan_b200 import _lib
+    from iisan_b200.optim import param_groups
+    lib = _lib.load()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    state_dtype = torch.bfloat16 if a.compute == "bf16" else torch.float32
+    model, args, cfg = build_model(device, a.compute)
+    model.train()
+    train_model = model
+    if world > 1:
+        model.negatives = "global"
+        train_model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], find_unused_parameters=False)
+    opt = torch.optim.Adam(param_groups(model, args), fused=True)
+    gen = torch.Generator(device=device).manual_seed(SEED + rank)
+    B = a.batch
+    n_rot = 3                                               # 3 x 225 MB (bf16) rotating inputs >> 126 MB L2
+    batches = make_device_batches(n_rot, B, device, state_dtype, gen)
+
+    def step(i, data=None):
+        ids, image, text, lm = data if data is not None else batches[i % n_rot]
+        opt.zero_grad(set_to_none=True)
+        loss = train_model(ids, image, text, lm, local)
+        loss.backward()
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(n, fn):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.time()
+        e0.record()
+        for i in range(n):
+            last = fn(i)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, t0, time.time(), last
+
+    for i in range(max(a.warmup, 3)):
+        step(i)
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start(); time.sleep(0.3)
+    launches0 = lib.iisan_launch_count(-1)
+    ms, t0, t1, last = timed(a.steps, step)
+    launches = lib.iisan_launch_count(-1) - launches0
+    if sampler:
+        time.sleep(0.2); sampler.stop()
+    clocks = sampler.summary(t0, t1) if sampler else None
+    value = world * B * a.steps / (ms / 1e3)
+    loss_val = float(last.item())
+
+    # ---- per-kernel-class device time (same K steps again, CUDA events around every launch) ----
+    import ctypes as C
+    lib.iisan_timing_enable(1)
+    ms_prof, _, _, _ = timed(a.steps, step)
+    lib.iisan_timing_enable(0)
+    classes = {}
+    for k, name in enumerate(_lib.KERNEL_CLASSES):
+        tot, n = C.c_double(0), C.c_int64(0)
+        lib.iisan_timing_read(k, C.byref(tot), C.byref(n))
+        classes[name] = {"ms_per_step": tot.value / a.steps, "launches_per_step": n.value / a.steps}
+
+    # ---- end-to-end through the reference-facing call with HOST buffers ----
+    host = []
+    for ids, image, text, lm in batches[:2]:
+        host.append(tuple(t.cpu().pin_memory() for t in (ids, image, text, lm)))
+    h2d = sum(t.numel() * t.element_size() for t in host[0])
+
+    def e2e_step(i):
+        hb = host[i % len(host)]
+        data = tuple(t.to(device, non_blocking=True) for t in hb)        # exactly run.py:370-371
+        loss = step(i, data)
+        return loss.item()                                               # D2H read of the result (run.py:382,387)
+
+    for i in range(2):
+        e2e_step(i)
+    e2e_steps = max(3, min(a.steps, 10))
+    ms_e2e, _, _, _ = timed(e2e_steps, e2e_step)
+    e2e_value = world * B * e2e_steps / (ms_e2e / 1e3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk):
+        peaks = json.load(open(pk))
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    tf_peak = peaks.get("bf16_tflops_sustained", 1400.0)
+    peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
+    elt = 2 if state_dtype == torch.bfloat16 else 4
+    # algorithmic bytes of the streaming kernels per step: forward reads the 7+7 selected layers of every
+    # item once; the backward's gate-gradient pass re-streams them once -> 2x.
+    stream_bytes = 2 * B * 11 * (7 * 768 + 7 * 768) * elt
+    stream = classes["stream"]
+    dom = max(classes.items(), key=lambda kv: kv[1]["ms_per_step"])
+    flops_step = B * 291e6                                   # fwd+bwd FLOPs / sample
+    roof = {
+        "bound": "hbm", "kernel_class": "stream (layer-select gather + gate fusion fwd, gate-grad re-stream bwd)",
+        "achieved": stream_bytes / (stream["ms_per_step"] / 1e3) / 1e9 if stream["ms_per_step"] > 0 else None,
+        "peak": hbm_peak, "unit": "GB/s", "traffic": None, "peak_source": peak_src,
+        "algorithmic_bytes_per_step": stream_bytes, "ms_per_step": stream["ms_per_step"],
+    }
+    roof["frac"] = (roof["achieved"] / hbm_peak) if roof["achieved"] else None
+    gemm_ms = classes["gemm"]["ms_per_step"] + classes["chain"]["ms_per_step"]
+    roof_tensor = {"bound": "tensor", "achieved": (B * 11 * 3 * 7987200 / (gemm_ms / 1e3) / 1e12) if gemm_ms > 0 else None,
+                   "peak": tf_peak, "unit": "TFLOP/s", "ms_per_step": gemm_ms,
+                   "note": "SAN adapter/head GEMM FLOPs (fwd+bwd = 3x 7.99 MFLOP/item) over the summed GEMM-class kernel time"}
+    roof_tensor["frac"] = (roof_tensor["achieved"] / tf_peak) if roof_tensor["achieved"] else None
+
+    cpu = None
+    if world == 1 and not a.no_cpu_baseline:
+        sps, sec, cores, _ = cpu_reference_steps(a.cpu_batch, a.cpu_steps, 1)
+        cpu = {"value": sps, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{a.cpu_steps} full train steps of B={a.cpu_batch} dense users (fp32, torch CPU, oracle port of the reference "
+                         f"algorithm; {sec:.2f} s/step)"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+        "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": a.compute, "data": "synthetic",
+        "config": {"workload": f"IISAN(Cached) Instrument shape: item_num {ITEM_NUM}, B={B} users/GPU x 11 slots, BERT-base+ViT-B/16 "
+                               f"cached states [13,768] stored {str(state_dtype).split('.')[-1]}, 7 of 13 layers, r=64, E=64, random-init adapters, "
+                               f"dense batch, fwd+bwd+Adam",
+                   "negatives": "global (all-gather)" if world > 1 else "local",
+                   "l2_policy": f"inputs rotate over {n_rot} batches of {2 * B * 11 * 13 * 768 * elt / 1e6:.0f} MB (> 126 MB L2)",
+                   "parallelism": f"dp{world}"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                "ms_per_step": ms_e2e / e2e_steps,
+                "note": "ModelMM.forward called with pinned HOST batch tensors; .to(device) copies + loss.item() inside the timed region"},
+        "gpu_launches": int(launches),
+        "gpu_launches_per_step": launches / a.steps,
+        "clocks": clocks,
+        "roofline": roof, "roofline_tensor": roof_tensor,
+        "kernel_classes": classes, "dominant_class": dom[0], "ms_per_step_with_kernel_events": ms_prof / a.steps,
+        "cpu_baseline": cpu, "loss": loss_val,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        run_reference_arm(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -13,6 +13,8 @@ MAX_BLOCKS = 8
 ABI_VERSION = 1
 
 F32, BF16, F16 = 0, 1, 2
+K_STREAM, K_GEMM, K_USER, K_CE, K_MISC, K_CHAIN = range(6)
+KERNEL_CLASSES = ("stream", "gemm", "user", "ce", "misc", "chain")
 COMPUTE_FP32, COMPUTE_BF16 = 0, 1
 
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libiisan_b200.so")
@@ -73,6 +75,9 @@ _SIGNATURES = {
     "iisan_last_cuda_error": (C.c_int, []),
     "iisan_last_cuda_error_string": (C.c_char_p, []),
     "iisan_sizeof": (C.c_size_t, [C.c_int]),
+    "iisan_launch_count": (C.c_int64, [C.c_int]),
+    "iisan_timing_enable": (C.c_int, [C.c_int]),
+    "iisan_timing_read": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "iisan_san_workspace_bytes": (C.c_size_t, [C.POINTER(SanDesc)]),
     "iisan_san_forward": (C.c_int, [C.POINTER(SanDesc), C.POINTER(SanParams), vp, vp, vp, C.c_size_t, vp, vp]),
     "iisan_san_backward": (C.c_int, [C.POINTER(SanDesc), C.POINTER(SanParams), C.POINTER(SanParams), vp, vp, vp, C.c_size_t, vp, vp]),

@@ -1,9 +1,45 @@
 // C-ABI plumbing: version/status/error reporting, the dense layer (com_dense) and the cached-state gather.
 #include "common.cuh"
 #include "gemm_simt.cuh"
+#include "launch.cuh"
+
+#include <atomic>
+#include <mutex>
+#include <vector>
 
 namespace iisan {
 thread_local cudaError_t g_last_cuda_error = cudaSuccess;
+
+// ---- launch accounting / timing ------------------------------------------------------------------------
+static std::atomic<int64_t> g_launches[IISAN_K_COUNT];
+static std::atomic<int> g_timing_on{0};
+struct TimedLaunch { cudaEvent_t beg, end; int kclass; bool used; };
+static std::vector<TimedLaunch> g_timed;
+static std::mutex g_timed_mu;
+constexpr size_t kMaxTimed = 1u << 16;
+
+void launch_scope_begin(int kclass, cudaStream_t st, int* slot) {
+  g_launches[kclass].fetch_add(1, std::memory_order_relaxed);
+  *slot = -1;
+  if (!g_timing_on.load(std::memory_order_relaxed)) return;
+  std::lock_guard<std::mutex> lk(g_timed_mu);
+  int idx = -1;
+  for (size_t i = 0; i < g_timed.size(); ++i) if (!g_timed[i].used) { idx = (int)i; break; }
+  if (idx < 0) {
+    if (g_timed.size() >= kMaxTimed) return;
+    TimedLaunch t{};
+    if (cudaEventCreate(&t.beg) != cudaSuccess || cudaEventCreate(&t.end) != cudaSuccess) return;
+    g_timed.push_back(t);
+    idx = (int)g_timed.size() - 1;
+  }
+  g_timed[idx].used = true; g_timed[idx].kclass = kclass;
+  cudaEventRecord(g_timed[idx].beg, st);
+  *slot = idx;
+}
+void launch_scope_end(int slot, cudaStream_t st) {
+  std::lock_guard<std::mutex> lk(g_timed_mu);
+  cudaEventRecord(g_timed[slot].end, st);
+}
 
 // ---- cached-state gather -----------------------------------------------------------------------------
 // out[i, a, :] = table[ids[i], sel[a], :]  (zeros when ids[i] == 0).  One CTA handles a group of
@@ -44,6 +80,27 @@ extern "C" const char* iisan_status_string(int s) {
     case IISAN_EUNSUPPORTED: return "configuration valid in the reference but not built here";
   }
   return "unknown status";
+}
+
+extern "C" int64_t iisan_launch_count(int kclass) {
+  int64_t t = 0;
+  for (int k = 0; k < IISAN_K_COUNT; ++k) if (kclass < 0 || kclass == k) t += g_launches[k].load();
+  return t;
+}
+extern "C" int iisan_timing_enable(int on) { g_timing_on.store(on ? 1 : 0); return IISAN_OK; }
+extern "C" int iisan_timing_read(int kclass, double* total_ms, int64_t* launches) {
+  if (kclass < 0 || kclass >= IISAN_K_COUNT || !total_ms || !launches) return IISAN_EINVAL;
+  std::lock_guard<std::mutex> lk(g_timed_mu);
+  double tot = 0.0; int64_t n = 0;
+  for (auto& t : g_timed) {
+    if (!t.used || t.kclass != kclass) continue;
+    IISAN_CUDA_OK(cudaEventSynchronize(t.end));
+    float ms = 0.f;
+    IISAN_CUDA_OK(cudaEventElapsedTime(&ms, t.beg, t.end));
+    tot += ms; ++n; t.used = false;
+  }
+  *total_ms = tot; *launches = n;
+  return IISAN_OK;
 }
 
 extern "C" size_t iisan_sizeof(int which) {
@@ -103,9 +160,9 @@ extern "C" int iisan_gather_states(const void* table, int32_t dtype, int64_t n_t
   const int blocks = (int)imin64((total + 255) / 256, 148 * 16);
   cudaStream_t st = as_stream(stream);
   if (bpe == 4)
-    gather_states_kernel<4><<<blocks, 256, 0, st>>>((const uint4*)table, n_table_items, layers, d, ids, n, sel, n_sel, (uint4*)out);
+    { LaunchScope ls_(IISAN_K_MISC, st); gather_states_kernel<4><<<blocks, 256, 0, st>>>((const uint4*)table, n_table_items, layers, d, ids, n, sel, n_sel, (uint4*)out); }
   else
-    gather_states_kernel<2><<<blocks, 256, 0, st>>>((const uint4*)table, n_table_items, layers, d, ids, n, sel, n_sel, (uint4*)out);
+    { LaunchScope ls_(IISAN_K_MISC, st); gather_states_kernel<2><<<blocks, 256, 0, st>>>((const uint4*)table, n_table_items, layers, d, ids, n, sel, n_sel, (uint4*)out); }
   IISAN_LAUNCH_OK();
   return IISAN_OK;
 }

@@ -1,5 +1,6 @@
 // fp32 FMA GEMM + column-sum kernels (exact mode building blocks); see gemm_simt.cuh.
 #include "gemm_simt.cuh"
+#include "launch.cuh"
 
 namespace iisan {
 
@@ -107,7 +108,7 @@ int launch_gemm(const GemmBatch& b, cudaStream_t st) {
     if (P.splitk > max_split) max_split = P.splitk;
   }
   dim3 grid(max_tiles, max_split, b.n);
-  gemm_simt_kernel<<<grid, 256, 0, st>>>(b);
+  { LaunchScope ls_(IISAN_K_GEMM, st); gemm_simt_kernel<<<grid, 256, 0, st>>>(b); }
   IISAN_LAUNCH_OK();
   return IISAN_OK;
 }
@@ -138,7 +139,7 @@ int launch_colsum(const ColsumBatch& b, cudaStream_t st) {
   for (int i = 0; i < b.n; ++i) { maxN = max(maxN, b.p[i].N); maxM = max(maxM, b.p[i].M); }
   const int rows_per_cta = 256;
   dim3 grid((maxN + 31) / 32, (maxM + rows_per_cta - 1) / rows_per_cta, b.n);
-  colsum_kernel<<<grid, 256, 0, st>>>(b, rows_per_cta);
+  { LaunchScope ls_(IISAN_K_MISC, st); colsum_kernel<<<grid, 256, 0, st>>>(b, rows_per_cta); }
   IISAN_LAUNCH_OK();
   return IISAN_OK;
 }

@@ -11,6 +11,7 @@
 // (row-user, column), evaluated in-tile; the [B*L, C] logits are never written to memory: the
 // forward keeps one log-sum-exp per row, the backward recomputes the tile.
 #include "common.cuh"
+#include "launch.cuh"
 
 namespace iisan {
 
@@ -272,9 +273,9 @@ extern "C" int iisan_inbatch_ce_forward(const iisan_ce_desc* desc, const float* 
   CeLayout W(*desc, workspace);
   const CeArgs a = make_args(*desc, prec, score, ids_rows, ids_cols, log_mask_rows, log_mask_cols, pop_prob);
   IISAN_CUDA_OK(cudaMemsetAsync(W.acc_sum, 0, 256 + sizeof(int), st));   // acc_sum and acc_cnt are adjacent 256 B slots
-  ce_fwd_kernel<<<a.B * a.L, 256, 0, st>>>(a, W.lse, W.acc_sum, W.acc_cnt);
+  { LaunchScope ls_(IISAN_K_CE, st); ce_fwd_kernel<<<a.B * a.L, 256, 0, st>>>(a, W.lse, W.acc_sum, W.acc_cnt); }
   IISAN_LAUNCH_OK();
-  ce_finalize_kernel<<<1, 1, 0, st>>>(W.acc_sum, W.acc_cnt, loss_sum, n_valid, loss);
+  { LaunchScope ls_(IISAN_K_CE, st); ce_finalize_kernel<<<1, 1, 0, st>>>(W.acc_sum, W.acc_cnt, loss_sum, n_valid, loss); }
   IISAN_LAUNCH_OK();
   return IISAN_OK;
 }
@@ -292,9 +293,9 @@ extern "C" int iisan_inbatch_ce_backward(const iisan_ce_desc* desc, const float*
   cudaStream_t st = as_stream(stream);
   CeLayout W(*desc, workspace);
   const CeArgs a = make_args(*desc, prec, score, ids_rows, ids_cols, log_mask_rows, log_mask_cols, pop_prob);
-  ce_bwd_rows_kernel<<<a.B * a.L, 256, 0, st>>>(a, W.lse, grad_loss_sum, grad_loss_mean, n_valid, d_prec);
+  { LaunchScope ls_(IISAN_K_CE, st); ce_bwd_rows_kernel<<<a.B * a.L, 256, 0, st>>>(a, W.lse, grad_loss_sum, grad_loss_mean, n_valid, d_prec); }
   IISAN_LAUNCH_OK();
-  ce_bwd_cols_kernel<<<(unsigned)a.C, 256, 0, st>>>(a, W.lse, grad_loss_sum, grad_loss_mean, n_valid, d_score);
+  { LaunchScope ls_(IISAN_K_CE, st); ce_bwd_cols_kernel<<<(unsigned)a.C, 256, 0, st>>>(a, W.lse, grad_loss_sum, grad_loss_mean, n_valid, d_score); }
   IISAN_LAUNCH_OK();
   return IISAN_OK;
 }
@@ -304,7 +305,7 @@ extern "C" int iisan_inbatch_ce_masks(const iisan_ce_desc* desc, const int64_t* 
   IISAN_TRY(ce_validate(desc));
   if (!ids_rows || !ids_cols || !log_mask_rows || !log_mask_cols || !out) return IISAN_EINVAL;
   const CeArgs a = make_args(*desc, nullptr, nullptr, ids_rows, ids_cols, log_mask_rows, log_mask_cols, nullptr);
-  ce_masks_kernel<<<a.B * a.L, 256, 0, as_stream(stream)>>>(a, out);
+  { LaunchScope ls_(IISAN_K_CE, as_stream(stream)); ce_masks_kernel<<<a.B * a.L, 256, 0, as_stream(stream)>>>(a, out); }
   IISAN_LAUNCH_OK();
   return IISAN_OK;
 }

@@ -11,6 +11,7 @@
 // (row pitch layers*d, 128-bit loads of the selected layer only).  The forward stashes, per stage
 // and tower, x_s [N,d], z_s [N,r] and last_s [N,d] in the workspace for the backward.
 #include "common.cuh"
+#include "launch.cuh"
 #include "gemm_simt.cuh"
 #include "san_layout.cuh"
 
@@ -139,7 +140,7 @@ static int launch_mix(const MixBatch& b, cudaStream_t st) {
   int64_t mx = 0;
   for (int i = 0; i < b.n; ++i) mx = max(mx, (int64_t)b.p[i].N * (b.p[i].d / 4));
   int blocks = (int)imin64((mx + 255) / 256, 148 * 8);
-  mix_kernel<T><<<dim3(blocks, b.n), 256, 0, st>>>(b);
+  { LaunchScope ls_(IISAN_K_STREAM, st); mix_kernel<T><<<dim3(blocks, b.n), 256, 0, st>>>(b); }
   IISAN_LAUNCH_OK();
   return IISAN_OK;
 }
@@ -149,7 +150,7 @@ static int launch_mix_bwd(const MixBwdBatch& b, cudaStream_t st) {
   int64_t mx = 0;
   for (int i = 0; i < b.n; ++i) mx = max(mx, (int64_t)b.p[i].N * (b.p[i].d / 4));
   int blocks = (int)imin64((mx + 255) / 256, 148 * 4);
-  mix_bwd_kernel<T><<<dim3(blocks, b.n), 256, 0, st>>>(b);
+  { LaunchScope ls_(IISAN_K_STREAM, st); mix_bwd_kernel<T><<<dim3(blocks, b.n), 256, 0, st>>>(b); }
   IISAN_LAUNCH_OK();
   return IISAN_OK;
 }

@@ -10,6 +10,7 @@
 // Dropout uses a counter-based Philox stream (philox.cuh) instead of torch's generator; with
 // drop_rate 0 / eval mode the result is the reference's.
 #include "common.cuh"
+#include "launch.cuh"
 #include "gemm_simt.cuh"
 #include "philox.cuh"
 
@@ -295,8 +296,8 @@ extern "C" int iisan_user_encoder_forward(const iisan_ue_desc* desc, const iisan
   const DropCfg dc = drop_cfg(D);
   const int ln_blocks = (R * 32 + 255) / 256;
   if (attn_smem(D, true) > 48 * 1024) return IISAN_EUNSUPPORTED;
-  ue_ln_fwd_kernel<0><<<ln_blocks, 256, 0, st>>>(R, L, E, embs, ld_user, P->pos_emb, P->ln_w, P->ln_b, W.pre0, W.stat0,
-                                                W.b[0].x_in, dc, 0u);
+  { LaunchScope ls_(IISAN_K_USER, st); ue_ln_fwd_kernel<0><<<ln_blocks, 256, 0, st>>>(R, L, E, embs, ld_user, P->pos_emb, P->ln_w, P->ln_b, W.pre0, W.stat0,
+                                                W.b[0].x_in, dc, 0u); }
   IISAN_LAUNCH_OK();
   for (int b = 0; b < D.n_blocks; ++b) {
     const iisan_ue_block_ptrs& bp = P->blocks[b];
@@ -306,12 +307,12 @@ extern "C" int iisan_user_encoder_forward(const iisan_ue_desc* desc, const iisan
     qkv.p[1] = prob_linear(X.x_in, E, bp.w_k, nullptr, X.k, E, R, E, E);
     qkv.p[2] = prob_linear(X.x_in, E, bp.w_v, nullptr, X.v, E, R, E, E);
     IISAN_TRY(launch_gemm(qkv, st));
-    ue_attn_fwd_kernel<<<D.users, 128, attn_smem(D, false), st>>>(L, E, H, X.q, X.k, X.v, log_mask, X.p, X.ctx, dc, 1u + 4u * b);
+    { LaunchScope ls_(IISAN_K_USER, st); ue_attn_fwd_kernel<<<D.users, 128, attn_smem(D, false), st>>>(L, E, H, X.q, X.k, X.v, log_mask, X.p, X.ctx, dc, 1u + 4u * b); }
     IISAN_LAUNCH_OK();
     GemmBatch fc{}; fc.n = 1;
     fc.p[0] = prob_linear(X.ctx, E, bp.w_fc, nullptr, W.lin, E, R, E, E);
     IISAN_TRY(launch_gemm(fc, st));
-    ue_ln_fwd_kernel<1><<<ln_blocks, 256, 0, st>>>(R, L, E, X.x_in, 0, W.lin, bp.ln1_w, bp.ln1_b, X.pre1, X.stat1, X.xmid, dc, 2u + 4u * b);
+    { LaunchScope ls_(IISAN_K_USER, st); ue_ln_fwd_kernel<1><<<ln_blocks, 256, 0, st>>>(R, L, E, X.x_in, 0, W.lin, bp.ln1_w, bp.ln1_b, X.pre1, X.stat1, X.xmid, dc, 2u + 4u * b); }
     IISAN_LAUNCH_OK();
     GemmBatch f1{}; f1.n = 1;
     f1.p[0] = prob_linear(X.xmid, E, bp.w1, bp.b1, X.h1, 4 * E, R, 4 * E, E, 1);
@@ -320,7 +321,7 @@ extern "C" int iisan_user_encoder_forward(const iisan_ue_desc* desc, const iisan
     f2.p[0] = prob_linear(X.h1, 4 * E, bp.w2, bp.b2, W.lin, E, R, E, 4 * E);
     IISAN_TRY(launch_gemm(f2, st));
     float* dst = (b + 1 < D.n_blocks) ? W.b[b + 1].x_in : out;
-    ue_ln_fwd_kernel<1><<<ln_blocks, 256, 0, st>>>(R, L, E, X.xmid, 0, W.lin, bp.ln2_w, bp.ln2_b, X.pre2, X.stat2, dst, dc, 3u + 4u * b);
+    { LaunchScope ls_(IISAN_K_USER, st); ue_ln_fwd_kernel<1><<<ln_blocks, 256, 0, st>>>(R, L, E, X.xmid, 0, W.lin, bp.ln2_w, bp.ln2_b, X.pre2, X.stat2, dst, dc, 3u + 4u * b); }
     IISAN_LAUNCH_OK();
   }
   return IISAN_OK;
@@ -344,7 +345,7 @@ extern "C" int iisan_user_encoder_backward(const iisan_ue_desc* desc, const iisa
     const iisan_ue_block_ptrs& bg = G->blocks[b];
     UeBlockBufs& X = W.b[b];
     // LN2: dA = d pre2 (residual), df = dropout_bwd(dA) (w2 branch)
-    ue_ln_bwd_kernel<1><<<lnb, 256, 0, st>>>(R, L, E, dy, X.pre2, X.stat2, bp.ln2_w, bg.ln2_w, bg.ln2_b, W.dA, 0, W.df, dc, 3u + 4u * b);
+    { LaunchScope ls_(IISAN_K_USER, st); ue_ln_bwd_kernel<1><<<lnb, 256, 0, st>>>(R, L, E, dy, X.pre2, X.stat2, bp.ln2_w, bg.ln2_w, bg.ln2_b, W.dA, 0, W.df, dc, 3u + 4u * b); }
     IISAN_LAUNCH_OK();
     {
       GemmBatch g{}; g.n = 1; g.p[0] = prob_wgrad(W.df, E, X.h1, 4 * E, bg.w2, R, E, 4 * E); IISAN_TRY(launch_gemm(g, st));
@@ -356,13 +357,13 @@ extern "C" int iisan_user_encoder_backward(const iisan_ue_desc* desc, const iisa
       GemmBatch d1{}; d1.n = 1; d1.p[0] = prob_dgrad(W.dh1, 4 * E, bp.w1, W.dB, E, R, 4 * E, E, nullptr, 0, W.dA, E); IISAN_TRY(launch_gemm(d1, st));
     }
     // LN1: dA = d pre1 (residual to x_in), df = dropout_bwd (fc branch)
-    ue_ln_bwd_kernel<1><<<lnb, 256, 0, st>>>(R, L, E, W.dB, X.pre1, X.stat1, bp.ln1_w, bg.ln1_w, bg.ln1_b, W.dA, 0, W.df, dc, 2u + 4u * b);
+    { LaunchScope ls_(IISAN_K_USER, st); ue_ln_bwd_kernel<1><<<lnb, 256, 0, st>>>(R, L, E, W.dB, X.pre1, X.stat1, bp.ln1_w, bg.ln1_w, bg.ln1_b, W.dA, 0, W.df, dc, 2u + 4u * b); }
     IISAN_LAUNCH_OK();
     {
       GemmBatch g{}; g.n = 1; g.p[0] = prob_wgrad(W.df, E, X.ctx, E, bg.w_fc, R, E, E); IISAN_TRY(launch_gemm(g, st));
       GemmBatch d{}; d.n = 1; d.p[0] = prob_dgrad(W.df, E, bp.w_fc, W.dctx, E, R, E, E); IISAN_TRY(launch_gemm(d, st));
     }
-    ue_attn_bwd_kernel<<<D.users, 128, attn_smem(D, true), st>>>(L, E, H, X.q, X.k, X.v, X.p, W.dctx, W.dq, W.dk, W.dv, dc, 1u + 4u * b);
+    { LaunchScope ls_(IISAN_K_USER, st); ue_attn_bwd_kernel<<<D.users, 128, attn_smem(D, true), st>>>(L, E, H, X.q, X.k, X.v, X.p, W.dctx, W.dq, W.dk, W.dv, dc, 1u + 4u * b); }
     IISAN_LAUNCH_OK();
     {
       GemmBatch g{}; g.n = 3;
@@ -380,7 +381,7 @@ extern "C" int iisan_user_encoder_backward(const iisan_ue_desc* desc, const iisa
     dy = W.dctx;
   }
   // entry LN + position embedding
-  ue_ln_bwd_kernel<0><<<lnb, 256, 0, st>>>(R, L, E, dy, W.pre0, W.stat0, P->ln_w, G->ln_w, G->ln_b, d_embs, ld_user, W.df, dc, 0u);
+  { LaunchScope ls_(IISAN_K_USER, st); ue_ln_bwd_kernel<0><<<lnb, 256, 0, st>>>(R, L, E, dy, W.pre0, W.stat0, P->ln_w, G->ln_w, G->ln_b, d_embs, ld_user, W.df, dc, 0u); }
   IISAN_LAUNCH_OK();
   ColsumBatch c{}; c.n = 1; c.p[0] = {W.df, (int64_t)L * E, D.users, L * E, G->pos_emb};
   IISAN_TRY(launch_colsum(c, st));

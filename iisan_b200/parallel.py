@@ -1,0 +1,100 @@
+"""Data-parallel helpers for the hot path (one process per GPU, torch.distributed over NCCL/NVLink).
+
+The reference shards users across ranks with DistributedSampler and wraps the model in DDP
+(Code_Cached/run.py:124,258); its in-batch negatives stay rank-local.  Both behaviours keep working
+with the modules of this package (every parameter receives a gradient every step).  On top of that this
+module adds the *global* negative pool asked for by BASELINE config 3:
+
+  rank w owns users [w*B, (w+1)*B).  Item embeddings, ids and log-masks are all-gathered so that every
+  local row is scored against the W*B*11 item slots of the whole job; the gradient of the gathered
+  embeddings is reduce-scattered (summed) back to the owners; the loss is normalised by the all-reduced
+  number of valid rows.  Parity oracle: the reference ModelMM.forward run single-process on the
+  concatenated batch.
+
+Only the exchange steps use collectives; SAN / SASRec / loss tiles never leave the rank.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+class AllGatherRows(torch.autograd.Function):
+    """[n, E] -> [W*n, E] (rank-major).  Backward: reduce-scatter(sum) of the gathered gradient."""
+
+    @staticmethod
+    def forward(ctx, x, group):
+        ctx.group = group
+        world = dist.get_world_size(group)
+        x = x.contiguous()
+        out = torch.empty((world * x.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+        dist.all_gather_into_tensor(out, x, group=group)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        world = dist.get_world_size(ctx.group)
+        g = g.contiguous()
+        out = torch.empty((g.shape[0] // world,) + tuple(g.shape[1:]), dtype=g.dtype, device=g.device)
+        if dist.get_backend(ctx.group) == "gloo":
+            # gloo has no reduce_scatter_tensor: all-reduce and slice (CPU test path only)
+            dist.all_reduce(g, group=ctx.group)
+            r = dist.get_rank(ctx.group)
+            out.copy_(g[r * out.shape[0]:(r + 1) * out.shape[0]])
+        else:
+            dist.reduce_scatter_tensor(out, g, op=dist.ReduceOp.SUM, group=ctx.group)
+        return out, None
+
+
+def _gather_plain(x, group):
+    world = dist.get_world_size(group)
+    x = x.contiguous()
+    out = torch.empty((world * x.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+    dist.all_gather_into_tensor(out, x, group=group)
+    return out
+
+
+def _cuda_ce(prec, score_all, ids, ids_all, lm, lm_all, pop, user_offset, compute):
+    from .ops import InBatchCeFn
+    loss_sum, n_valid, _ = InBatchCeFn.apply(prec, score_all, ids, ids_all, lm, lm_all, pop, user_offset, compute)
+    return loss_sum, n_valid
+
+
+def global_negative_loss(prec, score, ids, log_mask, pop, group=None, compute=0, ce_fn=None, grad_average=True):
+    """In-batch CE of the local rows against the all-gathered item pool.
+
+    Returns ``W * loss_sum_local / n_valid_global`` when ``grad_average`` (so that DDP's mean over ranks
+    of the parameter gradients equals the gradient of the single-process loss on the concatenated batch),
+    else ``loss_sum_local / n_valid_global`` (use with a SUM all-reduce of gradients).
+    ``ce_fn`` is injectable for the CPU/gloo tests; the default is the CUDA kernel.
+    """
+    group = group if group is not None else dist.group.WORLD
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    b = log_mask.shape[0]
+    score_all = AllGatherRows.apply(score, group)
+    ids_all = _gather_plain(ids.view(b, -1), group)
+    lm_all = _gather_plain(log_mask, group)
+    ce = ce_fn or _cuda_ce
+    loss_sum, n_valid = ce(prec, score_all, ids.view(b, -1), ids_all, log_mask, lm_all, pop, rank * b, compute)
+    n_total = n_valid.clone().to(torch.int64) if n_valid.dtype != torch.int64 else n_valid.clone()
+    dist.all_reduce(n_total, group=group)
+    scale = float(world) if grad_average else 1.0
+    return loss_sum * scale / n_total.to(loss_sum.dtype).reshape(())
+
+
+def allreduce_gradients(parameters, group=None, average=True):
+    """Flat-bucket gradient all-reduce for training loops that do not use DDP.  One NCCL call over a single
+    contiguous fp32 bucket (the base model's 4.1 M parameters are 16.5 MB)."""
+    group = group if group is not None else dist.group.WORLD
+    grads = [p.grad for p in parameters if p.grad is not None]
+    if not grads:
+        return
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    dist.all_reduce(flat, group=group)
+    if average:
+        flat /= dist.get_world_size(group)
+    off = 0
+    for g in grads:
+        n = g.numel()
+        g.copy_(flat[off:off + n].view_as(g))
+        off += n

@@ -57,6 +57,25 @@ const char* iisan_last_cuda_error_string(void);
  * which = 0 iisan_san_desc, 1 iisan_san_params, 2 iisan_ue_desc, 3 iisan_ue_params, 4 iisan_ce_desc. */
 size_t iisan_sizeof(int which);
 
+/* Launch accounting and live kernel timing (used by bench.py for the roofline numbers).
+ * Every kernel launch of the library belongs to one class. */
+enum iisan_kernel_class {
+  IISAN_K_STREAM = 0, /* hidden-state streaming: layer-select gather + gate fusion (fwd) and its backward */
+  IISAN_K_GEMM = 1,   /* adapter / head / dense-layer GEMMs */
+  IISAN_K_USER = 2,   /* SASRec layer-norm / attention kernels */
+  IISAN_K_CE = 3,     /* fused in-batch cross-entropy */
+  IISAN_K_MISC = 4,   /* reductions, gathers, optimizer */
+  IISAN_K_CHAIN = 5,  /* fused tcgen05 adapter-chain kernels */
+  IISAN_K_COUNT = 6
+};
+/* total kernels launched by this process through the library, per class (kclass < 0: all classes) */
+int64_t iisan_launch_count(int kclass);
+/* on != 0: bracket every launch with CUDA events on its stream (pool of 1<<16 pairs, then stops recording) */
+int iisan_timing_enable(int on);
+/* synchronise the recorded events, return summed device milliseconds and launches of `kclass` since the last
+ * read, and recycle the pool entries of that class */
+int iisan_timing_read(int kclass, double* total_ms, int64_t* launches);
+
 /* ---------------------------------------------------------------------------------------------
  * Side-adapter network  (CC/model/model.py:257-349  IISANAdaptedMModel ;
  *                        CA/model/model.py:257-429  IISAN-Versa: group layer-drop + dim alignment ;
