@@ -83,6 +83,7 @@ _SIGNATURES = {
     "iisan_san_backward": (C.c_int, [C.POINTER(SanDesc), C.POINTER(SanParams), C.POINTER(SanParams), vp, vp, vp, C.c_size_t, vp, vp]),
     "iisan_linear_forward": (C.c_int, [i32, i32, i32, vp, C.c_int64, vp, vp, vp, C.c_int64, i32, vp]),
     "iisan_linear_backward": (C.c_int, [i32, i32, i32, vp, C.c_int64, vp, vp, C.c_int64, vp, C.c_int64, vp, vp, i32, vp]),
+    "iisan_gemm_bf16": (C.c_int, [i32, i32, i32, vp, C.c_int64, i32, vp, C.c_int64, i32, vp, C.c_int64, vp, C.c_int64, vp, i32, i32, vp]),
     "iisan_user_encoder_workspace_bytes": (C.c_size_t, [C.POINTER(UeDesc)]),
     "iisan_user_encoder_forward": (C.c_int, [C.POINTER(UeDesc), C.POINTER(UeParams), vp, C.c_int64, vp, vp, C.c_size_t, vp, vp]),
     "iisan_user_encoder_backward": (C.c_int, [C.POINTER(UeDesc), C.POINTER(UeParams), C.POINTER(UeParams), vp, C.c_int64, vp, vp,

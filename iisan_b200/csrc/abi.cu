@@ -2,6 +2,7 @@
 #include "common.cuh"
 #include "gemm_simt.cuh"
 #include "launch.cuh"
+#include "umma_gemm.cuh"
 
 #include <atomic>
 #include <mutex>
@@ -165,4 +166,22 @@ extern "C" int iisan_gather_states(const void* table, int32_t dtype, int64_t n_t
     { LaunchScope ls_(IISAN_K_MISC, st); gather_states_kernel<2><<<blocks, 256, 0, st>>>((const uint4*)table, n_table_items, layers, d, ids, n, sel, n_sel, (uint4*)out); }
   IISAN_LAUNCH_OK();
   return IISAN_OK;
+}
+
+extern "C" int iisan_gemm_bf16(int32_t M, int32_t N, int32_t K, const void* A, int64_t a_pitch, int32_t a_mn_major, const void* B,
+                               int64_t b_pitch, int32_t b_mn_major, float* out_f32, int64_t ld_f32, void* out_bf16, int64_t ld_bf16,
+                               const float* bias, int32_t relu, int32_t splitk, iisan_stream_t stream) {
+  if (!A || !B || (!out_f32 && !out_bf16) || M <= 0 || N <= 0 || K <= 0) return IISAN_EINVAL;
+  UmmaBatch b{}; b.n = 1;
+  UmmaProblem& P = b.p[0];
+  P.A.ptr = (const __nv_bfloat16*)A; P.A.pitch = a_pitch;
+  if (a_mn_major) { P.A.rows = K; P.A.cols = M; } else { P.A.rows = M; P.A.cols = K; }
+  P.B.ptr = (const __nv_bfloat16*)B; P.B.pitch = b_pitch;
+  if (b_mn_major) { P.B.rows = K; P.B.cols = N; } else { P.B.rows = N; P.B.cols = K; }
+  P.a_mn_major = a_mn_major; P.b_mn_major = b_mn_major;
+  P.M = M; P.N = N; P.K = K; P.splitk = splitk < 1 ? 1 : splitk;
+  P.epi.out_f32 = out_f32; P.epi.ld_f32 = ld_f32;
+  P.epi.out_bf16 = (__nv_bfloat16*)out_bf16; P.epi.ld_bf16 = ld_bf16;
+  P.epi.bias = bias; P.epi.relu = relu; P.epi.atomic = P.splitk > 1 ? 1 : 0;
+  return launch_umma_gemm(b, as_stream(stream));
 }
