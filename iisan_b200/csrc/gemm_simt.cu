@@ -121,7 +121,10 @@ __global__ void __launch_bounds__(256) colsum_kernel(const ColsumBatch batch, in
   const int r1 = min(P.M, r0 + rows_per_cta);
   float s = 0.f;
   if (col < P.N)
-    for (int r = r0 + threadIdx.x / 32; r < r1; r += 8) s += __ldg(P.Y + (int64_t)r * P.ld + col);
+  {
+    if (P.Y) { for (int r = r0 + threadIdx.x / 32; r < r1; r += 8) s += __ldg(P.Y + (int64_t)r * P.ld + col); }
+    else { for (int r = r0 + threadIdx.x / 32; r < r1; r += 8) s += __bfloat162float(P.Yb[(int64_t)r * P.ld + col]); }
+  }
   __shared__ float red[8][33];
   red[threadIdx.x / 32][threadIdx.x % 32] = s;
   __syncthreads();

@@ -72,7 +72,7 @@ inline GemmProb prob_wgrad(const float* dy, int64_t lddy, const float* x, int64_
 }
 
 // ---- column sums: out[n] += sum_m Y[m,n]  (bias gradients) --------------------------------------------
-struct ColsumProb { const float* Y; int64_t ld; int M, N; float* out; };
+struct ColsumProb { const float* Y; int64_t ld; int M, N; float* out; const __nv_bfloat16* Yb; };   // Y (fp32) or Yb (bf16)
 struct ColsumBatch { ColsumProb p[kMaxProbs * 2]; int n; };
 
 int launch_colsum(const ColsumBatch& b, cudaStream_t st);

@@ -14,175 +14,27 @@
 #include "launch.cuh"
 #include "gemm_simt.cuh"
 #include "san_layout.cuh"
+#include "san_mix.cuh"
 
 namespace iisan {
 
 // ------------------------------------------------------------------------------------------------
-// elementwise stage kernels
-// ------------------------------------------------------------------------------------------------
-struct MixSrc {
-  const void* p;       // null => zeros
-  int64_t row_stride;  // elements between consecutive rows
-  int is_state;        // 1: cached hidden state of dtype T; 0: dense fp32
-};
-
-template <typename T>
-__device__ __forceinline__ float4 mix_load(const MixSrc& s, int64_t row, int col) {
-  if (s.p == nullptr) return make_float4(0.f, 0.f, 0.f, 0.f);
-  if (s.is_state) return load4<T>(reinterpret_cast<const T*>(s.p) + row * s.row_stride + col);
-  return *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(s.p) + row * s.row_stride + col);
-}
-
-struct MixProb {
-  MixSrc P, Q, R;
-  const float* gate;  // device pointer to the [1] gate parameter
-  int mode;           // 0: x = g*P + (1-g)*R ; 1: x = R + g*P + (1-g)*Q ; 2: x = P (layer gather)
-  float* X;           // [N, d] dense fp32
-  int N, d;
-};
-struct MixBatch { MixProb p[kMaxProbs]; int n; };
-
-template <typename T>
-__global__ void __launch_bounds__(256) mix_kernel(const MixBatch batch) {
-  const MixProb& M = batch.p[blockIdx.y];
-  const int d4 = M.d / 4;
-  const int64_t total = (int64_t)M.N * d4;
-  float g = 0.f;
-  if (M.mode != 2) g = gate_value(M.gate);
-  const float omg = 1.0f - g;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t row = i / d4;
-    const int col = (int)(i % d4) * 4;
-    const float4 p = mix_load<T>(M.P, row, col);
-    float4 x;
-    if (M.mode == 0) {
-      const float4 r = mix_load<T>(M.R, row, col);
-      // exact reference order, no fma contraction: (g*h) + ((1-g)*last)
-      x.x = __fadd_rn(__fmul_rn(g, p.x), __fmul_rn(omg, r.x));
-      x.y = __fadd_rn(__fmul_rn(g, p.y), __fmul_rn(omg, r.y));
-      x.z = __fadd_rn(__fmul_rn(g, p.z), __fmul_rn(omg, r.z));
-      x.w = __fadd_rn(__fmul_rn(g, p.w), __fmul_rn(omg, r.w));
-    } else if (M.mode == 1) {
-      const float4 q = mix_load<T>(M.Q, row, col);
-      const float4 r = mix_load<T>(M.R, row, col);
-      // (last + g*h_cv) + (1-g)*h_text
-      x.x = __fadd_rn(__fadd_rn(r.x, __fmul_rn(g, p.x)), __fmul_rn(omg, q.x));
-      x.y = __fadd_rn(__fadd_rn(r.y, __fmul_rn(g, p.y)), __fmul_rn(omg, q.y));
-      x.z = __fadd_rn(__fadd_rn(r.z, __fmul_rn(g, p.z)), __fmul_rn(omg, q.z));
-      x.w = __fadd_rn(__fadd_rn(r.w, __fmul_rn(g, p.w)), __fmul_rn(omg, q.w));
-    } else {
-      x = p;
-    }
-    *reinterpret_cast<float4*>(M.X + row * M.d + col) = x;
-  }
-}
-
-// Backward of the fusion: given dx [N,d]
-//   mode 0: dgate += sum dx*(P - R) * g(1-g)/0.1 ; dR = (1-g)*dx            (written to dPrev if non-null)
-//   mode 1: dgate += sum dx*(P - Q) * g(1-g)/0.1 ; dR = dx (caller aliases) ;
-//           dP_out = g*dx (if non-null), dQ_out = (1-g)*dx (if non-null)      (down_project inputs)
-struct MixBwdProb {
-  MixSrc P, Q, R;
-  const float* gate;
-  float* dgate;
-  int mode;
-  const float* dX;   // [N,d]
-  float* dPrev;      // mode 0: [N,d] or null
-  float* dP_out;     // mode 1: [N,d] or null
-  float* dQ_out;     // mode 1: [N,d] or null
-  int N, d;
-};
-struct MixBwdBatch { MixBwdProb p[kMaxProbs]; int n; };
-
-template <typename T>
-__global__ void __launch_bounds__(256) mix_bwd_kernel(const MixBwdBatch batch) {
-  const MixBwdProb& M = batch.p[blockIdx.y];
-  const int d4 = M.d / 4;
-  const int64_t total = (int64_t)M.N * d4;
-  const float g = gate_value(M.gate);
-  const float omg = 1.0f - g;
-  double part = 0.0;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t row = i / d4;
-    const int col = (int)(i % d4) * 4;
-    const float4 dx = *reinterpret_cast<const float4*>(M.dX + row * M.d + col);
-    const float4 p = mix_load<T>(M.P, row, col);
-    const float4 o = (M.mode == 0) ? mix_load<T>(M.R, row, col) : mix_load<T>(M.Q, row, col);
-    float s = dx.x * (p.x - o.x);
-    s = fmaf(dx.y, p.y - o.y, s);
-    s = fmaf(dx.z, p.z - o.z, s);
-    s = fmaf(dx.w, p.w - o.w, s);
-    part += (double)s;
-    if (M.mode == 0) {
-      if (M.dPrev) *reinterpret_cast<float4*>(M.dPrev + row * M.d + col) = make_float4(omg * dx.x, omg * dx.y, omg * dx.z, omg * dx.w);
-    } else {
-      if (M.dP_out) *reinterpret_cast<float4*>(M.dP_out + row * M.d + col) = make_float4(g * dx.x, g * dx.y, g * dx.z, g * dx.w);
-      if (M.dQ_out) *reinterpret_cast<float4*>(M.dQ_out + row * M.d + col) = make_float4(omg * dx.x, omg * dx.y, omg * dx.z, omg * dx.w);
-    }
-  }
-  // block reduction (double) -> one atomic per CTA
-  __shared__ double red[8];
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double t = 0.0;
-    for (int i = 0; i < 8; ++i) t += red[i];
-    // d sigmoid(p/0.1)/dp = g(1-g)/0.1
-    atomicAdd(M.dgate, (float)(t * (double)g * (double)omg / 0.1));
-  }
-}
-
-template <typename T>
-static int launch_mix(const MixBatch& b, cudaStream_t st) {
-  if (b.n == 0) return IISAN_OK;
-  int64_t mx = 0;
-  for (int i = 0; i < b.n; ++i) mx = max(mx, (int64_t)b.p[i].N * (b.p[i].d / 4));
-  int blocks = (int)imin64((mx + 255) / 256, 148 * 8);
-  { LaunchScope ls_(IISAN_K_STREAM, st); mix_kernel<T><<<dim3(blocks, b.n), 256, 0, st>>>(b); }
-  IISAN_LAUNCH_OK();
-  return IISAN_OK;
-}
-template <typename T>
-static int launch_mix_bwd(const MixBwdBatch& b, cudaStream_t st) {
-  if (b.n == 0) return IISAN_OK;
-  int64_t mx = 0;
-  for (int i = 0; i < b.n; ++i) mx = max(mx, (int64_t)b.p[i].N * (b.p[i].d / 4));
-  int blocks = (int)imin64((mx + 255) / 256, 148 * 4);
-  { LaunchScope ls_(IISAN_K_STREAM, st); mix_bwd_kernel<T><<<dim3(blocks, b.n), 256, 0, st>>>(b); }
-  IISAN_LAUNCH_OK();
-  return IISAN_OK;
-}
-
-// ------------------------------------------------------------------------------------------------
 // orchestration
 // ------------------------------------------------------------------------------------------------
-static int validate(const iisan_san_desc* d) {
+int san_validate(const iisan_san_desc* d) {
   if (!d) return IISAN_EINVAL;
   if (d->n_items <= 0 || d->n_stages <= 0 || d->n_stages > IISAN_MAX_STAGES) return IISAN_EINVAL;
   if (d->d_text % 4 || d->d_img % 4 || d->d_mm % 4 || d->emb % 4) return IISAN_EINVAL;
   if (d->d_mm != (d->d_text < d->d_img ? d->d_text : d->d_img)) return IISAN_EINVAL;
   if (d->out_ld < 3 * d->emb) return IISAN_EINVAL;
   if (d->state_dtype < IISAN_F32 || d->state_dtype > IISAN_F16) return IISAN_EINVAL;
+  if (d->compute != IISAN_COMPUTE_FP32 && d->compute != IISAN_COMPUTE_BF16) return IISAN_EINVAL;
   for (int s = 0; s < d->n_stages; ++s) {
     if (d->text_adapter[s] >= 0 && (d->text_layer[s] < 0 || d->text_layer[s] >= d->layers_text)) return IISAN_EINVAL;
     if (d->img_adapter[s] >= 0 && (d->img_layer[s] < 0 || d->img_layer[s] >= d->layers_img)) return IISAN_EINVAL;
     if (d->mm_index[s] >= 0 && (d->text_adapter[s] < 0 || d->img_adapter[s] < 0)) return IISAN_EINVAL;
   }
   return IISAN_OK;
-}
-
-template <typename T>
-static MixSrc state_src(const void* base, int layers, int d, int layer) {
-  MixSrc s;
-  s.p = reinterpret_cast<const T*>(base) + (int64_t)layer * d;
-  s.row_stride = (int64_t)layers * d;
-  s.is_state = 1;
-  return s;
-}
-static MixSrc dense_src(const float* p, int d) {
-  MixSrc s; s.p = p; s.row_stride = d; s.is_state = 0; return s;
 }
 
 template <typename T>
@@ -400,7 +252,8 @@ static int san_backward_fp32(const iisan_san_desc* D, const iisan_san_params* P,
 using namespace iisan;
 
 extern "C" size_t iisan_san_workspace_bytes(const iisan_san_desc* desc) {
-  if (validate(desc) != IISAN_OK) return 0;
+  if (san_validate(desc) != IISAN_OK) return 0;
+  if (desc->compute == IISAN_COMPUTE_BF16) return san_bf16_supported(*desc) ? san_bf16_workspace_bytes(*desc) : 0;
   SanLayout L(*desc, nullptr);
   return L.bytes;
 }
@@ -408,10 +261,12 @@ extern "C" size_t iisan_san_workspace_bytes(const iisan_san_desc* desc) {
 extern "C" int iisan_san_forward(const iisan_san_desc* desc, const iisan_san_params* params, const void* image,
                                  const void* text, void* workspace, size_t workspace_bytes, float* out,
                                  iisan_stream_t stream) {
-  IISAN_TRY(validate(desc));
+  IISAN_TRY(san_validate(desc));
   if (!params || !image || !text || !workspace || !out) return IISAN_EINVAL;
+  if (desc->compute == IISAN_COMPUTE_BF16 && !san_bf16_supported(*desc)) return IISAN_EUNSUPPORTED;
   if (workspace_bytes < iisan_san_workspace_bytes(desc)) return IISAN_EWORKSPACE;
   cudaStream_t st = as_stream(stream);
+  if (desc->compute == IISAN_COMPUTE_BF16) return san_forward_bf16(desc, params, image, text, workspace, out, st);
   switch (desc->state_dtype) {
     case IISAN_F32: return san_forward_fp32<float>(desc, params, image, text, workspace, out, st);
     case IISAN_BF16: return san_forward_fp32<__nv_bfloat16>(desc, params, image, text, workspace, out, st);
@@ -424,10 +279,12 @@ extern "C" int iisan_san_backward(const iisan_san_desc* desc, const iisan_san_pa
                                   const iisan_san_params* grads, const void* image, const void* text,
                                   void* workspace, size_t workspace_bytes, const float* d_out,
                                   iisan_stream_t stream) {
-  IISAN_TRY(validate(desc));
+  IISAN_TRY(san_validate(desc));
   if (!params || !grads || !image || !text || !workspace || !d_out) return IISAN_EINVAL;
+  if (desc->compute == IISAN_COMPUTE_BF16 && !san_bf16_supported(*desc)) return IISAN_EUNSUPPORTED;
   if (workspace_bytes < iisan_san_workspace_bytes(desc)) return IISAN_EWORKSPACE;
   cudaStream_t st = as_stream(stream);
+  if (desc->compute == IISAN_COMPUTE_BF16) return san_backward_bf16(desc, params, grads, image, text, workspace, d_out, st);
   switch (desc->state_dtype) {
     case IISAN_F32: return san_backward_fp32<float>(desc, params, grads, image, text, workspace, d_out, st);
     case IISAN_BF16: return san_backward_fp32<__nv_bfloat16>(desc, params, grads, image, text, workspace, d_out, st);

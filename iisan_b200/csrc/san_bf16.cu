@@ -1,0 +1,501 @@
+// Side-adapter network, fast mode (IISAN_COMPUTE_BF16): every contraction runs on the tcgen05 GEMM primitive
+// (umma_gemm.cu) with bf16 operands and fp32 accumulation in TMEM; elementwise stages emit bf16 operands.
+// This is the general ("layered") fast path: any widths / bottlenecks / stage plans (IISAN-Versa included).
+//
+// Algorithm restated from the reference's PyTorch modules (nothing ported):
+//   gated fusion       CC/model/model.py:319-326 ; inter-modal mix CC/model/model.py:335-337
+//   AdapterBlock       CC/model/modules.py:113-116 ; heads CC/model/model.py:340-347
+//   Versa extensions   CA/model/model.py:353-417 (solo stages, down_project dim alignment)
+//
+// HBM layout (workspace): bf16 copies of every weight in both orientations ([out,in] for forward, [in,out] for the data
+// gradients), refreshed by one cast+transpose launch per forward; per stage and tower the stash x_s [N,d], z_s [N,r],
+// last_s [N,d] (all bf16); backward scratch dy/dx (fp32 running gradient + bf16 operand twins), dz (bf16).
+// bf16 cached states are consumed in place by TMA (row pitch layers*d) wherever they are a GEMM operand.
+#include <type_traits>
+
+#include "common.cuh"
+#include "gemm_simt.cuh"
+#include "launch.cuh"
+#include "san_layout.cuh"
+#include "san_mix.cuh"
+#include "umma_gemm.cuh"
+
+namespace iisan {
+
+using bf16 = __nv_bfloat16;
+
+// ------------------------------------------------------------------------------------------------
+// weight preparation: dst[r,c] = bf16(src[r,c]) and dstT[c,r] = bf16(src[r,c])
+// ------------------------------------------------------------------------------------------------
+struct CastJob { const float* src; bf16* dst; bf16* dstT; int rows, cols; };
+constexpr int kCastJobs = 48;
+struct CastBatch { CastJob j[kCastJobs]; int n; };
+
+__global__ void __launch_bounds__(256) cast_transpose_kernel(const CastBatch batch) {
+  const CastJob& J = batch.j[blockIdx.y];
+  __shared__ float tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+  const int tiles_c = (J.cols + 31) / 32, tiles_r = (J.rows + 31) / 32;
+  for (int t = blockIdx.x; t < tiles_c * tiles_r; t += gridDim.x) {
+    const int r0 = (t / tiles_c) * 32, c0 = (t % tiles_c) * 32;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int r = r0 + ty + k * 8, c = c0 + tx;
+      float v = 0.f;
+      if (r < J.rows && c < J.cols) {
+        v = J.src[(int64_t)r * J.cols + c];
+        J.dst[(int64_t)r * J.cols + c] = __float2bfloat16_rn(v);
+      }
+      tile[ty + k * 8][tx] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int c = c0 + ty + k * 8, r = r0 + tx;
+      if (r < J.rows && c < J.cols) J.dstT[(int64_t)c * J.rows + r] = __float2bfloat16_rn(tile[tx][ty + k * 8]);
+    }
+    __syncthreads();
+  }
+}
+
+struct CastList {
+  CastBatch b; cudaStream_t st; int status;
+  explicit CastList(cudaStream_t s) : st(s), status(IISAN_OK) { b.n = 0; }
+  void flush() {
+    if (b.n == 0 || status != IISAN_OK) { b.n = 0; return; }
+    int mx = 1;
+    for (int i = 0; i < b.n; ++i) mx = max(mx, ((b.j[i].rows + 31) / 32) * ((b.j[i].cols + 31) / 32));
+    { LaunchScope ls_(IISAN_K_MISC, st); cast_transpose_kernel<<<dim3(min(mx, 64), b.n), 256, 0, st>>>(b); }
+    if (cudaPeekAtLastError() != cudaSuccess) status = cuda_fail(cudaGetLastError());
+    b.n = 0;
+  }
+  void add(const float* src, bf16* dst, bf16* dstT, int rows, int cols) {
+    if (!src) { status = IISAN_EINVAL; return; }
+    b.j[b.n++] = CastJob{src, dst, dstT, rows, cols};
+    if (b.n == kCastJobs) flush();
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// workspace layout
+// ------------------------------------------------------------------------------------------------
+struct WCopy { bf16* w; bf16* wt; };
+
+struct SanLayoutBf16 {
+  WCopy t_down[IISAN_MAX_STAGES], t_up[IISAN_MAX_STAGES], i_down[IISAN_MAX_STAGES], i_up[IISAN_MAX_STAGES];
+  WCopy m_down[IISAN_MAX_STAGES], m_up[IISAN_MAX_STAGES], dpw[IISAN_MAX_STAGES];
+  WCopy fc_t, fc_i, fc_m, pre_t, pre_i, pre_m;
+  bf16 *x_t[IISAN_MAX_STAGES], *z_t[IISAN_MAX_STAGES], *last_t[IISAN_MAX_STAGES];
+  bf16 *x_i[IISAN_MAX_STAGES], *z_i[IISAN_MAX_STAGES], *last_i[IISAN_MAX_STAGES];
+  bf16 *x_m[IISAN_MAX_STAGES], *z_m[IISAN_MAX_STAGES], *last_m[IISAN_MAX_STAGES];
+  float* dpo[IISAN_MAX_STAGES];          // down_project output [N, d_mm] (Versa)
+  bf16 *head_t, *head_i, *head_m;
+  bf16* wide_b;                          // [N, max d] bf16 copy of one wide layer when the states are not bf16
+  // backward scratch
+  bf16* doutb;
+  bf16 *dhead_t, *dhead_i, *dhead_m;
+  float *dy_t, *dx_t, *dy_i, *dx_i, *dy_m, *dx_m;
+  bf16 *dyb_t, *dxb_t, *dzb_t, *dyb_i, *dxb_i, *dzb_i, *dyb_m, *dxb_m, *dzb_m;
+  bf16* ddpb;
+  size_t bytes;
+
+  static WCopy takew(Arena& a, size_t n) { WCopy c; c.w = a.take<bf16>(n); c.wt = a.take<bf16>(n); return c; }
+
+  SanLayoutBf16(const iisan_san_desc& D, void* ws) {
+    Arena a(ws);
+    const size_t N = (size_t)D.n_items;
+    const int E = D.emb;
+    const bool dimdiff = D.d_text != D.d_img;
+    const int dwide = D.d_text > D.d_img ? D.d_text : D.d_img;
+    const int ft = D.asym ? E : D.d_text, fi = D.asym ? E : D.d_img, fm = D.d_mm;
+    for (int s = 0; s < IISAN_MAX_STAGES; ++s) {
+      t_down[s] = t_up[s] = i_down[s] = i_up[s] = m_down[s] = m_up[s] = dpw[s] = WCopy{nullptr, nullptr};
+      x_t[s] = z_t[s] = last_t[s] = x_i[s] = z_i[s] = last_i[s] = x_m[s] = z_m[s] = last_m[s] = nullptr;
+      dpo[s] = nullptr;
+    }
+    for (int s = 0; s < D.n_stages; ++s) {
+      const int ta = D.text_adapter[s], ia = D.img_adapter[s], mi = D.mm_index[s];
+      if (ta >= 0) {
+        t_down[ta] = takew(a, (size_t)D.r_text * D.d_text); t_up[ta] = takew(a, (size_t)D.r_text * D.d_text);
+        x_t[s] = a.take<bf16>(N * D.d_text); z_t[s] = a.take<bf16>(N * D.r_text); last_t[s] = a.take<bf16>(N * D.d_text);
+      }
+      if (ia >= 0) {
+        i_down[ia] = takew(a, (size_t)D.r_img * D.d_img); i_up[ia] = takew(a, (size_t)D.r_img * D.d_img);
+        x_i[s] = a.take<bf16>(N * D.d_img); z_i[s] = a.take<bf16>(N * D.r_img); last_i[s] = a.take<bf16>(N * D.d_img);
+      }
+      if (mi >= 0) {
+        m_down[mi] = takew(a, (size_t)D.r_mm * D.d_mm); m_up[mi] = takew(a, (size_t)D.r_mm * D.d_mm);
+        x_m[s] = a.take<bf16>(N * D.d_mm); z_m[s] = a.take<bf16>(N * D.r_mm); last_m[s] = a.take<bf16>(N * D.d_mm);
+        if (dimdiff) { dpw[mi] = takew(a, (size_t)D.d_mm * dwide); dpo[s] = a.take<float>(N * D.d_mm); }
+      }
+    }
+    fc_t = takew(a, (size_t)ft * D.d_text); fc_i = takew(a, (size_t)fi * D.d_img); fc_m = takew(a, (size_t)fm * D.d_mm);
+    pre_t = takew(a, (size_t)E * ft); pre_i = takew(a, (size_t)E * fi); pre_m = takew(a, (size_t)E * fm);
+    head_t = a.take<bf16>(N * ft); head_i = a.take<bf16>(N * fi); head_m = a.take<bf16>(N * fm);
+    wide_b = (dimdiff && D.state_dtype != IISAN_BF16) ? a.take<bf16>(N * dwide) : nullptr;
+    doutb = a.take<bf16>(N * 3 * E);
+    dhead_t = a.take<bf16>(N * ft); dhead_i = a.take<bf16>(N * fi); dhead_m = a.take<bf16>(N * fm);
+    dy_t = a.take<float>(N * D.d_text); dx_t = a.take<float>(N * D.d_text);
+    dy_i = a.take<float>(N * D.d_img); dx_i = a.take<float>(N * D.d_img);
+    dy_m = a.take<float>(N * D.d_mm); dx_m = a.take<float>(N * D.d_mm);
+    dyb_t = a.take<bf16>(N * D.d_text); dxb_t = a.take<bf16>(N * D.d_text); dzb_t = a.take<bf16>(N * D.r_text);
+    dyb_i = a.take<bf16>(N * D.d_img); dxb_i = a.take<bf16>(N * D.d_img); dzb_i = a.take<bf16>(N * D.r_img);
+    dyb_m = a.take<bf16>(N * D.d_mm); dxb_m = a.take<bf16>(N * D.d_mm); dzb_m = a.take<bf16>(N * D.r_mm);
+    ddpb = dimdiff ? a.take<bf16>(N * D.d_mm) : nullptr;
+    bytes = a.off;
+  }
+};
+
+size_t san_bf16_workspace_bytes(const iisan_san_desc& D) {
+  SanLayoutBf16 L(D, nullptr);
+  return L.bytes;
+}
+
+// TMA needs 16-byte row pitches and the UMMA N extent a multiple of 8.
+int san_bf16_supported(const iisan_san_desc& D) {
+  return (D.d_text % 8 == 0 && D.d_img % 8 == 0 && D.r_text % 8 == 0 && D.r_img % 8 == 0 && D.r_mm % 8 == 0 && D.emb % 8 == 0 &&
+          D.out_ld % 4 == 0)
+             ? 1
+             : 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// problem builders
+// ------------------------------------------------------------------------------------------------
+// y[M,N] = x[M,K] W[N,K]^T
+static UmmaProblem mk_linear(const bf16* x, int64_t ldx, const bf16* w, int M, int N, int K) {
+  UmmaProblem p{};
+  p.A = UmmaOperand{x, M, K, ldx};
+  p.B = UmmaOperand{w, N, K, K};
+  p.a_mn_major = p.b_mn_major = 0;
+  p.M = M; p.N = N; p.K = K; p.splitk = 1;
+  return p;
+}
+
+static int pick_split(int M, int N, int K, int nprob) {
+  const int bn = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
+  const int tiles = ((M + 127) / 128) * ((N + bn - 1) / bn) * (nprob < 1 ? 1 : nprob);
+  const int kb = (K + 63) / 64;
+  int s = (2 * 148 + tiles - 1) / tiles;
+  if (s > kb / 2) s = kb / 2;
+  if (s < 1) s = 1;
+  if (s > 64) s = 64;
+  return s;
+}
+
+// out[m,n] += y[rows,m]^T x[rows,n]   (weight gradient: reduction over the item rows, split-K + red.add)
+// The larger of (m, n) is mapped to the UMMA M dimension; if that is n the tile is written transposed.
+static UmmaProblem mk_wgrad(const bf16* y, int64_t ldy, int m, const bf16* x, int64_t ldx, int n, int rows, float* out, int nprob) {
+  UmmaProblem p{};
+  p.a_mn_major = p.b_mn_major = 1;
+  p.K = rows;
+  if (m >= n) {
+    p.A = UmmaOperand{y, rows, m, ldy}; p.B = UmmaOperand{x, rows, n, ldx};
+    p.M = m; p.N = n; p.epi.transpose_out = 0;
+  } else {
+    p.A = UmmaOperand{x, rows, n, ldx}; p.B = UmmaOperand{y, rows, m, ldy};
+    p.M = n; p.N = m; p.epi.transpose_out = 1;
+  }
+  p.epi.out_f32 = out; p.epi.ld_f32 = n; p.epi.atomic = 1;
+  p.splitk = pick_split(p.M, p.N, p.K, nprob);
+  return p;
+}
+
+template <typename T>
+static const bf16* wide_operand(const iisan_san_desc* D, const void* base, int layers, int d, int layer, SanLayoutBf16& L,
+                                int64_t* pitch, cudaStream_t st, int* status) {
+  if (std::is_same<T, bf16>::value) {
+    *pitch = (int64_t)layers * d;
+    return reinterpret_cast<const bf16*>(base) + (int64_t)layer * d;
+  }
+  MixBatch gb{}; gb.n = 1;
+  MixProb& g = gb.p[0];
+  g.P = state_src<T>(base, layers, d, layer);
+  g.mode = 2; g.X = nullptr; g.Xb = L.wide_b; g.N = D->n_items; g.d = d;
+  *status = launch_mix<T>(gb, st);
+  *pitch = d;
+  return L.wide_b;
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+static int san_forward_bf16_t(const iisan_san_desc* D, const iisan_san_params* P, const void* image, const void* text, void* ws,
+                              float* out, cudaStream_t st) {
+  SanLayoutBf16 L(*D, ws);
+  const int N = D->n_items, E = D->emb;
+  const bool dimdiff = D->d_text != D->d_img;
+  const bool text_wide = D->d_text > D->d_img;
+  const int dwide = text_wide ? D->d_text : D->d_img;
+  const int ft = D->asym ? E : D->d_text, fi = D->asym ? E : D->d_img, fm = D->d_mm;
+  // ---- bf16 weight copies (the fp32 nn.Parameters stay the source of truth) ----
+  {
+    CastList c(st);
+    for (int s = 0; s < D->n_stages; ++s) {
+      const int ta = D->text_adapter[s], ia = D->img_adapter[s], mi = D->mm_index[s];
+      if (ta >= 0) { c.add(P->text[ta].w_down, L.t_down[ta].w, L.t_down[ta].wt, D->r_text, D->d_text); c.add(P->text[ta].w_up, L.t_up[ta].w, L.t_up[ta].wt, D->d_text, D->r_text); }
+      if (ia >= 0) { c.add(P->img[ia].w_down, L.i_down[ia].w, L.i_down[ia].wt, D->r_img, D->d_img); c.add(P->img[ia].w_up, L.i_up[ia].w, L.i_up[ia].wt, D->d_img, D->r_img); }
+      if (mi >= 0) {
+        c.add(P->mm[mi].w_down, L.m_down[mi].w, L.m_down[mi].wt, D->r_mm, D->d_mm); c.add(P->mm[mi].w_up, L.m_up[mi].w, L.m_up[mi].wt, D->d_mm, D->r_mm);
+        if (dimdiff) c.add(P->down_project[mi].w, L.dpw[mi].w, L.dpw[mi].wt, D->d_mm, dwide);
+      }
+    }
+    c.add(P->fc_text.w, L.fc_t.w, L.fc_t.wt, ft, D->d_text); c.add(P->fc_img.w, L.fc_i.w, L.fc_i.wt, fi, D->d_img);
+    c.add(P->fc_mm.w, L.fc_m.w, L.fc_m.wt, fm, D->d_mm);
+    c.add(P->pre_text.w, L.pre_t.w, L.pre_t.wt, E, ft); c.add(P->pre_img.w, L.pre_i.w, L.pre_i.wt, E, fi);
+    c.add(P->mm_down.w, L.pre_m.w, L.pre_m.wt, E, fm);
+    c.flush();
+    IISAN_TRY(c.status);
+  }
+  const bf16* last_t = nullptr; const bf16* last_i = nullptr; const bf16* last_m = nullptr;
+  bool first_t = true, first_i = true;
+  for (int s = 0; s < D->n_stages; ++s) {
+    const int ta = D->text_adapter[s], ia = D->img_adapter[s], mi = D->mm_index[s];
+    // ---- dim alignment GEMM on the raw wide state (CA/model/model.py:406-411) ----
+    const float* dp = nullptr;
+    if (mi >= 0 && dimdiff) {
+      int status = IISAN_OK; int64_t pitch = 0;
+      const bf16* a = text_wide ? wide_operand<T>(D, text, D->layers_text, D->d_text, D->text_layer[s], L, &pitch, st, &status)
+                                : wide_operand<T>(D, image, D->layers_img, D->d_img, D->img_layer[s], L, &pitch, st, &status);
+      IISAN_TRY(status);
+      UmmaBatch b{}; b.n = 1;
+      b.p[0] = mk_linear(a, pitch, L.dpw[mi].w, N, D->d_mm, dwide);
+      b.p[0].epi.bias = P->down_project[mi].b; b.p[0].epi.out_f32 = L.dpo[s]; b.p[0].epi.ld_f32 = D->d_mm;
+      IISAN_TRY(launch_umma_gemm(b, st));
+      dp = L.dpo[s];
+    }
+    MixBatch mb{}; UmmaBatch down{}, up{};
+    auto tower = [&](const iisan_adapter_ptrs& p, const WCopy& wd, const WCopy& wu, bf16* x, bf16* z, bf16* last, int d, int r) {
+      UmmaProblem& dn = down.p[down.n++];
+      dn = mk_linear(x, d, wd.w, N, r, d);
+      dn.epi.bias = p.b_down; dn.epi.relu = 1; dn.epi.out_bf16 = z; dn.epi.ld_bf16 = r;
+      UmmaProblem& u = up.p[up.n++];
+      u = mk_linear(z, r, wu.w, N, d, r);
+      u.epi.bias = p.b_up; u.epi.resid_bf16 = x; u.epi.ld_resid_bf16 = d; u.epi.out_bf16 = last; u.epi.ld_bf16 = d;
+    };
+    if (ta >= 0) {
+      MixProb& m = mb.p[mb.n++];
+      m.P = state_src<T>(text, D->layers_text, D->d_text, D->text_layer[s]);
+      if (first_t && D->remove_first) m.R = state_src<T>(text, D->layers_text, D->d_text, 0);
+      else if (last_t) m.R = dense_bf16_src(last_t, D->d_text);
+      else m.R = MixSrc{nullptr, 0, 0};
+      m.gate = P->gate_text[ta]; m.mode = 0; m.X = nullptr; m.Xb = L.x_t[s]; m.N = N; m.d = D->d_text;
+      tower(P->text[ta], L.t_down[ta], L.t_up[ta], L.x_t[s], L.z_t[s], L.last_t[s], D->d_text, D->r_text);
+    }
+    if (ia >= 0) {
+      MixProb& m = mb.p[mb.n++];
+      m.P = state_src<T>(image, D->layers_img, D->d_img, D->img_layer[s]);
+      if (first_i && D->remove_first) m.R = state_src<T>(image, D->layers_img, D->d_img, 0);
+      else if (last_i) m.R = dense_bf16_src(last_i, D->d_img);
+      else m.R = MixSrc{nullptr, 0, 0};
+      m.gate = P->gate_img[ia]; m.mode = 0; m.X = nullptr; m.Xb = L.x_i[s]; m.N = N; m.d = D->d_img;
+      tower(P->img[ia], L.i_down[ia], L.i_up[ia], L.x_i[s], L.z_i[s], L.last_i[s], D->d_img, D->r_img);
+    }
+    if (mi >= 0) {
+      MixProb& m = mb.p[mb.n++];
+      m.P = (dp && !text_wide) ? dense_src(dp, D->d_mm) : state_src<T>(image, D->layers_img, D->d_img, D->img_layer[s]);
+      m.Q = (dp && text_wide) ? dense_src(dp, D->d_mm) : state_src<T>(text, D->layers_text, D->d_text, D->text_layer[s]);
+      m.R = last_m ? dense_bf16_src(last_m, D->d_mm) : MixSrc{nullptr, 0, 0};
+      m.gate = P->gate_mm[mi]; m.mode = 1; m.X = nullptr; m.Xb = L.x_m[s]; m.N = N; m.d = D->d_mm;
+      tower(P->mm[mi], L.m_down[mi], L.m_up[mi], L.x_m[s], L.z_m[s], L.last_m[s], D->d_mm, D->r_mm);
+    }
+    IISAN_TRY(launch_mix<T>(mb, st));
+    IISAN_TRY(launch_umma_gemm(down, st));
+    IISAN_TRY(launch_umma_gemm(up, st));
+    if (ta >= 0) { last_t = L.last_t[s]; first_t = false; }
+    if (ia >= 0) { last_i = L.last_i[s]; first_i = false; }
+    if (mi >= 0) last_m = L.last_m[s];
+  }
+  if (!last_t || !last_i || !last_m) return IISAN_EINVAL;
+  // ---- heads: e = pre(fc(last)) ----
+  UmmaBatch fc{}; fc.n = 3;
+  fc.p[0] = mk_linear(last_i, D->d_img, L.fc_i.w, N, fi, D->d_img);
+  fc.p[0].epi.bias = P->fc_img.b; fc.p[0].epi.out_bf16 = L.head_i; fc.p[0].epi.ld_bf16 = fi;
+  fc.p[1] = mk_linear(last_t, D->d_text, L.fc_t.w, N, ft, D->d_text);
+  fc.p[1].epi.bias = P->fc_text.b; fc.p[1].epi.out_bf16 = L.head_t; fc.p[1].epi.ld_bf16 = ft;
+  fc.p[2] = mk_linear(last_m, D->d_mm, L.fc_m.w, N, fm, D->d_mm);
+  fc.p[2].epi.bias = P->fc_mm.b; fc.p[2].epi.out_bf16 = L.head_m; fc.p[2].epi.ld_bf16 = fm;
+  IISAN_TRY(launch_umma_gemm(fc, st));
+  UmmaBatch pre{}; pre.n = 3;
+  pre.p[0] = mk_linear(L.head_i, fi, L.pre_i.w, N, E, fi);
+  pre.p[0].epi.bias = P->pre_img.b; pre.p[0].epi.out_f32 = out; pre.p[0].epi.ld_f32 = D->out_ld;
+  pre.p[1] = mk_linear(L.head_t, ft, L.pre_t.w, N, E, ft);
+  pre.p[1].epi.bias = P->pre_text.b; pre.p[1].epi.out_f32 = out + E; pre.p[1].epi.ld_f32 = D->out_ld;
+  pre.p[2] = mk_linear(L.head_m, fm, L.pre_m.w, N, E, fm);
+  pre.p[2].epi.bias = P->mm_down.b; pre.p[2].epi.out_f32 = out + 2 * E; pre.p[2].epi.ld_f32 = D->out_ld;
+  IISAN_TRY(launch_umma_gemm(pre, st));
+  return IISAN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+static int san_backward_bf16_t(const iisan_san_desc* D, const iisan_san_params* P, const iisan_san_params* G, const void* image,
+                               const void* text, void* ws, const float* d_out, cudaStream_t st) {
+  SanLayoutBf16 L(*D, ws);
+  const int N = D->n_items, E = D->emb;
+  const bool dimdiff = D->d_text != D->d_img;
+  const bool text_wide = D->d_text > D->d_img;
+  const int dwide = text_wide ? D->d_text : D->d_img;
+  const int ft = D->asym ? E : D->d_text, fi = D->asym ? E : D->d_img, fm = D->d_mm;
+  int ls_t = -1, ls_i = -1, ls_m = -1;
+  for (int s = 0; s < D->n_stages; ++s) {
+    if (D->text_adapter[s] >= 0) ls_t = s;
+    if (D->img_adapter[s] >= 0) ls_i = s;
+    if (D->mm_index[s] >= 0) ls_m = s;
+  }
+  if (ls_t < 0 || ls_i < 0 || ls_m < 0) return IISAN_EINVAL;
+  // ---- bf16 operand copy of d_out ----
+  {
+    MixBatch cb{}; cb.n = 1;
+    MixProb& c = cb.p[0];
+    c.P = dense_src(d_out, D->out_ld); c.mode = 2; c.X = nullptr; c.Xb = L.doutb; c.N = N; c.d = 3 * E;
+    IISAN_TRY(launch_mix<T>(cb, st));
+  }
+  const bf16* do_i = L.doutb; const bf16* do_t = L.doutb + E; const bf16* do_m = L.doutb + 2 * E;
+  const int ldo = 3 * E;
+  // ---- heads backward ----
+  {
+    UmmaBatch w{}; w.n = 3;   // d pre weights [E, f] += dout^T head
+    w.p[0] = mk_wgrad(do_i, ldo, E, L.head_i, fi, fi, N, G->pre_img.w, 3);
+    w.p[1] = mk_wgrad(do_t, ldo, E, L.head_t, ft, ft, N, G->pre_text.w, 3);
+    w.p[2] = mk_wgrad(do_m, ldo, E, L.head_m, fm, fm, N, G->mm_down.w, 3);
+    IISAN_TRY(launch_umma_gemm(w, st));
+    ColsumBatch c{}; c.n = 3;
+    c.p[0] = {d_out, D->out_ld, N, E, G->pre_img.b};
+    c.p[1] = {d_out + E, D->out_ld, N, E, G->pre_text.b};
+    c.p[2] = {d_out + 2 * E, D->out_ld, N, E, G->mm_down.b};
+    IISAN_TRY(launch_colsum(c, st));
+    UmmaBatch dh{}; dh.n = 3;  // d head = d_out W_pre
+    dh.p[0] = mk_linear(do_i, ldo, L.pre_i.wt, N, fi, E); dh.p[0].epi.out_bf16 = L.dhead_i; dh.p[0].epi.ld_bf16 = fi;
+    dh.p[1] = mk_linear(do_t, ldo, L.pre_t.wt, N, ft, E); dh.p[1].epi.out_bf16 = L.dhead_t; dh.p[1].epi.ld_bf16 = ft;
+    dh.p[2] = mk_linear(do_m, ldo, L.pre_m.wt, N, fm, E); dh.p[2].epi.out_bf16 = L.dhead_m; dh.p[2].epi.ld_bf16 = fm;
+    IISAN_TRY(launch_umma_gemm(dh, st));
+    UmmaBatch wf{}; wf.n = 3;  // d fc weights [f, d] += dhead^T last
+    wf.p[0] = mk_wgrad(L.dhead_i, fi, fi, L.last_i[ls_i], D->d_img, D->d_img, N, G->fc_img.w, 3);
+    wf.p[1] = mk_wgrad(L.dhead_t, ft, ft, L.last_t[ls_t], D->d_text, D->d_text, N, G->fc_text.w, 3);
+    wf.p[2] = mk_wgrad(L.dhead_m, fm, fm, L.last_m[ls_m], D->d_mm, D->d_mm, N, G->fc_mm.w, 3);
+    IISAN_TRY(launch_umma_gemm(wf, st));
+    ColsumBatch cf{}; cf.n = 3;
+    cf.p[0] = {nullptr, fi, N, fi, G->fc_img.b, L.dhead_i};
+    cf.p[1] = {nullptr, ft, N, ft, G->fc_text.b, L.dhead_t};
+    cf.p[2] = {nullptr, fm, N, fm, G->fc_mm.b, L.dhead_m};
+    IISAN_TRY(launch_colsum(cf, st));
+    UmmaBatch dl{}; dl.n = 3;  // d last = d head W_fc
+    dl.p[0] = mk_linear(L.dhead_i, fi, L.fc_i.wt, N, D->d_img, fi);
+    dl.p[0].epi.out_f32 = L.dy_i; dl.p[0].epi.ld_f32 = D->d_img; dl.p[0].epi.out_bf16 = L.dyb_i; dl.p[0].epi.ld_bf16 = D->d_img;
+    dl.p[1] = mk_linear(L.dhead_t, ft, L.fc_t.wt, N, D->d_text, ft);
+    dl.p[1].epi.out_f32 = L.dy_t; dl.p[1].epi.ld_f32 = D->d_text; dl.p[1].epi.out_bf16 = L.dyb_t; dl.p[1].epi.ld_bf16 = D->d_text;
+    dl.p[2] = mk_linear(L.dhead_m, fm, L.fc_m.wt, N, D->d_mm, fm);
+    dl.p[2].epi.out_f32 = L.dy_m; dl.p[2].epi.ld_f32 = D->d_mm; dl.p[2].epi.out_bf16 = L.dyb_m; dl.p[2].epi.ld_bf16 = D->d_mm;
+    IISAN_TRY(launch_umma_gemm(dl, st));
+  }
+  // ---- stages in reverse: dy_* holds d last_s on entry to stage s and d last_{s-1} on exit ----
+  float* dy_t = L.dy_t; float* dx_t = L.dx_t; bf16* dyb_t = L.dyb_t; bf16* dxb_t = L.dxb_t;
+  float* dy_i = L.dy_i; float* dx_i = L.dx_i; bf16* dyb_i = L.dyb_i; bf16* dxb_i = L.dxb_i;
+  float* dy_m = L.dy_m; float* dx_m = L.dx_m; bf16* dyb_m = L.dyb_m; bf16* dxb_m = L.dxb_m;
+  for (int s = D->n_stages - 1; s >= 0; --s) {
+    const int ta = D->text_adapter[s], ia = D->img_adapter[s], mi = D->mm_index[s];
+    int ps_t = -1, ps_i = -1;
+    for (int q = 0; q < s; ++q) {
+      if (D->text_adapter[q] >= 0) ps_t = q;
+      if (D->img_adapter[q] >= 0) ps_i = q;
+    }
+    const int nt = (ta >= 0) + (ia >= 0) + (mi >= 0);
+    UmmaBatch wu{}, dz{}, wd{}, dx{}; ColsumBatch cu{}, cd{};
+    auto add = [&](const iisan_adapter_ptrs& g, const WCopy& wdn, const WCopy& wup, const bf16* x, const bf16* z, bf16* dzb,
+                   const float* dy, const bf16* dyb, float* dxo, bf16* dxob, int d, int r) {
+      wu.p[wu.n++] = mk_wgrad(dyb, d, d, z, r, r, N, g.w_up, nt);               // dWu[d,r] += dy^T z
+      cu.p[cu.n++] = {dy, d, N, d, g.b_up};
+      UmmaProblem& q = dz.p[dz.n++];                                             // dz = (dy Wu) * (z > 0)
+      q = mk_linear(dyb, d, wup.wt, N, r, d);
+      q.epi.mask = z; q.epi.ld_mask = r; q.epi.out_bf16 = dzb; q.epi.ld_bf16 = r;
+      wd.p[wd.n++] = mk_wgrad(dzb, r, r, x, d, d, N, g.w_down, nt);             // dWd[r,d] += dz^T x
+      cd.p[cd.n++] = {nullptr, r, N, r, g.b_down, dzb};
+      UmmaProblem& u = dx.p[dx.n++];                                             // dx = dy + dz Wd
+      u = mk_linear(dzb, r, wdn.wt, N, d, r);
+      u.epi.resid_f32 = dy; u.epi.ld_resid_f32 = d; u.epi.out_f32 = dxo; u.epi.ld_f32 = d; u.epi.out_bf16 = dxob; u.epi.ld_bf16 = d;
+    };
+    if (ta >= 0) add(G->text[ta], L.t_down[ta], L.t_up[ta], L.x_t[s], L.z_t[s], L.dzb_t, dy_t, dyb_t, dx_t, dxb_t, D->d_text, D->r_text);
+    if (ia >= 0) add(G->img[ia], L.i_down[ia], L.i_up[ia], L.x_i[s], L.z_i[s], L.dzb_i, dy_i, dyb_i, dx_i, dxb_i, D->d_img, D->r_img);
+    if (mi >= 0) add(G->mm[mi], L.m_down[mi], L.m_up[mi], L.x_m[s], L.z_m[s], L.dzb_m, dy_m, dyb_m, dx_m, dxb_m, D->d_mm, D->r_mm);
+    IISAN_TRY(launch_umma_gemm(wu, st));
+    IISAN_TRY(launch_colsum(cu, st));
+    IISAN_TRY(launch_umma_gemm(dz, st));
+    IISAN_TRY(launch_umma_gemm(wd, st));
+    IISAN_TRY(launch_colsum(cd, st));
+    IISAN_TRY(launch_umma_gemm(dx, st));
+    // ---- fusion backward ----
+    MixBwdBatch mb{};
+    const bool has_dp = (mi >= 0 && dimdiff);
+    if (ta >= 0) {
+      MixBwdProb& m = mb.p[mb.n++];
+      m.P = state_src<T>(text, D->layers_text, D->d_text, D->text_layer[s]);
+      if (ps_t < 0) { if (D->remove_first) m.R = state_src<T>(text, D->layers_text, D->d_text, 0); else m.R = MixSrc{nullptr, 0, 0}; }
+      else m.R = dense_bf16_src(L.last_t[ps_t], D->d_text);
+      m.gate = P->gate_text[ta]; m.dgate = G->gate_text[ta]; m.mode = 0; m.dX = dx_t;
+      m.dPrev = (ps_t >= 0) ? dy_t : nullptr; m.dPrevb = (ps_t >= 0) ? dyb_t : nullptr; m.N = N; m.d = D->d_text;
+    }
+    if (ia >= 0) {
+      MixBwdProb& m = mb.p[mb.n++];
+      m.P = state_src<T>(image, D->layers_img, D->d_img, D->img_layer[s]);
+      if (ps_i < 0) { if (D->remove_first) m.R = state_src<T>(image, D->layers_img, D->d_img, 0); else m.R = MixSrc{nullptr, 0, 0}; }
+      else m.R = dense_bf16_src(L.last_i[ps_i], D->d_img);
+      m.gate = P->gate_img[ia]; m.dgate = G->gate_img[ia]; m.mode = 0; m.dX = dx_i;
+      m.dPrev = (ps_i >= 0) ? dy_i : nullptr; m.dPrevb = (ps_i >= 0) ? dyb_i : nullptr; m.N = N; m.d = D->d_img;
+    }
+    if (mi >= 0) {
+      MixBwdProb& m = mb.p[mb.n++];
+      const float* dp = has_dp ? L.dpo[s] : nullptr;
+      m.P = (dp && !text_wide) ? dense_src(dp, D->d_mm) : state_src<T>(image, D->layers_img, D->d_img, D->img_layer[s]);
+      m.Q = (dp && text_wide) ? dense_src(dp, D->d_mm) : state_src<T>(text, D->layers_text, D->d_text, D->text_layer[s]);
+      m.gate = P->gate_mm[mi]; m.dgate = G->gate_mm[mi]; m.mode = 1; m.dX = dx_m;
+      m.dP_outb = (has_dp && !text_wide) ? L.ddpb : nullptr;
+      m.dQ_outb = (has_dp && text_wide) ? L.ddpb : nullptr;
+      m.N = N; m.d = D->d_mm;
+    }
+    IISAN_TRY(launch_mix_bwd<T>(mb, st));
+    if (mi >= 0) {   // d last_mm_{s-1} = dx_mm
+      float* t = dy_m; dy_m = dx_m; dx_m = t;
+      bf16* tb = dyb_m; dyb_m = dxb_m; dxb_m = tb;
+    }
+    if (has_dp) {
+      // down_project gradients: dW[d_mm, dwide] += ddp^T h_wide ; db += colsum(ddp)
+      int status = IISAN_OK; int64_t pitch = 0;
+      const bf16* hw = text_wide ? wide_operand<T>(D, text, D->layers_text, D->d_text, D->text_layer[s], L, &pitch, st, &status)
+                                 : wide_operand<T>(D, image, D->layers_img, D->d_img, D->img_layer[s], L, &pitch, st, &status);
+      IISAN_TRY(status);
+      UmmaBatch w{}; w.n = 1;
+      w.p[0] = mk_wgrad(L.ddpb, D->d_mm, D->d_mm, hw, pitch, dwide, N, G->down_project[mi].w, 1);
+      IISAN_TRY(launch_umma_gemm(w, st));
+      ColsumBatch c{}; c.n = 1;
+      c.p[0] = {nullptr, D->d_mm, N, D->d_mm, G->down_project[mi].b, L.ddpb};
+      IISAN_TRY(launch_colsum(c, st));
+    }
+  }
+  return IISAN_OK;
+}
+
+int san_forward_bf16(const iisan_san_desc* D, const iisan_san_params* P, const void* image, const void* text, void* ws, float* out,
+                     cudaStream_t st) {
+  switch (D->state_dtype) {
+    case IISAN_F32: return san_forward_bf16_t<float>(D, P, image, text, ws, out, st);
+    case IISAN_BF16: return san_forward_bf16_t<bf16>(D, P, image, text, ws, out, st);
+    case IISAN_F16: return san_forward_bf16_t<__half>(D, P, image, text, ws, out, st);
+  }
+  return IISAN_EINVAL;
+}
+
+int san_backward_bf16(const iisan_san_desc* D, const iisan_san_params* P, const iisan_san_params* G, const void* image,
+                      const void* text, void* ws, const float* d_out, cudaStream_t st) {
+  switch (D->state_dtype) {
+    case IISAN_F32: return san_backward_bf16_t<float>(D, P, G, image, text, ws, d_out, st);
+    case IISAN_BF16: return san_backward_bf16_t<bf16>(D, P, G, image, text, ws, d_out, st);
+    case IISAN_F16: return san_backward_bf16_t<__half>(D, P, G, image, text, ws, d_out, st);
+  }
+  return IISAN_EINVAL;
+}
+
+}  // namespace iisan

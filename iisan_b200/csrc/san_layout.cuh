@@ -5,6 +5,15 @@
 
 namespace iisan {
 
+int san_validate(const iisan_san_desc* d);
+// bf16 tensor-core mode (san_bf16.cu)
+size_t san_bf16_workspace_bytes(const iisan_san_desc& D);
+int san_bf16_supported(const iisan_san_desc& D);
+int san_forward_bf16(const iisan_san_desc* D, const iisan_san_params* P, const void* image, const void* text, void* ws,
+                     float* out, cudaStream_t st);
+int san_backward_bf16(const iisan_san_desc* D, const iisan_san_params* P, const iisan_san_params* G, const void* image,
+                      const void* text, void* ws, const float* d_out, cudaStream_t st);
+
 struct SanLayout {
   // per stage stash (null where the tower is idle in that stage)
   float* x_t[IISAN_MAX_STAGES]; float* z_t[IISAN_MAX_STAGES]; float* last_t[IISAN_MAX_STAGES];

@@ -179,7 +179,16 @@ __global__ void __launch_bounds__(UTHREADS, 1) umma_gemm_kernel(const __grid_con
             }
           }
         }
-        if (E.out_f32) {
+        if (E.out_f32 && E.transpose_out) {
+          float* op = E.out_f32 + (int64_t)col * E.ld_f32 + row;      // lanes (rows) are contiguous: coalesced
+          if (E.atomic) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (j < ncol) atomicAdd(op + (int64_t)j * E.ld_f32, v[j]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (j < ncol) op[(int64_t)j * E.ld_f32] = v[j];
+          }
+        } else if (E.out_f32) {
           float* op = E.out_f32 + (int64_t)row * E.ld_f32 + col;
           if (E.atomic) {
 #pragma unroll

@@ -30,6 +30,7 @@ struct UmmaEpilogue {
   const float* resid_f32; int64_t ld_resid_f32;
   int relu;
   int atomic;                                     // 1: red.add into out_f32 (split-K partial sums)
+  int transpose_out;                              // 1: out_f32 is addressed [n * ld_f32 + m] (fp32 output only)
 };
 
 struct UmmaProblem {

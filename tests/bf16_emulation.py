@@ -1,0 +1,85 @@
+"""TEST INFRASTRUCTURE -- torch emulation of the fast mode's rounding points.
+
+The fast mode (IISAN_COMPUTE_BF16) rounds GEMM operands and the stage stash to bf16 and accumulates in fp32.  Against
+the fp32 oracle its *gradients* differ by ReLU activations that flip under the rounding noise (a per-element effect that
+only averages out over large batches), so the backward kernels are pinned against this emulation instead: the oracle's
+forward (oracle/iisan_oracle.py, same reference citations) with a straight-through bf16 rounding inserted exactly where
+the CUDA path rounds.  Loss / embeddings of the fast mode are still compared with the fp32 reference itself.
+"""
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from oracle import iisan_oracle as O
+
+
+def rb(x):
+    """bf16 rounding with a straight-through gradient."""
+    return x + (x.detach().bfloat16().float() - x.detach())
+
+
+def _lin(x, w, b=None):
+    return F.linear(x, rb(w), b)
+
+
+def san_forward_emul(P, image, text, cfg, prefix="mm_encoder."):
+    h_cv = image.reshape(-1, image.shape[-2], image.shape[-1]).float()
+    h_tx = text.reshape(-1, text.shape[-2], text.shape[-1]).float()
+    N = h_cv.shape[0]
+    dev = h_cv.device
+    d_mm = min(cfg.d_text, cfg.d_img) if cfg.asym else cfg.d_text
+    if cfg.remove_first == "TRUE":
+        last_cv, last_tx = h_cv[:, 0], h_tx[:, 0]
+    else:
+        last_cv = torch.zeros(N, cfg.d_img, device=dev); last_tx = torch.zeros(N, cfg.d_text, device=dev)
+    last_mm = torch.zeros(N, d_mm, device=dev)
+
+    def adapter(pfx, x):
+        z = rb(F.relu(_lin(x, P[pfx + ".fc_down.weight"], P[pfx + ".fc_down.bias"])))
+        return rb(_lin(z, P[pfx + ".fc_up.weight"], P[pfx + ".fc_up.bias"]) + x)
+
+    for (ta, tl, ia, il, mi) in O.stage_plan(cfg):
+        if ia is not None:
+            g = O._gate(P[f"{prefix}side_gate_params_cv.{ia}"])
+            x_cv = rb(g * h_cv[:, il] + (1 - g) * last_cv)
+        if ta is not None:
+            g = O._gate(P[f"{prefix}side_gate_params_text.{ta}"])
+            x_tx = rb(g * h_tx[:, tl] + (1 - g) * last_tx)
+        if ta is not None:
+            last_tx = adapter(f"{prefix}bert_adapter_list.{ta}", x_tx)
+        if ia is not None:
+            last_cv = adapter(f"{prefix}cv_adapter_list.{ia}", x_cv)
+        if mi is not None:
+            mm_tx, mm_cv = h_tx[:, tl], h_cv[:, il]
+            if cfg.asym and cfg.d_text > cfg.d_img:
+                mm_tx = _lin(rb(mm_tx), P[f"{prefix}down_project_list.{mi}.weight"], P[f"{prefix}down_project_list.{mi}.bias"])
+            elif cfg.asym and cfg.d_img > cfg.d_text:
+                mm_cv = _lin(rb(mm_cv), P[f"{prefix}down_project_list.{mi}.weight"], P[f"{prefix}down_project_list.{mi}.bias"])
+            g = O._gate(P[f"{prefix}side_gate_params_mm.{mi}"])
+            x_mm = rb(last_mm + g * mm_cv + (1 - g) * mm_tx)
+            last_mm = adapter(f"{prefix}mm_adapter_list.{mi}", x_mm)
+    lin = lambda n, x: _lin(x, P[f"{prefix}{n}.weight"], P[f"{prefix}{n}.bias"])
+    e_tx = lin("bert_pre_fc", rb(lin("fc_bert", last_tx)))
+    e_cv = lin("cv_pre_fc", rb(lin("fc_cv", last_cv)))
+    e_mm = lin("fc_mm_down", rb(lin("fc_mm", last_mm)))
+    return e_cv, e_tx, e_mm
+
+
+def train_step_grads_emul(params_np, batch, pop_prob, cfg, ce_bf16=False):
+    """Like oracle.train_step_grads with the fast mode's rounding points (CPU fp32 torch)."""
+    P = O.params_to_torch(params_np)
+    ids, lm = batch["ids"], batch["log_mask"]
+    B, S = ids.shape
+    image = torch.as_tensor(batch["image"]); text = torch.as_tensor(batch["text"])
+    debias = torch.log(torch.from_numpy(pop_prob)[torch.from_numpy(ids.reshape(-1))])
+    e_cv, e_tx, e_mm = san_forward_emul(P, image, text, cfg)
+    score = F.linear(torch.cat([e_cv, e_tx, e_mm], dim=1), P["com_dense.weight"], P["com_dense.bias"])
+    embs = score.view(B, S, cfg.embedding_dim)
+    prec = O.user_encoder_forward(P, embs[:, :-1], torch.from_numpy(lm), cfg).reshape(-1, cfg.embedding_dim)
+    if ce_bf16:
+        loss, _ = O.inbatch_ce(rb(prec), rb(score), debias, ids, lm, ids, lm)
+    else:
+        loss, _ = O.inbatch_ce(prec, score, debias, ids, lm, ids, lm)
+    loss.backward()
+    grads = {k: (None if v.grad is None else v.grad.detach().numpy()) for k, v in P.items()}
+    return {"loss": loss.detach().numpy(), "score_embs": score.detach().numpy()}, grads
