@@ -12,6 +12,7 @@
 // forward keeps one log-sum-exp per row, the backward recomputes the tile.
 #include "common.cuh"
 #include "launch.cuh"
+#include "ce_umma.cuh"
 
 namespace iisan {
 
@@ -258,6 +259,7 @@ using namespace iisan;
 
 extern "C" size_t iisan_inbatch_ce_workspace_bytes(const iisan_ce_desc* desc) {
   if (ce_validate(desc) != IISAN_OK) return 0;
+  if (desc->compute == IISAN_COMPUTE_BF16 && ce_fast_supported(*desc)) return ce_fast_workspace_bytes(*desc);
   CeLayout L(*desc, nullptr);
   return L.bytes;
 }
@@ -270,6 +272,8 @@ extern "C" int iisan_inbatch_ce_forward(const iisan_ce_desc* desc, const float* 
   if (!prec || !score || !ids_rows || !ids_cols || !log_mask_rows || !log_mask_cols || !pop_prob || !workspace) return IISAN_EINVAL;
   if (workspace_bytes < iisan_inbatch_ce_workspace_bytes(desc)) return IISAN_EWORKSPACE;
   cudaStream_t st = as_stream(stream);
+  if (desc->compute == IISAN_COMPUTE_BF16 && ce_fast_supported(*desc))
+    return ce_fast_forward(*desc, prec, score, ids_rows, ids_cols, log_mask_rows, log_mask_cols, pop_prob, workspace, loss_sum, n_valid, loss, st);
   CeLayout W(*desc, workspace);
   const CeArgs a = make_args(*desc, prec, score, ids_rows, ids_cols, log_mask_rows, log_mask_cols, pop_prob);
   IISAN_CUDA_OK(cudaMemsetAsync(W.acc_sum, 0, 256 + sizeof(int), st));   // acc_sum and acc_cnt are adjacent 256 B slots
@@ -291,6 +295,8 @@ extern "C" int iisan_inbatch_ce_backward(const iisan_ce_desc* desc, const float*
     return IISAN_EINVAL;
   if (workspace_bytes < iisan_inbatch_ce_workspace_bytes(desc)) return IISAN_EWORKSPACE;
   cudaStream_t st = as_stream(stream);
+  if (desc->compute == IISAN_COMPUTE_BF16 && ce_fast_supported(*desc))
+    return ce_fast_backward(*desc, log_mask_rows, log_mask_cols, workspace, grad_loss_sum, grad_loss_mean, n_valid, d_prec, d_score, st);
   CeLayout W(*desc, workspace);
   const CeArgs a = make_args(*desc, prec, score, ids_rows, ids_cols, log_mask_rows, log_mask_cols, pop_prob);
   { LaunchScope ls_(IISAN_K_CE, st); ce_bwd_rows_kernel<<<a.B * a.L, 256, 0, st>>>(a, W.lse, grad_loss_sum, grad_loss_mean, n_valid, d_prec); }
@@ -308,4 +314,14 @@ extern "C" int iisan_inbatch_ce_masks(const iisan_ce_desc* desc, const int64_t* 
   { LaunchScope ls_(IISAN_K_CE, as_stream(stream)); ce_masks_kernel<<<a.B * a.L, 256, 0, as_stream(stream)>>>(a, out); }
   IISAN_LAUNCH_OK();
   return IISAN_OK;
+}
+
+extern "C" int iisan_inbatch_ce_masks_fast(const iisan_ce_desc* desc, const int64_t* ids_rows, const int64_t* ids_cols,
+                                           const float* log_mask_rows, const float* log_mask_cols, void* workspace,
+                                           size_t workspace_bytes, uint8_t* out, iisan_stream_t stream) {
+  IISAN_TRY(ce_validate(desc));
+  if (!ids_rows || !ids_cols || !log_mask_rows || !log_mask_cols || !workspace || !out) return IISAN_EINVAL;
+  if (desc->compute != IISAN_COMPUTE_BF16 || !ce_fast_supported(*desc)) return IISAN_EUNSUPPORTED;
+  if (workspace_bytes < ce_fast_workspace_bytes(*desc)) return IISAN_EWORKSPACE;
+  return ce_fast_masks(*desc, ids_rows, ids_cols, log_mask_rows, log_mask_cols, workspace, out, as_stream(stream));
 }

@@ -209,12 +209,21 @@ class InBatchCeFn(torch.autograd.Function):
         return d_prec, d_score, None, None, None, None, None, None, None
 
 
-def inbatch_ce_masks(ids_rows, ids_cols, lm_rows, lm_cols, user_offset=0):
-    """uint8 [B*L, C] mask bits straight from the CUDA path (parity probe)."""
+def inbatch_ce_masks(ids_rows, ids_cols, lm_rows, lm_cols, user_offset=0, fast=False):
+    """uint8 [B*L, C] mask bits straight from the CUDA path (parity probe).  ``fast``: the bit-per-(user, column) masks of
+    the tensor-core CE (bit0 = masked incl. the label exception, bit2 = label, bit3 = row valid)."""
     lib = L.load()
     L.require_cuda(ids_rows, "ids")
     b, l = lm_rows.shape
     bc = lm_cols.shape[0]
+    if fast:
+        desc = make_ce_desc(b, bc, l, 64, user_offset, L.COMPUTE_BF16)
+        ws = _workspace(lib.iisan_inbatch_ce_workspace_bytes(C.byref(desc)), ids_rows.device)
+        out = torch.empty(b * l, bc * (l + 1), dtype=torch.uint8, device=ids_rows.device)
+        L.check(lib.iisan_inbatch_ce_masks_fast(C.byref(desc), _p(ids_rows.contiguous().view(-1)), _p(ids_cols.contiguous().view(-1)),
+                                                _p(lm_rows.contiguous().float()), _p(lm_cols.contiguous().float()), _p(ws), ws.numel(),
+                                                _p(out), _stream()), "iisan_inbatch_ce_masks_fast")
+        return out
     desc = make_ce_desc(b, bc, l, 32, user_offset, 0)
     out = torch.empty(b * l, bc * (l + 1), dtype=torch.uint8, device=ids_rows.device)
     L.check(lib.iisan_inbatch_ce_masks(C.byref(desc), _p(ids_rows.contiguous().view(-1)), _p(ids_cols.contiguous().view(-1)),

@@ -254,6 +254,14 @@ int iisan_inbatch_ce_masks(const iisan_ce_desc* desc, const int64_t* ids_rows,
                            const int64_t* ids_cols, const float* log_mask_rows,
                            const float* log_mask_cols, uint8_t* out, iisan_stream_t stream);
 
+/* Same probe for the fast mode (desc->compute == IISAN_COMPUTE_BF16, emb == 64): the tensor-core CE evaluates its masks
+ * from one bit per (row-user, column) built by exact int64 compares; this expands those bits: bit0 = masked as applied by
+ * the kernels (column-pad OR reject, the label column escaping the reject), bit2 = label column, bit3 = row valid.
+ * `workspace` as for iisan_inbatch_ce_forward. */
+int iisan_inbatch_ce_masks_fast(const iisan_ce_desc* desc, const int64_t* ids_rows, const int64_t* ids_cols,
+                                const float* log_mask_rows, const float* log_mask_cols, void* workspace,
+                                size_t workspace_bytes, uint8_t* out, iisan_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Cached hidden-state path (CC/data_utils/dataset.py:29-34,65-92 ; CC/run.py:368-377):
  * per-item, per-layer gather from an item table into the dense train batch.

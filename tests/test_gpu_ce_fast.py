@@ -1,0 +1,75 @@
+"""Tensor-core in-batch cross-entropy (fast mode) against the oracle's CE evaluated on the bf16-rounded operands.
+Masks / labels / valid rows: bit-exact.  Loss: 1e-4 relative (fp32 accumulation of exact bf16 products; __expf).
+Gradients: 5e-3 of the largest entry (the softmax weights are rounded to bf16 before the second MMA)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _case(B, Bc, off, seed, mode, item_num):
+    from oracle.synthetic import PathConfig, make_ids, make_pop_prob
+    cfg = PathConfig(item_num=item_num)
+    ids_all, lm_all = make_ids(Bc, cfg, seed, mode)
+    pop = make_pop_prob(cfg, seed)
+    g = torch.Generator().manual_seed(seed)
+    prec = torch.randn(B * 10, 64, generator=g) * 0.7
+    score = torch.randn(Bc * 11, 64, generator=g) * 0.5
+    return cfg, ids_all, lm_all, pop, prec, score
+
+
+@pytest.mark.parametrize("B,Bc,off,mode,item_num", [(512, 512, 0, "dense", 19246), (512, 512, 0, "realistic", 300),
+                                                     (37, 37, 0, "realistic", 50), (13, 13, 0, "dense", 20),
+                                                     (64, 256, 128, "realistic", 200), (128, 1024, 896, "dense", 5000)])
+def test_fast_ce_matches_oracle(B, Bc, off, mode, item_num):
+    from iisan_b200 import _lib
+    from iisan_b200.ops import InBatchCeFn, inbatch_ce_masks
+    from oracle import iisan_oracle as O
+    cfg, ids_all, lm_all, pop, prec, score = _case(B, Bc, off, 100 + B, mode, item_num)
+    ids, lm = ids_all[off:off + B], lm_all[off:off + B]
+    # ---- masks, labels, valid rows: bit-exact ----
+    idc = torch.from_numpy(ids_all).cuda(); lmc = torch.from_numpy(lm_all).cuda()
+    bits = inbatch_ce_masks(idc[off:off + B], idc, lmc[off:off + B], lmc, user_offset=off, fast=True).cpu().numpy()
+    rej = O.reject_mask(ids, ids_all, 10, user_offset=off)
+    colm = np.broadcast_to(~O.column_valid(lm_all), rej.shape)
+    lab = O.ce_labels(B, 10, off)
+    expect = rej | colm
+    expect[np.arange(B * 10), lab] = colm[np.arange(B * 10), lab]
+    assert np.array_equal((bits & 1) != 0, expect)
+    assert np.array_equal(np.argmax((bits & 4) != 0, axis=1), lab)
+    assert ((bits & 4) != 0).sum(axis=1).max() == 1
+    assert np.array_equal(np.nonzero(bits[:, 0] & 8)[0], O.valid_rows(lm))
+    # ---- loss and gradients ----
+    pb = prec.bfloat16().float().requires_grad_(True)
+    sb = score.bfloat16().float().requires_grad_(True)
+    debias = torch.log(torch.from_numpy(pop)[torch.from_numpy(ids_all.reshape(-1))])
+    ref_loss, _ = O.inbatch_ce(pb, sb, debias, ids, lm, ids_all, lm_all, user_offset=off)
+    ref_loss.backward()
+    p = prec.cuda().requires_grad_(True); s = score.cuda().requires_grad_(True)
+    loss_sum, n_valid, loss = InBatchCeFn.apply(p, s, idc[off:off + B], idc, lmc[off:off + B], lmc, torch.from_numpy(pop).cuda(), off,
+                                                _lib.COMPUTE_BF16)
+    loss.backward()
+    assert int(n_valid.item()) == len(O.valid_rows(lm))
+    assert abs(loss.item() - ref_loss.item()) <= 1e-4 * abs(ref_loss.item()), (loss.item(), ref_loss.item())
+    assert abs(loss_sum.item() - ref_loss.item() * int(n_valid.item())) <= 1e-4 * abs(loss_sum.item())
+    for got, ref, name in ((p.grad, pb.grad, "d_prec"), (s.grad, sb.grad, "d_score")):
+        err = (got.cpu() - ref).abs().max().item() / ref.abs().max().item()
+        assert err <= 5e-3, f"{name}: {err}"
+
+
+def test_fast_ce_vs_exact_mode_kernel():
+    """Both CUDA CE paths on the same fp32 inputs: the fast mode differs from the exact one only by the bf16 operand rounding."""
+    from iisan_b200 import _lib
+    from iisan_b200.ops import InBatchCeFn
+    cfg, ids, lm, pop, prec, score = _case(96, 96, 0, 7, "realistic", 150)
+    idc = torch.from_numpy(ids).cuda(); lmc = torch.from_numpy(lm).cuda(); popc = torch.from_numpy(pop).cuda()
+    out = []
+    for mode in (_lib.COMPUTE_FP32, _lib.COMPUTE_BF16):
+        p = prec.cuda().requires_grad_(True); s = score.cuda().requires_grad_(True)
+        _, _, loss = InBatchCeFn.apply(p, s, idc, idc, lmc, lmc, popc, 0, mode)
+        loss.backward()
+        out.append((loss.item(), p.grad.clone(), s.grad.clone()))
+    assert abs(out[0][0] - out[1][0]) <= 1e-2 * abs(out[0][0])
+    for k in (1, 2):
+        assert (out[0][k] - out[1][k]).abs().max().item() <= 3e-2 * out[0][k].abs().max().item()
