@@ -16,8 +16,10 @@ using namespace umma;
 
 constexpr int UBM = 128;          // rows per tile (UMMA M)
 constexpr int UBK = 64;           // k-block: one 128-byte swizzle atom of bf16
-constexpr int USTAGES = 4;
-constexpr int UTHREADS = 192;
+constexpr int USTAGES = 4;        // at most; short reductions use fewer so that two CTAs share an SM
+constexpr int UTHREADS = 320;     // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int UEPI_WARPS = 8;
+constexpr int USTG_FLOATS = 32 * 33;   // per-warp transpose staging (padded: conflict-free both ways)
 
 struct UmmaDevProblem {
   CUtensorMap map_a, map_b;
@@ -27,6 +29,7 @@ struct UmmaDevProblem {
 };
 struct UmmaDevBatch {
   UmmaDevProblem p[kUmmaMaxProbs];
+  int stages;
 };
 
 template <int BN>
@@ -34,12 +37,72 @@ struct UmmaSmem {
   static constexpr int kABytes = UBM * UBK * 2;
   static constexpr int kBBytes = BN * UBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kTotal = USTAGES * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kEpiBytes = UEPI_WARPS * USTG_FLOATS * 4;
+  static int total(int stages) { return stages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kEpiBytes; }
 };
 
+
+// One 32x32 output block of the epilogue, transposed domain (lane = column).  The feature set is a template so that the
+// per-element code carries no pointer checks; rows advance by pointer increments.
+template <bool MASK, bool RESB, bool RESF, bool OUTF, bool OUTB, bool ATOMIC>
+__device__ __forceinline__ void epi_block(const UmmaEpilogue& E, const float* __restrict__ stg, int lane, int64_t row_base, int nrow,
+                                          int col, float bias_v, float lo) {
+  const __nv_bfloat16* mp = MASK ? E.mask + row_base * E.ld_mask + col : nullptr;
+  const __nv_bfloat16* rb = RESB ? E.resid_bf16 + row_base * E.ld_resid_bf16 + col : nullptr;
+  const float* rf = RESF ? E.resid_f32 + row_base * E.ld_resid_f32 + col : nullptr;
+  float* of = OUTF ? E.out_f32 + row_base * E.ld_f32 + col : nullptr;
+  __nv_bfloat16* ob = OUTB ? E.out_bf16 + row_base * E.ld_bf16 + col : nullptr;
+#pragma unroll 1
+  for (int r0 = 0; r0 < nrow; r0 += 8) {
+    float add[8]; bool keep[8];
+    // all global loads of the group first: the output pointers may alias the inputs as far as the compiler knows
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      add[i] = 0.f; keep[i] = true;
+      if (r0 + i < nrow) {
+        if (MASK) keep[i] = __bfloat162float(mp[(int64_t)i * E.ld_mask]) > 0.f;
+        if (RESB) add[i] += __bfloat162float(rb[(int64_t)i * E.ld_resid_bf16]);
+        if (RESF) add[i] += rf[(int64_t)i * E.ld_resid_f32];
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (r0 + i < nrow) {
+        float v = fmaxf(stg[(r0 + i) * 33 + lane] + bias_v, lo);
+        if (MASK) v = keep[i] ? v : 0.f;
+        v += add[i];
+        if (OUTF) { if (ATOMIC) atomicAdd(of + (int64_t)i * E.ld_f32, v); else of[(int64_t)i * E.ld_f32] = v; }
+        if (OUTB) ob[(int64_t)i * E.ld_bf16] = __float2bfloat16_rn(v);
+      }
+    }
+    if (MASK) mp += 8 * E.ld_mask;
+    if (RESB) rb += 8 * E.ld_resid_bf16;
+    if (RESF) rf += 8 * E.ld_resid_f32;
+    if (OUTF) of += 8 * E.ld_f32;
+    if (OUTB) ob += 8 * E.ld_bf16;
+  }
+}
+
+// generic fallback: every feature decided at run time
+__device__ __noinline__ void epi_block_generic(const UmmaEpilogue& E, const float* stg, int lane, int64_t row_base, int nrow, int col,
+                                               float bias_v, float lo) {
+  for (int r = 0; r < nrow; ++r) {
+    const int64_t row = row_base + r;
+    float v = fmaxf(stg[r * 33 + lane] + bias_v, lo);
+    if (E.mask) { if (!(__bfloat162float(E.mask[row * E.ld_mask + col]) > 0.f)) v = 0.f; }
+    if (E.resid_bf16) v += __bfloat162float(E.resid_bf16[row * E.ld_resid_bf16 + col]);
+    if (E.resid_f32) v += E.resid_f32[row * E.ld_resid_f32 + col];
+    if (E.out_f32) { if (E.atomic) atomicAdd(E.out_f32 + row * E.ld_f32 + col, v); else E.out_f32[row * E.ld_f32 + col] = v; }
+    if (E.out_bf16) E.out_bf16[row * E.ld_bf16 + col] = __float2bfloat16_rn(v);
+  }
+}
+
+enum : int { EPI_MASK = 1, EPI_RESB = 2, EPI_RESF = 4, EPI_OUTF = 8, EPI_OUTB = 16, EPI_ATOMIC = 32 };
+
 template <int BN, bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(UTHREADS, 1) umma_gemm_kernel(const __grid_constant__ UmmaDevBatch batch) {
+__global__ void __launch_bounds__(UTHREADS, 2) umma_gemm_kernel(const __grid_constant__ UmmaDevBatch batch) {
   const UmmaDevProblem& P = batch.p[blockIdx.z];
+  const int NSTG = batch.stages;
   const int tiles_n = (P.N + BN - 1) / BN;
   const int tiles_m = (P.M + UBM - 1) / UBM;
   if ((int)blockIdx.x >= tiles_m * tiles_n) return;
@@ -52,16 +115,17 @@ __global__ void __launch_bounds__(UTHREADS, 1) umma_gemm_kernel(const __grid_con
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   using S = UmmaSmem<BN>;
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + USTAGES * S::kStageBytes);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + NSTG * S::kStageBytes);
   uint64_t* empty = full + USTAGES;
   uint64_t* accum_full = empty + USTAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_full + 1);
+  float* staging = reinterpret_cast<float*>(smem + NSTG * S::kStageBytes + 256);
 
   const int warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&P.map_a);
     tma_prefetch_desc(&P.map_b);
-    for (int s = 0; s < USTAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < NSTG; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     mbar_init(accum_full, 1);
     fence_barrier_init();
   }
@@ -92,7 +156,7 @@ __global__ void __launch_bounds__(UTHREADS, 1) umma_gemm_kernel(const __grid_con
         } else {
           tma_load_2d(sb, &P.map_b, &full[stage], k0, n0);
         }
-        if (++stage == USTAGES) { stage = 0; phase ^= 1; }
+        if (++stage == NSTG) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -112,106 +176,69 @@ __global__ void __launch_bounds__(UTHREADS, 1) umma_gemm_kernel(const __grid_con
           mma_bf16_ss(tmem_base, ad, bd, idesc, (kb > kb_beg || k > 0) ? 1u : 0u);
         }
         mma_commit(&empty[stage]);                 // frees the smem slot when these MMAs retire
-        if (++stage == USTAGES) { stage = 0; phase ^= 1; }
+        if (++stage == NSTG) { stage = 0; phase ^= 1; }
       }
       mma_commit(accum_full);
     }
   } else {
-    // ---- epilogue: warp w owns TMEM lanes [32*(w%4), +32) == output rows m0 + 32*(w%4) + lane ----
+    // ---- epilogue: 8 warps; warp w may touch TMEM lanes [32*(w%4), +32) == output rows m0 + 32*(w%4) + lane; the two warps
+    //      of a quadrant take alternate 32-column chunks.  Each 32x32 block is transposed through padded shared memory so
+    //      that global loads (bias / mask / residual) and stores are row-contiguous (coalesced 64/128-byte segments). ----
+    const int ew = warp - 2;
     const int quad = warp & 3;
+    const int csel = ew >> 2;
     const int lane = threadIdx.x & 31;
-    const int row = m0 + quad * 32 + lane;
+    float* stg = staging + ew * USTG_FLOATS;
     mbar_wait(accum_full, 0);
     tc_fence_after();
     const UmmaEpilogue& E = P.epi;
     const bool first_split = (blockIdx.y == 0);
+    const int row_base = m0 + quad * 32;
+    const int features = (E.mask ? EPI_MASK : 0) | (E.resid_bf16 ? EPI_RESB : 0) | (E.resid_f32 ? EPI_RESF : 0) | (E.out_f32 ? EPI_OUTF : 0) |
+                         (E.out_bf16 ? EPI_OUTB : 0) | ((E.atomic && E.out_f32) ? EPI_ATOMIC : 0);
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
+    for (int c0 = csel * 32; c0 < BN; c0 += 64) {
       if (n0 + c0 >= P.N) break;                   // warp-uniform
       uint32_t raw[32];
       tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, raw);
       tmem_ld_wait();
-      if (row < P.M) {
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
-        const int ncol = min(32, P.N - (n0 + c0));
-        const int col = n0 + c0;
-        if (E.bias && (!E.atomic || first_split)) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) if (j < ncol) v[j] += __ldg(E.bias + col + j);
-        }
-        if (E.relu) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-        }
-        if (E.mask) {
-          const __nv_bfloat16* mp = E.mask + (int64_t)row * E.ld_mask + col;
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            if (j < ncol) {
-              const uint4 q = *reinterpret_cast<const uint4*>(mp + j);
-              const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(&q);
-#pragma unroll
-              for (int t = 0; t < 8; ++t) if (!(__bfloat162float(h[t]) > 0.f)) v[j + t] = 0.f;
-            }
-          }
-        }
-        if (E.resid_bf16) {
-          const __nv_bfloat16* rp = E.resid_bf16 + (int64_t)row * E.ld_resid_bf16 + col;
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            if (j < ncol) {
-              const uint4 q = *reinterpret_cast<const uint4*>(rp + j);
-              const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(&q);
-#pragma unroll
-              for (int t = 0; t < 8; ++t) v[j + t] += __bfloat162float(h[t]);
-            }
-          }
-        }
-        if (E.resid_f32) {
-          const float* rp = E.resid_f32 + (int64_t)row * E.ld_resid_f32 + col;
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            if (j < ncol) {
-              const float4 q = *reinterpret_cast<const float4*>(rp + j);
-              v[j] += q.x; v[j + 1] += q.y; v[j + 2] += q.z; v[j + 3] += q.w;
-            }
-          }
-        }
-        if (E.out_f32 && E.transpose_out) {
-          float* op = E.out_f32 + (int64_t)col * E.ld_f32 + row;      // lanes (rows) are contiguous: coalesced
+      if (E.transpose_out) {
+        // out[n * ld + m]: the lanes (rows m) are already contiguous in memory
+        const int row = row_base + lane;
+        if (row < P.M) {
+          const int ncol = min(32, P.N - (n0 + c0));
+          float* op = E.out_f32 + (int64_t)(n0 + c0) * E.ld_f32 + row;
           if (E.atomic) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) if (j < ncol) atomicAdd(op + (int64_t)j * E.ld_f32, v[j]);
+            for (int j = 0; j < 32; ++j) if (j < ncol) atomicAdd(op + (int64_t)j * E.ld_f32, __uint_as_float(raw[j]));
           } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) if (j < ncol) op[(int64_t)j * E.ld_f32] = v[j];
-          }
-        } else if (E.out_f32) {
-          float* op = E.out_f32 + (int64_t)row * E.ld_f32 + col;
-          if (E.atomic) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) if (j < ncol) atomicAdd(op + j, v[j]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) if (j < ncol) *reinterpret_cast<float4*>(op + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            for (int j = 0; j < 32; ++j) if (j < ncol) op[(int64_t)j * E.ld_f32] = __uint_as_float(raw[j]);
           }
         }
-        if (E.out_bf16) {
-          __nv_bfloat16* op = E.out_bf16 + (int64_t)row * E.ld_bf16 + col;
+        continue;
+      }
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            if (j < ncol) {
-              uint4 q;
-              __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&q);
-#pragma unroll
-              for (int t = 0; t < 4; ++t) h2[t] = __floats2bfloat162_rn(v[j + 2 * t], v[j + 2 * t + 1]);
-              *reinterpret_cast<uint4*>(op + j) = q;
-            }
-          }
+      for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = __uint_as_float(raw[j]);
+      __syncwarp();
+      const int col = n0 + c0 + lane;
+      const bool col_ok = col < P.N;
+      const float bias_v = (E.bias && col_ok && (!E.atomic || first_split)) ? __ldg(E.bias + col) : 0.f;
+      const int nrow = min(32, P.M - row_base);    // warp-uniform
+      if (col_ok) {
+        const float lo = E.relu ? 0.f : -INFINITY;
+        switch (features) {
+          case EPI_OUTB: epi_block<false, false, false, false, true, false>(E, stg, lane, row_base, nrow, col, bias_v, lo); break;
+          case EPI_RESB | EPI_OUTB: epi_block<false, true, false, false, true, false>(E, stg, lane, row_base, nrow, col, bias_v, lo); break;
+          case EPI_OUTF: epi_block<false, false, false, true, false, false>(E, stg, lane, row_base, nrow, col, bias_v, lo); break;
+          case EPI_OUTF | EPI_OUTB: epi_block<false, false, false, true, true, false>(E, stg, lane, row_base, nrow, col, bias_v, lo); break;
+          case EPI_MASK | EPI_OUTB: epi_block<true, false, false, false, true, false>(E, stg, lane, row_base, nrow, col, bias_v, lo); break;
+          case EPI_RESF | EPI_OUTF | EPI_OUTB: epi_block<false, false, true, true, true, false>(E, stg, lane, row_base, nrow, col, bias_v, lo); break;
+          case EPI_ATOMIC | EPI_OUTF: epi_block<false, false, false, true, false, true>(E, stg, lane, row_base, nrow, col, bias_v, lo); break;
+          default: epi_block_generic(E, stg, lane, row_base, nrow, col, bias_v, lo);
         }
       }
+      __syncwarp();
     }
   }
   tc_fence_before();
@@ -284,7 +311,7 @@ int make_tensor_map_bf16(CUtensorMap* out, const void* ptr, int64_t rows, int64_
 template <int BN, bool A_MN, bool B_MN>
 static int launch_cfg(const UmmaBatch& b, cudaStream_t st) {
   UmmaDevBatch dev;
-  int max_tiles = 0, max_split = 1;
+  int max_tiles = 0, max_split = 1, max_kb = 1;
   for (int i = 0; i < b.n; ++i) {
     const UmmaProblem& P = b.p[i];
     UmmaDevProblem& D = dev.p[i];
@@ -303,14 +330,16 @@ static int launch_cfg(const UmmaBatch& b, cudaStream_t st) {
     const int tiles = ((P.M + UBM - 1) / UBM) * ((P.N + BN - 1) / BN);
     if (tiles > max_tiles) max_tiles = tiles;
     if (split > max_split) max_split = split;
+    if (D.kblocks_per_split > max_kb) max_kb = D.kblocks_per_split;
   }
   static bool attr_set = false;
   if (!attr_set) {
-    IISAN_CUDA_OK(cudaFuncSetAttribute(umma_gemm_kernel<BN, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaSmem<BN>::kTotal));
+    IISAN_CUDA_OK(cudaFuncSetAttribute(umma_gemm_kernel<BN, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaSmem<BN>::total(USTAGES)));
     attr_set = true;
   }
+  dev.stages = max_kb < 1 ? 1 : (max_kb > USTAGES ? USTAGES : max_kb);
   dim3 grid(max_tiles, max_split, b.n);
-  { LaunchScope ls_(IISAN_K_GEMM, st); umma_gemm_kernel<BN, A_MN, B_MN><<<grid, UTHREADS, UmmaSmem<BN>::kTotal, st>>>(dev); }
+  { LaunchScope ls_(IISAN_K_GEMM, st); umma_gemm_kernel<BN, A_MN, B_MN><<<grid, UTHREADS, UmmaSmem<BN>::total(dev.stages), st>>>(dev); }
   IISAN_LAUNCH_OK();
   return IISAN_OK;
 }
@@ -325,7 +354,12 @@ int launch_umma_gemm(const UmmaBatch& b, cudaStream_t st) {
     if (b.p[i].N > maxN) maxN = b.p[i].N;
   }
   if (a_mn != b_mn) return IISAN_EUNSUPPORTED;
-  const int bn = maxN <= 64 ? 64 : (maxN <= 128 ? 128 : 256);
+  int bn = maxN <= 64 ? 64 : (maxN <= 128 ? 128 : 256);
+  if (bn == 256) {   // short grids: 128-wide tiles keep two to three CTAs per SM busy instead of one partial wave of wide tiles
+    int64_t ctas = 0;
+    for (int i = 0; i < b.n; ++i) ctas += (int64_t)((b.p[i].M + UBM - 1) / UBM) * ((b.p[i].N + 255) / 256) * (b.p[i].splitk < 1 ? 1 : b.p[i].splitk);
+    if (ctas < 2 * 148 * 2) bn = 128;
+  }
   if (!a_mn) {
     if (bn == 64) return launch_cfg<64, false, false>(b, st);
     if (bn == 128) return launch_cfg<128, false, false>(b, st);
