@@ -11,12 +11,14 @@
 // gradients), refreshed by one cast+transpose launch per forward; per stage and tower the stash x_s [N,d], z_s [N,r],
 // last_s [N,d] (all bf16); backward scratch dy/dx (fp32 running gradient + bf16 operand twins), dz (bf16).
 // bf16 cached states are consumed in place by TMA (row pitch layers*d) wherever they are a GEMM operand.
+#include <cstdlib>
 #include <type_traits>
 
 #include "common.cuh"
 #include "gemm_simt.cuh"
 #include "launch.cuh"
 #include "san_layout.cuh"
+#include "san_chain.cuh"
 #include "san_mix.cuh"
 #include "umma_gemm.cuh"
 
@@ -44,7 +46,7 @@ __global__ void __launch_bounds__(256) cast_transpose_kernel(const CastBatch bat
       float v = 0.f;
       if (r < J.rows && c < J.cols) {
         v = J.src[(int64_t)r * J.cols + c];
-        J.dst[(int64_t)r * J.cols + c] = __float2bfloat16_rn(v);
+        if (J.dst) J.dst[(int64_t)r * J.cols + c] = __float2bfloat16_rn(v);
       }
       tile[ty + k * 8][tx] = v;
     }
@@ -52,7 +54,7 @@ __global__ void __launch_bounds__(256) cast_transpose_kernel(const CastBatch bat
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const int c = c0 + ty + k * 8, r = r0 + tx;
-      if (r < J.rows && c < J.cols) J.dstT[(int64_t)c * J.rows + r] = __float2bfloat16_rn(tile[tx][ty + k * 8]);
+      if (J.dstT && r < J.rows && c < J.cols) J.dstT[(int64_t)c * J.rows + r] = __float2bfloat16_rn(tile[tx][ty + k * 8]);
     }
     __syncthreads();
   }
@@ -79,6 +81,16 @@ struct CastList {
 // ------------------------------------------------------------------------------------------------
 // workspace layout
 // ------------------------------------------------------------------------------------------------
+// The fused chain kernel (san_chain.cu) covers the symmetric configurations: equal widths, r = 64, bf16 cached states, every
+// tower active in every stage (no group layer-drop), towers starting from zero.
+static bool san_chain_eligible(const iisan_san_desc& D) {
+  if (D.d_text != D.d_img || D.d_text % 64 || D.r_text != 64 || D.r_img != 64 || D.r_mm != 64) return false;
+  if (D.state_dtype != IISAN_BF16 || D.remove_first || D.n_stages > kChainMaxStages) return false;
+  for (int s = 0; s < D.n_stages; ++s)
+    if (D.text_adapter[s] < 0 || D.img_adapter[s] < 0 || D.mm_index[s] < 0) return false;
+  return true;
+}
+
 struct WCopy { bf16* w; bf16* wt; };
 
 struct SanLayoutBf16 {
@@ -97,6 +109,7 @@ struct SanLayoutBf16 {
   float *dy_t, *dx_t, *dy_i, *dx_i, *dy_m, *dx_m;
   bf16 *dyb_t, *dxb_t, *dzb_t, *dyb_i, *dxb_i, *dzb_i, *dyb_m, *dxb_m, *dzb_m;
   bf16* ddpb;
+  bf16 *wd_pack[3], *wu_pack[3];          // fused chain: per tower (text, img, mm) all stages' weights, contiguous
   size_t bytes;
 
   static WCopy takew(Arena& a, size_t n) { WCopy c; c.w = a.take<bf16>(n); c.wt = a.take<bf16>(n); return c; }
@@ -142,9 +155,19 @@ struct SanLayoutBf16 {
     dyb_i = a.take<bf16>(N * D.d_img); dxb_i = a.take<bf16>(N * D.d_img); dzb_i = a.take<bf16>(N * D.r_img);
     dyb_m = a.take<bf16>(N * D.d_mm); dxb_m = a.take<bf16>(N * D.d_mm); dzb_m = a.take<bf16>(N * D.r_mm);
     ddpb = dimdiff ? a.take<bf16>(N * D.d_mm) : nullptr;
+    for (int t = 0; t < 3; ++t) wd_pack[t] = wu_pack[t] = nullptr;
+    if (san_chain_eligible(D)) {
+      for (int t = 0; t < 3; ++t) {
+        wd_pack[t] = a.take<bf16>((size_t)D.n_stages * D.r_mm * D.d_mm);
+        wu_pack[t] = a.take<bf16>((size_t)D.n_stages * D.r_mm * D.d_mm);
+      }
+    }
     bytes = a.off;
   }
 };
+
+// test / profiling switch: IISAN_B200_NO_CHAIN=1 forces the layered path
+static const bool g_disable_chain = [] { const char* e = getenv("IISAN_B200_NO_CHAIN"); return e && e[0] == '1'; }();
 
 size_t san_bf16_workspace_bytes(const iisan_san_desc& D) {
   SanLayoutBf16 L(D, nullptr);
@@ -229,6 +252,7 @@ static int san_forward_bf16_t(const iisan_san_desc* D, const iisan_san_params* P
   const bool text_wide = D->d_text > D->d_img;
   const int dwide = text_wide ? D->d_text : D->d_img;
   const int ft = D->asym ? E : D->d_text, fi = D->asym ? E : D->d_img, fm = D->d_mm;
+  const bool chain = san_chain_eligible(*D) && !g_disable_chain;
   // ---- bf16 weight copies (the fp32 nn.Parameters stay the source of truth) ----
   {
     CastList c(st);
@@ -241,6 +265,15 @@ static int san_forward_bf16_t(const iisan_san_desc* D, const iisan_san_params* P
         if (dimdiff) c.add(P->down_project[mi].w, L.dpw[mi].w, L.dpw[mi].wt, D->d_mm, dwide);
       }
     }
+    if (chain) {
+      for (int s = 0; s < D->n_stages; ++s) {
+        const int ta = D->text_adapter[s], ia = D->img_adapter[s], mi = D->mm_index[s];
+        const size_t off = (size_t)s * D->r_mm * D->d_mm;
+        c.add(P->text[ta].w_down, L.wd_pack[0] + off, nullptr, D->r_text, D->d_text); c.add(P->text[ta].w_up, L.wu_pack[0] + off, nullptr, D->d_text, D->r_text);
+        c.add(P->img[ia].w_down, L.wd_pack[1] + off, nullptr, D->r_img, D->d_img); c.add(P->img[ia].w_up, L.wu_pack[1] + off, nullptr, D->d_img, D->r_img);
+        c.add(P->mm[mi].w_down, L.wd_pack[2] + off, nullptr, D->r_mm, D->d_mm); c.add(P->mm[mi].w_up, L.wu_pack[2] + off, nullptr, D->d_mm, D->r_mm);
+      }
+    }
     c.add(P->fc_text.w, L.fc_t.w, L.fc_t.wt, ft, D->d_text); c.add(P->fc_img.w, L.fc_i.w, L.fc_i.wt, fi, D->d_img);
     c.add(P->fc_mm.w, L.fc_m.w, L.fc_m.wt, fm, D->d_mm);
     c.add(P->pre_text.w, L.pre_t.w, L.pre_t.wt, E, ft); c.add(P->pre_img.w, L.pre_i.w, L.pre_i.wt, E, fi);
@@ -250,7 +283,27 @@ static int san_forward_bf16_t(const iisan_san_desc* D, const iisan_san_params* P
   }
   const bf16* last_t = nullptr; const bf16* last_i = nullptr; const bf16* last_m = nullptr;
   bool first_t = true, first_i = true;
-  for (int s = 0; s < D->n_stages; ++s) {
+  if (chain) {
+    // ---- all stages of all three towers in one launch (san_chain.cu) ----
+    ChainArgs ca{};
+    ca.n_items = N; ca.d = D->d_mm; ca.n_stages = D->n_stages;
+    IISAN_TRY(chain_fill_tower(&ca.tower[0], 0, text, N, (int64_t)D->layers_text * D->d_text, nullptr, 0, L.wd_pack[0], L.wu_pack[0], D->n_stages, D->d_text));
+    IISAN_TRY(chain_fill_tower(&ca.tower[1], 0, image, N, (int64_t)D->layers_img * D->d_img, nullptr, 0, L.wd_pack[1], L.wu_pack[1], D->n_stages, D->d_img));
+    IISAN_TRY(chain_fill_tower(&ca.tower[2], 1, image, N, (int64_t)D->layers_img * D->d_img, text, (int64_t)D->layers_text * D->d_text, L.wd_pack[2], L.wu_pack[2], D->n_stages, D->d_mm));
+    for (int s = 0; s < D->n_stages; ++s) {
+      const int ta = D->text_adapter[s], ia = D->img_adapter[s], mi = D->mm_index[s];
+      ChainTower& t0 = ca.tower[0]; ChainTower& t1 = ca.tower[1]; ChainTower& t2 = ca.tower[2];
+      t0.layer[s] = D->text_layer[s]; t0.gate[s] = P->gate_text[ta]; t0.b_down[s] = P->text[ta].b_down; t0.b_up[s] = P->text[ta].b_up;
+      t0.x_stash[s] = L.x_t[s]; t0.z_stash[s] = L.z_t[s]; t0.last_stash[s] = L.last_t[s];
+      t1.layer[s] = D->img_layer[s]; t1.gate[s] = P->gate_img[ia]; t1.b_down[s] = P->img[ia].b_down; t1.b_up[s] = P->img[ia].b_up;
+      t1.x_stash[s] = L.x_i[s]; t1.z_stash[s] = L.z_i[s]; t1.last_stash[s] = L.last_i[s];
+      t2.layer[s] = D->img_layer[s]; t2.layer2[s] = D->text_layer[s]; t2.gate[s] = P->gate_mm[mi]; t2.b_down[s] = P->mm[mi].b_down; t2.b_up[s] = P->mm[mi].b_up;
+      t2.x_stash[s] = L.x_m[s]; t2.z_stash[s] = L.z_m[s]; t2.last_stash[s] = L.last_m[s];
+    }
+    IISAN_TRY(launch_san_chain_fwd(ca, 3, st));
+    last_t = L.last_t[D->n_stages - 1]; last_i = L.last_i[D->n_stages - 1]; last_m = L.last_m[D->n_stages - 1];
+  }
+  for (int s = 0; s < (chain ? 0 : D->n_stages); ++s) {
     const int ta = D->text_adapter[s], ia = D->img_adapter[s], mi = D->mm_index[s];
     // ---- dim alignment GEMM on the raw wide state (CA/model/model.py:406-411) ----
     const float* dp = nullptr;

@@ -1,0 +1,359 @@
+// Fused side-adapter chain, forward (fast mode, symmetric configurations: d_text == d_img, r == 64, every tower active in
+// every stage, bf16 cached states).  One CTA owns 128 items of ONE tower and walks all A stages without leaving the SM:
+//
+//   x_0       = fuse(h_0, 0)                                   gated fusion   CC/model/model.py:319-326 (mm: :335-337)
+//   z_s       = relu(x_s Wd_s^T + bd_s)                        AdapterBlock   CC/model/modules.py:113-116
+//   last_s    = z_s Wu_s^T + bu_s + x_s
+//   x_{s+1}   = fuse(h_{s+1}, last_s)                          (mm tower: last_s + g h_cv + (1-g) h_text)
+//
+// The running state never exists as a whole on chip (128 x 768 fp32 is larger than TMEM); it streams through 64-column
+// chunks instead.  For chunk c of stage s the up-projection tile U_c = z_s Wu_s[c]^T is one tcgen05.mma group into a
+// double-buffered TMEM accumulator; the epilogue warps add bias and residual, fuse the next stage's hidden-state chunk (TMA
+// ring, read in place from the caller's [N, layers, d] tensor: only selected layers are ever touched), and write the bf16
+// result both to the backward stash and, 128B-swizzled, to shared memory where it is immediately the A operand of the next
+// stage's down-projection MMA (z_{s+1} accumulates in TMEM across the chunks).  Per item and stage the kernel moves the
+// compulsory bytes only: one read of h (two for the inter-modal tower), one write of the x stash (+ z), weights from L2.
+//
+// warp roles: 0 weight TMA producer | 1 TMEM allocator + MMA issuer | 2 hidden-state TMA producer | 3..10 epilogue
+#include "common.cuh"
+#include "launch.cuh"
+#include "san_chain.cuh"
+#include "umma.cuh"
+
+namespace iisan {
+
+using namespace umma;
+using bf16 = __nv_bfloat16;
+
+constexpr int CH_ROWS = 128;
+constexpr int CH_CW = 64;                    // chunk width (columns) == one 128-byte swizzle atom
+constexpr int CH_R = 64;                     // adapter bottleneck handled by this kernel
+constexpr int CH_NW = 4;                     // weight ring (units)
+constexpr int CH_NH = 6;                     // hidden-state ring (tiles)
+constexpr int CH_THREADS = 352;              // 11 warps
+constexpr int CH_TILE_BYTES = CH_ROWS * CH_CW * 2;   // 16 KB : h tile, x k-block, z operand
+constexpr int CH_W_BYTES = CH_CW * CH_R * 2;         // 8 KB  : one weight chunk (Wu or Wd)
+constexpr int CH_TMEM_COLS = 256;
+constexpr int CH_ZACC = 0, CH_UACC = 64;     // TMEM columns: z accumulator, two U accumulators
+
+struct ChainSmem {
+  static constexpr int kZ = 0;                                   // z operand [128 x 64]
+  static constexpr int kXk = kZ + CH_TILE_BYTES;                 // 2 x-chunk operands
+  static constexpr int kW = kXk + 2 * CH_TILE_BYTES;             // CH_NW x (Wu chunk | Wd chunk)
+  static constexpr int kH = kW + CH_NW * 2 * CH_W_BYTES;         // CH_NH hidden-state tiles
+  static constexpr int kBar = kH + CH_NH * CH_TILE_BYTES;
+  static constexpr int kTotal = kBar + 512 + 1024;
+};
+
+__device__ __forceinline__ void chain_epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+__device__ __forceinline__ void unpack8(const uint4& q, float* f) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { const float2 t = __bfloat1622float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  uint4 q;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&q);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  return q;
+}
+
+__global__ void __launch_bounds__(CH_THREADS, 1) san_chain_fwd_kernel(const __grid_constant__ ChainArgs a) {
+  const ChainTower& T = a.tower[blockIdx.y];
+  const bool is_mm = (T.mode == 1);
+  const int NC = a.d / CH_CW;
+  const int A = a.n_stages;
+  const int m0 = blockIdx.x * CH_ROWS;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ChainSmem::kBar);
+  uint64_t* w_full = bars;                       // CH_NW
+  uint64_t* w_empty = w_full + CH_NW;            // CH_NW
+  uint64_t* h_full = w_empty + CH_NW;            // CH_NH
+  uint64_t* h_empty = h_full + CH_NH;            // CH_NH
+  uint64_t* xk_full = h_empty + CH_NH;           // 2
+  uint64_t* xk_empty = xk_full + 2;              // 2
+  uint64_t* u_full = xk_empty + 2;               // 2
+  uint64_t* u_empty = u_full + 2;                // 2
+  uint64_t* z_full = u_empty + 2;                // 1
+  uint64_t* z_ready = z_full + 1;                // 1
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(z_ready + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&T.map_wd); tma_prefetch_desc(&T.map_wu); tma_prefetch_desc(&T.map_h);
+    if (is_mm) tma_prefetch_desc(&T.map_h2);
+    for (int i = 0; i < CH_NW; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+    for (int i = 0; i < CH_NH; ++i) { mbar_init(&h_full[i], 1); mbar_init(&h_empty[i], 8); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&xk_full[i], 8); mbar_init(&xk_empty[i], 1); mbar_init(&u_full[i], 1); mbar_init(&u_empty[i], 8); }
+    mbar_init(z_full, 1); mbar_init(z_ready, 8);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, CH_TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // unit u = (sv + 1) * NC + c, sv = -1 .. A-1 : Wu_sv[c] (sv >= 0) and Wd_{sv+1}[c] (sv+1 < A) ; hidden tiles of x_{sv+1}[c]
+  const int n_units = (A + 1) * NC;
+
+  if (warp == 0) {
+    // ===================== weight producer =====================
+    if (elect_one()) {
+      for (int u = 0; u < n_units; ++u) {
+        const int sv = u / NC - 1, c = u % NC;
+        const int slot = u % CH_NW; const uint32_t ph = (uint32_t)(u / CH_NW) & 1u;
+        const bool has_wu = sv >= 0, has_wd = sv + 1 < A;
+        if (!has_wu && !has_wd) continue;
+        mbar_wait(&w_empty[slot], ph ^ 1u);
+        uint8_t* dst = smem + ChainSmem::kW + slot * 2 * CH_W_BYTES;
+        mbar_expect_tx(&w_full[slot], (has_wu ? CH_W_BYTES : 0) + (has_wd ? CH_W_BYTES : 0));
+        if (has_wu) tma_load_2d(dst, &T.map_wu, &w_full[slot], 0, sv * a.d + c * CH_CW);                 // Wu_sv rows [c*64, +64), all r
+        if (has_wd) tma_load_2d(dst + CH_W_BYTES, &T.map_wd, &w_full[slot], c * CH_CW, (sv + 1) * CH_R);  // Wd_{sv+1} all r rows, cols chunk
+      }
+    }
+  } else if (warp == 2) {
+    // ===================== hidden-state producer =====================
+    if (elect_one()) {
+      int n_h = 0;
+      for (int s = 0; s < A; ++s) {
+        for (int c = 0; c < NC; ++c) {
+          for (int k = 0; k < (is_mm ? 2 : 1); ++k) {
+            const int slot = n_h % CH_NH; const uint32_t ph = (uint32_t)(n_h / CH_NH) & 1u;
+            mbar_wait(&h_empty[slot], ph ^ 1u);
+            mbar_expect_tx(&h_full[slot], CH_TILE_BYTES);
+            const CUtensorMap* m = (k == 0) ? &T.map_h : &T.map_h2;
+            const int layer = (k == 0) ? T.layer[s] : T.layer2[s];
+            tma_load_2d(smem + ChainSmem::kH + slot * CH_TILE_BYTES, m, &h_full[slot], layer * a.d + c * CH_CW, m0);
+            ++n_h;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (elect_one()) {
+      constexpr uint32_t idesc = instr_desc_bf16(CH_ROWS, 64, 0, 0);   // [128 x 64] += A (K-major) x B^T (K-major), K = 64
+      const uint32_t sz = smem_u32(smem + ChainSmem::kZ);
+      int n_x = 0;     // x-chunk operands consumed
+      int n_u = 0;     // U accumulators produced
+      auto down = [&](int unit, int c) {        // z_acc (+)= xk x Wd[c]^T
+        const int b = n_x & 1; const uint32_t ph = (uint32_t)(n_x >> 1) & 1u;
+        const int slot = unit % CH_NW;
+        mbar_wait(&xk_full[b], ph);
+        tc_fence_after();
+        const uint32_t sx = smem_u32(smem + ChainSmem::kXk + b * CH_TILE_BYTES);
+        const uint32_t sw = smem_u32(smem + ChainSmem::kW + slot * 2 * CH_W_BYTES + CH_W_BYTES);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          mma_bf16_ss(tmem_base + CH_ZACC, smem_desc_sw128(sx + k * 32, 16, 1024), smem_desc_sw128(sw + k * 32, 16, 1024), idesc, (c > 0 || k > 0) ? 1u : 0u);
+        mma_commit(&xk_empty[b]);
+        mma_commit(&w_empty[slot]);
+        ++n_x;
+      };
+      // stage "-1": x_0 chunks arrive from the epilogue warps
+      for (int c = 0; c < NC; ++c) {
+        const int unit = c; const uint32_t wph = (uint32_t)(unit / CH_NW) & 1u;
+        mbar_wait(&w_full[unit % CH_NW], wph);
+        down(unit, c);
+      }
+      mma_commit(z_full);
+      for (int s = 0; s < A; ++s) {
+        const bool more = s + 1 < A;
+        mbar_wait(z_ready, (uint32_t)s & 1u);
+        tc_fence_after();
+        for (int c = 0; c < NC; ++c) {
+          const int unit = (s + 1) * NC + c; const int slot = unit % CH_NW; const uint32_t wph = (uint32_t)(unit / CH_NW) & 1u;
+          const int b = n_u & 1; const uint32_t uph = (uint32_t)(n_u >> 1) & 1u;
+          mbar_wait(&w_full[slot], wph);
+          mbar_wait(&u_empty[b], uph ^ 1u);
+          tc_fence_after();
+          const uint32_t sw = smem_u32(smem + ChainSmem::kW + slot * 2 * CH_W_BYTES);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            mma_bf16_ss(tmem_base + CH_UACC + b * 64, smem_desc_sw128(sz + k * 32, 16, 1024), smem_desc_sw128(sw + k * 32, 16, 1024), idesc, k > 0 ? 1u : 0u);
+          mma_commit(&u_full[b]);
+          ++n_u;
+          if (!more) mma_commit(&w_empty[slot]);                 // last stage: only Wu lives in the slot
+          else if (c >= 1) down(unit - 1, c - 1);                // overlap: the previous chunk's down-projection
+        }
+        if (more) { down((s + 1) * NC + NC - 1, NC - 1); mma_commit(z_full); }
+      }
+    }
+  } else {
+    // ===================== epilogue warps =====================
+    const int ew = warp - 3;                  // 0..7
+    const int quad = warp & 3;                // TMEM lane quadrant
+    const int hf = ew >> 2;                   // which 32 of the chunk's 64 columns
+    const int m = quad * 32 + lane;           // row inside the tile
+    const int64_t row = (int64_t)m0 + m;
+    const bool row_ok = row < a.n_items;
+    const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+    const int sw_row = (m >> 3) * 1024 + (m & 7) * 128;      // byte offset of row m inside a swizzled [128 x 64] bf16 tile
+    int n_h = 0, n_x = 0, n_u = 0;
+
+    // x chunk -> stash (global) and A operand (shared, swizzled); signals the MMA warp
+    auto emit_x = [&](const float* xv, bf16* stash, int c) {
+      const int b = n_x & 1; const uint32_t ph = (uint32_t)(n_x >> 1) & 1u;
+      mbar_wait(&xk_empty[b], ph ^ 1u);
+      uint8_t* tile = smem + ChainSmem::kXk + b * CH_TILE_BYTES + sw_row;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint4 pk = pack8(xv + q * 8);
+        *reinterpret_cast<uint4*>(tile + (((hf * 4 + q) ^ (m & 7)) << 4)) = pk;
+        if (row_ok) *reinterpret_cast<uint4*>(stash + row * a.d + c * CH_CW + hf * 32 + q * 8) = pk;
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&xk_full[b]);
+      ++n_x;
+    };
+    // read this thread's 32 columns of a hidden-state tile
+    auto read_h = [&](float* hv) {
+      const int slot = n_h % CH_NH; const uint32_t ph = (uint32_t)(n_h / CH_NH) & 1u;
+      mbar_wait(&h_full[slot], ph);
+      const uint8_t* tile = smem + ChainSmem::kH + slot * CH_TILE_BYTES + sw_row;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) unpack8(*reinterpret_cast<const uint4*>(tile + (((hf * 4 + q) ^ (m & 7)) << 4)), hv + q * 8);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&h_empty[slot]);
+      ++n_h;
+    };
+
+    // ---- x_0 = fuse(h_0, 0) ----
+    {
+      const float g = gate_value(T.gate[0]);
+      const float omg = 1.0f - g;
+      for (int c = 0; c < NC; ++c) {
+        float hv[32], xv[32];
+        read_h(hv);
+        if (is_mm) {
+          float h2[32];
+          read_h(h2);
+#pragma unroll
+          for (int k = 0; k < 32; ++k) xv[k] = __fadd_rn(__fmul_rn(g, hv[k]), __fmul_rn(omg, h2[k]));
+        } else {
+#pragma unroll
+          for (int k = 0; k < 32; ++k) xv[k] = __fmul_rn(g, hv[k]);
+        }
+        emit_x(xv, T.x_stash[0], c);
+      }
+    }
+    for (int s = 0; s < A; ++s) {
+      const bool more = s + 1 < A;
+      // ---- z_s = relu(zacc + bd) -> A operand + stash ----
+      {
+        mbar_wait(z_full, (uint32_t)s & 1u);
+        tc_fence_after();
+        uint32_t raw[32];
+        tmem_ld_32x32(tmem_base + lane_addr + (uint32_t)(CH_ZACC + hf * 32), raw);
+        tmem_ld_wait();
+        float zv[32];
+        const float4* bd = reinterpret_cast<const float4*>(T.b_down[s] + hf * 32);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 bq = __ldg(bd + q);
+          zv[4 * q] = fmaxf(__uint_as_float(raw[4 * q]) + bq.x, 0.f); zv[4 * q + 1] = fmaxf(__uint_as_float(raw[4 * q + 1]) + bq.y, 0.f);
+          zv[4 * q + 2] = fmaxf(__uint_as_float(raw[4 * q + 2]) + bq.z, 0.f); zv[4 * q + 3] = fmaxf(__uint_as_float(raw[4 * q + 3]) + bq.w, 0.f);
+        }
+        uint8_t* tile = smem + ChainSmem::kZ + sw_row;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint4 pk = pack8(zv + q * 8);
+          *reinterpret_cast<uint4*>(tile + (((hf * 4 + q) ^ (m & 7)) << 4)) = pk;
+          if (row_ok) *reinterpret_cast<uint4*>(T.z_stash[s] + row * CH_R + hf * 32 + q * 8) = pk;
+        }
+        tc_fence_before();
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(z_ready);
+      }
+      const float g = more ? gate_value(T.gate[s + 1]) : 0.f;
+      const float omg = 1.0f - g;
+      for (int c = 0; c < NC; ++c) {
+        // residual x_s chunk: written by this very thread one stage earlier (program order makes it visible)
+        float xr[32];
+        {
+          const bf16* xp = T.x_stash[s] + row * a.d + c * CH_CW + hf * 32;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            if (row_ok) v = *reinterpret_cast<const uint4*>(xp + q * 8);
+            unpack8(v, xr + q * 8);
+          }
+        }
+        const int b = n_u & 1; const uint32_t uph = (uint32_t)(n_u >> 1) & 1u;
+        mbar_wait(&u_full[b], uph);
+        tc_fence_after();
+        uint32_t raw[32];
+        tmem_ld_32x32(tmem_base + lane_addr + (uint32_t)(CH_UACC + b * 64 + hf * 32), raw);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&u_empty[b]);
+        ++n_u;
+        float lv[32];
+        const float4* bu = reinterpret_cast<const float4*>(T.b_up[s] + c * CH_CW + hf * 32);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 bq = __ldg(bu + q);
+          lv[4 * q] = __uint_as_float(raw[4 * q]) + bq.x + xr[4 * q]; lv[4 * q + 1] = __uint_as_float(raw[4 * q + 1]) + bq.y + xr[4 * q + 1];
+          lv[4 * q + 2] = __uint_as_float(raw[4 * q + 2]) + bq.z + xr[4 * q + 2]; lv[4 * q + 3] = __uint_as_float(raw[4 * q + 3]) + bq.w + xr[4 * q + 3];
+        }
+        if (T.last_stash[s] && row_ok) {
+          bf16* lp = T.last_stash[s] + row * a.d + c * CH_CW + hf * 32;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4*>(lp + q * 8) = pack8(lv + q * 8);
+        }
+        if (more) {
+          float hv[32];
+          read_h(hv);
+          if (is_mm) {
+            float h2[32];
+            read_h(h2);
+#pragma unroll
+            for (int k = 0; k < 32; ++k) lv[k] = __fadd_rn(__fadd_rn(lv[k], __fmul_rn(g, hv[k])), __fmul_rn(omg, h2[k]));
+          } else {
+#pragma unroll
+            for (int k = 0; k < 32; ++k) lv[k] = __fadd_rn(__fmul_rn(g, hv[k]), __fmul_rn(omg, lv[k]));
+          }
+          emit_x(lv, T.x_stash[s + 1], c);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, CH_TMEM_COLS);
+}
+
+int make_tensor_map_bf16(CUtensorMap* out, const void* ptr, int64_t rows, int64_t cols, int64_t pitch, int box_inner, int box_outer);
+
+int chain_fill_tower(ChainTower* T, int mode, const void* h, int64_t h_rows, int64_t h_pitch_cols, const void* h2, int64_t h2_pitch_cols,
+                     const bf16* wd_pack, const bf16* wu_pack, int n_stages, int d) {
+  T->mode = mode;
+  IISAN_TRY(make_tensor_map_bf16(&T->map_h, h, h_rows, h_pitch_cols, h_pitch_cols, CH_CW, CH_ROWS));
+  if (mode == 1) IISAN_TRY(make_tensor_map_bf16(&T->map_h2, h2, h_rows, h2_pitch_cols, h2_pitch_cols, CH_CW, CH_ROWS));
+  else T->map_h2 = T->map_h;
+  IISAN_TRY(make_tensor_map_bf16(&T->map_wd, wd_pack, (int64_t)n_stages * CH_R, d, d, CH_CW, CH_R));
+  IISAN_TRY(make_tensor_map_bf16(&T->map_wu, wu_pack, (int64_t)n_stages * d, CH_R, CH_R, CH_R, CH_CW));
+  return IISAN_OK;
+}
+
+int launch_san_chain_fwd(const ChainArgs& args, int n_towers, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    IISAN_CUDA_OK(cudaFuncSetAttribute(san_chain_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ChainSmem::kTotal));
+    attr_set = true;
+  }
+  const int tiles = (args.n_items + CH_ROWS - 1) / CH_ROWS;
+  { LaunchScope ls_(IISAN_K_CHAIN, st); san_chain_fwd_kernel<<<dim3(tiles, n_towers), CH_THREADS, ChainSmem::kTotal, st>>>(args); }
+  IISAN_LAUNCH_OK();
+  return IISAN_OK;
+}
+
+}  // namespace iisan

@@ -22,7 +22,9 @@ def _lin(x, w, b=None):
     return F.linear(x, rb(w), b)
 
 
-def san_forward_emul(P, image, text, cfg, prefix="mm_encoder."):
+def san_forward_emul(P, image, text, cfg, prefix="mm_encoder.", fused_chain=False):
+    """``fused_chain``: the fused chain kernel keeps last_s in fp32 registers when it fuses the next stage (only the stash
+    and the final stage, which feeds the heads, are rounded)."""
     h_cv = image.reshape(-1, image.shape[-2], image.shape[-1]).float()
     h_tx = text.reshape(-1, text.shape[-2], text.shape[-1]).float()
     N = h_cv.shape[0]
@@ -34,11 +36,15 @@ def san_forward_emul(P, image, text, cfg, prefix="mm_encoder."):
         last_cv = torch.zeros(N, cfg.d_img, device=dev); last_tx = torch.zeros(N, cfg.d_text, device=dev)
     last_mm = torch.zeros(N, d_mm, device=dev)
 
-    def adapter(pfx, x):
-        z = rb(F.relu(_lin(x, P[pfx + ".fc_down.weight"], P[pfx + ".fc_down.bias"])))
-        return rb(_lin(z, P[pfx + ".fc_up.weight"], P[pfx + ".fc_up.bias"]) + x)
+    plan = O.stage_plan(cfg)
 
-    for (ta, tl, ia, il, mi) in O.stage_plan(cfg):
+    def adapter(pfx, x, final):
+        z = rb(F.relu(_lin(x, P[pfx + ".fc_down.weight"], P[pfx + ".fc_down.bias"])))
+        y = _lin(z, P[pfx + ".fc_up.weight"], P[pfx + ".fc_up.bias"]) + x
+        return y if (fused_chain and not final) else rb(y)
+
+    for si, (ta, tl, ia, il, mi) in enumerate(plan):
+        final = si == len(plan) - 1
         if ia is not None:
             g = O._gate(P[f"{prefix}side_gate_params_cv.{ia}"])
             x_cv = rb(g * h_cv[:, il] + (1 - g) * last_cv)
@@ -46,9 +52,9 @@ def san_forward_emul(P, image, text, cfg, prefix="mm_encoder."):
             g = O._gate(P[f"{prefix}side_gate_params_text.{ta}"])
             x_tx = rb(g * h_tx[:, tl] + (1 - g) * last_tx)
         if ta is not None:
-            last_tx = adapter(f"{prefix}bert_adapter_list.{ta}", x_tx)
+            last_tx = adapter(f"{prefix}bert_adapter_list.{ta}", x_tx, final)
         if ia is not None:
-            last_cv = adapter(f"{prefix}cv_adapter_list.{ia}", x_cv)
+            last_cv = adapter(f"{prefix}cv_adapter_list.{ia}", x_cv, final)
         if mi is not None:
             mm_tx, mm_cv = h_tx[:, tl], h_cv[:, il]
             if cfg.asym and cfg.d_text > cfg.d_img:
@@ -57,7 +63,7 @@ def san_forward_emul(P, image, text, cfg, prefix="mm_encoder."):
                 mm_cv = _lin(rb(mm_cv), P[f"{prefix}down_project_list.{mi}.weight"], P[f"{prefix}down_project_list.{mi}.bias"])
             g = O._gate(P[f"{prefix}side_gate_params_mm.{mi}"])
             x_mm = rb(last_mm + g * mm_cv + (1 - g) * mm_tx)
-            last_mm = adapter(f"{prefix}mm_adapter_list.{mi}", x_mm)
+            last_mm = adapter(f"{prefix}mm_adapter_list.{mi}", x_mm, final)
     lin = lambda n, x: _lin(x, P[f"{prefix}{n}.weight"], P[f"{prefix}{n}.bias"])
     e_tx = lin("bert_pre_fc", rb(lin("fc_bert", last_tx)))
     e_cv = lin("cv_pre_fc", rb(lin("fc_cv", last_cv)))
@@ -65,14 +71,14 @@ def san_forward_emul(P, image, text, cfg, prefix="mm_encoder."):
     return e_cv, e_tx, e_mm
 
 
-def train_step_grads_emul(params_np, batch, pop_prob, cfg, ce_bf16=False):
+def train_step_grads_emul(params_np, batch, pop_prob, cfg, ce_bf16=False, fused_chain=False):
     """Like oracle.train_step_grads with the fast mode's rounding points (CPU fp32 torch)."""
     P = O.params_to_torch(params_np)
     ids, lm = batch["ids"], batch["log_mask"]
     B, S = ids.shape
     image = torch.as_tensor(batch["image"]); text = torch.as_tensor(batch["text"])
     debias = torch.log(torch.from_numpy(pop_prob)[torch.from_numpy(ids.reshape(-1))])
-    e_cv, e_tx, e_mm = san_forward_emul(P, image, text, cfg)
+    e_cv, e_tx, e_mm = san_forward_emul(P, image, text, cfg, fused_chain=fused_chain)
     score = F.linear(torch.cat([e_cv, e_tx, e_mm], dim=1), P["com_dense.weight"], P["com_dense.bias"])
     embs = score.view(B, S, cfg.embedding_dim)
     prec = O.user_encoder_forward(P, embs[:, :-1], torch.from_numpy(lm), cfg).reshape(-1, cfg.embedding_dim)

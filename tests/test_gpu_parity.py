@@ -116,7 +116,10 @@ def test_train_step_bf16_mode(name, state_dtype):
     if dt == torch.bfloat16:                     # the references see exactly the stored (rounded) states
         batch = dict(batch, image=_bf16_round(batch["image"]), text=_bf16_round(batch["text"]))
     ref_out, ref_grads = O.train_step_grads(params, batch, pop, cfg)
-    emu_out, emu_grads = train_step_grads_emul(params, batch, pop, cfg, ce_bf16=(cfg.embedding_dim == 64))
+    plan = O.stage_plan(cfg)
+    fused = (dt == torch.bfloat16 and cfg.d_text == cfg.d_img and cfg.d_text % 64 == 0 and cfg.r_cv == 64 and cfg.r_bert == 64 and
+             cfg.remove_first != "TRUE" and len(plan) <= 8 and all(None not in st for st in plan))       # san_chain_eligible
+    emu_out, emu_grads = train_step_grads_emul(params, batch, pop, cfg, ce_bf16=(cfg.embedding_dim == 64), fused_chain=fused)
     set_compute_mode("bf16")
     try:
         model = build_product(cfg, params, pop).eval()
@@ -129,7 +132,7 @@ def test_train_step_bf16_mode(name, state_dtype):
     ref_loss, ref_score = float(ref_out["loss"]), ref_out["score_embs"]
     assert abs(float(loss) - ref_loss) <= BF16_LOSS_RTOL * abs(ref_loss), (float(loss), ref_loss)
     assert np.abs(score - ref_score).max() <= BF16_EMB_RTOL * np.abs(ref_score).max()
-    assert abs(float(loss) - float(emu_out["loss"])) <= 1e-4 * abs(ref_loss)
+    assert abs(float(loss) - float(emu_out["loss"])) <= 3e-4 * abs(ref_loss)
     assert np.abs(score - emu_out["score_embs"]).max() <= 2e-3 * np.abs(ref_score).max()
     errs, dot, n1, n2 = [], 0.0, 0.0, 0.0
     gate_ref, gate_got = [], []
