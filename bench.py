@@ -29,6 +29,8 @@ METRIC = "iisan_cached_train_samples_per_s"
 UNIT = "samples/s"
 ITEM_NUM = 19246          # Instrument catalogue
 SEED = 12345              # reference seed (Code_Cached/scripts/run_IISAN.py:44)
+# dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed ncu --set full capture (profiles/), per launch
+TRAFFIC_NCU = None
 LRS = dict(lr=2e-4, adapter_cv_lr=1e-4, adapter_bert_lr=1e-4, fine_tune_lr_image=1e-4, fine_tune_lr_text=5e-5)
 
 
@@ -43,6 +45,7 @@ def parse():
     ap.add_argument("--cpu-batch", type=int, default=512)
     ap.add_argument("--cpu-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="run the step eagerly instead of replaying a CUDA graph")
     return ap.parse_args()
 
 
@@ -189,9 +192,11 @@ def make_device_batches(n, B, device, dtype, gen):
 
 
 def run_ours(a):
+    import ctypes as C
     import torch
     import torch.distributed as dist
     from iisan_b200 import _lib
+    from iisan_b200.engine import TrainStep
     from iisan_b200.optim import param_groups
     lib = _lib.load()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -203,23 +208,17 @@ def run_ours(a):
     state_dtype = torch.bfloat16 if a.compute == "bf16" else torch.float32
     model, args, cfg = build_model(device, a.compute)
     model.train()
-    train_model = model
     if world > 1:
-        model.negatives = "global"
-        train_model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], find_unused_parameters=False)
-    opt = torch.optim.Adam(param_groups(model, args), fused=True)
+        model.negatives = "global"                                   # BASELINE configs[2]: item-embedding all-gather
+        for p in model.parameters():                                 # same initial replica on every rank (DDP does this at wrap time)
+            dist.broadcast(p.data, 0)
+    use_graph = not a.no_graph
+    opt = torch.optim.Adam(param_groups(model, args), fused=True, capturable=use_graph)
     gen = torch.Generator(device=device).manual_seed(SEED + rank)
     B = a.batch
     n_rot = 3                                               # 3 x 225 MB (bf16) rotating inputs >> 126 MB L2
     batches = make_device_batches(n_rot, B, device, state_dtype, gen)
-
-    def step(i, data=None):
-        ids, image, text, lm = data if data is not None else batches[i % n_rot]
-        opt.zero_grad(set_to_none=True)
-        loss = train_model(ids, image, text, lm, local)
-        loss.backward()
-        opt.step()
-        return loss
+    group = dist.group.WORLD if world > 1 else None
 
     def barrier():
         if world > 1:
@@ -242,24 +241,38 @@ def run_ours(a):
             ms = float(t.item())
         return ms, t0, time.time(), last
 
+    # ---- launches per step, counted on one eager step ----
+    eager = TrainStep(model, opt, use_graph=False, group=group)
+    eager(*batches[0])
+    torch.cuda.synchronize()
+    l0 = lib.iisan_launch_count(-1)
+    eager(*batches[1])
+    torch.cuda.synchronize()
+    launches_per_step = lib.iisan_launch_count(-1) - l0
+
+    # ---- the timed arm: inputs resident in HBM; one captured graph per resident batch (no staging copies) ----
+    if use_graph:
+        runners = [TrainStep(model, opt, use_graph=True, group=group) for _ in range(n_rot)]
+        for r, bt in zip(runners, batches):
+            r.capture(*bt)
+        step = lambda i: runners[i % n_rot].replay()
+    else:
+        step = lambda i: eager(*batches[i % n_rot])
     for i in range(max(a.warmup, 3)):
         step(i)
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start(); time.sleep(0.3)
-    launches0 = lib.iisan_launch_count(-1)
     ms, t0, t1, last = timed(a.steps, step)
-    launches = lib.iisan_launch_count(-1) - launches0
     if sampler:
         time.sleep(0.2); sampler.stop()
     clocks = sampler.summary(t0, t1) if sampler else None
     value = world * B * a.steps / (ms / 1e3)
     loss_val = float(last.item())
 
-    # ---- per-kernel-class device time (same K steps again, CUDA events around every launch) ----
-    import ctypes as C
+    # ---- per-kernel-class device time: K eager steps with CUDA events around every library launch ----
     lib.iisan_timing_enable(1)
-    ms_prof, _, _, _ = timed(a.steps, step)
+    ms_prof, _, _, _ = timed(a.steps, lambda i: eager(*batches[i % n_rot]))
     lib.iisan_timing_enable(0)
     classes = {}
     for k, name in enumerate(_lib.KERNEL_CLASSES):
@@ -267,19 +280,18 @@ def run_ours(a):
         lib.iisan_timing_read(k, C.byref(tot), C.byref(n))
         classes[name] = {"ms_per_step": tot.value / a.steps, "launches_per_step": n.value / a.steps}
 
-    # ---- end-to-end through the reference-facing call with HOST buffers ----
+    # ---- end-to-end through the public API with HOST buffers: pinned batch -> H2D -> step -> loss read back ----
     host = []
     for ids, image, text, lm in batches[:2]:
         host.append(tuple(t.cpu().pin_memory() for t in (ids, image, text, lm)))
     h2d = sum(t.numel() * t.element_size() for t in host[0])
+    e2e_runner = TrainStep(model, opt, use_graph=use_graph, group=group)
 
     def e2e_step(i):
-        hb = host[i % len(host)]
-        data = tuple(t.to(device, non_blocking=True) for t in hb)        # exactly run.py:370-371
-        loss = step(i, data)
+        loss = e2e_runner(*host[i % len(host)])                          # H2D copies (run.py:370-371) + the step
         return loss.item()                                               # D2H read of the result (run.py:382,387)
 
-    for i in range(2):
+    for i in range(3):
         e2e_step(i)
     e2e_steps = max(3, min(a.steps, 10))
     ms_e2e, _, _, _ = timed(e2e_steps, e2e_step)
@@ -298,23 +310,28 @@ def run_ours(a):
     tf_peak = peaks.get("bf16_tflops_sustained", 1400.0)
     peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
     elt = 2 if state_dtype == torch.bfloat16 else 4
-    # algorithmic bytes of the streaming kernels per step: forward reads the 7+7 selected layers of every
-    # item once; the backward's gate-gradient pass re-streams them once -> 2x.
-    stream_bytes = 2 * B * 11 * (7 * 768 + 7 * 768) * elt
-    stream = classes["stream"]
-    dom = max(classes.items(), key=lambda kv: kv[1]["ms_per_step"])
-    flops_step = B * 291e6                                   # fwd+bwd FLOPs / sample
+    # Dominant kernel of the hidden-state path: the fused chain forward (one launch per step).  Algorithmic bytes per launch
+    # (DESIGN.md): every selected layer of every item read once = S * (A_i*D_i + A_t*D_t) * sizeof(elt) per sample.
+    alg_bytes = B * 11 * (7 * 768 + 7 * 768) * elt
+    chain = classes["chain"]
+    if chain["launches_per_step"] > 0:
+        k_ms = chain["ms_per_step"] / chain["launches_per_step"]
+        kname = "san_chain_fwd_kernel (fused gather + gate fusion + adapter chain, forward)"
+    else:
+        k_ms = classes["stream"]["ms_per_step"]
+        kname = "mix kernels (layer-select gather + gate fusion fwd, gate-grad re-stream bwd), summed"
+        alg_bytes *= 2
     roof = {
-        "bound": "hbm", "kernel_class": "stream (layer-select gather + gate fusion fwd, gate-grad re-stream bwd)",
-        "achieved": stream_bytes / (stream["ms_per_step"] / 1e3) / 1e9 if stream["ms_per_step"] > 0 else None,
-        "peak": hbm_peak, "unit": "GB/s", "traffic": None, "peak_source": peak_src,
-        "algorithmic_bytes_per_step": stream_bytes, "ms_per_step": stream["ms_per_step"],
+        "bound": "hbm", "kernel": kname,
+        "achieved": alg_bytes / (k_ms / 1e3) / 1e9 if k_ms > 0 else None,
+        "peak": hbm_peak, "unit": "GB/s", "traffic": TRAFFIC_NCU, "peak_source": peak_src,
+        "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": k_ms,
     }
     roof["frac"] = (roof["achieved"] / hbm_peak) if roof["achieved"] else None
     gemm_ms = classes["gemm"]["ms_per_step"] + classes["chain"]["ms_per_step"]
     roof_tensor = {"bound": "tensor", "achieved": (B * 11 * 3 * 7987200 / (gemm_ms / 1e3) / 1e12) if gemm_ms > 0 else None,
                    "peak": tf_peak, "unit": "TFLOP/s", "ms_per_step": gemm_ms,
-                   "note": "SAN adapter/head GEMM FLOPs (fwd+bwd = 3x 7.99 MFLOP/item) over the summed GEMM-class kernel time"}
+                   "note": "SAN adapter/head GEMM FLOPs (fwd+bwd = 3x 7.99 MFLOP/item) over the summed GEMM-class + chain kernel time"}
     roof_tensor["frac"] = (roof_tensor["achieved"] / tf_peak) if roof_tensor["achieved"] else None
 
     cpu = None
@@ -332,16 +349,18 @@ def run_ours(a):
                                f"cached states [13,768] stored {str(state_dtype).split('.')[-1]}, 7 of 13 layers, r=64, E=64, random-init adapters, "
                                f"dense batch, fwd+bwd+Adam",
                    "negatives": "global (all-gather)" if world > 1 else "local",
-                   "l2_policy": f"inputs rotate over {n_rot} batches of {2 * B * 11 * 13 * 768 * elt / 1e6:.0f} MB (> 126 MB L2)",
+                   "l2_policy": f"inputs rotate over {n_rot} resident batches of {2 * B * 11 * 13 * 768 * elt / 1e6:.0f} MB (> 126 MB L2)",
+                   "step_runner": "CUDA graph replay (iisan_b200.engine.TrainStep)" if use_graph else "eager",
                    "parallelism": f"dp{world}"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / e2e_steps,
-                "note": "ModelMM.forward called with pinned HOST batch tensors; .to(device) copies + loss.item() inside the timed region"},
-        "gpu_launches": int(launches),
-        "gpu_launches_per_step": launches / a.steps,
+                "note": "TrainStep(ids, image, text, log_mask) with pinned HOST batch tensors of the reference shapes [B,11,13,768]: "
+                        "H2D copies + step + loss.item() inside the timed region"},
+        "gpu_launches": int(launches_per_step * a.steps),
+        "gpu_launches_per_step": launches_per_step,
         "clocks": clocks,
         "roofline": roof, "roofline_tensor": roof_tensor,
-        "kernel_classes": classes, "dominant_class": dom[0], "ms_per_step_with_kernel_events": ms_prof / a.steps,
+        "kernel_classes": classes, "ms_per_step_eager_with_kernel_events": ms_prof / a.steps,
         "cpu_baseline": cpu, "loss": loss_val,
     }
     print(json.dumps(line), flush=True)

@@ -10,7 +10,7 @@ import os
 
 MAX_STAGES = 64
 MAX_BLOCKS = 8
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 F32, BF16, F16 = 0, 1, 2
 K_STREAM, K_GEMM, K_USER, K_CE, K_MISC, K_CHAIN = range(6)
@@ -61,7 +61,8 @@ class UeParams(C.Structure):
 
 class UeDesc(C.Structure):
     _fields_ = [("users", i32), ("seq_len", i32), ("emb", i32), ("heads", i32), ("n_blocks", i32), ("training", i32),
-                ("dropout_p", C.c_float), ("seed", C.c_uint64), ("offset", C.c_uint64), ("compute", i32), ("reserved", i32)]
+                ("dropout_p", C.c_float), ("seed", C.c_uint64), ("offset", C.c_uint64), ("compute", i32), ("reserved", i32),
+                ("offset_dev", vp)]
 
 
 class CeDesc(C.Structure):

@@ -20,11 +20,12 @@ constexpr float kLnEps = 1e-6f;
 constexpr float kAttNeg = -1e9f;
 constexpr int kMaxEPerLane = 8;  // E <= 256
 
-struct DropCfg { int on; float p; float scale; uint64_t seed, offset; };
+struct DropCfg { int on; float p; float scale; uint64_t seed, offset; const uint64_t* offset_dev; };
 
 __device__ __forceinline__ float drop_apply(const DropCfg& c, uint32_t site, uint64_t idx, float v) {
   if (!c.on) return v;
-  return dropout_keep(c.seed, c.offset, site, idx, c.p) ? v * c.scale : 0.f;
+  const uint64_t off = c.offset_dev ? __ldg(reinterpret_cast<const unsigned long long*>(c.offset_dev)) : c.offset;
+  return dropout_keep(c.seed, off, site, idx, c.p) ? v * c.scale : 0.f;
 }
 
 // ---- LayerNorm forward -----------------------------------------------------------------------------------
@@ -264,7 +265,7 @@ static DropCfg drop_cfg(const iisan_ue_desc& D) {
   DropCfg c;
   c.on = (D.training && D.dropout_p > 0.f) ? 1 : 0;
   c.p = D.dropout_p; c.scale = c.on ? 1.0f / (1.0f - D.dropout_p) : 1.0f;
-  c.seed = D.seed; c.offset = D.offset;
+  c.seed = D.seed; c.offset = D.offset; c.offset_dev = D.offset_dev;
   return c;
 }
 

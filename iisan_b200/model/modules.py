@@ -64,7 +64,7 @@ class TransformerEncoder(nn.Module):
             TransformerBlock(d_model=d_model, n_heads=n_heads, d_inner=d_model * 4, dropout=dropout) for _ in range(n_layers))
         self._cfg = (d_model, n_heads, n_layers, float(dropout))
         self._binder = None
-        self._step = 0
+        self._step_dev = None
         self.dropout_seed = 0x5EED1154
 
     def _bind(self):
@@ -77,8 +77,16 @@ class TransformerEncoder(nn.Module):
     def forward(self, input_embs, log_mask, att_mask=None):
         # att_mask is implied by log_mask (causal + key padding, encoders.py:54-57) and rebuilt in-kernel.
         params = tuple(self.parameters())
-        self._step += 1
-        return UserEncoderFn.apply(self._bind(), input_embs, log_mask, self.training, self.dropout_seed, self._step,
+        d_model, n_heads, n_layers, p = self._cfg
+        offset = 0
+        if self.training and p > 0:
+            # Philox offset = a device-side step counter, advanced by a stream-ordered add: the same code path is valid
+            # eagerly and under CUDA-graph replay (a host counter would be frozen into the captured kernel arguments).
+            if self._step_dev is None or self._step_dev.device != input_embs.device:
+                self._step_dev = torch.zeros(1, dtype=torch.int64, device=input_embs.device)
+            self._step_dev += 1
+            offset = self._step_dev
+        return UserEncoderFn.apply(self._bind(), input_embs, log_mask, self.training, self.dropout_seed, offset,
                                    compute_mode(), *params)
 
 

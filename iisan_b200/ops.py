@@ -119,7 +119,11 @@ class UserEncoderFn(torch.autograd.Function):
             embs = embs.float().contiguous()
         b, l, e = embs.shape
         log_mask = log_mask.to(device=embs.device, dtype=torch.float32).contiguous()
-        desc = binder.desc(b, l, training, seed, offset, compute)
+        offset_dev = None
+        if torch.is_tensor(offset):                       # device-side step counter (CUDA-graph safe dropout stream)
+            ctx.offset_t = offset
+            offset_dev, offset = offset.data_ptr(), 0
+        desc = binder.desc(b, l, training, seed, offset, compute, offset_dev)
         ptrs = binder.param_table(params)
         nbytes = lib.iisan_user_encoder_workspace_bytes(C.byref(desc))
         if nbytes == 0:

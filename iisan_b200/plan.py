@@ -287,11 +287,12 @@ class UserEncoderBinder(_BinderBase):
             _ue_slot(t, n, base + 4 * o)
         return flat, views, t
 
-    def desc(self, users, seq_len, training, seed, offset, compute):
+    def desc(self, users, seq_len, training, seed, offset, compute, offset_dev=None):
         d = L.UeDesc()
         d.users, d.seq_len, d.emb, d.heads, d.n_blocks = users, seq_len, self.emb, self.heads, self.n_blocks
         d.training = int(bool(training) and self.dropout > 0)
         d.dropout_p = self.dropout
         d.seed, d.offset = int(seed), int(offset)
+        d.offset_dev = offset_dev
         d.compute = compute
         return d

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define IISAN_ABI_VERSION 1
+#define IISAN_ABI_VERSION 2
 #define IISAN_MAX_STAGES 64
 #define IISAN_MAX_BLOCKS 8
 
@@ -192,6 +192,7 @@ typedef struct iisan_ue_desc {
   uint64_t seed, offset; /* Philox counter-based dropout stream */
   int32_t compute;
   int32_t reserved;
+  const uint64_t* offset_dev; /* optional device counter read instead of `offset` (CUDA-graph replays advance it on the device) */
 } iisan_ue_desc;
 
 size_t iisan_user_encoder_workspace_bytes(const iisan_ue_desc* desc);
