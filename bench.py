@@ -251,10 +251,14 @@ def run_ours(a):
     launches_per_step = lib.iisan_launch_count(-1) - l0
 
     # ---- the timed arm: inputs resident in HBM; one captured graph per resident batch (no staging copies) ----
+    dbg = (lambda m: print(f"[bench rank {rank}] {m}", file=sys.stderr, flush=True)) if os.environ.get("IISAN_BENCH_DEBUG") else (lambda m: None)
+    dbg("eager ok")
+    runners_ref = []
     if use_graph:
-        runners = [TrainStep(model, opt, use_graph=True, group=group) for _ in range(n_rot)]
+        runners = runners_ref = [TrainStep(model, opt, use_graph=True, group=group) for _ in range(n_rot)]
         for r, bt in zip(runners, batches):
             r.capture(*bt)
+            dbg("captured")
         step = lambda i: runners[i % n_rot].replay()
     else:
         step = lambda i: eager(*batches[i % n_rot])
@@ -263,7 +267,9 @@ def run_ours(a):
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start(); time.sleep(0.3)
+    dbg("warm")
     ms, t0, t1, last = timed(a.steps, step)
+    dbg("timed")
     if sampler:
         time.sleep(0.2); sampler.stop()
     clocks = sampler.summary(t0, t1) if sampler else None
@@ -297,9 +303,26 @@ def run_ours(a):
     ms_e2e, _, _, _ = timed(e2e_steps, e2e_step)
     e2e_value = world * B * e2e_steps / (ms_e2e / 1e3)
 
-    if rank != 0:
-        if world > 1:
+    def shutdown():
+        """Release the captured graphs (they hold NCCL work) before tearing the process group down; a process that still
+        cannot finalise NCCL within 20 s exits anyway (the JSON line is already out)."""
+        if world == 1:
+            return
+        nonlocal runners_ref, e2e_runner
+        runners_ref.clear(); e2e_runner = None
+        torch.cuda.synchronize()
+        sys.stdout.flush(); sys.stderr.flush()
+        t = threading.Timer(20.0, lambda: os._exit(0))
+        t.daemon = True
+        t.start()
+        try:
+            dist.barrier()
             dist.destroy_process_group()
+        finally:
+            t.cancel()
+
+    if rank != 0:
+        shutdown()
         return
 
     peaks = {}
@@ -364,8 +387,7 @@ def run_ours(a):
         "cpu_baseline": cpu, "loss": loss_val,
     }
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    shutdown()
 
 
 def main():

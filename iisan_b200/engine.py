@@ -125,7 +125,8 @@ class TrainStep:
             torch.cuda.synchronize(device)
             self.opt.zero_grad(set_to_none=True)
             self.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph):
+            # thread_local: the NCCL watchdog thread may query its events while this thread captures
+            with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
                 self.static_loss = self._eager(*inputs)
             self._restore(saved)
         self.graph.replay()
