@@ -110,6 +110,8 @@ struct SanLayoutBf16 {
   bf16 *dyb_t, *dxb_t, *dzb_t, *dyb_i, *dxb_i, *dzb_i, *dyb_m, *dxb_m, *dzb_m;
   bf16* ddpb;
   bf16 *wd_pack[3], *wu_pack[3];          // fused chain: per tower (text, img, mm) all stages' weights, contiguous
+  bf16* dys[3];                           // fused chain backward: d last_s of all stages [A, N, d] per tower
+  bf16* dzs[3][IISAN_MAX_STAGES];         //                        dz_s [N, r]
   size_t bytes;
 
   static WCopy takew(Arena& a, size_t n) { WCopy c; c.w = a.take<bf16>(n); c.wt = a.take<bf16>(n); return c; }
@@ -130,16 +132,28 @@ struct SanLayoutBf16 {
       const int ta = D.text_adapter[s], ia = D.img_adapter[s], mi = D.mm_index[s];
       if (ta >= 0) {
         t_down[ta] = takew(a, (size_t)D.r_text * D.d_text); t_up[ta] = takew(a, (size_t)D.r_text * D.d_text);
-        x_t[s] = a.take<bf16>(N * D.d_text); z_t[s] = a.take<bf16>(N * D.r_text); last_t[s] = a.take<bf16>(N * D.d_text);
+        x_t[s] = a.take<bf16>(N * D.d_text); z_t[s] = a.take<bf16>(N * D.r_text);
       }
       if (ia >= 0) {
         i_down[ia] = takew(a, (size_t)D.r_img * D.d_img); i_up[ia] = takew(a, (size_t)D.r_img * D.d_img);
-        x_i[s] = a.take<bf16>(N * D.d_img); z_i[s] = a.take<bf16>(N * D.r_img); last_i[s] = a.take<bf16>(N * D.d_img);
+        x_i[s] = a.take<bf16>(N * D.d_img); z_i[s] = a.take<bf16>(N * D.r_img);
       }
       if (mi >= 0) {
         m_down[mi] = takew(a, (size_t)D.r_mm * D.d_mm); m_up[mi] = takew(a, (size_t)D.r_mm * D.d_mm);
-        x_m[s] = a.take<bf16>(N * D.d_mm); z_m[s] = a.take<bf16>(N * D.r_mm); last_m[s] = a.take<bf16>(N * D.d_mm);
+        x_m[s] = a.take<bf16>(N * D.d_mm); z_m[s] = a.take<bf16>(N * D.r_mm);
         if (dimdiff) { dpw[mi] = takew(a, (size_t)D.d_mm * dwide); dpo[s] = a.take<float>(N * D.d_mm); }
+      }
+    }
+    // last_s of one tower are contiguous over the stages (no 256-byte padding in between: N*d*2 is a multiple of 16 and the
+    // fused backward addresses them as one [A*N, d] matrix)
+    {
+      bf16* bt = a.take<bf16>((size_t)D.n_stages * N * D.d_text);
+      bf16* bi = a.take<bf16>((size_t)D.n_stages * N * D.d_img);
+      bf16* bm = a.take<bf16>((size_t)D.n_stages * N * D.d_mm);
+      for (int s = 0; s < D.n_stages; ++s) {
+        if (D.text_adapter[s] >= 0) last_t[s] = bt + (size_t)s * N * D.d_text;
+        if (D.img_adapter[s] >= 0) last_i[s] = bi + (size_t)s * N * D.d_img;
+        if (D.mm_index[s] >= 0) last_m[s] = bm + (size_t)s * N * D.d_mm;
       }
     }
     fc_t = takew(a, (size_t)ft * D.d_text); fc_i = takew(a, (size_t)fi * D.d_img); fc_m = takew(a, (size_t)fm * D.d_mm);
@@ -155,11 +169,13 @@ struct SanLayoutBf16 {
     dyb_i = a.take<bf16>(N * D.d_img); dxb_i = a.take<bf16>(N * D.d_img); dzb_i = a.take<bf16>(N * D.r_img);
     dyb_m = a.take<bf16>(N * D.d_mm); dxb_m = a.take<bf16>(N * D.d_mm); dzb_m = a.take<bf16>(N * D.r_mm);
     ddpb = dimdiff ? a.take<bf16>(N * D.d_mm) : nullptr;
-    for (int t = 0; t < 3; ++t) wd_pack[t] = wu_pack[t] = nullptr;
+    for (int t = 0; t < 3; ++t) wd_pack[t] = wu_pack[t] = dys[t] = nullptr;
     if (san_chain_eligible(D)) {
       for (int t = 0; t < 3; ++t) {
         wd_pack[t] = a.take<bf16>((size_t)D.n_stages * D.r_mm * D.d_mm);
         wu_pack[t] = a.take<bf16>((size_t)D.n_stages * D.r_mm * D.d_mm);
+        dys[t] = a.take<bf16>((size_t)D.n_stages * N * D.d_mm);
+        for (int s = 0; s < D.n_stages; ++s) dzs[t][s] = a.take<bf16>(N * D.r_mm);
       }
     }
     bytes = a.off;
@@ -400,6 +416,7 @@ static int san_backward_bf16_t(const iisan_san_desc* D, const iisan_san_params* 
     if (D->mm_index[s] >= 0) ls_m = s;
   }
   if (ls_t < 0 || ls_i < 0 || ls_m < 0) return IISAN_EINVAL;
+  const bool chain = san_chain_eligible(*D) && !g_disable_chain;
   // ---- bf16 operand copy of d_out ----
   {
     MixBatch cb{}; cb.n = 1;
@@ -437,13 +454,55 @@ static int san_backward_bf16_t(const iisan_san_desc* D, const iisan_san_params* 
     cf.p[2] = {nullptr, fm, N, fm, G->fc_mm.b, L.dhead_m};
     IISAN_TRY(launch_colsum(cf, st));
     UmmaBatch dl{}; dl.n = 3;  // d last = d head W_fc
+    const size_t lastoff = (size_t)(D->n_stages - 1) * N * D->d_mm;
     dl.p[0] = mk_linear(L.dhead_i, fi, L.fc_i.wt, N, D->d_img, fi);
-    dl.p[0].epi.out_f32 = L.dy_i; dl.p[0].epi.ld_f32 = D->d_img; dl.p[0].epi.out_bf16 = L.dyb_i; dl.p[0].epi.ld_bf16 = D->d_img;
     dl.p[1] = mk_linear(L.dhead_t, ft, L.fc_t.wt, N, D->d_text, ft);
-    dl.p[1].epi.out_f32 = L.dy_t; dl.p[1].epi.ld_f32 = D->d_text; dl.p[1].epi.out_bf16 = L.dyb_t; dl.p[1].epi.ld_bf16 = D->d_text;
     dl.p[2] = mk_linear(L.dhead_m, fm, L.fc_m.wt, N, D->d_mm, fm);
-    dl.p[2].epi.out_f32 = L.dy_m; dl.p[2].epi.ld_f32 = D->d_mm; dl.p[2].epi.out_bf16 = L.dyb_m; dl.p[2].epi.ld_bf16 = D->d_mm;
+    if (chain) {      // the fused backward takes d last_{A-1} as bf16 from the per-stage gradient stash
+      dl.p[0].epi.out_bf16 = L.dys[1] + lastoff; dl.p[0].epi.ld_bf16 = D->d_img;
+      dl.p[1].epi.out_bf16 = L.dys[0] + lastoff; dl.p[1].epi.ld_bf16 = D->d_text;
+      dl.p[2].epi.out_bf16 = L.dys[2] + lastoff; dl.p[2].epi.ld_bf16 = D->d_mm;
+    } else {
+      dl.p[0].epi.out_f32 = L.dy_i; dl.p[0].epi.ld_f32 = D->d_img; dl.p[0].epi.out_bf16 = L.dyb_i; dl.p[0].epi.ld_bf16 = D->d_img;
+      dl.p[1].epi.out_f32 = L.dy_t; dl.p[1].epi.ld_f32 = D->d_text; dl.p[1].epi.out_bf16 = L.dyb_t; dl.p[1].epi.ld_bf16 = D->d_text;
+      dl.p[2].epi.out_f32 = L.dy_m; dl.p[2].epi.ld_f32 = D->d_mm; dl.p[2].epi.out_bf16 = L.dyb_m; dl.p[2].epi.ld_bf16 = D->d_mm;
+    }
     IISAN_TRY(launch_umma_gemm(dl, st));
+  }
+  if (chain) {
+    // ---- data / gate / bias gradients of all stages and towers in one launch (san_chain.cu) ----
+    ChainBwdArgs ca{};
+    ca.n_items = N; ca.d = D->d_mm; ca.n_stages = D->n_stages;
+    IISAN_TRY(chain_fill_bwd_tower(&ca.tower[0], 0, text, N, (int64_t)D->layers_text * D->d_text, nullptr, 0, L.wd_pack[0], L.wu_pack[0], L.dys[0], L.last_t[0], D->n_stages, D->d_text));
+    IISAN_TRY(chain_fill_bwd_tower(&ca.tower[1], 0, image, N, (int64_t)D->layers_img * D->d_img, nullptr, 0, L.wd_pack[1], L.wu_pack[1], L.dys[1], L.last_i[0], D->n_stages, D->d_img));
+    IISAN_TRY(chain_fill_bwd_tower(&ca.tower[2], 1, image, N, (int64_t)D->layers_img * D->d_img, text, (int64_t)D->layers_text * D->d_text, L.wd_pack[2], L.wu_pack[2], L.dys[2], L.last_m[0], D->n_stages, D->d_mm));
+    for (int s = 0; s < D->n_stages; ++s) {
+      const int ta = D->text_adapter[s], ia = D->img_adapter[s], mi = D->mm_index[s];
+      ChainBwdTower& t0 = ca.tower[0]; ChainBwdTower& t1 = ca.tower[1]; ChainBwdTower& t2 = ca.tower[2];
+      t0.layer[s] = D->text_layer[s]; t0.gate[s] = P->gate_text[ta]; t0.g_gate[s] = G->gate_text[ta]; t0.g_b_down[s] = G->text[ta].b_down; t0.g_b_up[s] = G->text[ta].b_up;
+      t0.z_stash[s] = L.z_t[s]; t0.dz_stash[s] = L.dzs[0][s];
+      t1.layer[s] = D->img_layer[s]; t1.gate[s] = P->gate_img[ia]; t1.g_gate[s] = G->gate_img[ia]; t1.g_b_down[s] = G->img[ia].b_down; t1.g_b_up[s] = G->img[ia].b_up;
+      t1.z_stash[s] = L.z_i[s]; t1.dz_stash[s] = L.dzs[1][s];
+      t2.layer[s] = D->img_layer[s]; t2.layer2[s] = D->text_layer[s]; t2.gate[s] = P->gate_mm[mi]; t2.g_gate[s] = G->gate_mm[mi]; t2.g_b_down[s] = G->mm[mi].b_down; t2.g_b_up[s] = G->mm[mi].b_up;
+      t2.z_stash[s] = L.z_m[s]; t2.dz_stash[s] = L.dzs[2][s];
+    }
+    ca.tower[0].dy_stash = L.dys[0]; ca.tower[1].dy_stash = L.dys[1]; ca.tower[2].dy_stash = L.dys[2];
+    IISAN_TRY(launch_san_chain_bwd(ca, 3, st));
+    // ---- weight gradients: reductions over all items, split-K GEMMs over the stashes ----
+    for (int s = D->n_stages - 1; s >= 0; --s) {
+      const int ta = D->text_adapter[s], ia = D->img_adapter[s], mi = D->mm_index[s];
+      const size_t off = (size_t)s * N * D->d_mm;
+      UmmaBatch wu{}, wd{}; wu.n = wd.n = 3;
+      wu.p[0] = mk_wgrad(L.dys[0] + off, D->d_text, D->d_text, L.z_t[s], D->r_text, D->r_text, N, G->text[ta].w_up, 3);
+      wu.p[1] = mk_wgrad(L.dys[1] + off, D->d_img, D->d_img, L.z_i[s], D->r_img, D->r_img, N, G->img[ia].w_up, 3);
+      wu.p[2] = mk_wgrad(L.dys[2] + off, D->d_mm, D->d_mm, L.z_m[s], D->r_mm, D->r_mm, N, G->mm[mi].w_up, 3);
+      wd.p[0] = mk_wgrad(L.dzs[0][s], D->r_text, D->r_text, L.x_t[s], D->d_text, D->d_text, N, G->text[ta].w_down, 3);
+      wd.p[1] = mk_wgrad(L.dzs[1][s], D->r_img, D->r_img, L.x_i[s], D->d_img, D->d_img, N, G->img[ia].w_down, 3);
+      wd.p[2] = mk_wgrad(L.dzs[2][s], D->r_mm, D->r_mm, L.x_m[s], D->d_mm, D->d_mm, N, G->mm[mi].w_down, 3);
+      IISAN_TRY(launch_umma_gemm(wu, st));
+      IISAN_TRY(launch_umma_gemm(wd, st));
+    }
+    return IISAN_OK;
   }
   // ---- stages in reverse: dy_* holds d last_s on entry to stage s and d last_{s-1} on exit ----
   float* dy_t = L.dy_t; float* dx_t = L.dx_t; bf16* dyb_t = L.dyb_t; bf16* dxb_t = L.dxb_t;

@@ -331,6 +331,291 @@ __global__ void __launch_bounds__(CH_THREADS, 1) san_chain_fwd_kernel(const __gr
   if (warp == 1) tmem_dealloc(tmem_base, CH_TMEM_COLS);
 }
 
+
+// ================================================================================================================
+// Backward of the chain (data gradients + gate / bias gradients; the weight gradients are reductions over ALL items and
+// stay separate split-K GEMMs over the stashes this kernel writes).  Same skeleton as the forward, stages in reverse:
+//
+//   dz_s      = (dy_s Wu_s) * (z_s > 0)                dy_s = d last_s ; accumulated in TMEM chunk by chunk (K = d)
+//   dx_s      = dy_s + dz_s Wd_s                       one tcgen05.mma group per 64-column chunk
+//   dgate_s  += sum dx_s * (h_s - last_{s-1})          (mm tower: h_cv - h_text), scaled by g(1-g)/0.1 at the end
+//   dy_{s-1}  = (1 - g_s) dx_s                         (mm tower: dx_s) -> bf16 -> stash (wgrad operand) and, swizzled, the A
+//                                                      operand of the next stage's dz accumulation
+//   db_up_s  += colsum(dy_s) ; db_down_s += colsum(dz_s)   (warp butterfly, one red.add per column and warp)
+// Every global tile (dy_s, h_s, last_{s-1} / h_text) arrives through one TMA ring; dy_{s-1} is read back by TMA one stage
+// after this CTA wrote it with generic stores, ordered by fence.proxy.async + the ring's mbarrier chain.
+// ================================================================================================================
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+// sum over the 32 lanes of v[k] for each k: lane l ends with the total of column l (31 shuffles)
+__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int k = 0; k < off; ++k) {
+      const float send = upper ? v[k] : v[k + off];
+      const float recv = __shfl_xor_sync(0xffffffffu, send, off);
+      v[k] = (upper ? v[k + off] : v[k]) + recv;
+    }
+  }
+  return v[0];
+}
+
+__global__ void __launch_bounds__(CH_THREADS, 1) san_chain_bwd_kernel(const __grid_constant__ ChainBwdArgs a) {
+  const ChainBwdTower& T = a.tower[blockIdx.y];
+  const bool is_mm = (T.mode == 1);
+  const int NC = a.d / CH_CW;
+  const int A = a.n_stages;
+  const int m0 = blockIdx.x * CH_ROWS;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ChainSmem::kBar);
+  uint64_t* w_full = bars;
+  uint64_t* w_empty = w_full + CH_NW;
+  uint64_t* h_full = w_empty + CH_NW;
+  uint64_t* h_empty = h_full + CH_NH;
+  uint64_t* xk_full = h_empty + CH_NH;
+  uint64_t* xk_empty = xk_full + 2;
+  uint64_t* u_full = xk_empty + 2;
+  uint64_t* u_empty = u_full + 2;
+  uint64_t* z_full = u_empty + 2;
+  uint64_t* z_ready = z_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(z_ready + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&T.map_wd); tma_prefetch_desc(&T.map_wu); tma_prefetch_desc(&T.map_h); tma_prefetch_desc(&T.map_dy);
+    tma_prefetch_desc(&T.map_aux);
+    for (int i = 0; i < CH_NW; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+    for (int i = 0; i < CH_NH; ++i) { mbar_init(&h_full[i], 1); mbar_init(&h_empty[i], 8); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&xk_full[i], 8); mbar_init(&xk_empty[i], 1); mbar_init(&u_full[i], 1); mbar_init(&u_empty[i], 8); }
+    mbar_init(z_full, 1); mbar_init(z_ready, 8);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, CH_TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // unit u = (j + 1) * NC + c, j = -1 .. A-1, stage sv = A-1-j : first half Wd_sv[c] (j >= 0), second half Wu_{sv-1}[c]
+  // (sv-1 >= 0 ; for j = -1 that is Wu_{A-1}[c])
+  const int n_units = (A + 1) * NC;
+
+  if (warp == 0) {
+    // ===================== weight producer =====================
+    if (elect_one()) {
+      for (int u = 0; u < n_units; ++u) {
+        const int j = u / NC - 1, c = u % NC;
+        const int sv = A - 1 - j;                         // j = -1 -> A
+        const int slot = u % CH_NW; const uint32_t ph = (uint32_t)(u / CH_NW) & 1u;
+        const bool has_wd = j >= 0, has_wu = sv - 1 >= 0;
+        if (!has_wd && !has_wu) continue;
+        mbar_wait(&w_empty[slot], ph ^ 1u);
+        uint8_t* dst = smem + ChainSmem::kW + slot * 2 * CH_W_BYTES;
+        mbar_expect_tx(&w_full[slot], (has_wd ? CH_W_BYTES : 0) + (has_wu ? CH_W_BYTES : 0));
+        if (has_wd) tma_load_2d(dst, &T.map_wd, &w_full[slot], c * CH_CW, sv * CH_R);                       // Wd_sv[:, chunk] : [r, 64]
+        if (has_wu) tma_load_2d(dst + CH_W_BYTES, &T.map_wu, &w_full[slot], 0, (sv - 1) * a.d + c * CH_CW);  // Wu_{sv-1}[chunk, :] : [64, r]
+      }
+    }
+  } else if (warp == 2) {
+    // ===================== data producer =====================
+    if (elect_one()) {
+      int n_h = 0;
+      auto load = [&](const CUtensorMap* m, int col, int row) {
+        const int slot = n_h % CH_NH; const uint32_t ph = (uint32_t)(n_h / CH_NH) & 1u;
+        mbar_wait(&h_empty[slot], ph ^ 1u);
+        mbar_expect_tx(&h_full[slot], CH_TILE_BYTES);
+        tma_load_2d(smem + ChainSmem::kH + slot * CH_TILE_BYTES, m, &h_full[slot], col, row);
+        ++n_h;
+      };
+      for (int c = 0; c < NC; ++c) load(&T.map_dy, c * CH_CW, (A - 1) * a.n_items + m0);
+      for (int s = A - 1; s >= 0; --s) {
+        for (int c = 0; c < NC; ++c) {
+          load(&T.map_dy, c * CH_CW, s * a.n_items + m0);
+          load(&T.map_h, T.layer[s] * a.d + c * CH_CW, m0);
+          if (is_mm) load(&T.map_aux, T.layer2[s] * a.d + c * CH_CW, m0);
+          else if (s > 0) load(&T.map_aux, c * CH_CW, (s - 1) * a.n_items + m0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (elect_one()) {
+      constexpr uint32_t idesc = instr_desc_bf16(CH_ROWS, 64, 0, 1);   // A K-major, B MN-major ([K, N] row-major weight tiles)
+      const uint32_t sz = smem_u32(smem + ChainSmem::kZ);
+      int n_x = 0, n_u = 0;
+      auto dzacc_step = [&](int unit, int c) {        // dz_acc (+)= dy chunk x Wu[c]  (K = 64 columns of the chunk)
+        const int b = n_x & 1; const uint32_t ph = (uint32_t)(n_x >> 1) & 1u;
+        const int slot = unit % CH_NW;
+        mbar_wait(&xk_full[b], ph);
+        tc_fence_after();
+        const uint32_t sx = smem_u32(smem + ChainSmem::kXk + b * CH_TILE_BYTES);
+        const uint32_t sw = smem_u32(smem + ChainSmem::kW + slot * 2 * CH_W_BYTES + CH_W_BYTES);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          mma_bf16_ss(tmem_base + CH_ZACC, smem_desc_sw128(sx + k * 32, 16, 1024), smem_desc_sw128(sw + k * 2048, 8192, 1024), idesc, (c > 0 || k > 0) ? 1u : 0u);
+        mma_commit(&xk_empty[b]);
+        mma_commit(&w_empty[slot]);
+        ++n_x;
+      };
+      for (int c = 0; c < NC; ++c) {
+        const int unit = c; const uint32_t wph = (uint32_t)(unit / CH_NW) & 1u;
+        mbar_wait(&w_full[unit % CH_NW], wph);
+        dzacc_step(unit, c);
+      }
+      mma_commit(z_full);
+      for (int j = 0; j < A; ++j) {
+        const bool more = j + 1 < A;                  // stage sv = A-1-j > 0
+        mbar_wait(z_ready, (uint32_t)j & 1u);
+        tc_fence_after();
+        for (int c = 0; c < NC; ++c) {
+          const int unit = (j + 1) * NC + c; const int slot = unit % CH_NW; const uint32_t wph = (uint32_t)(unit / CH_NW) & 1u;
+          const int b = n_u & 1; const uint32_t uph = (uint32_t)(n_u >> 1) & 1u;
+          mbar_wait(&w_full[slot], wph);
+          mbar_wait(&u_empty[b], uph ^ 1u);
+          tc_fence_after();
+          const uint32_t sw = smem_u32(smem + ChainSmem::kW + slot * 2 * CH_W_BYTES);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)       // dx chunk = dz (K = r) x Wd[:, chunk]
+            mma_bf16_ss(tmem_base + CH_UACC + b * 64, smem_desc_sw128(sz + k * 32, 16, 1024), smem_desc_sw128(sw + k * 2048, 8192, 1024), idesc, k > 0 ? 1u : 0u);
+          mma_commit(&u_full[b]);
+          ++n_u;
+          if (!more) mma_commit(&w_empty[slot]);
+          else if (c >= 1) dzacc_step(unit - 1, c - 1);
+        }
+        if (more) { dzacc_step((j + 1) * NC + NC - 1, NC - 1); mma_commit(z_full); }
+      }
+    }
+  } else {
+    // ===================== epilogue warps =====================
+    const int ew = warp - 3;
+    const int quad = warp & 3;
+    const int hf = ew >> 2;
+    const int m = quad * 32 + lane;
+    const int64_t row = (int64_t)m0 + m;
+    const bool row_ok = row < a.n_items;
+    const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+    const int sw_row = (m >> 3) * 1024 + (m & 7) * 128;
+    int n_h = 0, n_x = 0, n_u = 0;
+
+    auto read_tile = [&](float* hv) {                 // this thread's 32 columns of the next ring tile (zeros for rows past N)
+      const int slot = n_h % CH_NH; const uint32_t ph = (uint32_t)(n_h / CH_NH) & 1u;
+      mbar_wait(&h_full[slot], ph);
+      const uint8_t* tile = smem + ChainSmem::kH + slot * CH_TILE_BYTES + sw_row;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) unpack8(*reinterpret_cast<const uint4*>(tile + (((hf * 4 + q) ^ (m & 7)) << 4)), hv + q * 8);
+      if (!row_ok) {
+#pragma unroll
+        for (int k = 0; k < 32; ++k) hv[k] = 0.f;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&h_empty[slot]);
+      ++n_h;
+    };
+    auto emit = [&](const float* xv, bf16* stash, int c) {     // bf16 chunk -> A operand (+ global stash)
+      const int b = n_x & 1; const uint32_t ph = (uint32_t)(n_x >> 1) & 1u;
+      mbar_wait(&xk_empty[b], ph ^ 1u);
+      uint8_t* tile = smem + ChainSmem::kXk + b * CH_TILE_BYTES + sw_row;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint4 pk = pack8(xv + q * 8);
+        *reinterpret_cast<uint4*>(tile + (((hf * 4 + q) ^ (m & 7)) << 4)) = pk;
+        if (stash && row_ok) *reinterpret_cast<uint4*>(stash + row * a.d + c * CH_CW + hf * 32 + q * 8) = pk;
+      }
+      fence_proxy_async_all();          // shared: the MMA reads the operand ; global: the TMA ring reads the stash back
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&xk_full[b]);
+      ++n_x;
+    };
+
+    // ---- stage "A": feed dy_{A-1} into the first dz accumulation ----
+    for (int c = 0; c < NC; ++c) {
+      float dv[32];
+      read_tile(dv);
+      emit(dv, nullptr, c);
+    }
+    for (int s = A - 1; s >= 0; --s) {
+      const int j = A - 1 - s;
+      const bool more = s > 0;
+      // ---- dz_s = dz_acc * (z_s > 0) ----
+      {
+        mbar_wait(z_full, (uint32_t)j & 1u);
+        tc_fence_after();
+        uint32_t raw[32];
+        tmem_ld_32x32(tmem_base + lane_addr + (uint32_t)(CH_ZACC + hf * 32), raw);
+        tmem_ld_wait();
+        float zv[32], dzv[32];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 v = make_uint4(0u, 0u, 0u, 0u);
+          if (row_ok) v = *reinterpret_cast<const uint4*>(T.z_stash[s] + row * CH_R + hf * 32 + q * 8);
+          unpack8(v, zv + q * 8);
+        }
+#pragma unroll
+        for (int k = 0; k < 32; ++k) dzv[k] = (zv[k] > 0.f && row_ok) ? __uint_as_float(raw[k]) : 0.f;
+        uint8_t* tile = smem + ChainSmem::kZ + sw_row;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint4 pk = pack8(dzv + q * 8);
+          *reinterpret_cast<uint4*>(tile + (((hf * 4 + q) ^ (m & 7)) << 4)) = pk;
+          if (row_ok) *reinterpret_cast<uint4*>(T.dz_stash[s] + row * CH_R + hf * 32 + q * 8) = pk;
+        }
+        tc_fence_before();
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(z_ready);
+        const float cs = warp_colsum32(dzv, lane);                       // db_down
+        atomicAdd(T.g_b_down[s] + hf * 32 + lane, cs);
+      }
+      const float g = gate_value(T.gate[s]);
+      const float omg = 1.0f - g;
+      float gpart = 0.f;
+      for (int c = 0; c < NC; ++c) {
+        float dy[32], hv[32], av[32];
+        read_tile(dy);
+        read_tile(hv);
+        const bool has_aux = is_mm || more;
+        if (has_aux) read_tile(av);
+        const int b = n_u & 1; const uint32_t uph = (uint32_t)(n_u >> 1) & 1u;
+        mbar_wait(&u_full[b], uph);
+        tc_fence_after();
+        uint32_t raw[32];
+        tmem_ld_32x32(tmem_base + lane_addr + (uint32_t)(CH_UACC + b * 64 + hf * 32), raw);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&u_empty[b]);
+        ++n_u;
+        float dx[32];
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+          dx[k] = row_ok ? __uint_as_float(raw[k]) + dy[k] : 0.f;
+          const float diff = has_aux ? hv[k] - av[k] : hv[k];
+          gpart = fmaf(dx[k], diff, gpart);
+        }
+        if (more) {
+          if (!is_mm) {
+#pragma unroll
+            for (int k = 0; k < 32; ++k) dx[k] *= omg;
+          }
+          emit(dx, T.dy_stash + (int64_t)(s - 1) * a.n_items * a.d, c);
+        }
+        const float cs = warp_colsum32(dy, lane);                        // db_up
+        atomicAdd(T.g_b_up[s] + c * CH_CW + hf * 32 + lane, cs);
+      }
+      // ---- gate gradient: d sigmoid(p/0.1)/dp = g(1-g)/0.1 ----
+      gpart = warp_sum(gpart);
+      if (lane == 0) atomicAdd(T.g_gate[s], gpart * g * omg / 0.1f);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, CH_TMEM_COLS);
+}
+
 int make_tensor_map_bf16(CUtensorMap* out, const void* ptr, int64_t rows, int64_t cols, int64_t pitch, int box_inner, int box_outer);
 
 int chain_fill_tower(ChainTower* T, int mode, const void* h, int64_t h_rows, int64_t h_pitch_cols, const void* h2, int64_t h2_pitch_cols,
@@ -341,6 +626,30 @@ int chain_fill_tower(ChainTower* T, int mode, const void* h, int64_t h_rows, int
   else T->map_h2 = T->map_h;
   IISAN_TRY(make_tensor_map_bf16(&T->map_wd, wd_pack, (int64_t)n_stages * CH_R, d, d, CH_CW, CH_R));
   IISAN_TRY(make_tensor_map_bf16(&T->map_wu, wu_pack, (int64_t)n_stages * d, CH_R, CH_R, CH_R, CH_CW));
+  return IISAN_OK;
+}
+
+int chain_fill_bwd_tower(ChainBwdTower* T, int mode, const void* h, int64_t h_rows, int64_t h_pitch_cols, const void* h2, int64_t h2_pitch_cols,
+                         const bf16* wd_pack, const bf16* wu_pack, const bf16* dy_all, const bf16* last_all, int n_stages, int d) {
+  T->mode = mode;
+  IISAN_TRY(make_tensor_map_bf16(&T->map_h, h, h_rows, h_pitch_cols, h_pitch_cols, CH_CW, CH_ROWS));
+  IISAN_TRY(make_tensor_map_bf16(&T->map_dy, dy_all, (int64_t)n_stages * h_rows, d, d, CH_CW, CH_ROWS));
+  if (mode == 1) IISAN_TRY(make_tensor_map_bf16(&T->map_aux, h2, h_rows, h2_pitch_cols, h2_pitch_cols, CH_CW, CH_ROWS));
+  else IISAN_TRY(make_tensor_map_bf16(&T->map_aux, last_all, (int64_t)n_stages * h_rows, d, d, CH_CW, CH_ROWS));
+  IISAN_TRY(make_tensor_map_bf16(&T->map_wd, wd_pack, (int64_t)n_stages * CH_R, d, d, CH_CW, CH_R));
+  IISAN_TRY(make_tensor_map_bf16(&T->map_wu, wu_pack, (int64_t)n_stages * d, CH_R, CH_R, CH_R, CH_CW));
+  return IISAN_OK;
+}
+
+int launch_san_chain_bwd(const ChainBwdArgs& args, int n_towers, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    IISAN_CUDA_OK(cudaFuncSetAttribute(san_chain_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ChainSmem::kTotal));
+    attr_set = true;
+  }
+  const int tiles = (args.n_items + CH_ROWS - 1) / CH_ROWS;
+  { LaunchScope ls_(IISAN_K_CHAIN, st); san_chain_bwd_kernel<<<dim3(tiles, n_towers), CH_THREADS, ChainSmem::kTotal, st>>>(args); }
+  IISAN_LAUNCH_OK();
   return IISAN_OK;
 }
 
