@@ -94,6 +94,7 @@ _SIGNATURES = {
     "iisan_inbatch_ce_backward": (C.c_int, [C.POINTER(CeDesc), vp, vp, vp, vp, vp, vp, vp, vp, C.c_size_t, vp, vp, vp, vp, vp, vp]),
     "iisan_inbatch_ce_masks": (C.c_int, [C.POINTER(CeDesc), vp, vp, vp, vp, vp, vp]),
     "iisan_inbatch_ce_masks_fast": (C.c_int, [C.POINTER(CeDesc), vp, vp, vp, vp, vp, C.c_size_t, vp, vp]),
+    "iisan_stage_states_h2d": (C.c_int, [vp, vp, C.c_int64, i32, i32, i32, C.POINTER(i32), i32, vp]),
     "iisan_gather_states": (C.c_int, [vp, i32, C.c_int64, i32, i32, vp, i32, vp, i32, vp, vp]),
 }
 

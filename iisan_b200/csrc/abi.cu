@@ -185,3 +185,21 @@ extern "C" int iisan_gemm_bf16(int32_t M, int32_t N, int32_t K, const void* A, i
   P.epi.bias = bias; P.epi.relu = relu; P.epi.atomic = P.splitk > 1 ? 1 : 0;
   return launch_umma_gemm(b, as_stream(stream));
 }
+
+extern "C" int iisan_stage_states_h2d(const void* host_src, void* dev_dst, int64_t n_rows, int32_t layers, int32_t d, int32_t dtype,
+                                      const int32_t* sel, int32_t n_sel, iisan_stream_t stream) {
+  if (!host_src || !dev_dst || !sel || n_rows <= 0 || layers <= 0 || d <= 0 || n_sel <= 0 || n_sel > layers) return IISAN_EINVAL;
+  const size_t bpe = dtype_size(dtype);
+  const size_t pitch = (size_t)layers * d * bpe;
+  cudaStream_t st = as_stream(stream);
+  int i = 0;
+  while (i < n_sel) {
+    if (sel[i] < 0 || sel[i] >= layers || (i > 0 && sel[i] <= sel[i - 1])) return IISAN_EINVAL;
+    int j = i;
+    while (j + 1 < n_sel && sel[j + 1] == sel[j] + 1) ++j;            // run of adjacent layers -> one DMA
+    const size_t off = (size_t)sel[i] * d * bpe, width = (size_t)(j - i + 1) * d * bpe;
+    IISAN_CUDA_OK(cudaMemcpy2DAsync((char*)dev_dst + off, pitch, (const char*)host_src + off, pitch, width, (size_t)n_rows, cudaMemcpyHostToDevice, st));
+    i = j + 1;
+  }
+  return IISAN_OK;
+}

@@ -131,3 +131,94 @@ class TrainStep:
             self._restore(saved)
         self.graph.replay()
         return self.static_loss
+
+
+def stage_states_h2d(dst, src, sel, stream=None):
+    """Copy the layers ``sel`` of a pinned host batch ``src`` [..., layers, d] into the device buffer ``dst`` of the same shape
+    (iisan_stage_states_h2d: one 2-D DMA per run of adjacent layers).  The other layers of ``dst`` keep their old content --
+    the kernels never read them (6 of the 13 cached layers are never used)."""
+    import ctypes as C
+    from . import _lib as L
+    lib = L.load()
+    if not src.is_pinned() or not src.is_contiguous() or not dst.is_contiguous() or src.shape != dst.shape or src.dtype != dst.dtype:
+        raise ValueError("stage_states_h2d needs a contiguous pinned host tensor and a device tensor of the same shape/dtype")
+    layers, d = src.shape[-2], src.shape[-1]
+    n_rows = src.numel() // (layers * d)
+    sel = sorted(set(int(v) for v in sel))
+    arr = (C.c_int32 * len(sel))(*sel)
+    st = stream if stream is not None else torch.cuda.current_stream(dst.device)
+    L.check(lib.iisan_stage_states_h2d(C.c_void_p(src.data_ptr()), C.c_void_p(dst.data_ptr()), n_rows, layers, d,
+                                       L.torch_dtype_code(src.dtype), arr, len(sel), C.c_void_p(st.cuda_stream)),
+            "iisan_stage_states_h2d")
+
+
+class PipelinedTrainStep:
+    """Double-buffered TrainStep for host-resident batches: while the graph of batch i runs, the selected layers of batch
+    i+1 stream over the host link on a copy stream.
+
+        pipe = PipelinedTrainStep(model, optimizer)
+        pipe.submit(first_batch)
+        for nxt in loader:                      # (ids, image, text, log_mask): pinned host tensors of the reference shapes
+            pipe.submit(nxt)                    # asynchronous H2D of the NEXT batch
+            loss = pipe.run()                   # step on the batch submitted before it
+        loss = pipe.run()
+    """
+
+    def __init__(self, model, optimizer, group=None, use_graph=True, depth=2):
+        self.model, self.opt, self.group, self.use_graph = model, optimizer, group, use_graph
+        self.depth = depth
+        self.steps = [TrainStep(model, optimizer, use_graph=use_graph, group=group) for _ in range(depth)]
+        self.bufs = [None] * depth
+        self.copied = [None] * depth
+        self.done = [None] * depth
+        self.copy_stream = None
+        self.n_sub = 0
+        self.n_run = 0
+        enc = getattr(model, "mm_encoder", None)
+        plan = getattr(enc, "plan", None)
+        self.sel_img = list(plan.layers_img_sel) if plan is not None else None
+        self.sel_text = list(plan.layers_text_sel) if plan is not None else None
+
+    def submit(self, ids, image, text, log_mask):
+        if self.n_sub - self.n_run >= self.depth:
+            raise RuntimeError("PipelinedTrainStep: run() the submitted batches before submitting more")
+        device = next(self.model.parameters()).device
+        k = self.n_sub % self.depth
+        if self.copy_stream is None:
+            self.copy_stream = torch.cuda.Stream(device=device)
+        if self.bufs[k] is None:
+            self.bufs[k] = tuple(torch.zeros(t.shape, dtype=t.dtype, device=device) for t in (ids.reshape(-1), image, text, log_mask))
+            self.copied[k] = torch.cuda.Event()
+            self.done[k] = torch.cuda.Event()
+            self.done[k].record(torch.cuda.current_stream(device))
+        cs = self.copy_stream
+        cs.wait_event(self.done[k])                           # the previous step on this buffer set has consumed it
+        d_ids, d_img, d_txt, d_lm = self.bufs[k]
+        with torch.cuda.stream(cs):
+            d_ids.copy_(ids.reshape(-1), non_blocking=True)
+            d_lm.copy_(log_mask, non_blocking=True)
+            for dst, src, sel in ((d_img, image, self.sel_img), (d_txt, text, self.sel_text)):
+                if (not src.is_cuda) and src.is_pinned() and sel is not None and src.dim() >= 3 and len(sel) < src.shape[-2]:
+                    stage_states_h2d(dst, src, sel, cs)
+                else:
+                    dst.copy_(src, non_blocking=True)
+            self.copied[k].record(cs)
+        self.n_sub += 1
+
+    def run(self):
+        if self.n_run >= self.n_sub:
+            raise RuntimeError("PipelinedTrainStep.run(): nothing submitted")
+        k = self.n_run % self.depth
+        device = self.bufs[k][0].device
+        cur = torch.cuda.current_stream(device)
+        cur.wait_event(self.copied[k])
+        st = self.steps[k]
+        if st.graph is None and self.use_graph:
+            loss = st.capture(*self.bufs[k])
+        elif self.use_graph:
+            loss = st.replay()
+        else:
+            loss = st(*self.bufs[k])
+        self.done[k].record(cur)
+        self.n_run += 1
+        return loss

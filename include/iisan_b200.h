@@ -274,6 +274,14 @@ int iisan_gather_states(const void* table, int32_t dtype, int64_t n_table_items,
                         int32_t d, const int64_t* ids, int32_t n, const int32_t* sel, int32_t n_sel,
                         void* out, iisan_stream_t stream);
 
+/* Host -> device staging of one train batch of cached states with layer selection (CC/run.py:370-374 moves all
+ * `layers` states of every slot; only the `n_sel` layers the towers read are needed).  host_src: PINNED host memory,
+ * [n_rows, layers, d] of `dtype`; dev_dst: device buffer of the same shape -- rows of unselected layers are left untouched
+ * (the kernels never read them).  `sel` is a HOST array, strictly increasing; adjacent layers are merged into one 2-D DMA.
+ * Asynchronous on `stream`. */
+int iisan_stage_states_h2d(const void* host_src, void* dev_dst, int64_t n_rows, int32_t layers, int32_t d, int32_t dtype,
+                           const int32_t* sel, int32_t n_sel, iisan_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
