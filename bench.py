@@ -30,7 +30,7 @@ UNIT = "samples/s"
 ITEM_NUM = 19246          # Instrument catalogue
 SEED = 12345              # reference seed (Code_Cached/scripts/run_IISAN.py:44)
 # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed ncu --set full capture (profiles/), per launch
-TRAFFIC_NCU = None
+TRAFFIC_NCU = {}
 LRS = dict(lr=2e-4, adapter_cv_lr=1e-4, adapter_bert_lr=1e-4, fine_tune_lr_image=1e-4, fine_tune_lr_text=5e-5)
 
 
@@ -337,25 +337,26 @@ def run_ours(a):
     tf_peak = peaks.get("bf16_tflops_sustained", 1400.0)
     peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
     elt = 2 if state_dtype == torch.bfloat16 else 4
-    # Dominant kernel of the hidden-state path: the fused chain forward (one launch per step).  Algorithmic bytes per launch
-    # (DESIGN.md): every selected layer of every item read once = S * (A_i*D_i + A_t*D_t) * sizeof(elt) per sample.
+    # Dominant kernels of the hidden-state path: the fused chain forward and backward (one launch each per step).
+    # Algorithmic bytes per launch: forward = every selected layer of every item read once,
+    # S * (A_i*D_i + A_t*D_t) * sizeof(elt) per sample; the backward re-streams the same layers once for the gate gradients.
     alg_bytes = B * 11 * (7 * 768 + 7 * 768) * elt
-    chain = classes["chain"]
-    if chain["launches_per_step"] > 0:
-        k_ms = chain["ms_per_step"] / chain["launches_per_step"]
-        kname = "san_chain_fwd_kernel (fused gather + gate fusion + adapter chain, forward)"
+
+    def hbm_roof(cls, kname, traffic):
+        c = classes[cls]
+        k_ms = c["ms_per_step"] / c["launches_per_step"] if c["launches_per_step"] > 0 else 0.0
+        r = {"bound": "hbm", "kernel": kname, "achieved": alg_bytes / (k_ms / 1e3) / 1e9 if k_ms > 0 else None, "peak": hbm_peak,
+             "unit": "GB/s", "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": k_ms}
+        r["frac"] = (r["achieved"] / hbm_peak) if r["achieved"] else None
+        return r
+
+    if classes["chain"]["launches_per_step"] > 0:
+        roof = hbm_roof("chain", "san_chain_fwd_kernel (fused layer-select gather + gate fusion + adapter chain, forward)", TRAFFIC_NCU.get("fwd"))
+        roof_bwd = hbm_roof("chain_bwd", "san_chain_bwd_kernel (fused data/gate/bias gradients of the chain)", TRAFFIC_NCU.get("bwd"))
     else:
-        k_ms = classes["stream"]["ms_per_step"]
-        kname = "mix kernels (layer-select gather + gate fusion fwd, gate-grad re-stream bwd), summed"
-        alg_bytes *= 2
-    roof = {
-        "bound": "hbm", "kernel": kname,
-        "achieved": alg_bytes / (k_ms / 1e3) / 1e9 if k_ms > 0 else None,
-        "peak": hbm_peak, "unit": "GB/s", "traffic": TRAFFIC_NCU, "peak_source": peak_src,
-        "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": k_ms,
-    }
-    roof["frac"] = (roof["achieved"] / hbm_peak) if roof["achieved"] else None
-    gemm_ms = classes["gemm"]["ms_per_step"] + classes["chain"]["ms_per_step"]
+        roof = hbm_roof("stream", "mix kernels (layer-select gather + gate fusion fwd, gate-grad re-stream bwd), summed", None)
+        roof_bwd = None
+    gemm_ms = classes["gemm"]["ms_per_step"] + classes["chain"]["ms_per_step"] + classes["chain_bwd"]["ms_per_step"]
     roof_tensor = {"bound": "tensor", "achieved": (B * 11 * 3 * 7987200 / (gemm_ms / 1e3) / 1e12) if gemm_ms > 0 else None,
                    "peak": tf_peak, "unit": "TFLOP/s", "ms_per_step": gemm_ms,
                    "note": "SAN adapter/head GEMM FLOPs (fwd+bwd = 3x 7.99 MFLOP/item) over the summed GEMM-class + chain kernel time"}
@@ -387,7 +388,7 @@ def run_ours(a):
         "gpu_launches": int(launches_per_step * a.steps),
         "gpu_launches_per_step": launches_per_step,
         "clocks": clocks,
-        "roofline": roof, "roofline_tensor": roof_tensor,
+        "roofline": roof, "roofline_chain_bwd": roof_bwd, "roofline_tensor": roof_tensor,
         "kernel_classes": classes, "ms_per_step_eager_with_kernel_events": ms_prof / a.steps,
         "cpu_baseline": cpu, "loss": loss_val,
     }

@@ -13,8 +13,8 @@ MAX_BLOCKS = 8
 ABI_VERSION = 2
 
 F32, BF16, F16 = 0, 1, 2
-K_STREAM, K_GEMM, K_USER, K_CE, K_MISC, K_CHAIN = range(6)
-KERNEL_CLASSES = ("stream", "gemm", "user", "ce", "misc", "chain")
+K_STREAM, K_GEMM, K_USER, K_CE, K_MISC, K_CHAIN, K_CHAIN_BWD = range(7)
+KERNEL_CLASSES = ("stream", "gemm", "user", "ce", "misc", "chain", "chain_bwd")
 COMPUTE_FP32, COMPUTE_BF16 = 0, 1
 
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libiisan_b200.so")

@@ -648,7 +648,7 @@ int launch_san_chain_bwd(const ChainBwdArgs& args, int n_towers, cudaStream_t st
     attr_set = true;
   }
   const int tiles = (args.n_items + CH_ROWS - 1) / CH_ROWS;
-  { LaunchScope ls_(IISAN_K_CHAIN, st); san_chain_bwd_kernel<<<dim3(tiles, n_towers), CH_THREADS, ChainSmem::kTotal, st>>>(args); }
+  { LaunchScope ls_(IISAN_K_CHAIN_BWD, st); san_chain_bwd_kernel<<<dim3(tiles, n_towers), CH_THREADS, ChainSmem::kTotal, st>>>(args); }
   IISAN_LAUNCH_OK();
   return IISAN_OK;
 }

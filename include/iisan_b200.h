@@ -65,8 +65,9 @@ enum iisan_kernel_class {
   IISAN_K_USER = 2,   /* SASRec layer-norm / attention kernels */
   IISAN_K_CE = 3,     /* fused in-batch cross-entropy */
   IISAN_K_MISC = 4,   /* reductions, gathers, optimizer */
-  IISAN_K_CHAIN = 5,  /* fused tcgen05 adapter-chain kernels */
-  IISAN_K_COUNT = 6
+  IISAN_K_CHAIN = 5,  /* fused tcgen05 adapter-chain kernel, forward */
+  IISAN_K_CHAIN_BWD = 6, /* fused tcgen05 adapter-chain kernel, backward */
+  IISAN_K_COUNT = 7
 };
 /* total kernels launched by this process through the library, per class (kclass < 0: all classes) */
 int64_t iisan_launch_count(int kclass);
