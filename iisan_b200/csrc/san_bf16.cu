@@ -132,28 +132,29 @@ struct SanLayoutBf16 {
       const int ta = D.text_adapter[s], ia = D.img_adapter[s], mi = D.mm_index[s];
       if (ta >= 0) {
         t_down[ta] = takew(a, (size_t)D.r_text * D.d_text); t_up[ta] = takew(a, (size_t)D.r_text * D.d_text);
-        x_t[s] = a.take<bf16>(N * D.d_text); z_t[s] = a.take<bf16>(N * D.r_text);
       }
       if (ia >= 0) {
         i_down[ia] = takew(a, (size_t)D.r_img * D.d_img); i_up[ia] = takew(a, (size_t)D.r_img * D.d_img);
-        x_i[s] = a.take<bf16>(N * D.d_img); z_i[s] = a.take<bf16>(N * D.r_img);
       }
       if (mi >= 0) {
         m_down[mi] = takew(a, (size_t)D.r_mm * D.d_mm); m_up[mi] = takew(a, (size_t)D.r_mm * D.d_mm);
-        x_m[s] = a.take<bf16>(N * D.d_mm); z_m[s] = a.take<bf16>(N * D.r_mm);
         if (dimdiff) { dpw[mi] = takew(a, (size_t)D.d_mm * dwide); dpo[s] = a.take<float>(N * D.d_mm); }
       }
     }
-    // last_s of one tower are contiguous over the stages (no 256-byte padding in between: N*d*2 is a multiple of 16 and the
-    // fused backward addresses them as one [A*N, d] matrix)
+    // x_s / z_s / last_s of one tower are contiguous over the stages, each stage padded to the 128-row tile of the fused chain
+    // kernels (which address them as one [A * NP, .] matrix; no 256-byte arena padding in between)
     {
-      bf16* bt = a.take<bf16>((size_t)D.n_stages * N * D.d_text);
-      bf16* bi = a.take<bf16>((size_t)D.n_stages * N * D.d_img);
-      bf16* bm = a.take<bf16>((size_t)D.n_stages * N * D.d_mm);
+      const size_t NP = (size_t)chain_n_pad(D.n_items);
+      bf16* xt = a.take<bf16>((size_t)D.n_stages * NP * D.d_text); bf16* xi = a.take<bf16>((size_t)D.n_stages * NP * D.d_img);
+      bf16* xm = a.take<bf16>((size_t)D.n_stages * NP * D.d_mm);
+      bf16* zt = a.take<bf16>((size_t)D.n_stages * NP * D.r_text); bf16* zi = a.take<bf16>((size_t)D.n_stages * NP * D.r_img);
+      bf16* zm = a.take<bf16>((size_t)D.n_stages * NP * D.r_mm);
+      bf16* bt = a.take<bf16>((size_t)D.n_stages * NP * D.d_text); bf16* bi = a.take<bf16>((size_t)D.n_stages * NP * D.d_img);
+      bf16* bm = a.take<bf16>((size_t)D.n_stages * NP * D.d_mm);
       for (int s = 0; s < D.n_stages; ++s) {
-        if (D.text_adapter[s] >= 0) last_t[s] = bt + (size_t)s * N * D.d_text;
-        if (D.img_adapter[s] >= 0) last_i[s] = bi + (size_t)s * N * D.d_img;
-        if (D.mm_index[s] >= 0) last_m[s] = bm + (size_t)s * N * D.d_mm;
+        if (D.text_adapter[s] >= 0) { x_t[s] = xt + (size_t)s * NP * D.d_text; z_t[s] = zt + (size_t)s * NP * D.r_text; last_t[s] = bt + (size_t)s * NP * D.d_text; }
+        if (D.img_adapter[s] >= 0) { x_i[s] = xi + (size_t)s * NP * D.d_img; z_i[s] = zi + (size_t)s * NP * D.r_img; last_i[s] = bi + (size_t)s * NP * D.d_img; }
+        if (D.mm_index[s] >= 0) { x_m[s] = xm + (size_t)s * NP * D.d_mm; z_m[s] = zm + (size_t)s * NP * D.r_mm; last_m[s] = bm + (size_t)s * NP * D.d_mm; }
       }
     }
     fc_t = takew(a, (size_t)ft * D.d_text); fc_i = takew(a, (size_t)fi * D.d_img); fc_m = takew(a, (size_t)fm * D.d_mm);
@@ -174,8 +175,10 @@ struct SanLayoutBf16 {
       for (int t = 0; t < 3; ++t) {
         wd_pack[t] = a.take<bf16>((size_t)D.n_stages * D.r_mm * D.d_mm);
         wu_pack[t] = a.take<bf16>((size_t)D.n_stages * D.r_mm * D.d_mm);
-        dys[t] = a.take<bf16>((size_t)D.n_stages * N * D.d_mm);
-        for (int s = 0; s < D.n_stages; ++s) dzs[t][s] = a.take<bf16>(N * D.r_mm);
+        const size_t NP = (size_t)chain_n_pad(D.n_items);
+        dys[t] = a.take<bf16>((size_t)D.n_stages * NP * D.d_mm);
+        bf16* dz = a.take<bf16>((size_t)D.n_stages * NP * D.r_mm);
+        for (int s = 0; s < D.n_stages; ++s) dzs[t][s] = dz + (size_t)s * NP * D.r_mm;
       }
     }
     bytes = a.off;
@@ -302,19 +305,18 @@ static int san_forward_bf16_t(const iisan_san_desc* D, const iisan_san_params* P
   if (chain) {
     // ---- all stages of all three towers in one launch (san_chain.cu) ----
     ChainArgs ca{};
-    ca.n_items = N; ca.d = D->d_mm; ca.n_stages = D->n_stages;
-    IISAN_TRY(chain_fill_tower(&ca.tower[0], 0, text, N, (int64_t)D->layers_text * D->d_text, nullptr, 0, L.wd_pack[0], L.wu_pack[0], D->n_stages, D->d_text));
-    IISAN_TRY(chain_fill_tower(&ca.tower[1], 0, image, N, (int64_t)D->layers_img * D->d_img, nullptr, 0, L.wd_pack[1], L.wu_pack[1], D->n_stages, D->d_img));
-    IISAN_TRY(chain_fill_tower(&ca.tower[2], 1, image, N, (int64_t)D->layers_img * D->d_img, text, (int64_t)D->layers_text * D->d_text, L.wd_pack[2], L.wu_pack[2], D->n_stages, D->d_mm));
+    ca.n_items = N; ca.n_pad = chain_n_pad(N); ca.d = D->d_mm; ca.n_stages = D->n_stages;
+    IISAN_TRY(chain_fill_tower(&ca.tower[0], 0, text, N, (int64_t)D->layers_text * D->d_text, nullptr, 0, L.wd_pack[0], L.wu_pack[0], L.x_t[0], L.last_t[0], L.z_t[0], D->n_stages, D->d_text));
+    IISAN_TRY(chain_fill_tower(&ca.tower[1], 0, image, N, (int64_t)D->layers_img * D->d_img, nullptr, 0, L.wd_pack[1], L.wu_pack[1], L.x_i[0], L.last_i[0], L.z_i[0], D->n_stages, D->d_img));
+    IISAN_TRY(chain_fill_tower(&ca.tower[2], 1, image, N, (int64_t)D->layers_img * D->d_img, text, (int64_t)D->layers_text * D->d_text, L.wd_pack[2], L.wu_pack[2], L.x_m[0], L.last_m[0], L.z_m[0], D->n_stages, D->d_mm));
+    ca.tower[0].store_last = 1; ca.tower[1].store_last = 1;      // the backward of the intra-modal towers reads last_{s-1}
+    ca.tower[2].store_last = 0;                                  // the inter-modal gate gradient only needs the raw states
     for (int s = 0; s < D->n_stages; ++s) {
       const int ta = D->text_adapter[s], ia = D->img_adapter[s], mi = D->mm_index[s];
       ChainTower& t0 = ca.tower[0]; ChainTower& t1 = ca.tower[1]; ChainTower& t2 = ca.tower[2];
       t0.layer[s] = D->text_layer[s]; t0.gate[s] = P->gate_text[ta]; t0.b_down[s] = P->text[ta].b_down; t0.b_up[s] = P->text[ta].b_up;
-      t0.x_stash[s] = L.x_t[s]; t0.z_stash[s] = L.z_t[s]; t0.last_stash[s] = L.last_t[s];
       t1.layer[s] = D->img_layer[s]; t1.gate[s] = P->gate_img[ia]; t1.b_down[s] = P->img[ia].b_down; t1.b_up[s] = P->img[ia].b_up;
-      t1.x_stash[s] = L.x_i[s]; t1.z_stash[s] = L.z_i[s]; t1.last_stash[s] = L.last_i[s];
       t2.layer[s] = D->img_layer[s]; t2.layer2[s] = D->text_layer[s]; t2.gate[s] = P->gate_mm[mi]; t2.b_down[s] = P->mm[mi].b_down; t2.b_up[s] = P->mm[mi].b_up;
-      t2.x_stash[s] = L.x_m[s]; t2.z_stash[s] = L.z_m[s]; t2.last_stash[s] = L.last_m[s];
     }
     IISAN_TRY(launch_san_chain_fwd(ca, 3, st));
     last_t = L.last_t[D->n_stages - 1]; last_i = L.last_i[D->n_stages - 1]; last_m = L.last_m[D->n_stages - 1];
@@ -454,7 +456,7 @@ static int san_backward_bf16_t(const iisan_san_desc* D, const iisan_san_params* 
     cf.p[2] = {nullptr, fm, N, fm, G->fc_mm.b, L.dhead_m};
     IISAN_TRY(launch_colsum(cf, st));
     UmmaBatch dl{}; dl.n = 3;  // d last = d head W_fc
-    const size_t lastoff = (size_t)(D->n_stages - 1) * N * D->d_mm;
+    const size_t lastoff = (size_t)(D->n_stages - 1) * chain_n_pad(N) * D->d_mm;
     dl.p[0] = mk_linear(L.dhead_i, fi, L.fc_i.wt, N, D->d_img, fi);
     dl.p[1] = mk_linear(L.dhead_t, ft, L.fc_t.wt, N, D->d_text, ft);
     dl.p[2] = mk_linear(L.dhead_m, fm, L.fc_m.wt, N, D->d_mm, fm);
@@ -472,26 +474,23 @@ static int san_backward_bf16_t(const iisan_san_desc* D, const iisan_san_params* 
   if (chain) {
     // ---- data / gate / bias gradients of all stages and towers in one launch (san_chain.cu) ----
     ChainBwdArgs ca{};
-    ca.n_items = N; ca.d = D->d_mm; ca.n_stages = D->n_stages;
-    IISAN_TRY(chain_fill_bwd_tower(&ca.tower[0], 0, text, N, (int64_t)D->layers_text * D->d_text, nullptr, 0, L.wd_pack[0], L.wu_pack[0], L.dys[0], L.last_t[0], D->n_stages, D->d_text));
-    IISAN_TRY(chain_fill_bwd_tower(&ca.tower[1], 0, image, N, (int64_t)D->layers_img * D->d_img, nullptr, 0, L.wd_pack[1], L.wu_pack[1], L.dys[1], L.last_i[0], D->n_stages, D->d_img));
-    IISAN_TRY(chain_fill_bwd_tower(&ca.tower[2], 1, image, N, (int64_t)D->layers_img * D->d_img, text, (int64_t)D->layers_text * D->d_text, L.wd_pack[2], L.wu_pack[2], L.dys[2], L.last_m[0], D->n_stages, D->d_mm));
+    ca.n_items = N; ca.n_pad = chain_n_pad(N); ca.d = D->d_mm; ca.n_stages = D->n_stages;
+    IISAN_TRY(chain_fill_bwd_tower(&ca.tower[0], 0, text, N, (int64_t)D->layers_text * D->d_text, nullptr, 0, L.wd_pack[0], L.wu_pack[0], L.dys[0], L.last_t[0], L.dzs[0][0], D->n_stages, D->d_text));
+    IISAN_TRY(chain_fill_bwd_tower(&ca.tower[1], 0, image, N, (int64_t)D->layers_img * D->d_img, nullptr, 0, L.wd_pack[1], L.wu_pack[1], L.dys[1], L.last_i[0], L.dzs[1][0], D->n_stages, D->d_img));
+    IISAN_TRY(chain_fill_bwd_tower(&ca.tower[2], 1, image, N, (int64_t)D->layers_img * D->d_img, text, (int64_t)D->layers_text * D->d_text, L.wd_pack[2], L.wu_pack[2], L.dys[2], L.last_m[0], L.dzs[2][0], D->n_stages, D->d_mm));
+    ca.tower[0].z_stash = L.z_t[0]; ca.tower[1].z_stash = L.z_i[0]; ca.tower[2].z_stash = L.z_m[0];
     for (int s = 0; s < D->n_stages; ++s) {
       const int ta = D->text_adapter[s], ia = D->img_adapter[s], mi = D->mm_index[s];
       ChainBwdTower& t0 = ca.tower[0]; ChainBwdTower& t1 = ca.tower[1]; ChainBwdTower& t2 = ca.tower[2];
       t0.layer[s] = D->text_layer[s]; t0.gate[s] = P->gate_text[ta]; t0.g_gate[s] = G->gate_text[ta]; t0.g_b_down[s] = G->text[ta].b_down; t0.g_b_up[s] = G->text[ta].b_up;
-      t0.z_stash[s] = L.z_t[s]; t0.dz_stash[s] = L.dzs[0][s];
       t1.layer[s] = D->img_layer[s]; t1.gate[s] = P->gate_img[ia]; t1.g_gate[s] = G->gate_img[ia]; t1.g_b_down[s] = G->img[ia].b_down; t1.g_b_up[s] = G->img[ia].b_up;
-      t1.z_stash[s] = L.z_i[s]; t1.dz_stash[s] = L.dzs[1][s];
       t2.layer[s] = D->img_layer[s]; t2.layer2[s] = D->text_layer[s]; t2.gate[s] = P->gate_mm[mi]; t2.g_gate[s] = G->gate_mm[mi]; t2.g_b_down[s] = G->mm[mi].b_down; t2.g_b_up[s] = G->mm[mi].b_up;
-      t2.z_stash[s] = L.z_m[s]; t2.dz_stash[s] = L.dzs[2][s];
     }
-    ca.tower[0].dy_stash = L.dys[0]; ca.tower[1].dy_stash = L.dys[1]; ca.tower[2].dy_stash = L.dys[2];
     IISAN_TRY(launch_san_chain_bwd(ca, 3, st));
     // ---- weight gradients: reductions over all items, split-K GEMMs over the stashes ----
     for (int s = D->n_stages - 1; s >= 0; --s) {
       const int ta = D->text_adapter[s], ia = D->img_adapter[s], mi = D->mm_index[s];
-      const size_t off = (size_t)s * N * D->d_mm;
+      const size_t off = (size_t)s * chain_n_pad(N) * D->d_mm;
       UmmaBatch wu{}, wd{}; wu.n = wd.n = 3;
       wu.p[0] = mk_wgrad(L.dys[0] + off, D->d_text, D->d_text, L.z_t[s], D->r_text, D->r_text, N, G->text[ta].w_up, 3);
       wu.p[1] = mk_wgrad(L.dys[1] + off, D->d_img, D->d_img, L.z_i[s], D->r_img, D->r_img, N, G->img[ia].w_up, 3);

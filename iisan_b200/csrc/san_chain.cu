@@ -1,20 +1,29 @@
-// Fused side-adapter chain, forward (fast mode, symmetric configurations: d_text == d_img, r == 64, every tower active in
-// every stage, bf16 cached states).  One CTA owns 128 items of ONE tower and walks all A stages without leaving the SM:
+// Fused side-adapter chain (fast mode, symmetric configurations: d_text == d_img, r == 64, every tower active in every
+// stage, bf16 cached states).  One CTA owns 128 items of ONE tower and walks all A stages without leaving the SM.
 //
-//   x_0       = fuse(h_0, 0)                                   gated fusion   CC/model/model.py:319-326 (mm: :335-337)
-//   z_s       = relu(x_s Wd_s^T + bd_s)                        AdapterBlock   CC/model/modules.py:113-116
+// forward                                                          reference
+//   x_0       = fuse(h_0, 0)                                       gated fusion   CC/model/model.py:319-326 (mm: :335-337)
+//   z_s       = relu(x_s Wd_s^T + bd_s)                            AdapterBlock   CC/model/modules.py:113-116
 //   last_s    = z_s Wu_s^T + bu_s + x_s
-//   x_{s+1}   = fuse(h_{s+1}, last_s)                          (mm tower: last_s + g h_cv + (1-g) h_text)
+//   x_{s+1}   = fuse(h_{s+1}, last_s)                              (mm tower: last_s + g h_cv + (1-g) h_text)
+// backward (data / gate / bias gradients; weight gradients are reductions over ALL items and stay split-K GEMMs over the
+// stashes written here)
+//   dz_s      = (dy_s Wu_s) * (z_s > 0)                            dy_s = d last_s
+//   dx_s      = dy_s + dz_s Wd_s
+//   dgate_s  += sum dx_s * (h_s - last_{s-1})                      (mm: h_cv - h_text), times g(1-g)/0.1
+//   dy_{s-1}  = (1 - g_s) dx_s                                     (mm: dx_s)
 //
-// The running state never exists as a whole on chip (128 x 768 fp32 is larger than TMEM); it streams through 64-column
-// chunks instead.  For chunk c of stage s the up-projection tile U_c = z_s Wu_s[c]^T is one tcgen05.mma group into a
-// double-buffered TMEM accumulator; the epilogue warps add bias and residual, fuse the next stage's hidden-state chunk (TMA
-// ring, read in place from the caller's [N, layers, d] tensor: only selected layers are ever touched), and write the bf16
-// result both to the backward stash and, 128B-swizzled, to shared memory where it is immediately the A operand of the next
-// stage's down-projection MMA (z_{s+1} accumulates in TMEM across the chunks).  Per item and stage the kernel moves the
-// compulsory bytes only: one read of h (two for the inter-modal tower), one write of the x stash (+ z), weights from L2.
+// The running state never exists as a whole on chip (128 x 768 fp32 exceeds TMEM); it streams through 64-column chunks.
+// For chunk c the per-chunk product (U_c = z_s Wu_s[c]^T, resp. dz_s Wd_s[:, c]) is one tcgen05.mma group into a
+// double-buffered TMEM accumulator; the 8 epilogue warps add bias / residual, fuse the next hidden-state chunk and write
+// the bf16 result 128B-swizzled into shared memory, where it is at once (i) the A operand of the next stage's accumulation
+// over the chunks (z_{s+1}, resp. dz_{s-1}, accumulates in TMEM) and (ii) the source of a TMA store into the stash.
+// All global traffic is TMA: the cached states are read in place from the caller's [N, layers, d] tensors (row pitch
+// layers*d: only selected layers are ever touched), the stashes are written by bulk tensor stores and read back one stage
+// later through the same ring (ordered by cp.async.bulk.wait_group on the issuing thread + the ring's mbarrier chain,
+// whose depth of ~2 chunks is far below the 12 chunks between a write and its re-read).
 //
-// warp roles: 0 weight TMA producer | 1 TMEM allocator + MMA issuer | 2 hidden-state TMA producer | 3..10 epilogue
+// warp roles: 0 weight TMA producer | 1 TMEM allocator + MMA issuer + TMA stores | 2 data TMA producer | 3..10 epilogue
 #include "common.cuh"
 #include "launch.cuh"
 #include "san_chain.cuh"
@@ -27,25 +36,34 @@ using bf16 = __nv_bfloat16;
 
 constexpr int CH_ROWS = 128;
 constexpr int CH_CW = 64;                    // chunk width (columns) == one 128-byte swizzle atom
-constexpr int CH_R = 64;                     // adapter bottleneck handled by this kernel
-constexpr int CH_NW = 4;                     // weight ring (units)
-constexpr int CH_NH = 6;                     // hidden-state ring (tiles)
+constexpr int CH_R = 64;                     // adapter bottleneck handled by these kernels
+constexpr int CH_NW = 3;                     // weight ring (units of two 8 KB chunks)
+constexpr int CH_NH = 5;                     // data ring (16 KB tiles)
 constexpr int CH_THREADS = 352;              // 11 warps
-constexpr int CH_TILE_BYTES = CH_ROWS * CH_CW * 2;   // 16 KB : h tile, x k-block, z operand
-constexpr int CH_W_BYTES = CH_CW * CH_R * 2;         // 8 KB  : one weight chunk (Wu or Wd)
+constexpr int CH_TILE_BYTES = CH_ROWS * CH_CW * 2;   // 16 KB
+constexpr int CH_W_BYTES = CH_CW * CH_R * 2;         // 8 KB
 constexpr int CH_TMEM_COLS = 256;
-constexpr int CH_ZACC = 0, CH_UACC = 64;     // TMEM columns: z accumulator, two U accumulators
+constexpr int CH_ZACC = 0, CH_UACC = 64;     // TMEM columns: z (dz) accumulator, two chunk accumulators
 
 struct ChainSmem {
-  static constexpr int kZ = 0;                                   // z operand [128 x 64]
-  static constexpr int kXk = kZ + CH_TILE_BYTES;                 // 2 x-chunk operands
-  static constexpr int kW = kXk + 2 * CH_TILE_BYTES;             // CH_NW x (Wu chunk | Wd chunk)
-  static constexpr int kH = kW + CH_NW * 2 * CH_W_BYTES;         // CH_NH hidden-state tiles
+  static constexpr int kZ = 0;                                   // z / dz operand [128 x 64]
+  static constexpr int kXk = kZ + CH_TILE_BYTES;                 // 2 chunk operands (x_{s+1}[c], resp. dy_{s-1}[c])
+  static constexpr int kLk = kXk + 2 * CH_TILE_BYTES;            // 2 staging tiles of last_s[c] (forward)
+  static constexpr int kW = kLk + 2 * CH_TILE_BYTES;             // CH_NW x (chunk | chunk)
+  static constexpr int kH = kW + CH_NW * 2 * CH_W_BYTES;         // CH_NH data tiles
   static constexpr int kBar = kH + CH_NH * CH_TILE_BYTES;
   static constexpr int kTotal = kBar + 512 + 1024;
 };
 
-__device__ __forceinline__ void chain_epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_3() { asm volatile("cp.async.bulk.wait_group 3;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 __device__ __forceinline__ void unpack8(const uint4& q, float* f) {
   const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
@@ -60,45 +78,68 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
   return q;
 }
 
-__global__ void __launch_bounds__(CH_THREADS, 1) san_chain_fwd_kernel(const __grid_constant__ ChainArgs a) {
-  const ChainTower& T = a.tower[blockIdx.y];
-  const bool is_mm = (T.mode == 1);
-  const int NC = a.d / CH_CW;
-  const int A = a.n_stages;
-  const int m0 = blockIdx.x * CH_ROWS;
+// sum over the 32 lanes of v[k] for each k: lane l ends with the total of column l (31 shuffles)
+__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int k = 0; k < off; ++k) {
+      const float send = upper ? v[k] : v[k + off];
+      const float recv = __shfl_xor_sync(0xffffffffu, send, off);
+      v[k] = (upper ? v[k + off] : v[k]) + recv;
+    }
+  }
+  return v[0];
+}
 
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ChainSmem::kBar);
-  uint64_t* w_full = bars;                       // CH_NW
-  uint64_t* w_empty = w_full + CH_NW;            // CH_NW
-  uint64_t* h_full = w_empty + CH_NW;            // CH_NH
-  uint64_t* h_empty = h_full + CH_NH;            // CH_NH
-  uint64_t* xk_full = h_empty + CH_NH;           // 2
-  uint64_t* xk_empty = xk_full + 2;              // 2
-  uint64_t* u_full = xk_empty + 2;               // 2
-  uint64_t* u_empty = u_full + 2;                // 2
-  uint64_t* z_full = u_empty + 2;                // 1
-  uint64_t* z_ready = z_full + 1;                // 1
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(z_ready + 1);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (threadIdx.x == 0) {
-    tma_prefetch_desc(&T.map_wd); tma_prefetch_desc(&T.map_wu); tma_prefetch_desc(&T.map_h);
-    if (is_mm) tma_prefetch_desc(&T.map_h2);
+struct ChainBars {
+  uint64_t *w_full, *w_empty, *h_full, *h_empty, *xk_full, *xk_empty, *u_full, *u_empty, *z_full, *z_ready;
+  uint32_t* tmem_slot;
+  __device__ explicit ChainBars(uint8_t* smem) {
+    uint64_t* b = reinterpret_cast<uint64_t*>(smem + ChainSmem::kBar);
+    w_full = b; w_empty = w_full + CH_NW; h_full = w_empty + CH_NW; h_empty = h_full + CH_NH;
+    xk_full = h_empty + CH_NH; xk_empty = xk_full + 2; u_full = xk_empty + 2; u_empty = u_full + 2;
+    z_full = u_empty + 2; z_ready = z_full + 1;
+    tmem_slot = reinterpret_cast<uint32_t*>(z_ready + 1);
+  }
+  __device__ void init() {
     for (int i = 0; i < CH_NW; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
     for (int i = 0; i < CH_NH; ++i) { mbar_init(&h_full[i], 1); mbar_init(&h_empty[i], 8); }
     for (int i = 0; i < 2; ++i) { mbar_init(&xk_full[i], 8); mbar_init(&xk_empty[i], 1); mbar_init(&u_full[i], 1); mbar_init(&u_empty[i], 8); }
     mbar_init(z_full, 1); mbar_init(z_ready, 8);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, CH_TMEM_COLS);
+};
+
+// ================================================================================================================
+// forward
+// ================================================================================================================
+__global__ void __launch_bounds__(CH_THREADS, 1) san_chain_fwd_kernel(const __grid_constant__ ChainArgs a) {
+  const ChainTower& T = a.tower[blockIdx.y];
+  const bool is_mm = (T.mode == 1);
+  const int NC = a.d / CH_CW;
+  const int A = a.n_stages;
+  const int m0 = blockIdx.x * CH_ROWS;
+  const int NP = a.n_pad;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  ChainBars B(smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&T.map_wd); tma_prefetch_desc(&T.map_wu); tma_prefetch_desc(&T.map_h); tma_prefetch_desc(&T.map_x);
+    tma_prefetch_desc(&T.map_last); tma_prefetch_desc(&T.map_z);
+    if (is_mm) tma_prefetch_desc(&T.map_h2);
+    B.init();
+  }
+  if (warp == 1) tmem_alloc(B.tmem_slot, CH_TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = *B.tmem_slot;
 
-  // unit u = (sv + 1) * NC + c, sv = -1 .. A-1 : Wu_sv[c] (sv >= 0) and Wd_{sv+1}[c] (sv+1 < A) ; hidden tiles of x_{sv+1}[c]
+  // unit u = (sv + 1) * NC + c, sv = -1 .. A-1 : first half Wu_sv[c] (sv >= 0), second half Wd_{sv+1}[c] (sv+1 < A)
   const int n_units = (A + 1) * NC;
 
   if (warp == 0) {
@@ -108,81 +149,112 @@ __global__ void __launch_bounds__(CH_THREADS, 1) san_chain_fwd_kernel(const __gr
         const int sv = u / NC - 1, c = u % NC;
         const int slot = u % CH_NW; const uint32_t ph = (uint32_t)(u / CH_NW) & 1u;
         const bool has_wu = sv >= 0, has_wd = sv + 1 < A;
-        if (!has_wu && !has_wd) continue;
-        mbar_wait(&w_empty[slot], ph ^ 1u);
+        mbar_wait(&B.w_empty[slot], ph ^ 1u);
         uint8_t* dst = smem + ChainSmem::kW + slot * 2 * CH_W_BYTES;
-        mbar_expect_tx(&w_full[slot], (has_wu ? CH_W_BYTES : 0) + (has_wd ? CH_W_BYTES : 0));
-        if (has_wu) tma_load_2d(dst, &T.map_wu, &w_full[slot], 0, sv * a.d + c * CH_CW);                 // Wu_sv rows [c*64, +64), all r
-        if (has_wd) tma_load_2d(dst + CH_W_BYTES, &T.map_wd, &w_full[slot], c * CH_CW, (sv + 1) * CH_R);  // Wd_{sv+1} all r rows, cols chunk
+        mbar_expect_tx(&B.w_full[slot], (has_wu ? CH_W_BYTES : 0) + (has_wd ? CH_W_BYTES : 0));
+        if (has_wu) tma_load_2d(dst, &T.map_wu, &B.w_full[slot], 0, sv * a.d + c * CH_CW);                 // Wu_sv rows [c*64, +64), all r
+        if (has_wd) tma_load_2d(dst + CH_W_BYTES, &T.map_wd, &B.w_full[slot], c * CH_CW, (sv + 1) * CH_R);  // Wd_{sv+1}: all r rows, chunk cols
       }
     }
   } else if (warp == 2) {
-    // ===================== hidden-state producer =====================
+    // ===================== data producer =====================
     if (elect_one()) {
       int n_h = 0;
+      auto load = [&](const CUtensorMap* m, int col, int row) {
+        const int slot = n_h % CH_NH; const uint32_t ph = (uint32_t)(n_h / CH_NH) & 1u;
+        mbar_wait(&B.h_empty[slot], ph ^ 1u);
+        mbar_expect_tx(&B.h_full[slot], CH_TILE_BYTES);
+        tma_load_2d(smem + ChainSmem::kH + slot * CH_TILE_BYTES, m, &B.h_full[slot], col, row);
+        ++n_h;
+      };
+      // consumption order of the epilogue: x_0[c] needs h_0[c] ; chunk c of stage s needs the residual x_s[c] (stored by this
+      // CTA one stage earlier) and, unless s is the last stage, h_{s+1}[c]
+      for (int c = 0; c < NC; ++c) {
+        load(&T.map_h, T.layer[0] * a.d + c * CH_CW, m0);
+        if (is_mm) load(&T.map_h2, T.layer2[0] * a.d + c * CH_CW, m0);
+      }
       for (int s = 0; s < A; ++s) {
         for (int c = 0; c < NC; ++c) {
-          for (int k = 0; k < (is_mm ? 2 : 1); ++k) {
-            const int slot = n_h % CH_NH; const uint32_t ph = (uint32_t)(n_h / CH_NH) & 1u;
-            mbar_wait(&h_empty[slot], ph ^ 1u);
-            mbar_expect_tx(&h_full[slot], CH_TILE_BYTES);
-            const CUtensorMap* m = (k == 0) ? &T.map_h : &T.map_h2;
-            const int layer = (k == 0) ? T.layer[s] : T.layer2[s];
-            tma_load_2d(smem + ChainSmem::kH + slot * CH_TILE_BYTES, m, &h_full[slot], layer * a.d + c * CH_CW, m0);
-            ++n_h;
+          load(&T.map_x, c * CH_CW, s * NP + m0);
+          if (s + 1 < A) {
+            load(&T.map_h, T.layer[s + 1] * a.d + c * CH_CW, m0);
+            if (is_mm) load(&T.map_h2, T.layer2[s + 1] * a.d + c * CH_CW, m0);
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
+    // ===================== MMA issuer + TMA stores =====================
     if (elect_one()) {
-      constexpr uint32_t idesc = instr_desc_bf16(CH_ROWS, 64, 0, 0);   // [128 x 64] += A (K-major) x B^T (K-major), K = 64
+      constexpr uint32_t idesc = instr_desc_bf16(CH_ROWS, 64, 0, 0);   // [128 x 64] (+)= A (K-major) x B^T (K-major), K = 64
       const uint32_t sz = smem_u32(smem + ChainSmem::kZ);
-      int n_x = 0;     // x-chunk operands consumed
-      int n_u = 0;     // U accumulators produced
-      auto down = [&](int unit, int c) {        // z_acc (+)= xk x Wd[c]^T
+      int n_x = 0, n_u = 0;
+      // chunk c of x_{sx} (and last_{sx-1} when staged) is in xk[b] / lk[b]: store it, feed z_acc (+)= xk x Wd_{sx}[c]^T
+      auto down = [&](int unit, int c, int sx, bool with_last) {
         const int b = n_x & 1; const uint32_t ph = (uint32_t)(n_x >> 1) & 1u;
         const int slot = unit % CH_NW;
-        mbar_wait(&xk_full[b], ph);
+        mbar_wait(&B.xk_full[b], ph);
         tc_fence_after();
-        const uint32_t sx = smem_u32(smem + ChainSmem::kXk + b * CH_TILE_BYTES);
+        const uint8_t* xk = smem + ChainSmem::kXk + b * CH_TILE_BYTES;
+        tma_store_2d(&T.map_x, xk, c * CH_CW, sx * NP + m0);
+        if (with_last) tma_store_2d(&T.map_last, smem + ChainSmem::kLk + b * CH_TILE_BYTES, c * CH_CW, (sx - 1) * NP + m0);
+        bulk_commit();
+        const uint32_t sx_a = smem_u32(xk);
         const uint32_t sw = smem_u32(smem + ChainSmem::kW + slot * 2 * CH_W_BYTES + CH_W_BYTES);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          mma_bf16_ss(tmem_base + CH_ZACC, smem_desc_sw128(sx + k * 32, 16, 1024), smem_desc_sw128(sw + k * 32, 16, 1024), idesc, (c > 0 || k > 0) ? 1u : 0u);
-        mma_commit(&xk_empty[b]);
-        mma_commit(&w_empty[slot]);
+          mma_bf16_ss(tmem_base + CH_ZACC, smem_desc_sw128(sx_a + k * 32, 16, 1024), smem_desc_sw128(sw + k * 32, 16, 1024), idesc, (c > 0 || k > 0) ? 1u : 0u);
+        bulk_wait_read0();                           // the stores have read their tiles: the buffers are free once the MMAs retire
+        bulk_wait_3();                               // stores older than 3 chunks are complete in memory (re-read 9+ chunks later)
+        mma_commit(&B.xk_empty[b]);
+        mma_commit(&B.w_empty[slot]);
         ++n_x;
       };
-      // stage "-1": x_0 chunks arrive from the epilogue warps
-      for (int c = 0; c < NC; ++c) {
+      // final stage: only last_{A-1}[c] sits in lk[b]
+      auto flush_last = [&](int c) {
+        const int b = n_x & 1; const uint32_t ph = (uint32_t)(n_x >> 1) & 1u;
+        mbar_wait(&B.xk_full[b], ph);
+        tma_store_2d(&T.map_last, smem + ChainSmem::kLk + b * CH_TILE_BYTES, c * CH_CW, (A - 1) * NP + m0);
+        bulk_commit();
+        bulk_wait_read0();
+        mbar_arrive(&B.xk_empty[b]);
+        ++n_x;
+      };
+      for (int c = 0; c < NC; ++c) {                 // x_0 chunks arrive from the epilogue warps
         const int unit = c; const uint32_t wph = (uint32_t)(unit / CH_NW) & 1u;
-        mbar_wait(&w_full[unit % CH_NW], wph);
-        down(unit, c);
+        mbar_wait(&B.w_full[unit % CH_NW], wph);
+        down(unit, c, 0, false);
       }
-      mma_commit(z_full);
+      mma_commit(B.z_full);
       for (int s = 0; s < A; ++s) {
         const bool more = s + 1 < A;
-        mbar_wait(z_ready, (uint32_t)s & 1u);
+        mbar_wait(B.z_ready, (uint32_t)s & 1u);
         tc_fence_after();
+        tma_store_2d(&T.map_z, smem + ChainSmem::kZ, 0, s * NP + m0);   // z_s stash
+        bulk_commit();
         for (int c = 0; c < NC; ++c) {
           const int unit = (s + 1) * NC + c; const int slot = unit % CH_NW; const uint32_t wph = (uint32_t)(unit / CH_NW) & 1u;
           const int b = n_u & 1; const uint32_t uph = (uint32_t)(n_u >> 1) & 1u;
-          mbar_wait(&w_full[slot], wph);
-          mbar_wait(&u_empty[b], uph ^ 1u);
+          mbar_wait(&B.w_full[slot], wph);
+          mbar_wait(&B.u_empty[b], uph ^ 1u);
           tc_fence_after();
           const uint32_t sw = smem_u32(smem + ChainSmem::kW + slot * 2 * CH_W_BYTES);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             mma_bf16_ss(tmem_base + CH_UACC + b * 64, smem_desc_sw128(sz + k * 32, 16, 1024), smem_desc_sw128(sw + k * 32, 16, 1024), idesc, k > 0 ? 1u : 0u);
-          mma_commit(&u_full[b]);
+          mma_commit(&B.u_full[b]);
           ++n_u;
-          if (!more) mma_commit(&w_empty[slot]);                 // last stage: only Wu lives in the slot
-          else if (c >= 1) down(unit - 1, c - 1);                // overlap: the previous chunk's down-projection
+          if (!more) {
+            mma_commit(&B.w_empty[slot]);                        // last stage: only Wu lives in the slot
+            if (c >= 1) flush_last(c - 1);
+          } else if (c >= 1) {
+            down(unit - 1, c - 1, s + 1, T.store_last != 0);     // overlap: the previous chunk's down-projection
+          }
         }
-        if (more) { down((s + 1) * NC + NC - 1, NC - 1); mma_commit(z_full); }
+        if (more) { down((s + 1) * NC + NC - 1, NC - 1, s + 1, T.store_last != 0); mma_commit(B.z_full); }
+        else flush_last(NC - 1);
       }
+      bulk_wait_0();
     }
   } else {
     // ===================== epilogue warps =====================
@@ -190,37 +262,34 @@ __global__ void __launch_bounds__(CH_THREADS, 1) san_chain_fwd_kernel(const __gr
     const int quad = warp & 3;                // TMEM lane quadrant
     const int hf = ew >> 2;                   // which 32 of the chunk's 64 columns
     const int m = quad * 32 + lane;           // row inside the tile
-    const int64_t row = (int64_t)m0 + m;
-    const bool row_ok = row < a.n_items;
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
     const int sw_row = (m >> 3) * 1024 + (m & 7) * 128;      // byte offset of row m inside a swizzled [128 x 64] bf16 tile
     int n_h = 0, n_x = 0, n_u = 0;
 
-    // x chunk -> stash (global) and A operand (shared, swizzled); signals the MMA warp
-    auto emit_x = [&](const float* xv, bf16* stash, int c) {
-      const int b = n_x & 1; const uint32_t ph = (uint32_t)(n_x >> 1) & 1u;
-      mbar_wait(&xk_empty[b], ph ^ 1u);
-      uint8_t* tile = smem + ChainSmem::kXk + b * CH_TILE_BYTES + sw_row;
+    auto put_tile = [&](uint8_t* tile_base, const float* v) {
+      uint8_t* tile = tile_base + sw_row;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const uint4 pk = pack8(xv + q * 8);
-        *reinterpret_cast<uint4*>(tile + (((hf * 4 + q) ^ (m & 7)) << 4)) = pk;
-        if (row_ok) *reinterpret_cast<uint4*>(stash + row * a.d + c * CH_CW + hf * 32 + q * 8) = pk;
-      }
+      for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4*>(tile + (((hf * 4 + q) ^ (m & 7)) << 4)) = pack8(v + q * 8);
+    };
+    // x chunk (and optionally the last chunk) -> swizzled shared memory; signals the MMA / store thread
+    auto emit = [&](const float (&xv)[32], const float (&lv)[32], bool has_x, bool has_l) {
+      const int b = n_x & 1; const uint32_t ph = (uint32_t)(n_x >> 1) & 1u;
+      mbar_wait(&B.xk_empty[b], ph ^ 1u);
+      if (has_x) put_tile(smem + ChainSmem::kXk + b * CH_TILE_BYTES, xv);
+      if (has_l) put_tile(smem + ChainSmem::kLk + b * CH_TILE_BYTES, lv);
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&xk_full[b]);
+      if (lane == 0) mbar_arrive(&B.xk_full[b]);
       ++n_x;
     };
-    // read this thread's 32 columns of a hidden-state tile
-    auto read_h = [&](float* hv) {
+    auto read_h = [&](float* hv) {            // this thread's 32 columns of the next ring tile
       const int slot = n_h % CH_NH; const uint32_t ph = (uint32_t)(n_h / CH_NH) & 1u;
-      mbar_wait(&h_full[slot], ph);
+      mbar_wait(&B.h_full[slot], ph);
       const uint8_t* tile = smem + ChainSmem::kH + slot * CH_TILE_BYTES + sw_row;
 #pragma unroll
       for (int q = 0; q < 4; ++q) unpack8(*reinterpret_cast<const uint4*>(tile + (((hf * 4 + q) ^ (m & 7)) << 4)), hv + q * 8);
       __syncwarp();
-      if (lane == 0) mbar_arrive(&h_empty[slot]);
+      if (lane == 0) mbar_arrive(&B.h_empty[slot]);
       ++n_h;
     };
 
@@ -240,14 +309,14 @@ __global__ void __launch_bounds__(CH_THREADS, 1) san_chain_fwd_kernel(const __gr
 #pragma unroll
           for (int k = 0; k < 32; ++k) xv[k] = __fmul_rn(g, hv[k]);
         }
-        emit_x(xv, T.x_stash[0], c);
+        emit(xv, xv, true, false);
       }
     }
     for (int s = 0; s < A; ++s) {
       const bool more = s + 1 < A;
-      // ---- z_s = relu(zacc + bd) -> A operand + stash ----
+      // ---- z_s = relu(zacc + bd) -> A operand (the MMA thread also stores it to the stash) ----
       {
-        mbar_wait(z_full, (uint32_t)s & 1u);
+        mbar_wait(B.z_full, (uint32_t)s & 1u);
         tc_fence_after();
         uint32_t raw[32];
         tmem_ld_32x32(tmem_base + lane_addr + (uint32_t)(CH_ZACC + hf * 32), raw);
@@ -260,41 +329,27 @@ __global__ void __launch_bounds__(CH_THREADS, 1) san_chain_fwd_kernel(const __gr
           zv[4 * q] = fmaxf(__uint_as_float(raw[4 * q]) + bq.x, 0.f); zv[4 * q + 1] = fmaxf(__uint_as_float(raw[4 * q + 1]) + bq.y, 0.f);
           zv[4 * q + 2] = fmaxf(__uint_as_float(raw[4 * q + 2]) + bq.z, 0.f); zv[4 * q + 3] = fmaxf(__uint_as_float(raw[4 * q + 3]) + bq.w, 0.f);
         }
-        uint8_t* tile = smem + ChainSmem::kZ + sw_row;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const uint4 pk = pack8(zv + q * 8);
-          *reinterpret_cast<uint4*>(tile + (((hf * 4 + q) ^ (m & 7)) << 4)) = pk;
-          if (row_ok) *reinterpret_cast<uint4*>(T.z_stash[s] + row * CH_R + hf * 32 + q * 8) = pk;
-        }
+        put_tile(smem + ChainSmem::kZ, zv);
         tc_fence_before();
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) mbar_arrive(z_ready);
+        if (lane == 0) mbar_arrive(B.z_ready);
       }
       const float g = more ? gate_value(T.gate[s + 1]) : 0.f;
       const float omg = 1.0f - g;
+      const bool keep_last = !more || T.store_last != 0;
       for (int c = 0; c < NC; ++c) {
-        // residual x_s chunk: written by this very thread one stage earlier (program order makes it visible)
         float xr[32];
-        {
-          const bf16* xp = T.x_stash[s] + row * a.d + c * CH_CW + hf * 32;
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            uint4 v = make_uint4(0u, 0u, 0u, 0u);
-            if (row_ok) v = *reinterpret_cast<const uint4*>(xp + q * 8);
-            unpack8(v, xr + q * 8);
-          }
-        }
+        read_h(xr);                            // residual x_s[c]
         const int b = n_u & 1; const uint32_t uph = (uint32_t)(n_u >> 1) & 1u;
-        mbar_wait(&u_full[b], uph);
+        mbar_wait(&B.u_full[b], uph);
         tc_fence_after();
         uint32_t raw[32];
         tmem_ld_32x32(tmem_base + lane_addr + (uint32_t)(CH_UACC + b * 64 + hf * 32), raw);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&u_empty[b]);
+        if (lane == 0) mbar_arrive(&B.u_empty[b]);
         ++n_u;
         float lv[32];
         const float4* bu = reinterpret_cast<const float4*>(T.b_up[s] + c * CH_CW + hf * 32);
@@ -304,24 +359,21 @@ __global__ void __launch_bounds__(CH_THREADS, 1) san_chain_fwd_kernel(const __gr
           lv[4 * q] = __uint_as_float(raw[4 * q]) + bq.x + xr[4 * q]; lv[4 * q + 1] = __uint_as_float(raw[4 * q + 1]) + bq.y + xr[4 * q + 1];
           lv[4 * q + 2] = __uint_as_float(raw[4 * q + 2]) + bq.z + xr[4 * q + 2]; lv[4 * q + 3] = __uint_as_float(raw[4 * q + 3]) + bq.w + xr[4 * q + 3];
         }
-        if (T.last_stash[s] && row_ok) {
-          bf16* lp = T.last_stash[s] + row * a.d + c * CH_CW + hf * 32;
-#pragma unroll
-          for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4*>(lp + q * 8) = pack8(lv + q * 8);
-        }
         if (more) {
-          float hv[32];
+          float hv[32], xv[32];
           read_h(hv);
           if (is_mm) {
             float h2[32];
             read_h(h2);
 #pragma unroll
-            for (int k = 0; k < 32; ++k) lv[k] = __fadd_rn(__fadd_rn(lv[k], __fmul_rn(g, hv[k])), __fmul_rn(omg, h2[k]));
+            for (int k = 0; k < 32; ++k) xv[k] = __fadd_rn(__fadd_rn(lv[k], __fmul_rn(g, hv[k])), __fmul_rn(omg, h2[k]));
           } else {
 #pragma unroll
-            for (int k = 0; k < 32; ++k) lv[k] = __fadd_rn(__fmul_rn(g, hv[k]), __fmul_rn(omg, lv[k]));
+            for (int k = 0; k < 32; ++k) xv[k] = __fadd_rn(__fmul_rn(g, hv[k]), __fmul_rn(omg, lv[k]));
           }
-          emit_x(lv, T.x_stash[s + 1], c);
+          emit(xv, lv, true, keep_last);
+        } else {
+          emit(lv, lv, false, true);
         }
       }
     }
@@ -331,74 +383,31 @@ __global__ void __launch_bounds__(CH_THREADS, 1) san_chain_fwd_kernel(const __gr
   if (warp == 1) tmem_dealloc(tmem_base, CH_TMEM_COLS);
 }
 
-
 // ================================================================================================================
-// Backward of the chain (data gradients + gate / bias gradients; the weight gradients are reductions over ALL items and
-// stay separate split-K GEMMs over the stashes this kernel writes).  Same skeleton as the forward, stages in reverse:
-//
-//   dz_s      = (dy_s Wu_s) * (z_s > 0)                dy_s = d last_s ; accumulated in TMEM chunk by chunk (K = d)
-//   dx_s      = dy_s + dz_s Wd_s                       one tcgen05.mma group per 64-column chunk
-//   dgate_s  += sum dx_s * (h_s - last_{s-1})          (mm tower: h_cv - h_text), scaled by g(1-g)/0.1 at the end
-//   dy_{s-1}  = (1 - g_s) dx_s                         (mm tower: dx_s) -> bf16 -> stash (wgrad operand) and, swizzled, the A
-//                                                      operand of the next stage's dz accumulation
-//   db_up_s  += colsum(dy_s) ; db_down_s += colsum(dz_s)   (warp butterfly, one red.add per column and warp)
-// Every global tile (dy_s, h_s, last_{s-1} / h_text) arrives through one TMA ring; dy_{s-1} is read back by TMA one stage
-// after this CTA wrote it with generic stores, ordered by fence.proxy.async + the ring's mbarrier chain.
+// backward
 // ================================================================================================================
-__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
-
-// sum over the 32 lanes of v[k] for each k: lane l ends with the total of column l (31 shuffles)
-__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
-#pragma unroll
-  for (int off = 16; off >= 1; off >>= 1) {
-    const bool upper = (lane & off) != 0;
-#pragma unroll
-    for (int k = 0; k < off; ++k) {
-      const float send = upper ? v[k] : v[k + off];
-      const float recv = __shfl_xor_sync(0xffffffffu, send, off);
-      v[k] = (upper ? v[k + off] : v[k]) + recv;
-    }
-  }
-  return v[0];
-}
-
 __global__ void __launch_bounds__(CH_THREADS, 1) san_chain_bwd_kernel(const __grid_constant__ ChainBwdArgs a) {
   const ChainBwdTower& T = a.tower[blockIdx.y];
   const bool is_mm = (T.mode == 1);
   const int NC = a.d / CH_CW;
   const int A = a.n_stages;
   const int m0 = blockIdx.x * CH_ROWS;
+  const int NP = a.n_pad;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ChainSmem::kBar);
-  uint64_t* w_full = bars;
-  uint64_t* w_empty = w_full + CH_NW;
-  uint64_t* h_full = w_empty + CH_NW;
-  uint64_t* h_empty = h_full + CH_NH;
-  uint64_t* xk_full = h_empty + CH_NH;
-  uint64_t* xk_empty = xk_full + 2;
-  uint64_t* u_full = xk_empty + 2;
-  uint64_t* u_empty = u_full + 2;
-  uint64_t* z_full = u_empty + 2;
-  uint64_t* z_ready = z_full + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(z_ready + 1);
-
+  ChainBars B(smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&T.map_wd); tma_prefetch_desc(&T.map_wu); tma_prefetch_desc(&T.map_h); tma_prefetch_desc(&T.map_dy);
-    tma_prefetch_desc(&T.map_aux);
-    for (int i = 0; i < CH_NW; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
-    for (int i = 0; i < CH_NH; ++i) { mbar_init(&h_full[i], 1); mbar_init(&h_empty[i], 8); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&xk_full[i], 8); mbar_init(&xk_empty[i], 1); mbar_init(&u_full[i], 1); mbar_init(&u_empty[i], 8); }
-    mbar_init(z_full, 1); mbar_init(z_ready, 8);
-    fence_barrier_init();
+    tma_prefetch_desc(&T.map_aux); tma_prefetch_desc(&T.map_dz);
+    B.init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, CH_TMEM_COLS);
+  if (warp == 1) tmem_alloc(B.tmem_slot, CH_TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = *B.tmem_slot;
 
   // unit u = (j + 1) * NC + c, j = -1 .. A-1, stage sv = A-1-j : first half Wd_sv[c] (j >= 0), second half Wu_{sv-1}[c]
   // (sv-1 >= 0 ; for j = -1 that is Wu_{A-1}[c])
@@ -412,12 +421,11 @@ __global__ void __launch_bounds__(CH_THREADS, 1) san_chain_bwd_kernel(const __gr
         const int sv = A - 1 - j;                         // j = -1 -> A
         const int slot = u % CH_NW; const uint32_t ph = (uint32_t)(u / CH_NW) & 1u;
         const bool has_wd = j >= 0, has_wu = sv - 1 >= 0;
-        if (!has_wd && !has_wu) continue;
-        mbar_wait(&w_empty[slot], ph ^ 1u);
+        mbar_wait(&B.w_empty[slot], ph ^ 1u);
         uint8_t* dst = smem + ChainSmem::kW + slot * 2 * CH_W_BYTES;
-        mbar_expect_tx(&w_full[slot], (has_wd ? CH_W_BYTES : 0) + (has_wu ? CH_W_BYTES : 0));
-        if (has_wd) tma_load_2d(dst, &T.map_wd, &w_full[slot], c * CH_CW, sv * CH_R);                       // Wd_sv[:, chunk] : [r, 64]
-        if (has_wu) tma_load_2d(dst + CH_W_BYTES, &T.map_wu, &w_full[slot], 0, (sv - 1) * a.d + c * CH_CW);  // Wu_{sv-1}[chunk, :] : [64, r]
+        mbar_expect_tx(&B.w_full[slot], (has_wd ? CH_W_BYTES : 0) + (has_wu ? CH_W_BYTES : 0));
+        if (has_wd) tma_load_2d(dst, &T.map_wd, &B.w_full[slot], c * CH_CW, sv * CH_R);                       // Wd_sv[:, chunk] : [r, 64]
+        if (has_wu) tma_load_2d(dst + CH_W_BYTES, &T.map_wu, &B.w_full[slot], 0, (sv - 1) * a.d + c * CH_CW);  // Wu_{sv-1}[chunk, :] : [64, r]
       }
     }
   } else if (warp == 2) {
@@ -426,68 +434,76 @@ __global__ void __launch_bounds__(CH_THREADS, 1) san_chain_bwd_kernel(const __gr
       int n_h = 0;
       auto load = [&](const CUtensorMap* m, int col, int row) {
         const int slot = n_h % CH_NH; const uint32_t ph = (uint32_t)(n_h / CH_NH) & 1u;
-        mbar_wait(&h_empty[slot], ph ^ 1u);
-        mbar_expect_tx(&h_full[slot], CH_TILE_BYTES);
-        tma_load_2d(smem + ChainSmem::kH + slot * CH_TILE_BYTES, m, &h_full[slot], col, row);
+        mbar_wait(&B.h_empty[slot], ph ^ 1u);
+        mbar_expect_tx(&B.h_full[slot], CH_TILE_BYTES);
+        tma_load_2d(smem + ChainSmem::kH + slot * CH_TILE_BYTES, m, &B.h_full[slot], col, row);
         ++n_h;
       };
-      for (int c = 0; c < NC; ++c) load(&T.map_dy, c * CH_CW, (A - 1) * a.n_items + m0);
+      for (int c = 0; c < NC; ++c) load(&T.map_dy, c * CH_CW, (A - 1) * NP + m0);
       for (int s = A - 1; s >= 0; --s) {
         for (int c = 0; c < NC; ++c) {
-          load(&T.map_dy, c * CH_CW, s * a.n_items + m0);
+          load(&T.map_dy, c * CH_CW, s * NP + m0);
           load(&T.map_h, T.layer[s] * a.d + c * CH_CW, m0);
           if (is_mm) load(&T.map_aux, T.layer2[s] * a.d + c * CH_CW, m0);
-          else if (s > 0) load(&T.map_aux, c * CH_CW, (s - 1) * a.n_items + m0);
+          else if (s > 0) load(&T.map_aux, c * CH_CW, (s - 1) * NP + m0);
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
+    // ===================== MMA issuer + TMA stores =====================
     if (elect_one()) {
       constexpr uint32_t idesc = instr_desc_bf16(CH_ROWS, 64, 0, 1);   // A K-major, B MN-major ([K, N] row-major weight tiles)
       const uint32_t sz = smem_u32(smem + ChainSmem::kZ);
       int n_x = 0, n_u = 0;
-      auto dzacc_step = [&](int unit, int c) {        // dz_acc (+)= dy chunk x Wu[c]  (K = 64 columns of the chunk)
+      // dy_{sp}[c] is in xk[b]: store it (sp >= 0), feed dz_acc (+)= dy chunk x Wu_{sp}[c]
+      auto dzacc_step = [&](int unit, int c, int sp, bool store) {
         const int b = n_x & 1; const uint32_t ph = (uint32_t)(n_x >> 1) & 1u;
         const int slot = unit % CH_NW;
-        mbar_wait(&xk_full[b], ph);
+        mbar_wait(&B.xk_full[b], ph);
         tc_fence_after();
-        const uint32_t sx = smem_u32(smem + ChainSmem::kXk + b * CH_TILE_BYTES);
+        const uint8_t* xk = smem + ChainSmem::kXk + b * CH_TILE_BYTES;
+        if (store) { tma_store_2d(&T.map_dy, xk, c * CH_CW, sp * NP + m0); bulk_commit(); }
+        const uint32_t sx = smem_u32(xk);
         const uint32_t sw = smem_u32(smem + ChainSmem::kW + slot * 2 * CH_W_BYTES + CH_W_BYTES);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           mma_bf16_ss(tmem_base + CH_ZACC, smem_desc_sw128(sx + k * 32, 16, 1024), smem_desc_sw128(sw + k * 2048, 8192, 1024), idesc, (c > 0 || k > 0) ? 1u : 0u);
-        mma_commit(&xk_empty[b]);
-        mma_commit(&w_empty[slot]);
+        if (store) { bulk_wait_read0(); bulk_wait_3(); }
+        mma_commit(&B.xk_empty[b]);
+        mma_commit(&B.w_empty[slot]);
         ++n_x;
       };
       for (int c = 0; c < NC; ++c) {
         const int unit = c; const uint32_t wph = (uint32_t)(unit / CH_NW) & 1u;
-        mbar_wait(&w_full[unit % CH_NW], wph);
-        dzacc_step(unit, c);
+        mbar_wait(&B.w_full[unit % CH_NW], wph);
+        dzacc_step(unit, c, A - 1, false);
       }
-      mma_commit(z_full);
+      mma_commit(B.z_full);
       for (int j = 0; j < A; ++j) {
-        const bool more = j + 1 < A;                  // stage sv = A-1-j > 0
-        mbar_wait(z_ready, (uint32_t)j & 1u);
+        const int s = A - 1 - j;
+        const bool more = s > 0;
+        mbar_wait(B.z_ready, (uint32_t)j & 1u);
         tc_fence_after();
+        tma_store_2d(&T.map_dz, smem + ChainSmem::kZ, 0, s * NP + m0);   // dz_s stash (wgrad operand)
+        bulk_commit();
         for (int c = 0; c < NC; ++c) {
           const int unit = (j + 1) * NC + c; const int slot = unit % CH_NW; const uint32_t wph = (uint32_t)(unit / CH_NW) & 1u;
           const int b = n_u & 1; const uint32_t uph = (uint32_t)(n_u >> 1) & 1u;
-          mbar_wait(&w_full[slot], wph);
-          mbar_wait(&u_empty[b], uph ^ 1u);
+          mbar_wait(&B.w_full[slot], wph);
+          mbar_wait(&B.u_empty[b], uph ^ 1u);
           tc_fence_after();
           const uint32_t sw = smem_u32(smem + ChainSmem::kW + slot * 2 * CH_W_BYTES);
 #pragma unroll
           for (int k = 0; k < 4; ++k)       // dx chunk = dz (K = r) x Wd[:, chunk]
             mma_bf16_ss(tmem_base + CH_UACC + b * 64, smem_desc_sw128(sz + k * 32, 16, 1024), smem_desc_sw128(sw + k * 2048, 8192, 1024), idesc, k > 0 ? 1u : 0u);
-          mma_commit(&u_full[b]);
+          mma_commit(&B.u_full[b]);
           ++n_u;
-          if (!more) mma_commit(&w_empty[slot]);
-          else if (c >= 1) dzacc_step(unit - 1, c - 1);
+          if (!more) mma_commit(&B.w_empty[slot]);
+          else if (c >= 1) dzacc_step(unit - 1, c - 1, s - 1, true);
         }
-        if (more) { dzacc_step((j + 1) * NC + NC - 1, NC - 1); mma_commit(z_full); }
+        if (more) { dzacc_step((j + 1) * NC + NC - 1, NC - 1, s - 1, true); mma_commit(B.z_full); }
       }
+      bulk_wait_0();
     }
   } else {
     // ===================== epilogue warps =====================
@@ -501,9 +517,14 @@ __global__ void __launch_bounds__(CH_THREADS, 1) san_chain_bwd_kernel(const __gr
     const int sw_row = (m >> 3) * 1024 + (m & 7) * 128;
     int n_h = 0, n_x = 0, n_u = 0;
 
+    auto put_tile = [&](uint8_t* tile_base, const float* v) {
+      uint8_t* tile = tile_base + sw_row;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4*>(tile + (((hf * 4 + q) ^ (m & 7)) << 4)) = pack8(v + q * 8);
+    };
     auto read_tile = [&](float* hv) {                 // this thread's 32 columns of the next ring tile (zeros for rows past N)
       const int slot = n_h % CH_NH; const uint32_t ph = (uint32_t)(n_h / CH_NH) & 1u;
-      mbar_wait(&h_full[slot], ph);
+      mbar_wait(&B.h_full[slot], ph);
       const uint8_t* tile = smem + ChainSmem::kH + slot * CH_TILE_BYTES + sw_row;
 #pragma unroll
       for (int q = 0; q < 4; ++q) unpack8(*reinterpret_cast<const uint4*>(tile + (((hf * 4 + q) ^ (m & 7)) << 4)), hv + q * 8);
@@ -512,22 +533,16 @@ __global__ void __launch_bounds__(CH_THREADS, 1) san_chain_bwd_kernel(const __gr
         for (int k = 0; k < 32; ++k) hv[k] = 0.f;
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(&h_empty[slot]);
+      if (lane == 0) mbar_arrive(&B.h_empty[slot]);
       ++n_h;
     };
-    auto emit = [&](const float* xv, bf16* stash, int c) {     // bf16 chunk -> A operand (+ global stash)
+    auto emit = [&](const float* xv) {                // bf16 chunk -> A operand (the MMA thread stores it to the stash)
       const int b = n_x & 1; const uint32_t ph = (uint32_t)(n_x >> 1) & 1u;
-      mbar_wait(&xk_empty[b], ph ^ 1u);
-      uint8_t* tile = smem + ChainSmem::kXk + b * CH_TILE_BYTES + sw_row;
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const uint4 pk = pack8(xv + q * 8);
-        *reinterpret_cast<uint4*>(tile + (((hf * 4 + q) ^ (m & 7)) << 4)) = pk;
-        if (stash && row_ok) *reinterpret_cast<uint4*>(stash + row * a.d + c * CH_CW + hf * 32 + q * 8) = pk;
-      }
-      fence_proxy_async_all();          // shared: the MMA reads the operand ; global: the TMA ring reads the stash back
+      mbar_wait(&B.xk_empty[b], ph ^ 1u);
+      put_tile(smem + ChainSmem::kXk + b * CH_TILE_BYTES, xv);
+      fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&xk_full[b]);
+      if (lane == 0) mbar_arrive(&B.xk_full[b]);
       ++n_x;
     };
 
@@ -535,14 +550,14 @@ __global__ void __launch_bounds__(CH_THREADS, 1) san_chain_bwd_kernel(const __gr
     for (int c = 0; c < NC; ++c) {
       float dv[32];
       read_tile(dv);
-      emit(dv, nullptr, c);
+      emit(dv);
     }
     for (int s = A - 1; s >= 0; --s) {
       const int j = A - 1 - s;
       const bool more = s > 0;
       // ---- dz_s = dz_acc * (z_s > 0) ----
       {
-        mbar_wait(z_full, (uint32_t)j & 1u);
+        mbar_wait(B.z_full, (uint32_t)j & 1u);
         tc_fence_after();
         uint32_t raw[32];
         tmem_ld_32x32(tmem_base + lane_addr + (uint32_t)(CH_ZACC + hf * 32), raw);
@@ -551,22 +566,16 @@ __global__ void __launch_bounds__(CH_THREADS, 1) san_chain_bwd_kernel(const __gr
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           uint4 v = make_uint4(0u, 0u, 0u, 0u);
-          if (row_ok) v = *reinterpret_cast<const uint4*>(T.z_stash[s] + row * CH_R + hf * 32 + q * 8);
+          if (row_ok) v = *reinterpret_cast<const uint4*>(T.z_stash + ((int64_t)s * NP + row) * CH_R + hf * 32 + q * 8);
           unpack8(v, zv + q * 8);
         }
 #pragma unroll
         for (int k = 0; k < 32; ++k) dzv[k] = (zv[k] > 0.f && row_ok) ? __uint_as_float(raw[k]) : 0.f;
-        uint8_t* tile = smem + ChainSmem::kZ + sw_row;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const uint4 pk = pack8(dzv + q * 8);
-          *reinterpret_cast<uint4*>(tile + (((hf * 4 + q) ^ (m & 7)) << 4)) = pk;
-          if (row_ok) *reinterpret_cast<uint4*>(T.dz_stash[s] + row * CH_R + hf * 32 + q * 8) = pk;
-        }
+        put_tile(smem + ChainSmem::kZ, dzv);
         tc_fence_before();
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) mbar_arrive(z_ready);
+        if (lane == 0) mbar_arrive(B.z_ready);
         const float cs = warp_colsum32(dzv, lane);                       // db_down
         atomicAdd(T.g_b_down[s] + hf * 32 + lane, cs);
       }
@@ -580,14 +589,14 @@ __global__ void __launch_bounds__(CH_THREADS, 1) san_chain_bwd_kernel(const __gr
         const bool has_aux = is_mm || more;
         if (has_aux) read_tile(av);
         const int b = n_u & 1; const uint32_t uph = (uint32_t)(n_u >> 1) & 1u;
-        mbar_wait(&u_full[b], uph);
+        mbar_wait(&B.u_full[b], uph);
         tc_fence_after();
         uint32_t raw[32];
         tmem_ld_32x32(tmem_base + lane_addr + (uint32_t)(CH_UACC + b * 64 + hf * 32), raw);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&u_empty[b]);
+        if (lane == 0) mbar_arrive(&B.u_empty[b]);
         ++n_u;
         float dx[32];
 #pragma unroll
@@ -601,7 +610,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) san_chain_bwd_kernel(const __gr
 #pragma unroll
             for (int k = 0; k < 32; ++k) dx[k] *= omg;
           }
-          emit(dx, T.dy_stash + (int64_t)(s - 1) * a.n_items * a.d, c);
+          emit(dx);
         }
         const float cs = warp_colsum32(dy, lane);                        // db_up
         atomicAdd(T.g_b_up[s] + c * CH_CW + hf * 32 + lane, cs);
@@ -616,29 +625,44 @@ __global__ void __launch_bounds__(CH_THREADS, 1) san_chain_bwd_kernel(const __gr
   if (warp == 1) tmem_dealloc(tmem_base, CH_TMEM_COLS);
 }
 
+// ================================================================================================================
+// host side
+// ================================================================================================================
 int make_tensor_map_bf16(CUtensorMap* out, const void* ptr, int64_t rows, int64_t cols, int64_t pitch, int box_inner, int box_outer);
 
-int chain_fill_tower(ChainTower* T, int mode, const void* h, int64_t h_rows, int64_t h_pitch_cols, const void* h2, int64_t h2_pitch_cols,
-                     const bf16* wd_pack, const bf16* wu_pack, int n_stages, int d) {
-  T->mode = mode;
-  IISAN_TRY(make_tensor_map_bf16(&T->map_h, h, h_rows, h_pitch_cols, h_pitch_cols, CH_CW, CH_ROWS));
-  if (mode == 1) IISAN_TRY(make_tensor_map_bf16(&T->map_h2, h2, h_rows, h2_pitch_cols, h2_pitch_cols, CH_CW, CH_ROWS));
-  else T->map_h2 = T->map_h;
-  IISAN_TRY(make_tensor_map_bf16(&T->map_wd, wd_pack, (int64_t)n_stages * CH_R, d, d, CH_CW, CH_R));
-  IISAN_TRY(make_tensor_map_bf16(&T->map_wu, wu_pack, (int64_t)n_stages * d, CH_R, CH_R, CH_R, CH_CW));
+int chain_n_pad(int n_items) { return (n_items + CH_ROWS - 1) / CH_ROWS * CH_ROWS; }
+
+static int fill_common(CUtensorMap* map_wd, CUtensorMap* map_wu, const bf16* wd_pack, const bf16* wu_pack, int n_stages, int d) {
+  IISAN_TRY(make_tensor_map_bf16(map_wd, wd_pack, (int64_t)n_stages * CH_R, d, d, CH_CW, CH_R));
+  IISAN_TRY(make_tensor_map_bf16(map_wu, wu_pack, (int64_t)n_stages * d, CH_R, CH_R, CH_R, CH_CW));
   return IISAN_OK;
 }
 
-int chain_fill_bwd_tower(ChainBwdTower* T, int mode, const void* h, int64_t h_rows, int64_t h_pitch_cols, const void* h2, int64_t h2_pitch_cols,
-                         const bf16* wd_pack, const bf16* wu_pack, const bf16* dy_all, const bf16* last_all, int n_stages, int d) {
+int chain_fill_tower(ChainTower* T, int mode, const void* h, int64_t n_items, int64_t h_pitch_cols, const void* h2, int64_t h2_pitch_cols,
+                     const bf16* wd_pack, const bf16* wu_pack, const bf16* x_all, const bf16* last_all, const bf16* z_all, int n_stages,
+                     int d) {
+  const int64_t np = chain_n_pad((int)n_items);
   T->mode = mode;
-  IISAN_TRY(make_tensor_map_bf16(&T->map_h, h, h_rows, h_pitch_cols, h_pitch_cols, CH_CW, CH_ROWS));
-  IISAN_TRY(make_tensor_map_bf16(&T->map_dy, dy_all, (int64_t)n_stages * h_rows, d, d, CH_CW, CH_ROWS));
-  if (mode == 1) IISAN_TRY(make_tensor_map_bf16(&T->map_aux, h2, h_rows, h2_pitch_cols, h2_pitch_cols, CH_CW, CH_ROWS));
-  else IISAN_TRY(make_tensor_map_bf16(&T->map_aux, last_all, (int64_t)n_stages * h_rows, d, d, CH_CW, CH_ROWS));
-  IISAN_TRY(make_tensor_map_bf16(&T->map_wd, wd_pack, (int64_t)n_stages * CH_R, d, d, CH_CW, CH_R));
-  IISAN_TRY(make_tensor_map_bf16(&T->map_wu, wu_pack, (int64_t)n_stages * d, CH_R, CH_R, CH_R, CH_CW));
-  return IISAN_OK;
+  IISAN_TRY(make_tensor_map_bf16(&T->map_h, h, n_items, h_pitch_cols, h_pitch_cols, CH_CW, CH_ROWS));
+  if (mode == 1) IISAN_TRY(make_tensor_map_bf16(&T->map_h2, h2, n_items, h2_pitch_cols, h2_pitch_cols, CH_CW, CH_ROWS));
+  else T->map_h2 = T->map_h;
+  IISAN_TRY(make_tensor_map_bf16(&T->map_x, x_all, (int64_t)n_stages * np, d, d, CH_CW, CH_ROWS));
+  IISAN_TRY(make_tensor_map_bf16(&T->map_last, last_all, (int64_t)n_stages * np, d, d, CH_CW, CH_ROWS));
+  IISAN_TRY(make_tensor_map_bf16(&T->map_z, z_all, (int64_t)n_stages * np, CH_R, CH_R, CH_R, CH_ROWS));
+  return fill_common(&T->map_wd, &T->map_wu, wd_pack, wu_pack, n_stages, d);
+}
+
+int chain_fill_bwd_tower(ChainBwdTower* T, int mode, const void* h, int64_t n_items, int64_t h_pitch_cols, const void* h2,
+                         int64_t h2_pitch_cols, const bf16* wd_pack, const bf16* wu_pack, const bf16* dy_all, const bf16* last_all,
+                         const bf16* dz_all, int n_stages, int d) {
+  const int64_t np = chain_n_pad((int)n_items);
+  T->mode = mode;
+  IISAN_TRY(make_tensor_map_bf16(&T->map_h, h, n_items, h_pitch_cols, h_pitch_cols, CH_CW, CH_ROWS));
+  IISAN_TRY(make_tensor_map_bf16(&T->map_dy, dy_all, (int64_t)n_stages * np, d, d, CH_CW, CH_ROWS));
+  if (mode == 1) IISAN_TRY(make_tensor_map_bf16(&T->map_aux, h2, n_items, h2_pitch_cols, h2_pitch_cols, CH_CW, CH_ROWS));
+  else IISAN_TRY(make_tensor_map_bf16(&T->map_aux, last_all, (int64_t)n_stages * np, d, d, CH_CW, CH_ROWS));
+  IISAN_TRY(make_tensor_map_bf16(&T->map_dz, dz_all, (int64_t)n_stages * np, CH_R, CH_R, CH_R, CH_ROWS));
+  return fill_common(&T->map_wd, &T->map_wu, wd_pack, wu_pack, n_stages, d);
 }
 
 int launch_san_chain_bwd(const ChainBwdArgs& args, int n_towers, cudaStream_t st) {
