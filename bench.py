@@ -197,7 +197,7 @@ def run_ours(a):
     import torch.distributed as dist
     from iisan_b200 import _lib
     from iisan_b200.engine import PipelinedTrainStep, TrainStep
-    from iisan_b200.optim import param_groups
+    from iisan_b200.optim import FusedAdam, param_groups
     lib = _lib.load()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -213,7 +213,7 @@ def run_ours(a):
         for p in model.parameters():                                 # same initial replica on every rank (DDP does this at wrap time)
             dist.broadcast(p.data, 0)
     use_graph = not a.no_graph
-    opt = torch.optim.Adam(param_groups(model, args), fused=True, capturable=use_graph)
+    opt = FusedAdam(param_groups(model, args))            # iisan_adam_step: Adam over the reference's 5 LR groups, 2 launches
     gen = torch.Generator(device=device).manual_seed(SEED + rank)
     B = a.batch
     n_rot = 3                                               # 3 x 225 MB (bf16) rotating inputs >> 126 MB L2

@@ -65,6 +65,11 @@ class UeDesc(C.Structure):
                 ("offset_dev", vp)]
 
 
+class AdamTensor(C.Structure):
+    _fields_ = [("param", vp), ("grad", vp), ("exp_avg", vp), ("exp_avg_sq", vp), ("numel", C.c_int64), ("lr", C.c_float),
+                ("reserved", i32)]
+
+
 class CeDesc(C.Structure):
     _fields_ = [("row_users", i32), ("col_users", i32), ("seq_len", i32), ("emb", i32), ("user_offset", C.c_int64),
                 ("compute", i32), ("reserved", i32)]
@@ -94,6 +99,7 @@ _SIGNATURES = {
     "iisan_inbatch_ce_backward": (C.c_int, [C.POINTER(CeDesc), vp, vp, vp, vp, vp, vp, vp, vp, C.c_size_t, vp, vp, vp, vp, vp, vp]),
     "iisan_inbatch_ce_masks": (C.c_int, [C.POINTER(CeDesc), vp, vp, vp, vp, vp, vp]),
     "iisan_inbatch_ce_masks_fast": (C.c_int, [C.POINTER(CeDesc), vp, vp, vp, vp, vp, C.c_size_t, vp, vp]),
+    "iisan_adam_step": (C.c_int, [C.POINTER(AdamTensor), i32, C.c_float, C.c_float, C.c_float, vp, i32, vp]),
     "iisan_stage_states_h2d": (C.c_int, [vp, vp, C.c_int64, i32, i32, i32, C.POINTER(i32), i32, vp]),
     "iisan_gather_states": (C.c_int, [vp, i32, C.c_int64, i32, i32, vp, i32, vp, i32, vp, vp]),
 }

@@ -54,11 +54,15 @@ class TrainStep:
         for p in self._params:
             st = self.opt.state.get(p, None)
             state.append(None if not st else {k: v.detach().clone() for k, v in st.items() if torch.is_tensor(v)})
-        return params, state
+        step_dev = getattr(self.opt, "_step_dev", None)
+        return params, state, (None if step_dev is None else step_dev.detach().clone())
 
     @torch.no_grad()
     def _restore(self, saved):
-        params, state = saved
+        params, state, step_dev = saved
+        cur = getattr(self.opt, "_step_dev", None)        # iisan_b200.optim.FusedAdam keeps its step count on the device
+        if cur is not None:
+            cur.copy_(step_dev) if step_dev is not None else cur.zero_()
         for p, q in zip(self._params, params):
             p.copy_(q)
         for p, old in zip(self._params, state):

@@ -10,6 +10,10 @@
 """
 from __future__ import annotations
 
+import ctypes as C
+
+import torch
+
 
 def param_groups(model, args):
     text_enc, image_net, recsys, ad_cv, ad_text = [], [], [], [], []
@@ -41,3 +45,56 @@ def param_groups(model, args):
         {"params": ad_cv, "lr": args.adapter_cv_lr},
         {"params": ad_text, "lr": args.adapter_bert_lr},
     ]
+
+
+class FusedAdam(torch.optim.Optimizer):
+    """torch.optim.Adam semantics (betas, eps; weight_decay 0, amsgrad off -- what the reference uses, Code_Cached/run.py:301-307)
+    through iisan_adam_step: two launches for the 146 tensors of the base model instead of one multi-tensor launch per
+    learning-rate group, step counter on the device (CUDA-graph capturable).  ``param_groups`` as for torch.optim.Adam."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, capturable=True))
+        self._table = None
+        self._key = None
+        self._step_dev = None
+
+    def _build(self):
+        from . import _lib as L
+        entries = []
+        for g in self.param_groups:
+            for p in g["params"]:
+                if p.grad is None:
+                    continue
+                if p.dtype != torch.float32 or not p.is_contiguous() or not p.is_cuda:
+                    raise L.IisanLibraryError("FusedAdam needs contiguous fp32 CUDA parameters")
+                st = self.state[p]
+                if not st:
+                    st["exp_avg"] = torch.zeros_like(p)
+                    st["exp_avg_sq"] = torch.zeros_like(p)
+                grad = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
+                entries.append((p, grad, st["exp_avg"], st["exp_avg_sq"], float(g["lr"])))
+        key = tuple((p.data_ptr(), gr.data_ptr(), lr) for p, gr, _, _, lr in entries)
+        if key != self._key:
+            arr = (L.AdamTensor * len(entries))()
+            for i, (p, gr, m, v, lr) in enumerate(entries):
+                arr[i].param, arr[i].grad, arr[i].exp_avg, arr[i].exp_avg_sq = p.data_ptr(), gr.data_ptr(), m.data_ptr(), v.data_ptr()
+                arr[i].numel, arr[i].lr = p.numel(), lr
+            self._table, self._key, self._keep = arr, key, [e[1] for e in entries]
+        return len(entries)
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        from . import _lib as L
+        if closure is not None:
+            raise NotImplementedError("FusedAdam does not take a closure")
+        n = self._build()
+        if n == 0:
+            return None
+        lib = L.load()
+        dev = self.param_groups[0]["params"][0].device
+        if self._step_dev is None:
+            self._step_dev = torch.zeros(1, dtype=torch.float32, device=dev)
+        b1, b2 = self.param_groups[0]["betas"]
+        L.check(lib.iisan_adam_step(self._table, n, b1, b2, self.param_groups[0]["eps"], C.c_void_p(self._step_dev.data_ptr()), 1,
+                                    C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), "iisan_adam_step")
+        return None

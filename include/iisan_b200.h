@@ -275,6 +275,21 @@ int iisan_gather_states(const void* table, int32_t dtype, int64_t n_table_items,
                         int32_t d, const int64_t* ids, int32_t n, const int32_t* sel, int32_t n_sel,
                         void* out, iisan_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Optimizer step (CC/run.py:260-307 name-routed LR groups, :383-385 step): fused multi-tensor Adam with torch.optim.Adam's
+ * default hyper-parameters semantics (weight_decay 0, amsgrad off).  `step_dev` is a device fp32 scalar holding the step count;
+ * with advance_step != 0 it is incremented (stream-ordered) before the update, so the call is CUDA-graph safe.
+ * ------------------------------------------------------------------------------------------- */
+#define IISAN_ADAM_MAX_TENSORS 80
+typedef struct iisan_adam_tensor {
+  float* param; const float* grad; float* exp_avg; float* exp_avg_sq;
+  int64_t numel;
+  float lr;
+  int32_t reserved;
+} iisan_adam_tensor;
+int iisan_adam_step(const iisan_adam_tensor* tensors, int32_t n, float beta1, float beta2, float eps, float* step_dev,
+                    int32_t advance_step, iisan_stream_t stream);
+
 /* Host -> device staging of one train batch of cached states with layer selection (CC/run.py:370-374 moves all
  * `layers` states of every slot; only the `n_sel` layers the towers read are needed).  host_src: PINNED host memory,
  * [n_rows, layers, d] of `dtype`; dev_dst: device buffer of the same shape -- rows of unselected layers are left untouched
