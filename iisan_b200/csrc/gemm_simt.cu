@@ -5,46 +5,49 @@
 namespace iisan {
 
 
+// BM x 64 output tile per CTA (BM = 64 or 32; the narrow tile doubles the CTA count of the skinny SASRec products), 256 threads,
+// each thread (BM/16) x 4 outputs; the next k-tile's global loads are issued into registers before the current tile's FMAs.
+template <int BM>
 __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmBatch batch) {
+  constexpr int TM = BM / 16;                 // rows per thread
+  constexpr int AL = BM * GBK / 256;          // A elements loaded per thread per k-tile
   const GemmProb& P = batch.p[blockIdx.z];
   const int tiles_n = (P.N + GBN - 1) / GBN;
-  const int tiles_m = (P.M + GBM - 1) / GBM;
+  const int tiles_m = (P.M + BM - 1) / BM;
   if ((int)blockIdx.x >= tiles_n * tiles_m) return;
   if ((int)blockIdx.y >= P.splitk) return;
   const int tm = blockIdx.x / tiles_n, tn = blockIdx.x % tiles_n;
-  const int m0 = tm * GBM, n0 = tn * GBN;
-  // K range of this split
+  const int m0 = tm * BM, n0 = tn * GBN;
   const int kt_total = (P.K + GBK - 1) / GBK;
   const int kt_per = (kt_total + P.splitk - 1) / P.splitk;
   const int kt_beg = blockIdx.y * kt_per;
   const int kt_end = min(kt_total, kt_beg + kt_per);
   if (kt_beg >= kt_end) return;
 
-  __shared__ float As[GBK][GBM + 4];
+  __shared__ float As[GBK][BM + 4];
   __shared__ float Bs[GBK][GBN + 4];
 
   const int tid = threadIdx.x;
-  const int tx = tid % 16, ty = tid / 16;   // thread computes rows ty*4.., cols tx*4..
+  const int tx = tid % 16, ty = tid / 16;   // thread computes rows ty*TM.., cols tx*4..
   const bool a_kc = (P.a_cs == 1);          // k contiguous in memory
   const bool b_nc = (P.b_cs == 1);          // n contiguous in memory
 
-  float acc[4][4];
+  float acc[TM][4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < TM; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
-  for (int kt = kt_beg; kt < kt_end; ++kt) {
+  float ra[AL], rb[4];
+  auto fetch = [&](int kt) {
     const int k0 = kt * GBK;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < AL; ++i) {
       const int e = tid + i * 256;
       int m, k;
-      if (a_kc) { k = e % GBK; m = e / GBK; } else { m = e % GBM; k = e / GBM; }
+      if (a_kc) { k = e % GBK; m = e / GBK; } else { m = e % BM; k = e / BM; }
       const int gm = m0 + m, gk = k0 + k;
-      float v = 0.f;
-      if (gm < P.M && gk < P.K) v = __ldg(P.A + (int64_t)gm * P.a_rs + (int64_t)gk * P.a_cs);
-      As[k][m] = v;
+      ra[i] = (gm < P.M && gk < P.K) ? __ldg(P.A + (int64_t)gm * P.a_rs + (int64_t)gk * P.a_cs) : 0.f;
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -52,19 +55,40 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmBatch batch) {
       int n, k;
       if (b_nc) { n = e % GBN; k = e / GBN; } else { k = e % GBK; n = e / GBK; }
       const int gn = n0 + n, gk = k0 + k;
-      float v = 0.f;
-      if (gn < P.N && gk < P.K) v = __ldg(P.B + (int64_t)gk * P.b_rs + (int64_t)gn * P.b_cs);
-      Bs[k][n] = v;
+      rb[i] = (gn < P.N && gk < P.K) ? __ldg(P.B + (int64_t)gk * P.b_rs + (int64_t)gn * P.b_cs) : 0.f;
     }
+  };
+  auto stage = [&]() {
+#pragma unroll
+    for (int i = 0; i < AL; ++i) {
+      const int e = tid + i * 256;
+      int m, k;
+      if (a_kc) { k = e % GBK; m = e / GBK; } else { m = e % BM; k = e / BM; }
+      As[k][m] = ra[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int e = tid + i * 256;
+      int n, k;
+      if (b_nc) { n = e % GBN; k = e / GBN; } else { k = e % GBK; n = e / GBK; }
+      Bs[k][n] = rb[i];
+    }
+  };
+
+  fetch(kt_beg);
+  for (int kt = kt_beg; kt < kt_end; ++kt) {
+    stage();
     __syncthreads();
+    if (kt + 1 < kt_end) fetch(kt + 1);      // in flight while this tile is multiplied
 #pragma unroll
     for (int k = 0; k < GBK; ++k) {
-      const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      float av[TM];
+#pragma unroll
+      for (int i = 0; i < TM; ++i) av[i] = As[k][ty * TM + i];
       const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
-      const float av[4] = {a.x, a.y, a.z, a.w};
       const float bv[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < TM; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
     }
@@ -73,8 +97,8 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmBatch batch) {
 
   const bool first_split = (blockIdx.y == 0);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int gm = m0 + ty * 4 + i;
+  for (int i = 0; i < TM; ++i) {
+    const int gm = m0 + ty * TM + i;
     if (gm >= P.M) continue;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -99,16 +123,25 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmBatch batch) {
 
 int launch_gemm(const GemmBatch& b, cudaStream_t st) {
   if (b.n <= 0) return IISAN_OK;
-  int max_tiles = 0, max_split = 1;
+  int max_tiles = 0, max_tiles32 = 0, max_split = 1;
+  int64_t ctas = 0;
   for (int i = 0; i < b.n; ++i) {
     const GemmProb& P = b.p[i];
     if (P.M <= 0 || P.N <= 0 || P.K <= 0) return IISAN_EINVAL;
-    int t = ((P.M + GBM - 1) / GBM) * ((P.N + GBN - 1) / GBN);
+    const int t = ((P.M + GBM - 1) / GBM) * ((P.N + GBN - 1) / GBN);
+    const int t32 = ((P.M + 31) / 32) * ((P.N + GBN - 1) / GBN);
     if (t > max_tiles) max_tiles = t;
+    if (t32 > max_tiles32) max_tiles32 = t32;
     if (P.splitk > max_split) max_split = P.splitk;
+    ctas += (int64_t)t * (P.splitk < 1 ? 1 : P.splitk);
   }
-  dim3 grid(max_tiles, max_split, b.n);
-  { LaunchScope ls_(IISAN_K_GEMM, st); gemm_simt_kernel<<<grid, 256, 0, st>>>(b); }
+  if (ctas < 2 * 148) {      // short grid: 32-row tiles
+    dim3 grid(max_tiles32, max_split, b.n);
+    { LaunchScope ls_(IISAN_K_GEMM, st); gemm_simt_kernel<32><<<grid, 256, 0, st>>>(b); }
+  } else {
+    dim3 grid(max_tiles, max_split, b.n);
+    { LaunchScope ls_(IISAN_K_GEMM, st); gemm_simt_kernel<64><<<grid, 256, 0, st>>>(b); }
+  }
   IISAN_LAUNCH_OK();
   return IISAN_OK;
 }

@@ -9,24 +9,15 @@
 //   feed-forward block        CC/model/modules.py:14-18    LN(y + dropout(W2 relu(W1 y)))
 // Dropout uses a counter-based Philox stream (philox.cuh) instead of torch's generator; with
 // drop_rate 0 / eval mode the result is the reference's.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "launch.cuh"
 #include "gemm_simt.cuh"
 #include "philox.cuh"
+#include "user_encoder.cuh"
 
 namespace iisan {
-
-constexpr float kLnEps = 1e-6f;
-constexpr float kAttNeg = -1e9f;
-constexpr int kMaxEPerLane = 8;  // E <= 256
-
-struct DropCfg { int on; float p; float scale; uint64_t seed, offset; const uint64_t* offset_dev; };
-
-__device__ __forceinline__ float drop_apply(const DropCfg& c, uint32_t site, uint64_t idx, float v) {
-  if (!c.on) return v;
-  const uint64_t off = c.offset_dev ? __ldg(reinterpret_cast<const unsigned long long*>(c.offset_dev)) : c.offset;
-  return dropout_keep(c.seed, off, site, idx, c.p) ? v * c.scale : 0.f;
-}
 
 // ---- LayerNorm forward -----------------------------------------------------------------------------------
 // MODE 0: pre = embs[u, t, :] + pos[t, :] ; out = dropout_site(LN(pre))
@@ -224,34 +215,6 @@ __global__ void __launch_bounds__(128) ue_attn_bwd_kernel(int L, int E, int H, c
   }
 }
 
-// ---- workspace layout --------------------------------------------------------------------------------------
-struct UeBlockBufs {
-  float *x_in, *q, *k, *v, *p, *ctx, *pre1, *stat1, *xmid, *h1, *pre2, *stat2;
-};
-struct UeLayout {
-  float *pre0, *stat0;
-  UeBlockBufs b[IISAN_MAX_BLOCKS];
-  float *lin;                       // [R, E] scratch: fc / w2 outputs
-  float *dA, *dB, *dq, *dk, *dv, *dctx, *dh1, *df;
-  size_t bytes;
-  UeLayout(const iisan_ue_desc& D, void* ws) {
-    Arena a(ws);
-    const size_t R = (size_t)D.users * D.seq_len, E = D.emb;
-    pre0 = a.take<float>(R * E); stat0 = a.take<float>(R * 2);
-    for (int i = 0; i < D.n_blocks; ++i) {
-      UeBlockBufs& x = b[i];
-      x.x_in = a.take<float>(R * E); x.q = a.take<float>(R * E); x.k = a.take<float>(R * E); x.v = a.take<float>(R * E);
-      x.p = a.take<float>((size_t)D.users * D.heads * D.seq_len * D.seq_len);
-      x.ctx = a.take<float>(R * E); x.pre1 = a.take<float>(R * E); x.stat1 = a.take<float>(R * 2);
-      x.xmid = a.take<float>(R * E); x.h1 = a.take<float>(R * 4 * E); x.pre2 = a.take<float>(R * E); x.stat2 = a.take<float>(R * 2);
-    }
-    lin = a.take<float>(R * E);
-    dA = a.take<float>(R * E); dB = a.take<float>(R * E); dq = a.take<float>(R * E); dk = a.take<float>(R * E);
-    dv = a.take<float>(R * E); dctx = a.take<float>(R * E); dh1 = a.take<float>(R * 4 * E); df = a.take<float>(R * E);
-    bytes = a.off;
-  }
-};
-
 static int ue_validate(const iisan_ue_desc* D) {
   if (!D) return IISAN_EINVAL;
   if (D->users <= 0 || D->seq_len <= 0 || D->seq_len > kMaxL) return IISAN_EINVAL;
@@ -259,14 +222,6 @@ static int ue_validate(const iisan_ue_desc* D) {
   if (D->n_blocks <= 0 || D->n_blocks > IISAN_MAX_BLOCKS) return IISAN_EINVAL;
   if (D->training && (D->dropout_p < 0.f || D->dropout_p >= 1.f)) return IISAN_EINVAL;
   return IISAN_OK;
-}
-
-static DropCfg drop_cfg(const iisan_ue_desc& D) {
-  DropCfg c;
-  c.on = (D.training && D.dropout_p > 0.f) ? 1 : 0;
-  c.p = D.dropout_p; c.scale = c.on ? 1.0f / (1.0f - D.dropout_p) : 1.0f;
-  c.seed = D.seed; c.offset = D.offset; c.offset_dev = D.offset_dev;
-  return c;
 }
 
 static size_t attn_smem(const iisan_ue_desc& D, bool bwd) {
@@ -277,6 +232,9 @@ static size_t attn_smem(const iisan_ue_desc& D, bool bwd) {
 }  // namespace iisan
 
 using namespace iisan;
+
+// test / profiling switch: IISAN_B200_NO_FUSED_UE=1 forces the per-operator path
+static const bool g_no_fused_ue = [] { const char* e = getenv("IISAN_B200_NO_FUSED_UE"); return e && e[0] == '1'; }();
 
 extern "C" size_t iisan_user_encoder_workspace_bytes(const iisan_ue_desc* desc) {
   if (ue_validate(desc) != IISAN_OK) return 0;
@@ -292,6 +250,7 @@ extern "C" int iisan_user_encoder_forward(const iisan_ue_desc* desc, const iisan
   if (workspace_bytes < iisan_user_encoder_workspace_bytes(desc)) return IISAN_EWORKSPACE;
   const iisan_ue_desc& D = *desc;
   cudaStream_t st = as_stream(stream);
+  if (ue_fused_supported(D) && !g_no_fused_ue) return ue_fused_forward(D, P, embs, ld_user, log_mask, workspace, out, st);
   UeLayout W(D, workspace);
   const int R = D.users * D.seq_len, E = D.emb, L = D.seq_len, H = D.heads;
   const DropCfg dc = drop_cfg(D);
@@ -336,6 +295,7 @@ extern "C" int iisan_user_encoder_backward(const iisan_ue_desc* desc, const iisa
   if (workspace_bytes < iisan_user_encoder_workspace_bytes(desc)) return IISAN_EWORKSPACE;
   const iisan_ue_desc& D = *desc;
   cudaStream_t st = as_stream(stream);
+  if (ue_fused_supported(D) && !g_no_fused_ue) return ue_fused_backward(D, P, G, embs, ld_user, log_mask, workspace, d_out, d_embs, st);
   UeLayout W(D, workspace);
   const int R = D.users * D.seq_len, E = D.emb, L = D.seq_len, H = D.heads;
   const DropCfg dc = drop_cfg(D);

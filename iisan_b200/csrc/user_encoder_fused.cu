@@ -1,0 +1,484 @@
+// SASRec user encoder, whole encoder per CTA (E = 64, L = 10; fp32 FMA in both arithmetic modes).
+//
+// Algorithm restated from the reference's PyTorch modules (nothing ported; same operator order as user_encoder.cu):
+//   entry                 CC/model/modules.py:89-96     x = dropout(LN(embs + pos_emb))
+//   attention block       CC/model/modules.py:21-32, 54-64 ; mask CC/model/encoders.py:53-58
+//   feed-forward block    CC/model/modules.py:14-18
+//
+// The per-operator path (user_encoder.cu) launches ~45 kernels for 512 users x 10 positions x 64 features: pure launch and
+// latency overhead.  Here one CTA owns 4 users (40 rows): the activations of the whole encoder stay in shared memory, the
+// weights (100 k parameters, 400 KB) are read through L1/L2 by every CTA, and each linear layer is a register-tiled FMA loop
+// (one weight row per thread against the CTA's rows, broadcast 128-bit shared-memory reads).  The forward writes the same
+// stash as the per-operator path; the backward recomputes nothing, accumulates the weight gradients of its 40 rows in
+// registers and adds them to the global gradient with one red.add per element and CTA.
+#include "common.cuh"
+#include "launch.cuh"
+#include "user_encoder.cuh"
+
+namespace iisan {
+
+constexpr int FE = 64;            // embedding width
+constexpr int FL = 10;            // sequence length
+constexpr int FUPC = 4;           // users per CTA
+constexpr int FR = FUPC * FL;     // rows per CTA
+constexpr int FF = 4 * FE;        // FFN width
+constexpr int FTHREADS = 256;
+constexpr int FMAXH = 4;
+
+struct FuArgs {
+  int users, H, n_blocks;
+  const float* embs; int64_t ld_user;
+  const float* log_mask;
+  iisan_ue_params P;
+  iisan_ue_params G;              // backward: gradient pointers
+  UeLayout W;
+  const float* d_out; float* d_embs;
+  float* out;
+  DropCfg dc;
+};
+
+struct FuSmem {
+  static constexpr int kX = 0;                       // [FR][FE] block input / running activation
+  static constexpr int kQ = kX + FR * FE;            // [FR][FE]
+  static constexpr int kK = kQ + FR * FE;
+  static constexpr int kV = kK + FR * FE;
+  static constexpr int kC = kV + FR * FE;            // [FR][FE] ctx / scratch
+  static constexpr int kM = kC + FR * FE;            // [FR][FE] xmid
+  static constexpr int kP = kM + FR * FE;            // [FUPC][FMAXH][FL][FL]
+  static constexpr int kH = kP + FUPC * FMAXH * FL * FL;   // [FR][FF]
+  static constexpr int kD = kH + FR * FF;            // backward only: second [FR][FF] buffer
+  static constexpr int kFwdFloats = kD;
+  static constexpr int kBwdFloats = kD + FR * FF;
+};
+
+// ys[r][o] = act(bias[o] + sum_k xs[r][k] W[o][k]) for the CTA's FR rows.  One output feature per thread, RT rows per thread.
+template <int IN, int OUT>
+__device__ __forceinline__ void cta_linear(const float* __restrict__ Wg, const float* __restrict__ bias, const float* xs, float* ys,
+                                           bool relu) {
+  constexpr int GROUPS = FTHREADS / OUT;     // row groups
+  constexpr int RT = FR / GROUPS;            // rows per thread
+  static_assert(FTHREADS % OUT == 0 && FR % GROUPS == 0, "tiling");
+  const int o = threadIdx.x % OUT, rg = threadIdx.x / OUT;
+  float acc[RT];
+#pragma unroll
+  for (int i = 0; i < RT; ++i) acc[i] = 0.f;
+  const float4* wrow = reinterpret_cast<const float4*>(Wg + (size_t)o * IN);
+#pragma unroll 2
+  for (int k4 = 0; k4 < IN / 4; ++k4) {
+    const float4 w = __ldg(wrow + k4);
+#pragma unroll
+    for (int i = 0; i < RT; ++i) {
+      const float4 x = *reinterpret_cast<const float4*>(xs + (rg * RT + i) * IN + k4 * 4);
+      acc[i] = fmaf(x.w, w.w, fmaf(x.z, w.z, fmaf(x.y, w.y, fmaf(x.x, w.x, acc[i]))));
+    }
+  }
+  const float b = bias ? __ldg(bias + o) : 0.f;
+#pragma unroll
+  for (int i = 0; i < RT; ++i) {
+    float v = acc[i] + b;
+    if (relu) v = fmaxf(v, 0.f);
+    ys[(rg * RT + i) * OUT + o] = v;
+  }
+}
+
+// dxs[r][i] (+)= sum_o dys[r][o] W[o][i]   (data gradient of a linear layer).  One input feature per thread.
+template <int IN, int OUT>
+__device__ __forceinline__ void cta_linear_t(const float* __restrict__ Wg, const float* dys, float* dxs, bool accumulate) {
+  constexpr int GROUPS = FTHREADS / IN;
+  constexpr int RT = FR / GROUPS;
+  static_assert(FTHREADS % IN == 0 && FR % GROUPS == 0, "tiling");
+  const int i = threadIdx.x % IN, rg = threadIdx.x / IN;
+  float acc[RT];
+#pragma unroll
+  for (int r = 0; r < RT; ++r) acc[r] = 0.f;
+#pragma unroll 2
+  for (int o4 = 0; o4 < OUT / 4; ++o4) {
+    const float w0 = __ldg(Wg + (size_t)(o4 * 4 + 0) * IN + i), w1 = __ldg(Wg + (size_t)(o4 * 4 + 1) * IN + i);
+    const float w2 = __ldg(Wg + (size_t)(o4 * 4 + 2) * IN + i), w3 = __ldg(Wg + (size_t)(o4 * 4 + 3) * IN + i);
+#pragma unroll
+    for (int r = 0; r < RT; ++r) {
+      const float4 d = *reinterpret_cast<const float4*>(dys + (rg * RT + r) * OUT + o4 * 4);
+      acc[r] = fmaf(d.w, w3, fmaf(d.z, w2, fmaf(d.y, w1, fmaf(d.x, w0, acc[r]))));
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < RT; ++r) {
+    float* p = dxs + (rg * RT + r) * IN + i;
+    *p = accumulate ? *p + acc[r] : acc[r];
+  }
+}
+
+// dW[o][i] += sum_r dys[r][o] xs[r][i] over the CTA's rows; 4x4 register tiles, one red.add per element.  db[o] += colsum.
+template <int IN, int OUT>
+__device__ __forceinline__ void cta_wgrad(float* __restrict__ dWg, float* __restrict__ dbg, const float* dys, const float* xs) {
+  constexpr int TI = IN / 4, TILES = (OUT / 4) * TI;
+  for (int t = threadIdx.x; t < TILES; t += FTHREADS) {
+    const int o0 = (t / TI) * 4, i0 = (t % TI) * 4;
+    float acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+#pragma unroll 4
+    for (int r = 0; r < FR; ++r) {
+      const float4 d = *reinterpret_cast<const float4*>(dys + r * OUT + o0);
+      const float4 x = *reinterpret_cast<const float4*>(xs + r * IN + i0);
+      const float dv[4] = {d.x, d.y, d.z, d.w}, xv[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(dv[a], xv[b], acc[a][b]);
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) atomicAdd(dWg + (size_t)(o0 + a) * IN + i0 + b, acc[a][b]);
+  }
+  if (dbg) {
+    for (int o = threadIdx.x; o < OUT; o += FTHREADS) {
+      float s = 0.f;
+      for (int r = 0; r < FR; ++r) s += dys[r * OUT + o];
+      atomicAdd(dbg + o, s);
+    }
+  }
+}
+
+// LayerNorm over FE = 64 of the CTA's rows, warp per row (lane owns e = lane, lane + 32).
+// MODE 0: pre = a_row + b_row                      ; out = dropout_site(LN(pre))     (entry)
+// MODE 1: pre = xs[r] + dropout_site(fs[r])        ; out = LN(pre)
+template <int MODE>
+__device__ __forceinline__ void cta_ln_fwd(const FuArgs& a, int u0, const float* xs, const float* fs, const float* __restrict__ gamma,
+                                           const float* __restrict__ beta, float* pre_g, float* stat_g, float* outs, float* out_g,
+                                           uint32_t site) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int r = warp; r < FR; r += FTHREADS / 32) {
+    const int ul = r / FL, t = r % FL, u = u0 + ul;
+    const bool ok = u < a.users;
+    const int64_t gr = (int64_t)u * FL + t;
+    float v[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int e = lane + 32 * i;
+      float x = 0.f;
+      if (ok) {
+        if (MODE == 0) x = a.embs[(int64_t)u * a.ld_user + (int64_t)t * FE + e] + __ldg(a.P.pos_emb + t * FE + e);
+        else x = xs[r * FE + e] + drop_apply(a.dc, site, (uint64_t)gr * FE + e, fs[r * FE + e]);
+      }
+      v[i] = x;
+    }
+    const float mean = warp_sum(v[0] + v[1]) / (float)FE;
+    const float d0 = v[0] - mean, d1 = v[1] - mean;
+    const float var = warp_sum(d0 * d0 + d1 * d1) / (float)FE;
+    const float rstd = 1.0f / sqrtf(var + kLnEps);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int e = lane + 32 * i;
+      float y = (v[i] - mean) * rstd * __ldg(gamma + e) + __ldg(beta + e);
+      if (MODE == 0 && ok) y = drop_apply(a.dc, site, (uint64_t)gr * FE + e, y);
+      if (!ok) y = 0.f;
+      outs[r * FE + e] = y;
+      if (ok) {
+        pre_g[gr * FE + e] = v[i];
+        if (out_g) out_g[gr * FE + e] = y;
+      }
+    }
+    if (ok && lane == 0) { stat_g[2 * gr] = mean; stat_g[2 * gr + 1] = rstd; }
+  }
+}
+
+// copy the CTA's rows of a [FR][W] shared buffer to the global stash (row-contiguous, coalesced)
+template <int W>
+__device__ __forceinline__ void cta_store_rows(const FuArgs& a, int u0, const float* s, float* g) {
+  for (int idx = threadIdx.x; idx < FR * W / 4; idx += FTHREADS) {
+    const int r = idx / (W / 4), c4 = idx % (W / 4);
+    const int u = u0 + r / FL;
+    if (u < a.users) reinterpret_cast<float4*>(g + ((int64_t)u * FL + r % FL) * W)[c4] = reinterpret_cast<const float4*>(s + r * W)[c4];
+  }
+}
+template <int W>
+__device__ __forceinline__ void cta_load_rows(const FuArgs& a, int u0, float* s, const float* g) {
+  for (int idx = threadIdx.x; idx < FR * W / 4; idx += FTHREADS) {
+    const int r = idx / (W / 4), c4 = idx % (W / 4);
+    const int u = u0 + r / FL;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (u < a.users) v = reinterpret_cast<const float4*>(g + ((int64_t)u * FL + r % FL) * W)[c4];
+    reinterpret_cast<float4*>(s + r * W)[c4] = v;
+  }
+}
+
+__global__ void __launch_bounds__(FTHREADS, 1) ue_fused_fwd_kernel(const __grid_constant__ FuArgs a) {
+  extern __shared__ float fsm[];
+  float* sX = fsm + FuSmem::kX; float* sQ = fsm + FuSmem::kQ; float* sK = fsm + FuSmem::kK; float* sV = fsm + FuSmem::kV;
+  float* sC = fsm + FuSmem::kC; float* sM = fsm + FuSmem::kM; float* sP = fsm + FuSmem::kP; float* sH = fsm + FuSmem::kH;
+  __shared__ float keyok[FR];
+  const int u0 = blockIdx.x * FUPC;
+  const int H = a.H, dk = FE / H;
+  const float temp = sqrtf((float)dk);
+  if (threadIdx.x < FR) {
+    const int u = u0 + threadIdx.x / FL;
+    keyok[threadIdx.x] = (u < a.users && a.log_mask[(int64_t)u * FL + threadIdx.x % FL] != 0.f) ? 1.f : 0.f;
+  }
+  // ---- entry: x = dropout(LN(embs + pos)) ----
+  cta_ln_fwd<0>(a, u0, nullptr, nullptr, a.P.ln_w, a.P.ln_b, a.W.pre0, a.W.stat0, sX, a.W.b[0].x_in, 0u);
+  __syncthreads();
+  for (int b = 0; b < a.n_blocks; ++b) {
+    const iisan_ue_block_ptrs& bp = a.P.blocks[b];
+    const UeBlockBufs& X = a.W.b[b];
+    // ---- q, k, v ----
+    cta_linear<FE, FE>(bp.w_q, nullptr, sX, sQ, false);
+    cta_linear<FE, FE>(bp.w_k, nullptr, sX, sK, false);
+    cta_linear<FE, FE>(bp.w_v, nullptr, sX, sV, false);
+    __syncthreads();
+    cta_store_rows<FE>(a, u0, sQ, X.q); cta_store_rows<FE>(a, u0, sK, X.k); cta_store_rows<FE>(a, u0, sV, X.v);
+    // ---- scores + mask ----
+    for (int idx = threadIdx.x; idx < FUPC * H * FL * FL; idx += FTHREADS) {
+      const int ul = idx / (H * FL * FL), rem = idx % (H * FL * FL);
+      const int h = rem / (FL * FL), i = (rem / FL) % FL, j = rem % FL;
+      const float* qr = sQ + (ul * FL + i) * FE + h * dk; const float* kr = sK + (ul * FL + j) * FE + h * dk;
+      float d = 0.f;
+      for (int c = 0; c < dk; ++c) d = fmaf(qr[c], kr[c], d);
+      const float m = (j <= i && keyok[ul * FL + j] != 0.f) ? 0.f : kAttNeg;
+      sP[idx] = __fadd_rn(__fdiv_rn(d, temp), m);
+    }
+    __syncthreads();
+    // ---- softmax rows, stash p, attention dropout ----
+    for (int r = threadIdx.x; r < FUPC * H * FL; r += FTHREADS) {
+      float* row = sP + r * FL;
+      const int ul = r / (H * FL), u = u0 + ul;
+      float mx = row[0];
+      for (int j = 1; j < FL; ++j) mx = fmaxf(mx, row[j]);
+      float s = 0.f;
+      for (int j = 0; j < FL; ++j) { row[j] = expf(row[j] - mx); s += row[j]; }
+      for (int j = 0; j < FL; ++j) {
+        const float p = row[j] / s;
+        const int64_t gi = (int64_t)u * H * FL * FL + (r % (H * FL)) * FL + j;
+        if (u < a.users) { X.p[gi] = p; row[j] = drop_apply(a.dc, 1u + 4u * b, (uint64_t)gi, p); }
+        else row[j] = 0.f;
+      }
+    }
+    __syncthreads();
+    // ---- ctx = p v ----
+    for (int idx = threadIdx.x; idx < FR * FE; idx += FTHREADS) {
+      const int r = idx / FE, e = idx % FE, ul = r / FL, i = r % FL, h = e / dk;
+      const float* pr = sP + ((ul * H + h) * FL + i) * FL;
+      float acc = 0.f;
+      for (int j = 0; j < FL; ++j) acc = fmaf(pr[j], sV[(ul * FL + j) * FE + e], acc);
+      sC[idx] = acc;
+    }
+    __syncthreads();
+    cta_store_rows<FE>(a, u0, sC, X.ctx);
+    // ---- fc + residual + LN1 ----
+    cta_linear<FE, FE>(bp.w_fc, nullptr, sC, sQ, false);          // sQ reused as the linear output
+    __syncthreads();
+    cta_ln_fwd<1>(a, u0, sX, sQ, bp.ln1_w, bp.ln1_b, X.pre1, X.stat1, sM, X.xmid, 2u + 4u * b);
+    __syncthreads();
+    // ---- FFN ----
+    cta_linear<FE, FF>(bp.w1, bp.b1, sM, sH, true);
+    __syncthreads();
+    cta_store_rows<FF>(a, u0, sH, X.h1);
+    cta_linear<FF, FE>(bp.w2, bp.b2, sH, sQ, false);
+    __syncthreads();
+    float* dst_g = (b + 1 < a.n_blocks) ? a.W.b[b + 1].x_in : a.out;
+    cta_ln_fwd<1>(a, u0, sM, sQ, bp.ln2_w, bp.ln2_b, X.pre2, X.stat2, sX, dst_g, 3u + 4u * b);
+    __syncthreads();
+  }
+}
+
+// LayerNorm backward over the CTA's rows (warp per row).  dys: [FR][FE] gradient of the LN output.
+// MODE 0 (entry): dys <- dropout_bwd(dys) first; d pre -> d_embs (global, strided by user); d pos via dfs (dense copy).
+// MODE 1: d pre -> dpre_s (residual branch) and dfs = dropout_bwd(d pre) (linear branch).
+template <int MODE>
+__device__ __forceinline__ void cta_ln_bwd(const FuArgs& a, int u0, const float* dys, const float* pre_g, const float* stat_g,
+                                           const float* __restrict__ gamma, float* dgamma_s, float* dbeta_s, float* dpre_s, float* dfs,
+                                           uint32_t site) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float ag[2] = {0.f, 0.f}, ab[2] = {0.f, 0.f};
+  for (int r = warp; r < FR; r += FTHREADS / 32) {
+    const int ul = r / FL, t = r % FL, u = u0 + ul;
+    const bool ok = u < a.users;
+    const int64_t gr = (int64_t)u * FL + t;
+    float mean = 0.f, rstd = 0.f;
+    if (ok) { mean = stat_g[2 * gr]; rstd = stat_g[2 * gr + 1]; }
+    float xh[2], g[2];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int e = lane + 32 * i;
+      float d = ok ? dys[r * FE + e] : 0.f;
+      if (MODE == 0 && ok) d = drop_apply(a.dc, site, (uint64_t)gr * FE + e, d);
+      xh[i] = ok ? (pre_g[gr * FE + e] - mean) * rstd : 0.f;
+      ag[i] += d * xh[i]; ab[i] += d;
+      g[i] = d * __ldg(gamma + e);
+      s1 += g[i]; s2 += g[i] * xh[i];
+    }
+    s1 = warp_sum(s1) / (float)FE; s2 = warp_sum(s2) / (float)FE;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int e = lane + 32 * i;
+      const float dp = ok ? rstd * (g[i] - s1 - xh[i] * s2) : 0.f;
+      if (MODE == 0) {
+        if (ok) a.d_embs[(int64_t)u * a.ld_user + (int64_t)t * FE + e] = dp;
+        dfs[r * FE + e] = dp;
+      } else {
+        dpre_s[r * FE + e] = dp;
+        dfs[r * FE + e] = ok ? drop_apply(a.dc, site, (uint64_t)gr * FE + e, dp) : 0.f;
+      }
+    }
+  }
+  // gamma / beta partials of this warp -> shared accumulators
+#pragma unroll
+  for (int i = 0; i < 2; ++i) { atomicAdd(dgamma_s + lane + 32 * i, ag[i]); atomicAdd(dbeta_s + lane + 32 * i, ab[i]); }
+}
+
+__global__ void __launch_bounds__(FTHREADS, 1) ue_fused_bwd_kernel(const __grid_constant__ FuArgs a) {
+  extern __shared__ float fsm[];
+  float* sX = fsm + FuSmem::kX;      // x_in of the block / d x_in accumulation target (see below)
+  float* sQ = fsm + FuSmem::kQ; float* sK = fsm + FuSmem::kK; float* sV = fsm + FuSmem::kV;
+  float* sC = fsm + FuSmem::kC; float* sM = fsm + FuSmem::kM; float* sP = fsm + FuSmem::kP;
+  float* sH = fsm + FuSmem::kH;      // h1
+  float* sD = fsm + FuSmem::kD;      // d h1
+  __shared__ float sgam[FE], sbet[FE];
+  const int u0 = blockIdx.x * FUPC;
+  const int H = a.H, dk = FE / H;
+  const float temp = sqrtf((float)dk);
+  // running gradient dY [FR][FE] lives in sC at block entry
+  cta_load_rows<FE>(a, u0, sC, a.d_out);
+  __syncthreads();
+  for (int b = a.n_blocks - 1; b >= 0; --b) {
+    const iisan_ue_block_ptrs& bp = a.P.blocks[b];
+    const iisan_ue_block_ptrs& bg = a.G.blocks[b];
+    const UeBlockBufs& X = a.W.b[b];
+    // ---- LN2 backward: sC = dY -> sM = d pre2 (residual to xmid), sQ = df (w2 branch) ----
+    if (threadIdx.x < FE) { sgam[threadIdx.x] = 0.f; sbet[threadIdx.x] = 0.f; }
+    cta_load_rows<FF>(a, u0, sH, X.h1);
+    __syncthreads();
+    cta_ln_bwd<1>(a, u0, sC, X.pre2, X.stat2, bp.ln2_w, sgam, sbet, sM, sQ, 3u + 4u * b);
+    __syncthreads();
+    if (threadIdx.x < FE) { atomicAdd(bg.ln2_w + threadIdx.x, sgam[threadIdx.x]); atomicAdd(bg.ln2_b + threadIdx.x, sbet[threadIdx.x]); }
+    // ---- W2: dW2 += df^T h1 ; db2 ; d h1 = (df W2) * (h1 > 0) ----
+    cta_wgrad<FF, FE>(bg.w2, bg.b2, sQ, sH);
+    cta_linear_t<FF, FE>(bp.w2, sQ, sD, false);
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < FR * FF; idx += FTHREADS) if (!(sH[idx] > 0.f)) sD[idx] = 0.f;
+    cta_load_rows<FE>(a, u0, sK, X.xmid);          // xmid for dW1
+    __syncthreads();
+    // ---- W1: dW1 += dh1^T xmid ; db1 ; d xmid = d pre2 + dh1 W1 ----
+    cta_wgrad<FE, FF>(bg.w1, bg.b1, sD, sK);
+    cta_linear_t<FE, FF>(bp.w1, sD, sM, true);
+    __syncthreads();
+    // ---- LN1 backward: sM = d xmid -> sC = d pre1 (residual to x_in), sQ = df (fc branch) ----
+    if (threadIdx.x < FE) { sgam[threadIdx.x] = 0.f; sbet[threadIdx.x] = 0.f; }
+    cta_load_rows<FE>(a, u0, sV, X.ctx);
+    __syncthreads();
+    cta_ln_bwd<1>(a, u0, sM, X.pre1, X.stat1, bp.ln1_w, sgam, sbet, sC, sQ, 2u + 4u * b);
+    __syncthreads();
+    if (threadIdx.x < FE) { atomicAdd(bg.ln1_w + threadIdx.x, sgam[threadIdx.x]); atomicAdd(bg.ln1_b + threadIdx.x, sbet[threadIdx.x]); }
+    // ---- fc: dWfc += df^T ctx ; d ctx = df Wfc -> sM ----
+    cta_wgrad<FE, FE>(bg.w_fc, nullptr, sQ, sV);
+    cta_linear_t<FE, FE>(bp.w_fc, sQ, sM, false);
+    __syncthreads();
+    // ---- attention backward: q,k,v,p from the stash, d ctx in sM -> dq, dk, dv ----
+    cta_load_rows<FE>(a, u0, sQ, X.q); cta_load_rows<FE>(a, u0, sK, X.k); cta_load_rows<FE>(a, u0, sV, X.v);
+    float* sPd = sH;                               // dropout(p)      [FUPC][H][FL][FL]   (h1 is dead)
+    float* sDs = sH + FUPC * FMAXH * FL * FL;      // d scores / temp
+    for (int idx = threadIdx.x; idx < FUPC * H * FL * FL; idx += FTHREADS) {
+      const int ul = idx / (H * FL * FL), u = u0 + ul;
+      const int64_t gi = (int64_t)u * H * FL * FL + idx % (H * FL * FL);
+      float p = 0.f, pd = 0.f;
+      if (u < a.users) { p = X.p[gi]; pd = drop_apply(a.dc, 1u + 4u * b, (uint64_t)gi, p); }
+      sP[idx] = p; sPd[idx] = pd;
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < FUPC * H * FL * FL; idx += FTHREADS) {       // d(dropout(p)) = dctx_i . v_j, then mask * scale
+      const int ul = idx / (H * FL * FL), rem = idx % (H * FL * FL), u = u0 + ul;
+      const int h = rem / (FL * FL), i = (rem / FL) % FL, j = rem % FL;
+      const float* dr = sM + (ul * FL + i) * FE + h * dk; const float* vr = sV + (ul * FL + j) * FE + h * dk;
+      float acc = 0.f;
+      for (int c = 0; c < dk; ++c) acc = fmaf(dr[c], vr[c], acc);
+      const int64_t gi = (int64_t)u * H * FL * FL + rem;
+      sDs[idx] = (u < a.users) ? drop_apply(a.dc, 1u + 4u * b, (uint64_t)gi, acc) : 0.f;
+    }
+    __syncthreads();
+    for (int r = threadIdx.x; r < FUPC * H * FL; r += FTHREADS) {                    // softmax backward, / temp
+      float dot = 0.f;
+      for (int j = 0; j < FL; ++j) dot = fmaf(sDs[r * FL + j], sP[r * FL + j], dot);
+      for (int j = 0; j < FL; ++j) sDs[r * FL + j] = sP[r * FL + j] * (sDs[r * FL + j] - dot) / temp;
+    }
+    __syncthreads();
+    float* sDq = sD; float* sDk = sD + FR * FE; float* sDv = sD + 2 * FR * FE;       // d h1 is dead
+    for (int idx = threadIdx.x; idx < FR * FE; idx += FTHREADS) {
+      const int r = idx / FE, e = idx % FE, ul = r / FL, i = r % FL, h = e / dk;
+      const float* ds = sDs + (ul * H + h) * FL * FL; const float* pd = sPd + (ul * H + h) * FL * FL;
+      float aq = 0.f, ak = 0.f, av = 0.f;
+      for (int j = 0; j < FL; ++j) {
+        aq = fmaf(ds[i * FL + j], sK[(ul * FL + j) * FE + e], aq);       // dq[i] = sum_j ds[i,j] k[j]
+        ak = fmaf(ds[j * FL + i], sQ[(ul * FL + j) * FE + e], ak);       // dk[i] = sum_j ds[j,i] q[j]
+        av = fmaf(pd[j * FL + i], sM[(ul * FL + j) * FE + e], av);       // dv[i] = sum_j pd[j,i] dctx[j]
+      }
+      sDq[idx] = aq; sDk[idx] = ak; sDv[idx] = av;
+    }
+    cta_load_rows<FE>(a, u0, sX, X.x_in);
+    __syncthreads();
+    // ---- q/k/v projections: dW += d^T x_in ; d x_in = d pre1 + dq Wq + dk Wk + dv Wv (accumulated into sC) ----
+    cta_wgrad<FE, FE>(bg.w_q, nullptr, sDq, sX);
+    cta_wgrad<FE, FE>(bg.w_k, nullptr, sDk, sX);
+    cta_wgrad<FE, FE>(bg.w_v, nullptr, sDv, sX);
+    cta_linear_t<FE, FE>(bp.w_q, sDq, sC, true);
+    __syncthreads();
+    cta_linear_t<FE, FE>(bp.w_k, sDk, sC, true);
+    __syncthreads();
+    cta_linear_t<FE, FE>(bp.w_v, sDv, sC, true);
+    __syncthreads();
+  }
+  // ---- entry LN + position embedding ----
+  if (threadIdx.x < FE) { sgam[threadIdx.x] = 0.f; sbet[threadIdx.x] = 0.f; }
+  __syncthreads();
+  cta_ln_bwd<0>(a, u0, sC, a.W.pre0, a.W.stat0, a.P.ln_w, sgam, sbet, nullptr, sQ, 0u);
+  __syncthreads();
+  if (threadIdx.x < FE) { atomicAdd(a.G.ln_w + threadIdx.x, sgam[threadIdx.x]); atomicAdd(a.G.ln_b + threadIdx.x, sbet[threadIdx.x]); }
+  for (int idx = threadIdx.x; idx < FL * FE; idx += FTHREADS) {       // d pos[t] = sum over the CTA's users
+    float s = 0.f;
+    for (int ul = 0; ul < FUPC; ++ul) s += sQ[(ul * FL) * FE + idx];
+    atomicAdd(a.G.pos_emb + idx, s);
+  }
+}
+
+bool ue_fused_supported(const iisan_ue_desc& D) {
+  return D.emb == FE && D.seq_len == FL && D.heads >= 1 && D.heads <= FMAXH && FE % D.heads == 0;
+}
+
+int ue_fused_forward(const iisan_ue_desc& D, const iisan_ue_params* P, const float* embs, int64_t ld_user, const float* log_mask,
+                     void* workspace, float* out, cudaStream_t st) {
+  static bool attr_set = false;
+  const size_t smem = FuSmem::kFwdFloats * sizeof(float);
+  if (!attr_set) {
+    IISAN_CUDA_OK(cudaFuncSetAttribute(ue_fused_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  FuArgs a{};
+  a.users = D.users; a.H = D.heads; a.n_blocks = D.n_blocks; a.embs = embs; a.ld_user = ld_user; a.log_mask = log_mask;
+  a.P = *P; a.W = UeLayout(D, workspace); a.out = out; a.dc = drop_cfg(D);
+  const int grid = (D.users + FUPC - 1) / FUPC;
+  { LaunchScope ls_(IISAN_K_USER, st); ue_fused_fwd_kernel<<<grid, FTHREADS, smem, st>>>(a); }
+  IISAN_LAUNCH_OK();
+  return IISAN_OK;
+}
+
+int ue_fused_backward(const iisan_ue_desc& D, const iisan_ue_params* P, const iisan_ue_params* G, const float* embs, int64_t ld_user,
+                      const float* log_mask, void* workspace, const float* d_out, float* d_embs, cudaStream_t st) {
+  static bool attr_set = false;
+  const size_t smem = FuSmem::kBwdFloats * sizeof(float);
+  if (!attr_set) {
+    IISAN_CUDA_OK(cudaFuncSetAttribute(ue_fused_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  FuArgs a{};
+  a.users = D.users; a.H = D.heads; a.n_blocks = D.n_blocks; a.embs = embs; a.ld_user = ld_user; a.log_mask = log_mask;
+  a.P = *P; a.G = *G; a.W = UeLayout(D, workspace); a.d_out = d_out; a.d_embs = d_embs; a.dc = drop_cfg(D);
+  const int grid = (D.users + FUPC - 1) / FUPC;
+  { LaunchScope ls_(IISAN_K_USER, st); ue_fused_bwd_kernel<<<grid, FTHREADS, smem, st>>>(a); }
+  IISAN_LAUNCH_OK();
+  return IISAN_OK;
+}
+
+}  // namespace iisan
