@@ -202,20 +202,20 @@ __global__ void __launch_bounds__(CE_THREADS, 1) ce_tile_kernel(const __grid_con
       const int b = t & 1; const uint32_t bph = (uint32_t)(t >> 1) & 1u;
       const int tt0 = (t_beg + t) * CT;                                  // first streamed entity of this tile
       // ---- stage streamed-side attributes (one entity per thread of the first 128) ----
-      float* at = attr_f + b * CT * 4;
+      float2* at = reinterpret_cast<float2*>(attr_f) + b * CT;          // OWNER_ROWS: .x = debias ; else (.x, .y) = (lse, label code)
       if (et < CT) {
         const int e = tt0 + et;
         if (OWNER_ROWS) {
-          at[et * 4 + 0] = (e < a.C) ? a.debias[e] : 0.f;
+          at[et] = make_float2((e < a.C) ? a.debias[e] : 0.f, 0.f);
         } else {
-          // streamed rows: lse (inf for invalid rows => weight 0), label column (-1 for invalid), label-masked flag
+          // streamed rows: lse (+inf for invalid rows => weight 0) and the label column with bit 30 = "label column is pad-masked"
+          // (-1 for invalid rows: never equal to a column index)
           const bool ok = (e < a.R) && (a.lm_rows[e] != 0.f);
           const int ec = e < a.R ? e : 0;
           const int i = ec / a.L, j = ec % a.L;
-          at[et * 4 + 0] = ok ? a.lse[ec] : INFINITY;
-          reinterpret_cast<int*>(at)[et * 4 + 1] = ok ? (int)((a.user_offset + i) * a.S + j + 1) : -1;
-          reinterpret_cast<int*>(at)[et * 4 + 2] = ((j + 1 < a.L) && (a.lm_cols[(a.user_offset + i) * a.L + j + 1] == 0.f)) ? 1 : 0;
-          reinterpret_cast<int*>(at)[et * 4 + 3] = i;
+          const bool lmk = (j + 1 < a.L) && (a.lm_cols[(a.user_offset + i) * a.L + j + 1] == 0.f);
+          const int code = ok ? ((int)((a.user_offset + i) * a.S + j + 1) | (lmk ? 0x40000000 : 0)) : -1;
+          at[et] = make_float2(ok ? a.lse[ec] : INFINITY, __int_as_float(code));
         }
       }
       epi_bar_sync();
@@ -237,13 +237,13 @@ __global__ void __launch_bounds__(CE_THREADS, 1) ce_tile_kernel(const __grid_con
 #pragma unroll
           for (int k = 0; k < 32; ++k) {
             const bool masked = (mw >> k) & 1u;
-            v[k] = masked ? kNegMaskF : __uint_as_float(raw[k]) - at[(k0 + k) * 4];
+            v[k] = masked ? kNegMaskF : __uint_as_float(raw[k]) - at[k0 + k].x;
           }
           if (o_label >= c0 && o_label < c0 + 32) {                       // the label column escapes the reject mask
             const int kl = o_label - c0;
 #pragma unroll
             for (int k = 0; k < 32; ++k)
-              if (k == kl) v[k] = o_lab_masked ? kNegMaskF : __uint_as_float(raw[k]) - at[(k0 + k) * 4];
+              if (k == kl) v[k] = o_lab_masked ? kNegMaskF : __uint_as_float(raw[k]) - at[k0 + k].x;
           }
           if (!BWD) {
             float cm = -INFINITY;
@@ -274,24 +274,28 @@ __global__ void __launch_bounds__(CE_THREADS, 1) ce_tile_kernel(const __grid_con
             }
           }
         } else {
-          // lanes = columns, chunk = 32 consecutive rows of the tile
+          // lanes = columns, chunk = 32 consecutive rows of the tile; the mask bit of (row-user, this column) changes only when
+          // the row's user changes (every L rows): one warp-uniform 32-bit load per user
           const int cw = (o0 + quad * 32) >> 5;                           // mask word of this warp's 32 columns
           const bool cw_ok = (o0 + quad * 32) < a.C;
-          int cur_user = -1; uint32_t mw = 0xffffffffu;
+          int r_user = (tt0 + k0) / a.L, r_rem = (tt0 + k0) % a.L;
+          bool mbit = true;
+          if (cw_ok && r_user < a.B) mbit = (__ldg(a.maskbits + (int64_t)r_user * a.Cw + cw) >> lane) & 1u;
 #pragma unroll
           for (int k = 0; k < 32; ++k) {
-            const float r_lse = at[(k0 + k) * 4];
-            const int r_label = reinterpret_cast<const int*>(at)[(k0 + k) * 4 + 1];
-            const int r_lm = reinterpret_cast<const int*>(at)[(k0 + k) * 4 + 2];
-            const int r_user = reinterpret_cast<const int*>(at)[(k0 + k) * 4 + 3];
-            if (r_user != cur_user && cw_ok) { cur_user = r_user; mw = __ldg(a.maskbits + (int64_t)r_user * a.Cw + cw); }   // warp-uniform
-            bool masked = (mw >> lane) & 1u;
-            const bool is_label = (o == r_label);
-            if (is_label) masked = (r_lm != 0);
+            const float2 ra = at[k0 + k];
+            const int code = __float_as_int(ra.y);
+            const bool is_label = (code >= 0) && ((code & 0x3fffffff) == o);
+            const bool masked = is_label ? ((code & 0x40000000) != 0) : mbit;
             const float lg = masked ? kNegMaskF : __uint_as_float(raw[k]) - o_debias;
-            float w = __expf(lg - r_lse);                                  // r_lse = +inf for invalid rows -> 0
+            float w = __expf(lg - ra.x);                                   // lse = +inf for invalid rows -> 0
             if (is_label) w -= 1.f;
             v[k] = o_ok ? w * scale : 0.f;
+            if (++r_rem == a.L) {                                          // next row belongs to the next user (warp-uniform)
+              r_rem = 0; ++r_user;
+              mbit = true;
+              if (cw_ok && r_user < a.B) mbit = (__ldg(a.maskbits + (int64_t)r_user * a.Cw + cw) >> lane) & 1u;
+            }
           }
         }
         if (BWD) {
@@ -399,10 +403,12 @@ __global__ void __launch_bounds__(256) ce_maskbits_kernel(const int64_t* __restr
       const int p = c % S;
       m = (p < L) && (lm_cols[(int64_t)(c / S) * L + p] == 0.f);
       const int64_t id = ids_cols[c];
-      bool hit = false;
+      if (!m) {
+        bool hit = false;
 #pragma unroll
-      for (int q = 0; q < 17; ++q) hit |= (rid[q] == id);
-      m = m || hit;
+        for (int q = 0; q < 17; ++q) if (q < S) hit |= (rid[q] == id);
+        m = hit;
+      }
     }
     word |= (m ? 1u : 0u) << k;
   }

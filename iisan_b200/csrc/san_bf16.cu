@@ -487,19 +487,22 @@ static int san_backward_bf16_t(const iisan_san_desc* D, const iisan_san_params* 
       t2.layer[s] = D->img_layer[s]; t2.layer2[s] = D->text_layer[s]; t2.gate[s] = P->gate_mm[mi]; t2.g_gate[s] = G->gate_mm[mi]; t2.g_b_down[s] = G->mm[mi].b_down; t2.g_b_up[s] = G->mm[mi].b_up;
     }
     IISAN_TRY(launch_san_chain_bwd(ca, 3, st));
-    // ---- weight gradients: reductions over all items, split-K GEMMs over the stashes ----
-    for (int s = D->n_stages - 1; s >= 0; --s) {
-      const int ta = D->text_adapter[s], ia = D->img_adapter[s], mi = D->mm_index[s];
-      const size_t off = (size_t)s * chain_n_pad(N) * D->d_mm;
-      UmmaBatch wu{}, wd{}; wu.n = wd.n = 3;
-      wu.p[0] = mk_wgrad(L.dys[0] + off, D->d_text, D->d_text, L.z_t[s], D->r_text, D->r_text, N, G->text[ta].w_up, 3);
-      wu.p[1] = mk_wgrad(L.dys[1] + off, D->d_img, D->d_img, L.z_i[s], D->r_img, D->r_img, N, G->img[ia].w_up, 3);
-      wu.p[2] = mk_wgrad(L.dys[2] + off, D->d_mm, D->d_mm, L.z_m[s], D->r_mm, D->r_mm, N, G->mm[mi].w_up, 3);
-      wd.p[0] = mk_wgrad(L.dzs[0][s], D->r_text, D->r_text, L.x_t[s], D->d_text, D->d_text, N, G->text[ta].w_down, 3);
-      wd.p[1] = mk_wgrad(L.dzs[1][s], D->r_img, D->r_img, L.x_i[s], D->d_img, D->d_img, N, G->img[ia].w_down, 3);
-      wd.p[2] = mk_wgrad(L.dzs[2][s], D->r_mm, D->r_mm, L.x_m[s], D->d_mm, D->d_mm, N, G->mm[mi].w_down, 3);
-      IISAN_TRY(launch_umma_gemm(wu, st));
-      IISAN_TRY(launch_umma_gemm(wd, st));
+    // ---- weight gradients: reductions over all items; the 6 x A split-K GEMMs over the stashes share ONE launch ----
+    {
+      static thread_local UmmaBatchBig wg;
+      wg.n = 0;
+      const int np = 6 * D->n_stages;
+      for (int s = D->n_stages - 1; s >= 0; --s) {
+        const int ta = D->text_adapter[s], ia = D->img_adapter[s], mi = D->mm_index[s];
+        const size_t off = (size_t)s * chain_n_pad(N) * D->d_mm;
+        wg.p[wg.n++] = mk_wgrad(L.dys[0] + off, D->d_text, D->d_text, L.z_t[s], D->r_text, D->r_text, N, G->text[ta].w_up, np);
+        wg.p[wg.n++] = mk_wgrad(L.dys[1] + off, D->d_img, D->d_img, L.z_i[s], D->r_img, D->r_img, N, G->img[ia].w_up, np);
+        wg.p[wg.n++] = mk_wgrad(L.dys[2] + off, D->d_mm, D->d_mm, L.z_m[s], D->r_mm, D->r_mm, N, G->mm[mi].w_up, np);
+        wg.p[wg.n++] = mk_wgrad(L.dzs[0][s], D->r_text, D->r_text, L.x_t[s], D->d_text, D->d_text, N, G->text[ta].w_down, np);
+        wg.p[wg.n++] = mk_wgrad(L.dzs[1][s], D->r_img, D->r_img, L.x_i[s], D->d_img, D->d_img, N, G->img[ia].w_down, np);
+        wg.p[wg.n++] = mk_wgrad(L.dzs[2][s], D->r_mm, D->r_mm, L.x_m[s], D->d_mm, D->d_mm, N, G->mm[mi].w_down, np);
+      }
+      IISAN_TRY(launch_umma_gemm_big(wg, st));
     }
     return IISAN_OK;
   }

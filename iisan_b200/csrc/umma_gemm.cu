@@ -27,8 +27,9 @@ struct UmmaDevProblem {
   int kblocks_per_split;
   UmmaEpilogue epi;
 };
-struct UmmaDevBatch {
-  UmmaDevProblem p[kUmmaMaxProbs];
+template <int NP>
+struct UmmaDevBatchT {
+  UmmaDevProblem p[NP];
   int stages;
 };
 
@@ -99,8 +100,8 @@ __device__ __noinline__ void epi_block_generic(const UmmaEpilogue& E, const floa
 
 enum : int { EPI_MASK = 1, EPI_RESB = 2, EPI_RESF = 4, EPI_OUTF = 8, EPI_OUTB = 16, EPI_ATOMIC = 32 };
 
-template <int BN, bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(UTHREADS, 2) umma_gemm_kernel(const __grid_constant__ UmmaDevBatch batch) {
+template <int BN, bool A_MN, bool B_MN, int NP>
+__global__ void __launch_bounds__(UTHREADS, 2) umma_gemm_kernel(const __grid_constant__ UmmaDevBatchT<NP> batch) {
   const UmmaDevProblem& P = batch.p[blockIdx.z];
   const int NSTG = batch.stages;
   const int tiles_n = (P.N + BN - 1) / BN;
@@ -308,12 +309,12 @@ int make_tensor_map_bf16(CUtensorMap* out, const void* ptr, int64_t rows, int64_
   return IISAN_OK;
 }
 
-template <int BN, bool A_MN, bool B_MN>
-static int launch_cfg(const UmmaBatch& b, cudaStream_t st) {
-  UmmaDevBatch dev;
+template <int BN, bool A_MN, bool B_MN, int NP>
+static int launch_cfg(const UmmaProblem* probs, int n_probs, cudaStream_t st) {
+  static thread_local UmmaDevBatchT<NP> dev;      // large for the batched variant: keep it off the stack (launches are serialised per thread by the callers)
   int max_tiles = 0, max_split = 1, max_kb = 1;
-  for (int i = 0; i < b.n; ++i) {
-    const UmmaProblem& P = b.p[i];
+  for (int i = 0; i < n_probs; ++i) {
+    const UmmaProblem& P = probs[i];
     UmmaDevProblem& D = dev.p[i];
     if (P.M <= 0 || P.N <= 0 || P.K <= 0 || (P.N % 8)) return IISAN_EINVAL;
     // A
@@ -334,12 +335,12 @@ static int launch_cfg(const UmmaBatch& b, cudaStream_t st) {
   }
   static bool attr_set = false;
   if (!attr_set) {
-    IISAN_CUDA_OK(cudaFuncSetAttribute(umma_gemm_kernel<BN, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaSmem<BN>::total(USTAGES)));
+    IISAN_CUDA_OK(cudaFuncSetAttribute(umma_gemm_kernel<BN, A_MN, B_MN, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaSmem<BN>::total(USTAGES)));
     attr_set = true;
   }
   dev.stages = max_kb < 1 ? 1 : (max_kb > USTAGES ? USTAGES : max_kb);
-  dim3 grid(max_tiles, max_split, b.n);
-  { LaunchScope ls_(IISAN_K_GEMM, st); umma_gemm_kernel<BN, A_MN, B_MN><<<grid, UTHREADS, UmmaSmem<BN>::total(dev.stages), st>>>(dev); }
+  dim3 grid(max_tiles, max_split, n_probs);
+  { LaunchScope ls_(IISAN_K_GEMM, st); umma_gemm_kernel<BN, A_MN, B_MN, NP><<<grid, UTHREADS, UmmaSmem<BN>::total(dev.stages), st>>>(dev); }
   IISAN_LAUNCH_OK();
   return IISAN_OK;
 }
@@ -361,13 +362,21 @@ int launch_umma_gemm(const UmmaBatch& b, cudaStream_t st) {
     if (ctas < 2 * 148 * 2) bn = 128;
   }
   if (!a_mn) {
-    if (bn == 64) return launch_cfg<64, false, false>(b, st);
-    if (bn == 128) return launch_cfg<128, false, false>(b, st);
-    return launch_cfg<256, false, false>(b, st);
+    if (bn == 64) return launch_cfg<64, false, false, kUmmaMaxProbs>(b.p, b.n, st);
+    if (bn == 128) return launch_cfg<128, false, false, kUmmaMaxProbs>(b.p, b.n, st);
+    return launch_cfg<256, false, false, kUmmaMaxProbs>(b.p, b.n, st);
   }
-  if (bn == 64) return launch_cfg<64, true, true>(b, st);
-  if (bn == 128) return launch_cfg<128, true, true>(b, st);
-  return launch_cfg<256, true, true>(b, st);
+  if (bn == 64) return launch_cfg<64, true, true, kUmmaMaxProbs>(b.p, b.n, st);
+  if (bn == 128) return launch_cfg<128, true, true, kUmmaMaxProbs>(b.p, b.n, st);
+  return launch_cfg<256, true, true, kUmmaMaxProbs>(b.p, b.n, st);
+}
+
+int launch_umma_gemm_big(const UmmaBatchBig& b, cudaStream_t st) {
+  if (b.n <= 0) return IISAN_OK;
+  if (b.n > kUmmaBigProbs) return IISAN_EINVAL;
+  for (int i = 0; i < b.n; ++i)
+    if (!b.p[i].a_mn_major || !b.p[i].b_mn_major || b.p[i].N > 64) return IISAN_EUNSUPPORTED;
+  return launch_cfg<64, true, true, kUmmaBigProbs>(b.p, b.n, st);
 }
 
 }  // namespace iisan

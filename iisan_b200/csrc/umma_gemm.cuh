@@ -49,4 +49,13 @@ struct UmmaBatch {
 // Enqueue the batch on `st`.  Shapes: N % 16 == 0, K % 8 == 0 (16-byte global pitch), pointers 16-byte aligned.
 int launch_umma_gemm(const UmmaBatch& batch, cudaStream_t st);
 
+// Many independent weight-gradient products (MN-major operands, N <= 64) in ONE launch: the 42 dW GEMMs of the chain backward.
+// (The argument block is ~18 KB; kernel parameters up to 32 KB are supported by CUDA 12.1+ on sm_70+.)
+constexpr int kUmmaBigProbs = 48;
+struct UmmaBatchBig {
+  UmmaProblem p[kUmmaBigProbs];
+  int n;
+};
+int launch_umma_gemm_big(const UmmaBatchBig& batch, cudaStream_t st);
+
 }  // namespace iisan

@@ -22,7 +22,7 @@ constexpr int FL = 10;            // sequence length
 constexpr int FUPC = 4;           // users per CTA
 constexpr int FR = FUPC * FL;     // rows per CTA
 constexpr int FF = 4 * FE;        // FFN width
-constexpr int FTHREADS = 256;
+constexpr int FTHREADS = 512;
 constexpr int FMAXH = 4;
 
 struct FuArgs {
@@ -63,7 +63,7 @@ __device__ __forceinline__ void cta_linear(const float* __restrict__ Wg, const f
 #pragma unroll
   for (int i = 0; i < RT; ++i) acc[i] = 0.f;
   const float4* wrow = reinterpret_cast<const float4*>(Wg + (size_t)o * IN);
-#pragma unroll 2
+#pragma unroll 4
   for (int k4 = 0; k4 < IN / 4; ++k4) {
     const float4 w = __ldg(wrow + k4);
 #pragma unroll
@@ -91,7 +91,7 @@ __device__ __forceinline__ void cta_linear_t(const float* __restrict__ Wg, const
   float acc[RT];
 #pragma unroll
   for (int r = 0; r < RT; ++r) acc[r] = 0.f;
-#pragma unroll 2
+#pragma unroll 4
   for (int o4 = 0; o4 < OUT / 4; ++o4) {
     const float w0 = __ldg(Wg + (size_t)(o4 * 4 + 0) * IN + i), w1 = __ldg(Wg + (size_t)(o4 * 4 + 1) * IN + i);
     const float w2 = __ldg(Wg + (size_t)(o4 * 4 + 2) * IN + i), w3 = __ldg(Wg + (size_t)(o4 * 4 + 3) * IN + i);
