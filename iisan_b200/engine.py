@@ -20,8 +20,9 @@ import torch.distributed as dist
 
 
 class TrainStep:
-    def __init__(self, model, optimizer, use_graph=True, group=None, warmup=3, autocast_dtype=None):
+    def __init__(self, model, optimizer, use_graph=True, group=None, warmup=3, autocast_dtype=None, store=None):
         self.model = model
+        self.store = store            # iisan_b200.store.CachedStateStore: batches are (ids, log_mask) only, states gathered on the device
         self.opt = optimizer
         self.use_graph = bool(use_graph)
         self.group = group
@@ -78,7 +79,11 @@ class TrainStep:
 
     def _eager(self, ids, image, text, log_mask):
         self.opt.zero_grad(set_to_none=True)
-        loss = self.model(ids, image, text, log_mask, ids.device)
+        if self.store is not None:
+            image, text = self.store.gather(ids)
+            loss = self.model(ids, image, text, log_mask, ids.device, packed=True)
+        else:
+            loss = self.model(ids, image, text, log_mask, ids.device)
         loss.backward()
         self._allreduce()
         self.opt.step()
@@ -87,8 +92,10 @@ class TrainStep:
     def _stage(self, ids, image, text, log_mask, device):
         src = (ids.reshape(-1), image, text, log_mask)
         if self.static_in is None:
-            self.static_in = tuple(torch.empty(t.shape, dtype=t.dtype, device=device) for t in src)
+            self.static_in = tuple(None if t is None else torch.empty(t.shape, dtype=t.dtype, device=device) for t in src)
         for dst, s in zip(self.static_in, src):
+            if dst is None:
+                continue
             if dst is s or (dst.data_ptr() == s.data_ptr() and dst.shape == s.shape):
                 continue
             if dst.shape != s.shape or dst.dtype != s.dtype:
@@ -101,7 +108,7 @@ class TrainStep:
         """Adopt the given DEVICE tensors as the static inputs (no staging copy) and capture the step on them; afterwards
         ``replay()`` re-runs the step on whatever those tensors then hold.  Applies one step."""
         self.static_in = (ids.reshape(-1), image, text, log_mask)
-        return self.__call__(*self.static_in)
+        return self.__call__(ids.reshape(-1), image, text, log_mask)
 
     def replay(self):
         self.graph.replay()
@@ -110,7 +117,7 @@ class TrainStep:
     def __call__(self, ids, image, text, log_mask):
         device = next(self.model.parameters()).device
         if not self.use_graph:
-            args = tuple(t.to(device, non_blocking=True) for t in (ids.reshape(-1), image, text, log_mask))
+            args = tuple(None if t is None else t.to(device, non_blocking=True) for t in (ids.reshape(-1), image, text, log_mask))
             return self._eager(*args)
         inputs = self._stage(ids, image, text, log_mask, device)
         if self.graph is None:
@@ -168,10 +175,11 @@ class PipelinedTrainStep:
         loss = pipe.run()
     """
 
-    def __init__(self, model, optimizer, group=None, use_graph=True, depth=2):
+    def __init__(self, model, optimizer, group=None, use_graph=True, depth=2, store=None):
         self.model, self.opt, self.group, self.use_graph = model, optimizer, group, use_graph
         self.depth = depth
-        self.steps = [TrainStep(model, optimizer, use_graph=use_graph, group=group) for _ in range(depth)]
+        self.store = store
+        self.steps = [TrainStep(model, optimizer, use_graph=use_graph, group=group, store=store) for _ in range(depth)]
         self.bufs = [None] * depth
         self.copied = [None] * depth
         self.done = [None] * depth
@@ -183,7 +191,8 @@ class PipelinedTrainStep:
         self.sel_img = list(plan.layers_img_sel) if plan is not None else None
         self.sel_text = list(plan.layers_text_sel) if plan is not None else None
 
-    def submit(self, ids, image, text, log_mask):
+    def submit(self, ids, image=None, text=None, log_mask=None):
+        """With a store attached the batch is ``submit(ids, log_mask=log_mask)``: only ids and mask cross the host link."""
         if self.n_sub - self.n_run >= self.depth:
             raise RuntimeError("PipelinedTrainStep: run() the submitted batches before submitting more")
         device = next(self.model.parameters()).device
@@ -191,7 +200,8 @@ class PipelinedTrainStep:
         if self.copy_stream is None:
             self.copy_stream = torch.cuda.Stream(device=device)
         if self.bufs[k] is None:
-            self.bufs[k] = tuple(torch.zeros(t.shape, dtype=t.dtype, device=device) for t in (ids.reshape(-1), image, text, log_mask))
+            self.bufs[k] = tuple(None if t is None else torch.zeros(t.shape, dtype=t.dtype, device=device)
+                                 for t in (ids.reshape(-1), image, text, log_mask))
             self.copied[k] = torch.cuda.Event()
             self.done[k] = torch.cuda.Event()
             self.done[k].record(torch.cuda.current_stream(device))
@@ -202,6 +212,8 @@ class PipelinedTrainStep:
             d_ids.copy_(ids.reshape(-1), non_blocking=True)
             d_lm.copy_(log_mask, non_blocking=True)
             for dst, src, sel in ((d_img, image, self.sel_img), (d_txt, text, self.sel_text)):
+                if dst is None:
+                    continue
                 if (not src.is_cuda) and src.is_pinned() and sel is not None and src.dim() >= 3 and len(sel) < src.shape[-2]:
                     stage_states_h2d(dst, src, sel, cs)
                 else:

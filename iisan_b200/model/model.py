@@ -69,9 +69,10 @@ class IISANAdaptedMModel(nn.Module):
             self._binder = SanBinder(self.plan, [n for n, _ in self.named_parameters()])
         return self._binder
 
-    def embed(self, sample_items_images, sample_items_text):
+    def embed(self, sample_items_images, sample_items_text, packed=False):
+        """``packed``: the tensors hold only the selected layers [N, A, d] (iisan_b200.store.CachedStateStore.gather)."""
         params = tuple(self.parameters())
-        return SanFn.apply(self._bind(), sample_items_images, sample_items_text, compute_mode(), *params)
+        return SanFn.apply(self._bind(), sample_items_images, sample_items_text, compute_mode(), bool(packed), *params)
 
     def forward(self, sample_items_images, sample_items_text):
         out = self.embed(sample_items_images, sample_items_text)
@@ -117,17 +118,17 @@ class ModelMM(nn.Module):
             self.pop_prob_list = self.pop_prob_list.to(device)
         return self.pop_prob_list
 
-    def item_embeddings(self, sample_items_images, sample_items_text):
+    def item_embeddings(self, sample_items_images, sample_items_text, packed=False):
         """score_embs [N, E] = com_dense(cat[cv, text, mm])  (model.py:66-72)."""
         enc = self.mm_encoder
         if not isinstance(enc, IISANAdaptedMModel):
             raise NotImplementedError("install the side-adapter network first: model.mm_encoder = "
                                       "IISANAdaptedMModel(model.mm_encoder, args)  (Code_Cached/run.py:182-183)")
-        return self.com_dense(enc.embed(sample_items_images, sample_items_text))
+        return self.com_dense(enc.embed(sample_items_images, sample_items_text, packed))
 
-    def forward(self, sample_items_id, sample_items_images, sample_items_text, log_mask, local_rank=None):
+    def forward(self, sample_items_id, sample_items_images, sample_items_text, log_mask, local_rank=None, packed=False):
         E, S = self.args.embedding_dim, self.max_seq_len + 1
-        score_embs = self.item_embeddings(sample_items_images, sample_items_text)
+        score_embs = self.item_embeddings(sample_items_images, sample_items_text, packed)
         device = score_embs.device
         ids = sample_items_id.to(device).view(-1)
         log_mask = log_mask.to(device=device, dtype=torch.float32)

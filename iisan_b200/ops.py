@@ -75,13 +75,13 @@ class SanFn(torch.autograd.Function):
     """out[N, 3E] = (cv | text | mm) embeddings.  `binder` builds descriptors and pointer tables."""
 
     @staticmethod
-    def forward(ctx, binder, image, text, compute, *params):
+    def forward(ctx, binder, image, text, compute, packed, *params):
         L.require_cuda(image, "image hidden states")
         L.require_cuda(text, "text hidden states")
         lib = L.load()
         image = image.contiguous()
         text = text.contiguous()
-        desc = binder.desc(image, text, compute)
+        desc = binder.desc(image, text, compute, packed)
         ptrs = binder.param_table(params)
         n, e = desc.n_items, desc.emb
         out = torch.empty(n, 3 * e, dtype=torch.float32, device=image.device)
@@ -104,7 +104,7 @@ class SanFn(torch.autograd.Function):
         L.check(lib.iisan_san_backward(C.byref(ctx.desc), C.byref(ctx.ptrs), C.byref(gptrs), _p(ctx.image), _p(ctx.text),
                                        _p(ctx.ws), ctx.ws.numel(), _p(d_out), _stream()), "iisan_san_backward")
         ctx.ws = None
-        return (None, None, None, None, *views)
+        return (None, None, None, None, None, *views)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -242,7 +242,8 @@ def gather_states(table, ids, sel):
     L.require_cuda(ids, "ids")
     n_items, layers, d = table.shape
     ids = ids.contiguous().view(-1)
-    sel_t = torch.as_tensor(sel, dtype=torch.int32, device=ids.device)
+    # a device int32 tensor is used as is (no H2D copy: legal during CUDA-graph capture)
+    sel_t = sel if torch.is_tensor(sel) else torch.as_tensor(sel, dtype=torch.int32, device=ids.device)
     out = torch.empty(ids.numel(), len(sel), d, dtype=table.dtype, device=ids.device)
     L.check(lib.iisan_gather_states(_p(table), L.torch_dtype_code(table.dtype), n_items, layers, d, _p(ids), ids.numel(),
                                     _p(sel_t), len(sel), _p(out), _stream()), "iisan_gather_states")

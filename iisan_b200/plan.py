@@ -199,7 +199,9 @@ class SanBinder(_BinderBase):
             _san_slot(t, n, base + 4 * o)
         return flat, views, t
 
-    def desc(self, image, text, compute):
+    def desc(self, image, text, compute, packed=False):
+        """``packed``: the tensors hold ONLY the selected layers, in increasing layer order (iisan_b200.store): layer index l of
+        the plan is addressed at its rank among the selected layers."""
         pl = self.plan
         if image.dim() not in (3, 4) or text.dim() not in (3, 4):
             raise L.IisanLibraryError("hidden states must be [B,11,layers,d] or [b,layers,d]")
@@ -212,9 +214,14 @@ class SanBinder(_BinderBase):
             raise L.IisanLibraryError("image and text batches disagree on the number of items")
         if di != pl.d_img or dt != pl.d_text:
             raise L.IisanLibraryError(f"hidden widths ({dt},{di}) do not match the module ({pl.d_text},{pl.d_img})")
-        if max(pl.layers_img_sel) >= li or max(pl.layers_text_sel) >= lt:
+        rank_i = {l: k for k, l in enumerate(sorted(set(pl.layers_img_sel)))}
+        rank_t = {l: k for k, l in enumerate(sorted(set(pl.layers_text_sel)))}
+        if packed:
+            if li != len(rank_i) or lt != len(rank_t):
+                raise L.IisanLibraryError(f"packed states must hold exactly the selected layers ({len(rank_i)} image, {len(rank_t)} text)")
+        elif max(pl.layers_img_sel) >= li or max(pl.layers_text_sel) >= lt:
             raise L.IisanLibraryError("a selected layer index is outside the cached states")
-        key = (n, li, lt, image.dtype, compute)
+        key = (n, li, lt, image.dtype, compute, bool(packed))
         d = self._desc_cache.get(key)
         if d is None:
             d = L.SanDesc()
@@ -223,8 +230,8 @@ class SanBinder(_BinderBase):
             d.r_text, d.r_img, d.r_mm, d.emb = pl.r_text, pl.r_img, pl.r_mm, pl.emb
             d.n_stages = len(pl.stages)
             for s, (ta, tl, ia, il, mi) in enumerate(pl.stages):
-                d.text_adapter[s], d.text_layer[s] = ta, tl
-                d.img_adapter[s], d.img_layer[s] = ia, il
+                d.text_adapter[s], d.text_layer[s] = ta, (rank_t[tl] if (packed and ta >= 0) else tl)
+                d.img_adapter[s], d.img_layer[s] = ia, (rank_i[il] if (packed and ia >= 0) else il)
                 d.mm_index[s] = mi
             d.asym, d.remove_first = int(pl.asym), int(pl.remove_first)
             d.state_dtype = L.torch_dtype_code(image.dtype)
