@@ -497,8 +497,10 @@ struct CeFastLayout {
   }
 };
 
+// One CTA per SM (512 TMEM columns, 129 KB smem): pick the split count so that owner_tiles * splits stays within ONE wave of
+// 148 CTAs (a 160-CTA grid would run a second, almost empty wave).
 int ce_fast_splits(int owner_tiles, int stream_tiles) {
-  int s = (148 + owner_tiles - 1) / owner_tiles;
+  int s = 148 / owner_tiles;
   if (s > stream_tiles) s = stream_tiles;
   if (s < 1) s = 1;
   const int per = (stream_tiles + s - 1) / s;
