@@ -81,3 +81,34 @@ def test_dropout_backward_finite_difference():
     enc.eval()
     out_eval = enc(x[:, :-1], lm, "cuda")
     assert (out - out_eval).abs().max() > 1e-3
+
+
+@pytest.mark.parametrize("B", [1, 5, 64, 130, 512])
+def test_fused_tensor_core_mode_matches_oracle(B):
+    """Fast mode: the linears of the fused encoder run as TF32 mma.sync tiles (operands rounded to 10 mantissa bits -- the
+    precision of the reference's fp16 autocast GEMMs -- fp32 accumulate); LayerNorm / softmax stay fp32.  Tolerances: outputs
+    2e-3 relative L2 (measured 5e-4), gradients 5e-2 relative L2 per tensor (measured <= 2.2e-2: ReLU units of the FFN whose
+    pre-activation lies within the operand rounding of zero flip, and a fraction f of flipped units moves the gradient by
+    ~sqrt(f))."""
+    from iisan_b200.precision import set_compute_mode
+    from oracle import iisan_oracle as O
+    from oracle.synthetic import PathConfig
+    set_compute_mode("bf16")
+    try:
+        enc = _encoder(0.0).eval()
+        x, lm = _inputs(B)
+        xs = x.clone().requires_grad_(True)
+        out = enc(xs[:, :-1], lm, "cuda")
+        w = torch.randn_like(out)
+        (out * w).sum().backward()
+    finally:
+        set_compute_mode("fp32")
+    P = {"user_encoder." + n: p.detach().cpu().clone().requires_grad_(True) for n, p in enc.named_parameters()}
+    xr = x.cpu().clone().requires_grad_(True)
+    ref = O.user_encoder_forward(P, xr[:, :-1], lm.cpu(), PathConfig())
+    (ref * w.cpu()).sum().backward()
+    rel = lambda a, b: float((a.detach() - b.detach()).norm() / (b.detach().norm() + 1e-12))
+    assert rel(out.cpu(), ref) <= 2e-3
+    assert rel(xs.grad.cpu(), xr.grad) <= 5e-2
+    for n, p in enc.named_parameters():
+        assert rel(p.grad.cpu(), P["user_encoder." + n].grad) <= 5e-2, n
