@@ -22,6 +22,7 @@
 #include "umma.cuh"
 #include "ce_umma.cuh"
 
+#include <cstdlib>
 #include <mutex>
 
 namespace iisan {
@@ -39,6 +40,7 @@ constexpr int CE_TILE_BYTES = CT * CE_E * 2;     // 16 KB
 constexpr int CE_A2_BYTES = CT * CT * 2;         // 32 KB
 constexpr int CE_TMEM_COLS = 512;
 constexpr int CE_ACC_COL = 256;
+constexpr int CE_DSC_COL = 320;    // MODE 3: two [128 x 64] accumulators of the per-tile d_score partial
 
 struct CeTileArgs {
   CUtensorMap map_prec, map_score;
@@ -53,6 +55,7 @@ struct CeTileArgs {
   const float* g_sum; const float* g_mean; const int32_t* n_valid;
   float* part_m; float* part_s; float* part_lab;   // forward partials [splits, R]
   float* d_out;                   // backward: d_prec [R, E] or d_score [C, E], accumulated atomically
+  float* d_out2;                  // MODE 3: d_score [C, E] (d_out = d_prec)
   int tiles_stream;               // number of streamed tiles in total
   int tiles_per_split;
 };
@@ -75,11 +78,19 @@ __device__ __forceinline__ float ce_scale_dev(const float* g_sum, const float* g
   return s;
 }
 
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 // MODE 0: forward partial log-sum-exp (OWNER_ROWS) ; MODE 1: d_prec (OWNER_ROWS) ; MODE 2: d_score (!OWNER_ROWS)
+// MODE 3: d_prec AND d_score in one pass (OWNER_ROWS): the bf16 weight tile W [128 rows x 128 columns] that feeds
+//         acc_prec += W x T is read a second time as an MN-major A operand, dsc = W^T x O (K = the CTA's 128 rows), and the
+//         [128 columns x 64] partial is added to d_score by vector reductions once per streamed tile.
 template <int MODE>
 __global__ void __launch_bounds__(CE_THREADS, 1) ce_tile_kernel(const __grid_constant__ CeTileArgs a) {
   constexpr bool OWNER_ROWS = (MODE != 2);
   constexpr bool BWD = (MODE != 0);
+  constexpr bool FUSED = (MODE == 3);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + CeSmem::kBar);
@@ -91,7 +102,9 @@ __global__ void __launch_bounds__(CE_THREADS, 1) ce_tile_kernel(const __grid_con
   uint64_t* a2_full = s_empty + 2;         // 2
   uint64_t* a2_empty = a2_full + 2;        // 2
   uint64_t* acc_full = a2_empty + 2;       // 1
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+  uint64_t* dsc_full = acc_full + 1;       // 2
+  uint64_t* dsc_empty = dsc_full + 2;      // 2
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dsc_empty + 2);
   float* attr_f = reinterpret_cast<float*>(smem + CeSmem::kAttr);   // [2][CT][4] floats / ints
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -109,6 +122,7 @@ __global__ void __launch_bounds__(CE_THREADS, 1) ce_tile_kernel(const __grid_con
     for (int s = 0; s < CE_NST; ++s) { mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&s_full[b], 1); mbar_init(&s_empty[b], 8); mbar_init(&a2_full[b], 8); mbar_init(&a2_empty[b], 1); }
     mbar_init(acc_full, 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(&dsc_full[b], 1); mbar_init(&dsc_empty[b], 8); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, CE_TMEM_COLS);
@@ -134,6 +148,7 @@ __global__ void __launch_bounds__(CE_THREADS, 1) ce_tile_kernel(const __grid_con
     if (elect_one()) {
       constexpr uint32_t idesc1 = instr_desc_bf16(CT, CT, 0, 0);       // S[128,128] = O (K-major) x T^T (K-major)
       constexpr uint32_t idesc2 = instr_desc_bf16(CT, CE_E, 0, 1);     // acc[128,64] += W (K-major) x T (MN-major)
+      constexpr uint32_t idesc3 = instr_desc_bf16(CT, CE_E, 1, 1);     // dsc[128,64]  = W^T (MN-major) x O (MN-major)
       const uint32_t so = smem_u32(smem + CeSmem::kO);
       auto issue_s = [&](int t) {
         const int st = t % CE_NST; const uint32_t ph = (uint32_t)(t / CE_NST) & 1u;
@@ -165,6 +180,18 @@ __global__ void __launch_bounds__(CE_THREADS, 1) ce_tile_kernel(const __grid_con
             for (int k = 0; k < 4; ++k)
               mma_bf16_ss(tmem_base + CE_ACC_COL, smem_desc_sw128(sa2 + kb * (CT * 64 * 2) + k * 32, 16, 1024),
                           smem_desc_sw128(stile + (kb * 4 + k) * 2048, 64 * 64 * 2, 1024), idesc2, (t > 0 || kb > 0 || k > 0) ? 1u : 0u);
+          if (FUSED) {
+            // d_score partial of this tile: rows of the CTA are the reduction dimension.  The W tile is stored as two 64-column
+            // blocks of [128 rows x 128 B]; read MN-major, a k-step of 16 rows advances by two 8-row swizzle atoms (2048 B) and
+            // the second 64-column atom lies one block (128 x 128 B) further (LBO).
+            mbar_wait(&dsc_empty[b], bph ^ 1u);
+            tc_fence_after();
+#pragma unroll
+            for (int k = 0; k < CT / 16; ++k)
+              mma_bf16_ss(tmem_base + CE_DSC_COL + b * CE_E, smem_desc_sw128(sa2 + k * 2048, CT * 64 * 2, 1024),
+                          smem_desc_sw128(so + k * 2048, 64 * 64 * 2, 1024), idesc3, k > 0 ? 1u : 0u);
+            mma_commit(&dsc_full[b]);
+          }
           mma_commit(&a2_empty[b]);
           mma_commit(&t_empty[st]);
         }
@@ -197,6 +224,27 @@ __global__ void __launch_bounds__(CE_THREADS, 1) ce_tile_kernel(const __grid_con
       o_debias = o_ok ? a.debias[o] : 0.f;
     }
     float run_m = -INFINITY, run_s = 0.f, lab_val = 0.f;
+
+    // MODE 3: add the d_score partial of streamed tile t (TMEM lanes = its 128 columns) to global memory
+    auto flush_dsc = [&](int t) {
+      const int b = t & 1; const uint32_t bph = (uint32_t)(t >> 1) & 1u;
+      mbar_wait(&dsc_full[b], bph);
+      tc_fence_after();
+      uint32_t raw[32];
+      tmem_ld_32x32(tmem_base + lane_addr + (uint32_t)(CE_DSC_COL + b * CE_E + half * 32), raw);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&dsc_empty[b]);
+      const int col = (t_beg + t) * CT + quad * 32 + lane;
+      if (col < a.C) {
+        float* op = a.d_out2 + (int64_t)col * CE_E + half * 32;
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          red_add_v4(op + 4 * q, __uint_as_float(raw[4 * q]), __uint_as_float(raw[4 * q + 1]), __uint_as_float(raw[4 * q + 2]),
+                     __uint_as_float(raw[4 * q + 3]));
+      }
+    };
 
     for (int t = 0; t < n_tiles; ++t) {
       const int b = t & 1; const uint32_t bph = (uint32_t)(t >> 1) & 1u;
@@ -323,8 +371,10 @@ __global__ void __launch_bounds__(CE_THREADS, 1) ce_tile_kernel(const __grid_con
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&a2_full[b]);
+        if (FUSED && t >= 1) flush_dsc(t - 1);
       }
     }
+    if (FUSED) flush_dsc(n_tiles - 1);
 
     if (!BWD) {
       // combine the two column halves of each row, then write the split's partial
@@ -587,6 +637,12 @@ int ce_fast_backward(const iisan_ce_desc& d, const float* lm_rows, const float* 
   IISAN_TRY(fill_args(d, W, &A, lm_rows, lm_cols));
   A.g_sum = g_sum; A.g_mean = g_mean; A.n_valid = n_valid;
   const int row_tiles = (R + CT - 1) / CT, col_tiles = (C + CT - 1) / CT;
+  static const bool split_bwd = [] { const char* e = getenv("IISAN_B200_CE_SPLIT_BWD"); return e && e[0] == '1'; }();
+  if (!split_bwd) {      // one pass: d_prec in the CTA's accumulator, d_score by per-tile reductions
+    const int splits = ce_fast_splits(row_tiles, col_tiles);
+    A.tiles_stream = col_tiles; A.tiles_per_split = (col_tiles + splits - 1) / splits; A.d_out = d_prec; A.d_out2 = d_score;
+    return launch_tile<3>(A, row_tiles, splits, st);
+  }
   {
     const int splits = ce_fast_splits(row_tiles, col_tiles);
     A.tiles_stream = col_tiles; A.tiles_per_split = (col_tiles + splits - 1) / splits; A.d_out = d_prec;

@@ -29,13 +29,17 @@ __host__ __device__ inline void philox4x32_10(uint64_t seed, uint64_t offset, ui
   out[0] = c[0]; out[1] = c[1]; out[2] = c[2]; out[3] = c[3];
 }
 
-// keep-probability test for element `idx` of dropout site `site`: u = r * 2^-32 ; keep iff u >= p
-__host__ __device__ inline bool dropout_keep(uint64_t seed, uint64_t offset, uint32_t site, uint64_t idx, float p) {
+// keep-probability test for element `idx` of dropout site `site`: u = r * 2^-32 ; keep iff u >= p, i.e. r >= thr(p)
+__host__ __device__ inline uint32_t dropout_threshold(float p) {
+  return (uint32_t)((double)p * 4294967296.0 > 4294967295.0 ? 4294967295.0 : (double)p * 4294967296.0);
+}
+__host__ __device__ inline bool dropout_keep_thr(uint64_t seed, uint64_t offset, uint32_t site, uint64_t idx, uint32_t thr) {
   uint32_t r[4];
   philox4x32_10(seed, offset, site, idx >> 2, r);
-  const uint32_t v = r[idx & 3];
-  const uint32_t thr = (uint32_t)((double)p * 4294967296.0 > 4294967295.0 ? 4294967295.0 : (double)p * 4294967296.0);
-  return v >= thr;
+  return r[idx & 3] >= thr;
+}
+__host__ __device__ inline bool dropout_keep(uint64_t seed, uint64_t offset, uint32_t site, uint64_t idx, float p) {
+  return dropout_keep_thr(seed, offset, site, idx, dropout_threshold(p));
 }
 
 }  // namespace iisan

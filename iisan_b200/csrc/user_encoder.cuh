@@ -10,12 +10,33 @@ constexpr float kLnEps = 1e-6f;
 constexpr float kAttNeg = -1e9f;
 constexpr int kMaxEPerLane = 8;  // E <= 256
 
-struct DropCfg { int on; float p; float scale; uint64_t seed, offset; const uint64_t* offset_dev; };
+struct DropCfg { int on; float p; float scale; uint64_t seed, offset; const uint64_t* offset_dev; uint32_t thr; };
 
 __device__ __forceinline__ float drop_apply(const DropCfg& c, uint32_t site, uint64_t idx, float v) {
   if (!c.on) return v;
   const uint64_t off = c.offset_dev ? __ldg(reinterpret_cast<const unsigned long long*>(c.offset_dev)) : c.offset;
-  return dropout_keep(c.seed, off, site, idx, c.p) ? v * c.scale : 0.f;
+  return dropout_keep_thr(c.seed, off, site, idx, c.thr) ? v * c.scale : 0.f;
+}
+
+// Per-thread dropout state of the fused kernels: the step offset is read once, and one Philox block serves the four
+// consecutive elements 4*idx4 .. 4*idx4+3 (same mask function as drop_apply).
+struct DropRt { bool on; uint32_t thr; float scale; uint64_t seed, off; };
+__device__ __forceinline__ DropRt drop_rt(const DropCfg& c) {
+  DropRt d;
+  d.on = c.on != 0; d.thr = c.thr; d.scale = c.scale; d.seed = c.seed;
+  d.off = (c.on && c.offset_dev) ? __ldg(reinterpret_cast<const unsigned long long*>(c.offset_dev)) : c.offset;
+  return d;
+}
+__device__ __forceinline__ void drop4(const DropRt& d, uint32_t site, uint64_t idx4, float (&v)[4]) {
+  if (!d.on) return;
+  uint32_t r[4];
+  philox4x32_10(d.seed, d.off, site, idx4, r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) v[i] = r[i] >= d.thr ? v[i] * d.scale : 0.f;
+}
+__device__ __forceinline__ float drop1(const DropRt& d, uint32_t site, uint64_t idx, float v) {
+  if (!d.on) return v;
+  return dropout_keep_thr(d.seed, d.off, site, idx, d.thr) ? v * d.scale : 0.f;
 }
 
 
@@ -53,7 +74,7 @@ inline DropCfg drop_cfg(const iisan_ue_desc& D) {
   DropCfg c;
   c.on = (D.training && D.dropout_p > 0.f) ? 1 : 0;
   c.p = D.dropout_p; c.scale = c.on ? 1.0f / (1.0f - D.dropout_p) : 1.0f;
-  c.seed = D.seed; c.offset = D.offset; c.offset_dev = D.offset_dev;
+  c.seed = D.seed; c.offset = D.offset; c.offset_dev = D.offset_dev; c.thr = dropout_threshold(D.dropout_p);
   return c;
 }
 

@@ -333,46 +333,60 @@ __device__ __forceinline__ void cta_wgrad(float* __restrict__ dWg, float* __rest
   }
 }
 
-// LayerNorm over FE = 64 of the CTA's rows, warp per row (lane owns e = lane, lane + 32).  SX: row stride of the smem buffers.
+// sum / max over the 16 lanes of a half-warp (xor shuffles stay inside the half)
+__device__ __forceinline__ float half_sum(float v) {
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float half_max(float v) {
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+static_assert(FE == 64 && FR % 8 == 0 && (FR - FTHREADS / 16) % 2 == 0, "half-warp row mapping: both halves of a warp are active together");
+
+// LayerNorm over FE = 64 of the CTA's rows, half-warp per row (lane owns e = 4 l .. 4 l + 3: 128-bit accesses, one Philox
+// block per lane and dropout site).  SX: row stride of the smem buffers.
 // MODE 0: pre = a_row + b_row                      ; out = dropout_site(LN(pre))     (entry)
 // MODE 1: pre = xs[r] + dropout_site(fs[r])        ; out = LN(pre)
 template <int MODE, int SX>
-__device__ __forceinline__ void cta_ln_fwd(const FuArgs& a, int u0, const float* xs, const float* fs, const float* __restrict__ gamma,
-                                           const float* __restrict__ beta, float* pre_g, float* stat_g, float* outs, float* out_g,
-                                           uint32_t site) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int r = warp; r < FR; r += FTHREADS / 32) {
+__device__ __forceinline__ void cta_ln_fwd(const FuArgs& a, const DropRt& dr, int u0, const float* xs, const float* fs,
+                                           const float* __restrict__ gamma, const float* __restrict__ beta, float* pre_g, float* stat_g,
+                                           float* outs, float* out_g, uint32_t site) {
+  const int hw = threadIdx.x >> 4, l = threadIdx.x & 15;
+  const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + l), bt = __ldg(reinterpret_cast<const float4*>(beta) + l);
+  for (int r = hw; r < FR; r += FTHREADS / 16) {
     const int ul = r / FL, t = r % FL, u = u0 + ul;
     const bool ok = u < a.users;
     const int64_t gr = (int64_t)u * FL + t;
-    float v[2];
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const int e = lane + 32 * i;
-      float x = 0.f;
-      if (ok) {
-        if (MODE == 0) x = a.embs[(int64_t)u * a.ld_user + (int64_t)t * FE + e] + __ldg(a.P.pos_emb + t * FE + e);
-        else x = xs[r * SX + e] + drop_apply(a.dc, site, (uint64_t)gr * FE + e, fs[r * SX + e]);
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (ok) {
+      if (MODE == 0) {
+        const float4 x = *reinterpret_cast<const float4*>(a.embs + (int64_t)u * a.ld_user + (int64_t)t * FE + 4 * l);
+        const float4 p = __ldg(reinterpret_cast<const float4*>(a.P.pos_emb + t * FE) + l);
+        v[0] = x.x + p.x; v[1] = x.y + p.y; v[2] = x.z + p.z; v[3] = x.w + p.w;
+      } else {
+        const float4 x = *reinterpret_cast<const float4*>(xs + r * SX + 4 * l);
+        const float4 f = *reinterpret_cast<const float4*>(fs + r * SX + 4 * l);
+        float fv[4] = {f.x, f.y, f.z, f.w};
+        drop4(dr, site, (uint64_t)gr * (FE / 4) + l, fv);
+        v[0] = x.x + fv[0]; v[1] = x.y + fv[1]; v[2] = x.z + fv[2]; v[3] = x.w + fv[3];
       }
-      v[i] = x;
     }
-    const float mean = warp_sum(v[0] + v[1]) / (float)FE;
-    const float d0 = v[0] - mean, d1 = v[1] - mean;
-    const float var = warp_sum(d0 * d0 + d1 * d1) / (float)FE;
+    const float mean = half_sum((v[0] + v[1]) + (v[2] + v[3])) / (float)FE;
+    const float d0 = v[0] - mean, d1 = v[1] - mean, d2 = v[2] - mean, d3 = v[3] - mean;
+    const float var = half_sum((d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3)) / (float)FE;
     const float rstd = 1.0f / sqrtf(var + kLnEps);
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const int e = lane + 32 * i;
-      float y = (v[i] - mean) * rstd * __ldg(gamma + e) + __ldg(beta + e);
-      if (MODE == 0 && ok) y = drop_apply(a.dc, site, (uint64_t)gr * FE + e, y);
-      if (!ok) y = 0.f;
-      outs[r * SX + e] = y;
-      if (ok) {
-        pre_g[gr * FE + e] = v[i];
-        if (out_g) out_g[gr * FE + e] = y;
-      }
+    float y[4] = {d0 * rstd * gm.x + bt.x, d1 * rstd * gm.y + bt.y, d2 * rstd * gm.z + bt.z, d3 * rstd * gm.w + bt.w};
+    if (MODE == 0 && ok) drop4(dr, site, (uint64_t)gr * (FE / 4) + l, y);
+    if (!ok) { y[0] = 0.f; y[1] = 0.f; y[2] = 0.f; y[3] = 0.f; }
+    *reinterpret_cast<float4*>(outs + r * SX + 4 * l) = make_float4(y[0], y[1], y[2], y[3]);
+    if (ok) {
+      reinterpret_cast<float4*>(pre_g + gr * FE)[l] = make_float4(v[0], v[1], v[2], v[3]);
+      if (out_g) reinterpret_cast<float4*>(out_g + gr * FE)[l] = make_float4(y[0], y[1], y[2], y[3]);
+      if (l == 0) *reinterpret_cast<float2*>(stat_g + 2 * gr) = make_float2(mean, rstd);
     }
-    if (ok && lane == 0) { stat_g[2 * gr] = mean; stat_g[2 * gr + 1] = rstd; }
   }
 }
 
@@ -407,12 +421,13 @@ __global__ void __launch_bounds__(FTHREADS, 1) ue_fused_fwd_kernel(const __grid_
   const int u0 = blockIdx.x * FUPC;
   const int H = a.H, dk = FE / H;
   const float temp = sqrtf((float)dk);
+  const DropRt drt = drop_rt(a.dc);
   if (threadIdx.x < FR) {
     const int u = u0 + threadIdx.x / FL;
     keyok[threadIdx.x] = (u < a.users && a.log_mask[(int64_t)u * FL + threadIdx.x % FL] != 0.f) ? 1.f : 0.f;
   }
   // ---- entry: x = dropout(LN(embs + pos)) ----
-  cta_ln_fwd<0, SX>(a, u0, nullptr, nullptr, a.P.ln_w, a.P.ln_b, a.W.pre0, a.W.stat0, sX, a.W.b[0].x_in, 0u);
+  cta_ln_fwd<0, SX>(a, drt, u0, nullptr, nullptr, a.P.ln_w, a.P.ln_b, a.W.pre0, a.W.stat0, sX, a.W.b[0].x_in, 0u);
   __syncthreads();
   for (int b = 0; b < a.n_blocks; ++b) {
     const iisan_ue_block_ptrs& bp = a.P.blocks[b];
@@ -423,30 +438,32 @@ __global__ void __launch_bounds__(FTHREADS, 1) ue_fused_fwd_kernel(const __grid_
     cta_linear<TC, FE, FE>(bp.w_v, nullptr, sX, sV, false);
     __syncthreads();
     cta_store_rows<FE, SX>(a, u0, sQ, X.q); cta_store_rows<FE, SX>(a, u0, sK, X.k); cta_store_rows<FE, SX>(a, u0, sV, X.v);
-    // ---- scores + mask ----
-    for (int idx = threadIdx.x; idx < FUPC * H * FL * FL; idx += FTHREADS) {
-      const int ul = idx / (H * FL * FL), rem = idx % (H * FL * FL);
-      const int h = rem / (FL * FL), i = (rem / FL) % FL, j = rem % FL;
-      const float* qr = sQ + (ul * FL + i) * SX + h * dk; const float* kr = sK + (ul * FL + j) * SX + h * dk;
-      float d = 0.f;
-      for (int c = 0; c < dk; ++c) d = fmaf(qr[c], kr[c], d);
-      const float m = (j <= i && keyok[ul * FL + j] != 0.f) ? 0.f : kAttNeg;
-      sP[idx] = __fadd_rn(__fdiv_rn(d, temp), m);
-    }
-    __syncthreads();
-    // ---- softmax rows, stash p, attention dropout ----
-    for (int r = threadIdx.x; r < FUPC * H * FL; r += FTHREADS) {
-      float* row = sP + r * FL;
-      const int ul = r / (H * FL), u = u0 + ul;
-      float mx = row[0];
-      for (int j = 1; j < FL; ++j) mx = fmaxf(mx, row[j]);
-      float s = 0.f;
-      for (int j = 0; j < FL; ++j) { row[j] = expf(row[j] - mx); s += row[j]; }
-      for (int j = 0; j < FL; ++j) {
-        const float p = row[j] / s;
-        const int64_t gi = (int64_t)u * H * FL * FL + (r % (H * FL)) * FL + j;
-        if (u < a.users) { X.p[gi] = p; row[j] = drop_apply(a.dc, 1u + 4u * b, (uint64_t)gi, p); }
-        else row[j] = 0.f;
+    // ---- scores + mask + softmax + attention dropout: a 16-lane group per (user, head, query) row, lane j = key ----
+    {
+      const int grp = threadIdx.x >> 4, j = threadIdx.x & 15;
+      for (int row = grp; row < FUPC * H * FL; row += FTHREADS / 16) {
+        const int ul = row / (H * FL), h = (row / FL) % H, i = row % FL, u = u0 + ul;
+        float sc = -3.0e38f;
+        if (j < FL) {
+          const float4* qr = reinterpret_cast<const float4*>(sQ + (ul * FL + i) * SX + h * dk);
+          const float4* kr = reinterpret_cast<const float4*>(sK + (ul * FL + j) * SX + h * dk);
+          float d = 0.f;
+          for (int c = 0; c < dk / 4; ++c) {
+            const float4 q = qr[c], k = kr[c];
+            d = fmaf(q.x, k.x, d); d = fmaf(q.y, k.y, d); d = fmaf(q.z, k.z, d); d = fmaf(q.w, k.w, d);
+          }
+          const float m = (j <= i && keyok[ul * FL + j] != 0.f) ? 0.f : kAttNeg;
+          sc = __fadd_rn(__fdiv_rn(d, temp), m);
+        }
+        const float mx = half_max(sc);
+        const float ex = j < FL ? expf(sc - mx) : 0.f;
+        const float p = ex / half_sum(ex);
+        if (j < FL) {
+          const int64_t gi = (int64_t)u * H * FL * FL + (row % (H * FL)) * FL + j;
+          float pd = 0.f;
+          if (u < a.users) { X.p[gi] = p; pd = drop1(drt, 1u + 4u * b, (uint64_t)gi, p); }
+          sP[row * FL + j] = pd;
+        }
       }
     }
     __syncthreads();
@@ -463,7 +480,7 @@ __global__ void __launch_bounds__(FTHREADS, 1) ue_fused_fwd_kernel(const __grid_
     // ---- fc + residual + LN1 ----
     cta_linear<TC, FE, FE>(bp.w_fc, nullptr, sC, sQ, false);          // sQ reused as the linear output
     __syncthreads();
-    cta_ln_fwd<1, SX>(a, u0, sX, sQ, bp.ln1_w, bp.ln1_b, X.pre1, X.stat1, sM, X.xmid, 2u + 4u * b);
+    cta_ln_fwd<1, SX>(a, drt, u0, sX, sQ, bp.ln1_w, bp.ln1_b, X.pre1, X.stat1, sM, X.xmid, 2u + 4u * b);
     __syncthreads();
     // ---- FFN ----
     cta_linear<TC, FE, FF>(bp.w1, bp.b1, sM, sH, true);
@@ -472,55 +489,60 @@ __global__ void __launch_bounds__(FTHREADS, 1) ue_fused_fwd_kernel(const __grid_
     cta_linear<TC, FF, FE>(bp.w2, bp.b2, sH, sQ, false);
     __syncthreads();
     float* dst_g = (b + 1 < a.n_blocks) ? a.W.b[b + 1].x_in : a.out;
-    cta_ln_fwd<1, SX>(a, u0, sM, sQ, bp.ln2_w, bp.ln2_b, X.pre2, X.stat2, sX, dst_g, 3u + 4u * b);
+    cta_ln_fwd<1, SX>(a, drt, u0, sM, sQ, bp.ln2_w, bp.ln2_b, X.pre2, X.stat2, sX, dst_g, 3u + 4u * b);
     __syncthreads();
   }
 }
 
-// LayerNorm backward over the CTA's rows (warp per row).  dys: [FR][FE] gradient of the LN output.
+// LayerNorm backward over the CTA's rows (half-warp per row).  dys: [FR][FE] gradient of the LN output.
 // MODE 0 (entry): dys <- dropout_bwd(dys) first; d pre -> d_embs (global, strided by user); d pos via dfs (dense copy).
 // MODE 1: d pre -> dpre_s (residual branch) and dfs = dropout_bwd(d pre) (linear branch).
 template <int MODE, int SX>
-__device__ __forceinline__ void cta_ln_bwd(const FuArgs& a, int u0, const float* dys, const float* pre_g, const float* stat_g,
-                                           const float* __restrict__ gamma, float* dgamma_s, float* dbeta_s, float* dpre_s, float* dfs,
-                                           uint32_t site) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float ag[2] = {0.f, 0.f}, ab[2] = {0.f, 0.f};
-  for (int r = warp; r < FR; r += FTHREADS / 32) {
+__device__ __forceinline__ void cta_ln_bwd(const FuArgs& a, const DropRt& dr, int u0, const float* dys, const float* pre_g,
+                                           const float* stat_g, const float* __restrict__ gamma, float* dgamma_s, float* dbeta_s,
+                                           float* dpre_s, float* dfs, uint32_t site) {
+  const int hw = threadIdx.x >> 4, l = threadIdx.x & 15;
+  const float4 gm4 = __ldg(reinterpret_cast<const float4*>(gamma) + l);
+  const float gm[4] = {gm4.x, gm4.y, gm4.z, gm4.w};
+  float ag[4] = {0.f, 0.f, 0.f, 0.f}, ab[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int r = hw; r < FR; r += FTHREADS / 16) {
     const int ul = r / FL, t = r % FL, u = u0 + ul;
     const bool ok = u < a.users;
     const int64_t gr = (int64_t)u * FL + t;
     float mean = 0.f, rstd = 0.f;
-    if (ok) { mean = stat_g[2 * gr]; rstd = stat_g[2 * gr + 1]; }
-    float xh[2], g[2];
+    float d[4] = {0.f, 0.f, 0.f, 0.f}, xh[4] = {0.f, 0.f, 0.f, 0.f}, g[4];
+    if (ok) {
+      const float2 st = *reinterpret_cast<const float2*>(stat_g + 2 * gr);
+      mean = st.x; rstd = st.y;
+      const float4 dv = *reinterpret_cast<const float4*>(dys + r * SX + 4 * l);
+      d[0] = dv.x; d[1] = dv.y; d[2] = dv.z; d[3] = dv.w;
+      if (MODE == 0) drop4(dr, site, (uint64_t)gr * (FE / 4) + l, d);
+      const float4 pv = reinterpret_cast<const float4*>(pre_g + gr * FE)[l];
+      xh[0] = (pv.x - mean) * rstd; xh[1] = (pv.y - mean) * rstd; xh[2] = (pv.z - mean) * rstd; xh[3] = (pv.w - mean) * rstd;
+    }
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const int e = lane + 32 * i;
-      float d = ok ? dys[r * SX + e] : 0.f;
-      if (MODE == 0 && ok) d = drop_apply(a.dc, site, (uint64_t)gr * FE + e, d);
-      xh[i] = ok ? (pre_g[gr * FE + e] - mean) * rstd : 0.f;
-      ag[i] += d * xh[i]; ab[i] += d;
-      g[i] = d * __ldg(gamma + e);
+    for (int i = 0; i < 4; ++i) {
+      ag[i] += d[i] * xh[i]; ab[i] += d[i];
+      g[i] = d[i] * gm[i];
       s1 += g[i]; s2 += g[i] * xh[i];
     }
-    s1 = warp_sum(s1) / (float)FE; s2 = warp_sum(s2) / (float)FE;
+    s1 = half_sum(s1) / (float)FE; s2 = half_sum(s2) / (float)FE;
+    float dp[4];
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const int e = lane + 32 * i;
-      const float dp = ok ? rstd * (g[i] - s1 - xh[i] * s2) : 0.f;
-      if (MODE == 0) {
-        if (ok) a.d_embs[(int64_t)u * a.ld_user + (int64_t)t * FE + e] = dp;
-        dfs[r * SX + e] = dp;
-      } else {
-        dpre_s[r * SX + e] = dp;
-        dfs[r * SX + e] = ok ? drop_apply(a.dc, site, (uint64_t)gr * FE + e, dp) : 0.f;
-      }
+    for (int i = 0; i < 4; ++i) dp[i] = ok ? rstd * (g[i] - s1 - xh[i] * s2) : 0.f;
+    if (MODE == 0) {
+      if (ok) *reinterpret_cast<float4*>(a.d_embs + (int64_t)u * a.ld_user + (int64_t)t * FE + 4 * l) = make_float4(dp[0], dp[1], dp[2], dp[3]);
+      *reinterpret_cast<float4*>(dfs + r * SX + 4 * l) = make_float4(dp[0], dp[1], dp[2], dp[3]);
+    } else {
+      *reinterpret_cast<float4*>(dpre_s + r * SX + 4 * l) = make_float4(dp[0], dp[1], dp[2], dp[3]);
+      if (ok) drop4(dr, site, (uint64_t)gr * (FE / 4) + l, dp);
+      *reinterpret_cast<float4*>(dfs + r * SX + 4 * l) = make_float4(dp[0], dp[1], dp[2], dp[3]);
     }
   }
-  // gamma / beta partials of this warp -> shared accumulators
+  // gamma / beta partials of this half-warp -> shared accumulators
 #pragma unroll
-  for (int i = 0; i < 2; ++i) { atomicAdd(dgamma_s + lane + 32 * i, ag[i]); atomicAdd(dbeta_s + lane + 32 * i, ab[i]); }
+  for (int i = 0; i < 4; ++i) { atomicAdd(dgamma_s + 4 * l + i, ag[i]); atomicAdd(dbeta_s + 4 * l + i, ab[i]); }
 }
 
 template <bool TC>
@@ -537,6 +559,7 @@ __global__ void __launch_bounds__(FTHREADS, 1) ue_fused_bwd_kernel(const __grid_
   const int u0 = blockIdx.x * FUPC;
   const int H = a.H, dk = FE / H;
   const float temp = sqrtf((float)dk);
+  const DropRt drt = drop_rt(a.dc);
   // running gradient dY [FR][FE] lives in sC at block entry
   cta_load_rows<FE, SX>(a, u0, sC, a.d_out);
   __syncthreads();
@@ -548,7 +571,7 @@ __global__ void __launch_bounds__(FTHREADS, 1) ue_fused_bwd_kernel(const __grid_
     if (threadIdx.x < FE) { sgam[threadIdx.x] = 0.f; sbet[threadIdx.x] = 0.f; }
     cta_load_rows<FF, SH>(a, u0, sH, X.h1);
     __syncthreads();
-    cta_ln_bwd<1, SX>(a, u0, sC, X.pre2, X.stat2, bp.ln2_w, sgam, sbet, sM, sQ, 3u + 4u * b);
+    cta_ln_bwd<1, SX>(a, drt, u0, sC, X.pre2, X.stat2, bp.ln2_w, sgam, sbet, sM, sQ, 3u + 4u * b);
     __syncthreads();
     if (threadIdx.x < FE) { atomicAdd(bg.ln2_w + threadIdx.x, sgam[threadIdx.x]); atomicAdd(bg.ln2_b + threadIdx.x, sbet[threadIdx.x]); }
     // ---- W2: dW2 += df^T h1 ; db2 ; d h1 = (df W2) * (h1 > 0) ----
@@ -569,7 +592,7 @@ __global__ void __launch_bounds__(FTHREADS, 1) ue_fused_bwd_kernel(const __grid_
     if (threadIdx.x < FE) { sgam[threadIdx.x] = 0.f; sbet[threadIdx.x] = 0.f; }
     cta_load_rows<FE, SX>(a, u0, sV, X.ctx);
     __syncthreads();
-    cta_ln_bwd<1, SX>(a, u0, sM, X.pre1, X.stat1, bp.ln1_w, sgam, sbet, sC, sQ, 2u + 4u * b);
+    cta_ln_bwd<1, SX>(a, drt, u0, sM, X.pre1, X.stat1, bp.ln1_w, sgam, sbet, sC, sQ, 2u + 4u * b);
     __syncthreads();
     if (threadIdx.x < FE) { atomicAdd(bg.ln1_w + threadIdx.x, sgam[threadIdx.x]); atomicAdd(bg.ln1_b + threadIdx.x, sbet[threadIdx.x]); }
     // ---- fc: dWfc += df^T ctx ; d ctx = df Wfc -> sM ----
@@ -584,7 +607,7 @@ __global__ void __launch_bounds__(FTHREADS, 1) ue_fused_bwd_kernel(const __grid_
       const int ul = idx / (H * FL * FL), u = u0 + ul;
       const int64_t gi = (int64_t)u * H * FL * FL + idx % (H * FL * FL);
       float p = 0.f, pd = 0.f;
-      if (u < a.users) { p = X.p[gi]; pd = drop_apply(a.dc, 1u + 4u * b, (uint64_t)gi, p); }
+      if (u < a.users) { p = X.p[gi]; pd = drop1(drt, 1u + 4u * b, (uint64_t)gi, p); }
       sP[idx] = p; sPd[idx] = pd;
     }
     __syncthreads();
@@ -595,7 +618,7 @@ __global__ void __launch_bounds__(FTHREADS, 1) ue_fused_bwd_kernel(const __grid_
       float acc = 0.f;
       for (int c = 0; c < dk; ++c) acc = fmaf(dr[c], vr[c], acc);
       const int64_t gi = (int64_t)u * H * FL * FL + rem;
-      sDs[idx] = (u < a.users) ? drop_apply(a.dc, 1u + 4u * b, (uint64_t)gi, acc) : 0.f;
+      sDs[idx] = (u < a.users) ? drop1(drt, 1u + 4u * b, (uint64_t)gi, acc) : 0.f;
     }
     __syncthreads();
     for (int r = threadIdx.x; r < FUPC * H * FL; r += FTHREADS) {                    // softmax backward, / temp
@@ -633,7 +656,7 @@ __global__ void __launch_bounds__(FTHREADS, 1) ue_fused_bwd_kernel(const __grid_
   // ---- entry LN + position embedding ----
   if (threadIdx.x < FE) { sgam[threadIdx.x] = 0.f; sbet[threadIdx.x] = 0.f; }
   __syncthreads();
-  cta_ln_bwd<0, SX>(a, u0, sC, a.W.pre0, a.W.stat0, a.P.ln_w, sgam, sbet, nullptr, sQ, 0u);
+  cta_ln_bwd<0, SX>(a, drt, u0, sC, a.W.pre0, a.W.stat0, a.P.ln_w, sgam, sbet, nullptr, sQ, 0u);
   __syncthreads();
   if (threadIdx.x < FE) { atomicAdd(a.G.ln_w + threadIdx.x, sgam[threadIdx.x]); atomicAdd(a.G.ln_b + threadIdx.x, sbet[threadIdx.x]); }
   for (int idx = threadIdx.x; idx < FL * FE; idx += FTHREADS) {       // d pos[t] = sum over the CTA's users

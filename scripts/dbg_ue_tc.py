@@ -19,7 +19,11 @@ for B in (1, 5, 64, 512):
         (out * w).sum().backward()
         P = {"user_encoder." + n: p.detach().cpu().clone().requires_grad_(True) for n, p in enc.named_parameters()}
         xr = x.cpu().clone().requires_grad_(True)
-        ref = O.user_encoder_forward(P, xr[:, :-1], lm.cpu(), PathConfig())
+        if mode == "bf16" and os.environ.get("EMUL", "1") == "1":
+            import bf16_emulation as EM
+            ref = EM.user_encoder_forward_emul(P, xr[:, :-1], lm.cpu(), PathConfig())
+        else:
+            ref = O.user_encoder_forward(P, xr[:, :-1], lm.cpu(), PathConfig())
         (ref * w.cpu()).sum().backward()
         errs = {n.replace("transformer_encoder.", "").replace("transformer_blocks.", "b"): rel(p.grad.cpu(), P["user_encoder." + n].grad) for n, p in enc.named_parameters()}
         worst = sorted(errs.items(), key=lambda kv: -kv[1])[:4]

@@ -18,8 +18,39 @@ def rb(x):
     return x + (x.detach().bfloat16().float() - x.detach())
 
 
+def rt(x):
+    """TF32 rounding (cvt.rna.tf32.f32: nearest, ties away from zero, 10 explicit mantissa bits), straight-through gradient."""
+    bits = x.detach().contiguous().view(torch.int32)
+    r = ((bits + 0x1000) & ~0x1FFF).view(torch.float32)
+    return x + (r - x.detach())
+
+
 def _lin(x, w, b=None):
     return F.linear(x, rb(w), b)
+
+
+def user_encoder_forward_emul(P, embs, log_mask, cfg, prefix="user_encoder.transformer_encoder."):
+    """oracle.user_encoder_forward (CC/model/encoders.py:53-58, CC/model/modules.py:14-18, 54-64, 89-96) with the operands of
+    every linear layer rounded to TF32, as the fused fast-mode kernel does (user_encoder_fused.cu, mma.sync TF32 tiles)."""
+    B, L, E = embs.shape
+    H = cfg.heads; dk = E // H
+    keep = torch.tril((log_mask != 0)[:, None, None, :].expand(B, 1, L, L))
+    att_mask = torch.where(keep, 0.0, O.ATT_NEG)
+    lin = lambda x, w, b=None: F.linear(rt(x), rt(P[w]), None if b is None else P[b])
+    x = O._ln(embs + P[prefix + "position_embedding.weight"][None, :L], P[prefix + "layer_norm.weight"], P[prefix + "layer_norm.bias"])
+    for b in range(cfg.blocks):
+        p = f"{prefix}transformer_blocks.{b}."
+        a = p + "multi_head_attention."
+        q = lin(x, a + "w_Q.weight").view(B, L, H, dk).transpose(1, 2)
+        k = lin(x, a + "w_K.weight").view(B, L, H, dk).transpose(1, 2)
+        v = lin(x, a + "w_V.weight").view(B, L, H, dk).transpose(1, 2)
+        att = torch.matmul(q, k.transpose(-2, -1)) / (dk ** 0.5) + att_mask
+        ctx = torch.matmul(torch.softmax(att, dim=-1), v).transpose(1, 2).reshape(B, L, E)
+        x = O._ln(x + lin(ctx, a + "fc.weight"), P[a + "layer_norm.weight"], P[a + "layer_norm.bias"])
+        f = p + "feed_forward."
+        y = lin(F.relu(lin(x, f + "w_1.weight", f + "w_1.bias")), f + "w_2.weight", f + "w_2.bias")
+        x = O._ln(x + y, P[f + "layer_norm.weight"], P[f + "layer_norm.bias"])
+    return x
 
 
 def san_forward_emul(P, image, text, cfg, prefix="mm_encoder.", fused_chain=False):
@@ -81,7 +112,9 @@ def train_step_grads_emul(params_np, batch, pop_prob, cfg, ce_bf16=False, fused_
     e_cv, e_tx, e_mm = san_forward_emul(P, image, text, cfg, fused_chain=fused_chain)
     score = F.linear(torch.cat([e_cv, e_tx, e_mm], dim=1), P["com_dense.weight"], P["com_dense.bias"])
     embs = score.view(B, S, cfg.embedding_dim)
-    prec = O.user_encoder_forward(P, embs[:, :-1], torch.from_numpy(lm), cfg).reshape(-1, cfg.embedding_dim)
+    tf32_ue = cfg.embedding_dim == 64 and S - 1 == 10 and cfg.heads <= 4          # ue_fused_supported (user_encoder_fused.cu)
+    ue = user_encoder_forward_emul if tf32_ue else O.user_encoder_forward
+    prec = ue(P, embs[:, :-1], torch.from_numpy(lm), cfg).reshape(-1, cfg.embedding_dim)
     if ce_bf16:
         loss, _ = O.inbatch_ce(rb(prec), rb(score), debias, ids, lm, ids, lm)
     else:
