@@ -309,8 +309,9 @@ static int san_forward_bf16_t(const iisan_san_desc* D, const iisan_san_params* P
     IISAN_TRY(chain_fill_tower(&ca.tower[0], 0, text, N, (int64_t)D->layers_text * D->d_text, nullptr, 0, L.wd_pack[0], L.wu_pack[0], L.x_t[0], L.last_t[0], L.z_t[0], D->n_stages, D->d_text));
     IISAN_TRY(chain_fill_tower(&ca.tower[1], 0, image, N, (int64_t)D->layers_img * D->d_img, nullptr, 0, L.wd_pack[1], L.wu_pack[1], L.x_i[0], L.last_i[0], L.z_i[0], D->n_stages, D->d_img));
     IISAN_TRY(chain_fill_tower(&ca.tower[2], 1, image, N, (int64_t)D->layers_img * D->d_img, text, (int64_t)D->layers_text * D->d_text, L.wd_pack[2], L.wu_pack[2], L.x_m[0], L.last_m[0], L.z_m[0], D->n_stages, D->d_mm));
-    ca.tower[0].store_last = 1; ca.tower[1].store_last = 1;      // the backward of the intra-modal towers reads last_{s-1}
-    ca.tower[2].store_last = 0;                                  // the inter-modal gate gradient only needs the raw states
+    // only last_{A-1} (the operand of the heads) is written: the backward recovers h_s - last_{s-1} of the intra-modal towers
+    // from the x_s stash, and the inter-modal gate gradient only needs the raw states
+    ca.tower[0].store_last = 0; ca.tower[1].store_last = 0; ca.tower[2].store_last = 0;
     for (int s = 0; s < D->n_stages; ++s) {
       const int ta = D->text_adapter[s], ia = D->img_adapter[s], mi = D->mm_index[s];
       ChainTower& t0 = ca.tower[0]; ChainTower& t1 = ca.tower[1]; ChainTower& t2 = ca.tower[2];
@@ -475,9 +476,9 @@ static int san_backward_bf16_t(const iisan_san_desc* D, const iisan_san_params* 
     // ---- data / gate / bias gradients of all stages and towers in one launch (san_chain.cu) ----
     ChainBwdArgs ca{};
     ca.n_items = N; ca.n_pad = chain_n_pad(N); ca.d = D->d_mm; ca.n_stages = D->n_stages;
-    IISAN_TRY(chain_fill_bwd_tower(&ca.tower[0], 0, text, N, (int64_t)D->layers_text * D->d_text, nullptr, 0, L.wd_pack[0], L.wu_pack[0], L.dys[0], L.last_t[0], L.dzs[0][0], D->n_stages, D->d_text));
-    IISAN_TRY(chain_fill_bwd_tower(&ca.tower[1], 0, image, N, (int64_t)D->layers_img * D->d_img, nullptr, 0, L.wd_pack[1], L.wu_pack[1], L.dys[1], L.last_i[0], L.dzs[1][0], D->n_stages, D->d_img));
-    IISAN_TRY(chain_fill_bwd_tower(&ca.tower[2], 1, image, N, (int64_t)D->layers_img * D->d_img, text, (int64_t)D->layers_text * D->d_text, L.wd_pack[2], L.wu_pack[2], L.dys[2], L.last_m[0], L.dzs[2][0], D->n_stages, D->d_mm));
+    IISAN_TRY(chain_fill_bwd_tower(&ca.tower[0], 0, text, N, (int64_t)D->layers_text * D->d_text, nullptr, 0, L.wd_pack[0], L.wu_pack[0], L.dys[0], L.x_t[0], L.dzs[0][0], D->n_stages, D->d_text));
+    IISAN_TRY(chain_fill_bwd_tower(&ca.tower[1], 0, image, N, (int64_t)D->layers_img * D->d_img, nullptr, 0, L.wd_pack[1], L.wu_pack[1], L.dys[1], L.x_i[0], L.dzs[1][0], D->n_stages, D->d_img));
+    IISAN_TRY(chain_fill_bwd_tower(&ca.tower[2], 1, image, N, (int64_t)D->layers_img * D->d_img, text, (int64_t)D->layers_text * D->d_text, L.wd_pack[2], L.wu_pack[2], L.dys[2], L.x_m[0], L.dzs[2][0], D->n_stages, D->d_mm));
     ca.tower[0].z_stash = L.z_t[0]; ca.tower[1].z_stash = L.z_i[0]; ca.tower[2].z_stash = L.z_m[0];
     for (int s = 0; s < D->n_stages; ++s) {
       const int ta = D->text_adapter[s], ia = D->img_adapter[s], mi = D->mm_index[s];

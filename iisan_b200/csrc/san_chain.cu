@@ -10,7 +10,8 @@
 // stashes written here)
 //   dz_s      = (dy_s Wu_s) * (z_s > 0)                            dy_s = d last_s
 //   dx_s      = dy_s + dz_s Wd_s
-//   dgate_s  += sum dx_s * (h_s - last_{s-1})                      (mm: h_cv - h_text), times g(1-g)/0.1
+//   dgate_s  += sum dx_s * (h_s - last_{s-1})                      (mm: h_cv - h_text), times g(1-g)/0.1 ; the intra-modal towers
+//                                                                  use (h_s - x_s) g/0.1 instead (x_s is stashed, last_{s-1} is not)
 //   dy_{s-1}  = (1 - g_s) dx_s                                     (mm: dx_s)
 //
 // The running state never exists as a whole on chip (128 x 768 fp32 exceeds TMEM); it streams through 64-column chunks.
@@ -159,13 +160,12 @@ __global__ void __launch_bounds__(CH_THREADS, 1) san_chain_fwd_kernel(const __gr
   } else if (warp == 2) {
     // ===================== data producer =====================
     if (elect_one()) {
-      int n_h = 0;
+      int slot = 0; uint32_t ph = 0;
       auto load = [&](const CUtensorMap* m, int col, int row) {
-        const int slot = n_h % CH_NH; const uint32_t ph = (uint32_t)(n_h / CH_NH) & 1u;
         mbar_wait(&B.h_empty[slot], ph ^ 1u);
         mbar_expect_tx(&B.h_full[slot], CH_TILE_BYTES);
         tma_load_2d(smem + ChainSmem::kH + slot * CH_TILE_BYTES, m, &B.h_full[slot], col, row);
-        ++n_h;
+        if (++slot == CH_NH) { slot = 0; ph ^= 1u; }
       };
       // consumption order of the epilogue: x_0[c] needs h_0[c] ; chunk c of stage s needs the residual x_s[c] (stored by this
       // CTA one stage earlier) and, unless s is the last stage, h_{s+1}[c]
@@ -264,7 +264,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) san_chain_fwd_kernel(const __gr
     const int m = quad * 32 + lane;           // row inside the tile
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
     const int sw_row = (m >> 3) * 1024 + (m & 7) * 128;      // byte offset of row m inside a swizzled [128 x 64] bf16 tile
-    int n_h = 0, n_x = 0, n_u = 0;
+    int n_x = 0, n_u = 0;
 
     auto put_tile = [&](uint8_t* tile_base, const float* v) {
       uint8_t* tile = tile_base + sw_row;
@@ -282,15 +282,15 @@ __global__ void __launch_bounds__(CH_THREADS, 1) san_chain_fwd_kernel(const __gr
       if (lane == 0) mbar_arrive(&B.xk_full[b]);
       ++n_x;
     };
+    int h_slot = 0; uint32_t h_ph = 0;
     auto read_h = [&](float* hv) {            // this thread's 32 columns of the next ring tile
-      const int slot = n_h % CH_NH; const uint32_t ph = (uint32_t)(n_h / CH_NH) & 1u;
-      mbar_wait(&B.h_full[slot], ph);
-      const uint8_t* tile = smem + ChainSmem::kH + slot * CH_TILE_BYTES + sw_row;
+      mbar_wait(&B.h_full[h_slot], h_ph);
+      const uint8_t* tile = smem + ChainSmem::kH + h_slot * CH_TILE_BYTES + sw_row;
 #pragma unroll
       for (int q = 0; q < 4; ++q) unpack8(*reinterpret_cast<const uint4*>(tile + (((hf * 4 + q) ^ (m & 7)) << 4)), hv + q * 8);
       __syncwarp();
-      if (lane == 0) mbar_arrive(&B.h_empty[slot]);
-      ++n_h;
+      if (lane == 0) mbar_arrive(&B.h_empty[h_slot]);
+      if (++h_slot == CH_NH) { h_slot = 0; h_ph ^= 1u; }
     };
 
     // ---- x_0 = fuse(h_0, 0) ----
@@ -304,10 +304,10 @@ __global__ void __launch_bounds__(CH_THREADS, 1) san_chain_fwd_kernel(const __gr
           float h2[32];
           read_h(h2);
 #pragma unroll
-          for (int k = 0; k < 32; ++k) xv[k] = __fadd_rn(__fmul_rn(g, hv[k]), __fmul_rn(omg, h2[k]));
+          for (int k = 0; k < 32; ++k) xv[k] = fmaf(g, hv[k], omg * h2[k]);
         } else {
 #pragma unroll
-          for (int k = 0; k < 32; ++k) xv[k] = __fmul_rn(g, hv[k]);
+          for (int k = 0; k < 32; ++k) xv[k] = g * hv[k];
         }
         emit(xv, xv, true, false);
       }
@@ -339,6 +339,12 @@ __global__ void __launch_bounds__(CH_THREADS, 1) san_chain_fwd_kernel(const __gr
       const float omg = 1.0f - g;
       const bool keep_last = !more || T.store_last != 0;
       for (int c = 0; c < NC; ++c) {
+        float4 bq[8];                          // bias chunk first: its global-load latency hides behind the ring / MMA waits
+        {
+          const float4* bu = reinterpret_cast<const float4*>(T.b_up[s] + c * CH_CW + hf * 32);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) bq[q] = __ldg(bu + q);
+        }
         float xr[32];
         read_h(xr);                            // residual x_s[c]
         const int b = n_u & 1; const uint32_t uph = (uint32_t)(n_u >> 1) & 1u;
@@ -352,12 +358,10 @@ __global__ void __launch_bounds__(CH_THREADS, 1) san_chain_fwd_kernel(const __gr
         if (lane == 0) mbar_arrive(&B.u_empty[b]);
         ++n_u;
         float lv[32];
-        const float4* bu = reinterpret_cast<const float4*>(T.b_up[s] + c * CH_CW + hf * 32);
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-          const float4 bq = __ldg(bu + q);
-          lv[4 * q] = __uint_as_float(raw[4 * q]) + bq.x + xr[4 * q]; lv[4 * q + 1] = __uint_as_float(raw[4 * q + 1]) + bq.y + xr[4 * q + 1];
-          lv[4 * q + 2] = __uint_as_float(raw[4 * q + 2]) + bq.z + xr[4 * q + 2]; lv[4 * q + 3] = __uint_as_float(raw[4 * q + 3]) + bq.w + xr[4 * q + 3];
+          lv[4 * q] = __uint_as_float(raw[4 * q]) + bq[q].x + xr[4 * q]; lv[4 * q + 1] = __uint_as_float(raw[4 * q + 1]) + bq[q].y + xr[4 * q + 1];
+          lv[4 * q + 2] = __uint_as_float(raw[4 * q + 2]) + bq[q].z + xr[4 * q + 2]; lv[4 * q + 3] = __uint_as_float(raw[4 * q + 3]) + bq[q].w + xr[4 * q + 3];
         }
         if (more) {
           float hv[32], xv[32];
@@ -366,10 +370,10 @@ __global__ void __launch_bounds__(CH_THREADS, 1) san_chain_fwd_kernel(const __gr
             float h2[32];
             read_h(h2);
 #pragma unroll
-            for (int k = 0; k < 32; ++k) xv[k] = __fadd_rn(__fadd_rn(lv[k], __fmul_rn(g, hv[k])), __fmul_rn(omg, h2[k]));
+            for (int k = 0; k < 32; ++k) xv[k] = fmaf(omg, h2[k], fmaf(g, hv[k], lv[k]));
           } else {
 #pragma unroll
-            for (int k = 0; k < 32; ++k) xv[k] = __fadd_rn(__fmul_rn(g, hv[k]), __fmul_rn(omg, lv[k]));
+            for (int k = 0; k < 32; ++k) xv[k] = fmaf(g, hv[k], omg * lv[k]);
           }
           emit(xv, lv, true, keep_last);
         } else {
@@ -431,13 +435,12 @@ __global__ void __launch_bounds__(CH_THREADS, 1) san_chain_bwd_kernel(const __gr
   } else if (warp == 2) {
     // ===================== data producer =====================
     if (elect_one()) {
-      int n_h = 0;
+      int slot = 0; uint32_t ph = 0;
       auto load = [&](const CUtensorMap* m, int col, int row) {
-        const int slot = n_h % CH_NH; const uint32_t ph = (uint32_t)(n_h / CH_NH) & 1u;
         mbar_wait(&B.h_empty[slot], ph ^ 1u);
         mbar_expect_tx(&B.h_full[slot], CH_TILE_BYTES);
         tma_load_2d(smem + ChainSmem::kH + slot * CH_TILE_BYTES, m, &B.h_full[slot], col, row);
-        ++n_h;
+        if (++slot == CH_NH) { slot = 0; ph ^= 1u; }
       };
       for (int c = 0; c < NC; ++c) load(&T.map_dy, c * CH_CW, (A - 1) * NP + m0);
       for (int s = A - 1; s >= 0; --s) {
@@ -445,7 +448,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) san_chain_bwd_kernel(const __gr
           load(&T.map_dy, c * CH_CW, s * NP + m0);
           load(&T.map_h, T.layer[s] * a.d + c * CH_CW, m0);
           if (is_mm) load(&T.map_aux, T.layer2[s] * a.d + c * CH_CW, m0);
-          else if (s > 0) load(&T.map_aux, c * CH_CW, (s - 1) * NP + m0);
+          else if (s > 0) load(&T.map_aux, c * CH_CW, s * NP + m0);          // x_s (the forward's stash)
         }
       }
     }
@@ -515,7 +518,8 @@ __global__ void __launch_bounds__(CH_THREADS, 1) san_chain_bwd_kernel(const __gr
     const bool row_ok = row < a.n_items;
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
     const int sw_row = (m >> 3) * 1024 + (m & 7) * 128;
-    int n_h = 0, n_x = 0, n_u = 0;
+    int n_x = 0, n_u = 0;
+    int h_slot = 0; uint32_t h_ph = 0;
 
     auto put_tile = [&](uint8_t* tile_base, const float* v) {
       uint8_t* tile = tile_base + sw_row;
@@ -523,9 +527,8 @@ __global__ void __launch_bounds__(CH_THREADS, 1) san_chain_bwd_kernel(const __gr
       for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4*>(tile + (((hf * 4 + q) ^ (m & 7)) << 4)) = pack8(v + q * 8);
     };
     auto read_tile = [&](float* hv) {                 // this thread's 32 columns of the next ring tile (zeros for rows past N)
-      const int slot = n_h % CH_NH; const uint32_t ph = (uint32_t)(n_h / CH_NH) & 1u;
-      mbar_wait(&B.h_full[slot], ph);
-      const uint8_t* tile = smem + ChainSmem::kH + slot * CH_TILE_BYTES + sw_row;
+      mbar_wait(&B.h_full[h_slot], h_ph);
+      const uint8_t* tile = smem + ChainSmem::kH + h_slot * CH_TILE_BYTES + sw_row;
 #pragma unroll
       for (int q = 0; q < 4; ++q) unpack8(*reinterpret_cast<const uint4*>(tile + (((hf * 4 + q) ^ (m & 7)) << 4)), hv + q * 8);
       if (!row_ok) {
@@ -533,8 +536,8 @@ __global__ void __launch_bounds__(CH_THREADS, 1) san_chain_bwd_kernel(const __gr
         for (int k = 0; k < 32; ++k) hv[k] = 0.f;
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(&B.h_empty[slot]);
-      ++n_h;
+      if (lane == 0) mbar_arrive(&B.h_empty[h_slot]);
+      if (++h_slot == CH_NH) { h_slot = 0; h_ph ^= 1u; }
     };
     auto emit = [&](const float* xv) {                // bf16 chunk -> A operand (the MMA thread stores it to the stash)
       const int b = n_x & 1; const uint32_t ph = (uint32_t)(n_x >> 1) & 1u;
@@ -615,9 +618,12 @@ __global__ void __launch_bounds__(CH_THREADS, 1) san_chain_bwd_kernel(const __gr
         const float cs = warp_colsum32(dy, lane);                        // db_up
         atomicAdd(T.g_b_up[s] + c * CH_CW + hf * 32 + lane, cs);
       }
-      // ---- gate gradient: d sigmoid(p/0.1)/dp = g(1-g)/0.1 ----
+      // ---- gate gradient: d x_s / d g = h_s - last_{s-1} (mm: h_cv - h_text), d sigmoid(p/0.1)/dp = g(1-g)/0.1.  The intra-modal
+      //      towers do not stash last_{s-1}: x_s = g h_s + (1-g) last_{s-1} gives h_s - last_{s-1} = (h_s - x_s) / (1-g), and the
+      //      (1-g) cancels against the sigmoid derivative (no division: a saturated gate is harmless) ----
       gpart = warp_sum(gpart);
-      if (lane == 0) atomicAdd(T.g_gate[s], gpart * g * omg / 0.1f);
+      const float gfac = (!is_mm && more) ? g / 0.1f : g * omg / 0.1f;
+      if (lane == 0) atomicAdd(T.g_gate[s], gpart * gfac);
     }
   }
   tc_fence_before();
@@ -653,14 +659,14 @@ int chain_fill_tower(ChainTower* T, int mode, const void* h, int64_t n_items, in
 }
 
 int chain_fill_bwd_tower(ChainBwdTower* T, int mode, const void* h, int64_t n_items, int64_t h_pitch_cols, const void* h2,
-                         int64_t h2_pitch_cols, const bf16* wd_pack, const bf16* wu_pack, const bf16* dy_all, const bf16* last_all,
+                         int64_t h2_pitch_cols, const bf16* wd_pack, const bf16* wu_pack, const bf16* dy_all, const bf16* x_all,
                          const bf16* dz_all, int n_stages, int d) {
   const int64_t np = chain_n_pad((int)n_items);
   T->mode = mode;
   IISAN_TRY(make_tensor_map_bf16(&T->map_h, h, n_items, h_pitch_cols, h_pitch_cols, CH_CW, CH_ROWS));
   IISAN_TRY(make_tensor_map_bf16(&T->map_dy, dy_all, (int64_t)n_stages * np, d, d, CH_CW, CH_ROWS));
   if (mode == 1) IISAN_TRY(make_tensor_map_bf16(&T->map_aux, h2, n_items, h2_pitch_cols, h2_pitch_cols, CH_CW, CH_ROWS));
-  else IISAN_TRY(make_tensor_map_bf16(&T->map_aux, last_all, (int64_t)n_stages * np, d, d, CH_CW, CH_ROWS));
+  else IISAN_TRY(make_tensor_map_bf16(&T->map_aux, x_all, (int64_t)n_stages * np, d, d, CH_CW, CH_ROWS));
   IISAN_TRY(make_tensor_map_bf16(&T->map_dz, dz_all, (int64_t)n_stages * np, CH_R, CH_R, CH_R, CH_ROWS));
   return fill_common(&T->map_wd, &T->map_wu, wd_pack, wu_pack, n_stages, d);
 }

