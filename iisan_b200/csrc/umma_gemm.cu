@@ -1,7 +1,9 @@
-// tcgen05 / TMEM / TMA GEMM (see umma_gemm.cuh).  One CTA computes one 128 x BN output tile:
-//   warp 0   : TMA producer   (one elected lane streams A/B k-blocks through a 4-stage smem ring)
+// tcgen05 / TMEM / TMA GEMM (see umma_gemm.cuh).  Persistent: one CTA per SM walks the 128 x BN output tiles of all problems
+// of the launch (tile = blockIdx.x + i * gridDim.x; column tiles fastest, so CTAs running side by side share their A rows in
+// L2), with TWO accumulators in TMEM: the epilogue of tile i overlaps the TMA / MMA main loop of tile i + 1.
+//   warp 0   : TMA producer   (one elected lane streams A/B k-blocks through a 4-stage smem ring, across tile boundaries)
 //   warp 1   : TMEM allocator + MMA issuer (one elected lane issues tcgen05.mma, commits to mbarriers)
-//   warps 2-5: epilogue       (tcgen05.ld 32 lanes x 32 columns -> bias / ReLU / mask / residual -> global)
+//   warps 2-9: epilogue       (tcgen05.ld 32 lanes x 32 columns -> bias / ReLU / mask / residual -> global)
 #include "umma_gemm.cuh"
 
 #include <mutex>
@@ -25,13 +27,32 @@ struct UmmaDevProblem {
   CUtensorMap map_a, map_b;
   int M, N, K;
   int kblocks_per_split;
+  int tile_start;             // first tile of this problem in the launch-wide tile list (tiles: split-major, then m, then n)
   UmmaEpilogue epi;
 };
 template <int NP>
 struct UmmaDevBatchT {
   UmmaDevProblem p[NP];
   int stages;
+  int n_probs, total_tiles;
 };
+
+struct UmmaTile { int prob, m0, n0, kb_beg, kb_end, split; };
+template <int BN, int NP>
+__device__ __forceinline__ UmmaTile umma_decode_tile(const UmmaDevBatchT<NP>& batch, int tile) {
+  int p = 0;
+  while (p + 1 < batch.n_probs && tile >= batch.p[p + 1].tile_start) ++p;
+  const UmmaDevProblem& P = batch.p[p];
+  const int tiles_n = (P.N + BN - 1) / BN, tiles_m = (P.M + UBM - 1) / UBM;
+  const int l = tile - P.tile_start;
+  const int split = l / (tiles_m * tiles_n), r = l % (tiles_m * tiles_n);
+  UmmaTile t;
+  t.prob = p; t.split = split; t.m0 = (r / tiles_n) * UBM; t.n0 = (r % tiles_n) * BN;
+  const int kb_total = (P.K + UBK - 1) / UBK;
+  t.kb_beg = split * P.kblocks_per_split;
+  t.kb_end = min(kb_total, t.kb_beg + P.kblocks_per_split);
+  return t;
+}
 
 template <int BN>
 struct UmmaSmem {
@@ -101,36 +122,25 @@ __device__ __noinline__ void epi_block_generic(const UmmaEpilogue& E, const floa
 enum : int { EPI_MASK = 1, EPI_RESB = 2, EPI_RESF = 4, EPI_OUTF = 8, EPI_OUTB = 16, EPI_ATOMIC = 32 };
 
 template <int BN, bool A_MN, bool B_MN, int NP>
-__global__ void __launch_bounds__(UTHREADS, 2) umma_gemm_kernel(const __grid_constant__ UmmaDevBatchT<NP> batch) {
-  const UmmaDevProblem& P = batch.p[blockIdx.z];
+__global__ void __launch_bounds__(UTHREADS, 1) umma_gemm_kernel(const __grid_constant__ UmmaDevBatchT<NP> batch) {
   const int NSTG = batch.stages;
-  const int tiles_n = (P.N + BN - 1) / BN;
-  const int tiles_m = (P.M + UBM - 1) / UBM;
-  if ((int)blockIdx.x >= tiles_m * tiles_n) return;
-  const int kb_total = (P.K + UBK - 1) / UBK;
-  const int kb_beg = blockIdx.y * P.kblocks_per_split;
-  const int kb_end = min(kb_total, kb_beg + P.kblocks_per_split);
-  if (kb_beg >= kb_end) return;
-  const int m0 = (blockIdx.x / tiles_n) * UBM, n0 = (blockIdx.x % tiles_n) * BN;
-
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   using S = UmmaSmem<BN>;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + NSTG * S::kStageBytes);
   uint64_t* empty = full + USTAGES;
-  uint64_t* accum_full = empty + USTAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_full + 1);
+  uint64_t* accum_full = empty + USTAGES;        // [2]
+  uint64_t* accum_empty = accum_full + 2;        // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_empty + 2);
   float* staging = reinterpret_cast<float*>(smem + NSTG * S::kStageBytes + 256);
 
   const int warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) {
-    tma_prefetch_desc(&P.map_a);
-    tma_prefetch_desc(&P.map_b);
     for (int s = 0; s < NSTG; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    mbar_init(accum_full, 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(&accum_full[b], 1); mbar_init(&accum_empty[b], UEPI_WARPS); }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, BN);
+  if (warp == 1) tmem_alloc(tmem_slot, 2 * BN);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -139,47 +149,59 @@ __global__ void __launch_bounds__(UTHREADS, 2) umma_gemm_kernel(const __grid_con
   if (warp == 0) {
     if (elect_one()) {
       int stage = 0; uint32_t phase = 0;
-      for (int kb = kb_beg; kb < kb_end; ++kb) {
-        mbar_wait(&empty[stage], phase ^ 1);
-        uint8_t* sa = smem + stage * S::kStageBytes;
-        uint8_t* sb = sa + S::kABytes;
-        mbar_expect_tx(&full[stage], S::kStageBytes);
-        const int k0 = kb * UBK;
-        if (A_MN) {
+      for (int tile = blockIdx.x; tile < batch.total_tiles; tile += gridDim.x) {
+        const UmmaTile t = umma_decode_tile<BN, NP>(batch, tile);
+        const UmmaDevProblem& P = batch.p[t.prob];
+        for (int kb = t.kb_beg; kb < t.kb_end; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * S::kStageBytes;
+          uint8_t* sb = sa + S::kABytes;
+          mbar_expect_tx(&full[stage], S::kStageBytes);
+          const int k0 = kb * UBK;
+          if (A_MN) {
 #pragma unroll
-          for (int i = 0; i < UBM / 64; ++i) tma_load_2d(sa + i * (64 * UBK * 2), &P.map_a, &full[stage], m0 + i * 64, k0);
-        } else {
-          tma_load_2d(sa, &P.map_a, &full[stage], k0, m0);
-        }
-        if (B_MN) {
+            for (int i = 0; i < UBM / 64; ++i) tma_load_2d(sa + i * (64 * UBK * 2), &P.map_a, &full[stage], t.m0 + i * 64, k0);
+          } else {
+            tma_load_2d(sa, &P.map_a, &full[stage], k0, t.m0);
+          }
+          if (B_MN) {
 #pragma unroll
-          for (int i = 0; i < BN / 64; ++i) tma_load_2d(sb + i * (64 * UBK * 2), &P.map_b, &full[stage], n0 + i * 64, k0);
-        } else {
-          tma_load_2d(sb, &P.map_b, &full[stage], k0, n0);
+            for (int i = 0; i < BN / 64; ++i) tma_load_2d(sb + i * (64 * UBK * 2), &P.map_b, &full[stage], t.n0 + i * 64, k0);
+          } else {
+            tma_load_2d(sb, &P.map_b, &full[stage], k0, t.n0);
+          }
+          if (++stage == NSTG) { stage = 0; phase ^= 1; }
         }
-        if (++stage == NSTG) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
     if (elect_one()) {
       constexpr uint32_t idesc = instr_desc_bf16(UBM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
       int stage = 0; uint32_t phase = 0;
-      for (int kb = kb_beg; kb < kb_end; ++kb) {
-        mbar_wait(&full[stage], phase);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < batch.total_tiles; tile += gridDim.x, ++it) {
+        const UmmaTile t = umma_decode_tile<BN, NP>(batch, tile);
+        const int ab = it & 1; const uint32_t aph = (uint32_t)(it >> 1) & 1u;
+        mbar_wait(&accum_empty[ab], aph ^ 1u);           // the epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t sa = smem_u32(smem + stage * S::kStageBytes);
-        const uint32_t sb = sa + S::kABytes;
+        const uint32_t tm = tmem_base + ab * BN;
+        for (int kb = t.kb_beg; kb < t.kb_end; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * S::kStageBytes);
+          const uint32_t sb = sa + S::kABytes;
 #pragma unroll
-        for (int k = 0; k < UBK / 16; ++k) {
-          // K-major: step 16 elements (32 B) inside the 128-byte swizzle row; MN-major: step 16 k-rows (2048 B)
-          const uint64_t ad = A_MN ? smem_desc_sw128(sa + k * 2048, 64 * UBK * 2, 1024) : smem_desc_sw128(sa + k * 32, 16, 1024);
-          const uint64_t bd = B_MN ? smem_desc_sw128(sb + k * 2048, 64 * UBK * 2, 1024) : smem_desc_sw128(sb + k * 32, 16, 1024);
-          mma_bf16_ss(tmem_base, ad, bd, idesc, (kb > kb_beg || k > 0) ? 1u : 0u);
+          for (int k = 0; k < UBK / 16; ++k) {
+            // K-major: step 16 elements (32 B) inside the 128-byte swizzle row; MN-major: step 16 k-rows (2048 B)
+            const uint64_t ad = A_MN ? smem_desc_sw128(sa + k * 2048, 64 * UBK * 2, 1024) : smem_desc_sw128(sa + k * 32, 16, 1024);
+            const uint64_t bd = B_MN ? smem_desc_sw128(sb + k * 2048, 64 * UBK * 2, 1024) : smem_desc_sw128(sb + k * 32, 16, 1024);
+            mma_bf16_ss(tm, ad, bd, idesc, (kb > t.kb_beg || k > 0) ? 1u : 0u);
+          }
+          mma_commit(&empty[stage]);                 // frees the smem slot when these MMAs retire
+          if (++stage == NSTG) { stage = 0; phase ^= 1; }
         }
-        mma_commit(&empty[stage]);                 // frees the smem slot when these MMAs retire
-        if (++stage == NSTG) { stage = 0; phase ^= 1; }
+        mma_commit(&accum_full[ab]);
       }
-      mma_commit(accum_full);
     }
   } else {
     // ---- epilogue: 8 warps; warp w may touch TMEM lanes [32*(w%4), +32) == output rows m0 + 32*(w%4) + lane; the two warps
@@ -190,61 +212,73 @@ __global__ void __launch_bounds__(UTHREADS, 2) umma_gemm_kernel(const __grid_con
     const int csel = ew >> 2;
     const int lane = threadIdx.x & 31;
     float* stg = staging + ew * USTG_FLOATS;
-    mbar_wait(accum_full, 0);
-    tc_fence_after();
-    const UmmaEpilogue& E = P.epi;
-    const bool first_split = (blockIdx.y == 0);
-    const int row_base = m0 + quad * 32;
-    const int features = (E.mask ? EPI_MASK : 0) | (E.resid_bf16 ? EPI_RESB : 0) | (E.resid_f32 ? EPI_RESF : 0) | (E.out_f32 ? EPI_OUTF : 0) |
-                         (E.out_bf16 ? EPI_OUTB : 0) | ((E.atomic && E.out_f32) ? EPI_ATOMIC : 0);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < batch.total_tiles; tile += gridDim.x, ++it) {
+      const UmmaTile t = umma_decode_tile<BN, NP>(batch, tile);
+      const UmmaDevProblem& P = batch.p[t.prob];
+      const int m0 = t.m0, n0 = t.n0;
+      const int ab = it & 1; const uint32_t aph = (uint32_t)(it >> 1) & 1u;
+      mbar_wait(&accum_full[ab], aph);
+      tc_fence_after();
+      const uint32_t tm = tmem_base + ab * BN;
+      const UmmaEpilogue& E = P.epi;
+      const bool first_split = (t.split == 0);
+      const int row_base = m0 + quad * 32;
+      const int features = (E.mask ? EPI_MASK : 0) | (E.resid_bf16 ? EPI_RESB : 0) | (E.resid_f32 ? EPI_RESF : 0) | (E.out_f32 ? EPI_OUTF : 0) |
+                           (E.out_bf16 ? EPI_OUTB : 0) | ((E.atomic && E.out_f32) ? EPI_ATOMIC : 0);
 #pragma unroll 1
-    for (int c0 = csel * 32; c0 < BN; c0 += 64) {
-      if (n0 + c0 >= P.N) break;                   // warp-uniform
-      uint32_t raw[32];
-      tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, raw);
-      tmem_ld_wait();
-      if (E.transpose_out) {
-        // out[n * ld + m]: the lanes (rows m) are already contiguous in memory
-        const int row = row_base + lane;
-        if (row < P.M) {
-          const int ncol = min(32, P.N - (n0 + c0));
-          float* op = E.out_f32 + (int64_t)(n0 + c0) * E.ld_f32 + row;
-          if (E.atomic) {
+      for (int c0 = csel * 32; c0 < BN; c0 += 64) {
+        if (n0 + c0 >= P.N) break;                   // warp-uniform
+        uint32_t raw[32];
+        tmem_ld_32x32(tm + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, raw);
+        tmem_ld_wait();
+        if (E.transpose_out) {
+          // out[n * ld + m]: the lanes (rows m) are already contiguous in memory
+          const int row = row_base + lane;
+          if (row < P.M) {
+            const int ncol = min(32, P.N - (n0 + c0));
+            float* op = E.out_f32 + (int64_t)(n0 + c0) * E.ld_f32 + row;
+            if (E.atomic) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) if (j < ncol) atomicAdd(op + (int64_t)j * E.ld_f32, __uint_as_float(raw[j]));
-          } else {
+              for (int j = 0; j < 32; ++j) if (j < ncol) atomicAdd(op + (int64_t)j * E.ld_f32, __uint_as_float(raw[j]));
+            } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) if (j < ncol) op[(int64_t)j * E.ld_f32] = __uint_as_float(raw[j]);
+              for (int j = 0; j < 32; ++j) if (j < ncol) op[(int64_t)j * E.ld_f32] = __uint_as_float(raw[j]);
+            }
+          }
+          continue;
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = __uint_as_float(raw[j]);
+        __syncwarp();
+        const int col = n0 + c0 + lane;
+        const bool col_ok = col < P.N;
+        const float bias_v = (E.bias && col_ok && (!E.atomic || first_split)) ? __ldg(E.bias + col) : 0.f;
+        const int nrow = min(32, P.M - row_base);    // warp-uniform
+        if (col_ok && nrow > 0) {
+          const float lo = E.relu ? 0.f : -INFINITY;
+          switch (features) {
+            case EPI_OUTB: epi_block<false, false, false, false, true, false>(E, stg, lane, row_base, nrow, col, bias_v, lo); break;
+            case EPI_RESB | EPI_OUTB: epi_block<false, true, false, false, true, false>(E, stg, lane, row_base, nrow, col, bias_v, lo); break;
+            case EPI_OUTF: epi_block<false, false, false, true, false, false>(E, stg, lane, row_base, nrow, col, bias_v, lo); break;
+            case EPI_OUTF | EPI_OUTB: epi_block<false, false, false, true, true, false>(E, stg, lane, row_base, nrow, col, bias_v, lo); break;
+            case EPI_MASK | EPI_OUTB: epi_block<true, false, false, false, true, false>(E, stg, lane, row_base, nrow, col, bias_v, lo); break;
+            case EPI_RESF | EPI_OUTF | EPI_OUTB: epi_block<false, false, true, true, true, false>(E, stg, lane, row_base, nrow, col, bias_v, lo); break;
+            case EPI_ATOMIC | EPI_OUTF: epi_block<false, false, false, true, false, true>(E, stg, lane, row_base, nrow, col, bias_v, lo); break;
+            default: epi_block_generic(E, stg, lane, row_base, nrow, col, bias_v, lo);
           }
         }
-        continue;
+        __syncwarp();
       }
-#pragma unroll
-      for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = __uint_as_float(raw[j]);
+      // accumulator drained (all tcgen05.ld of this warp have completed)
+      tc_fence_before();
       __syncwarp();
-      const int col = n0 + c0 + lane;
-      const bool col_ok = col < P.N;
-      const float bias_v = (E.bias && col_ok && (!E.atomic || first_split)) ? __ldg(E.bias + col) : 0.f;
-      const int nrow = min(32, P.M - row_base);    // warp-uniform
-      if (col_ok) {
-        const float lo = E.relu ? 0.f : -INFINITY;
-        switch (features) {
-          case EPI_OUTB: epi_block<false, false, false, false, true, false>(E, stg, lane, row_base, nrow, col, bias_v, lo); break;
-          case EPI_RESB | EPI_OUTB: epi_block<false, true, false, false, true, false>(E, stg, lane, row_base, nrow, col, bias_v, lo); break;
-          case EPI_OUTF: epi_block<false, false, false, true, false, false>(E, stg, lane, row_base, nrow, col, bias_v, lo); break;
-          case EPI_OUTF | EPI_OUTB: epi_block<false, false, false, true, true, false>(E, stg, lane, row_base, nrow, col, bias_v, lo); break;
-          case EPI_MASK | EPI_OUTB: epi_block<true, false, false, false, true, false>(E, stg, lane, row_base, nrow, col, bias_v, lo); break;
-          case EPI_RESF | EPI_OUTF | EPI_OUTB: epi_block<false, false, true, true, true, false>(E, stg, lane, row_base, nrow, col, bias_v, lo); break;
-          case EPI_ATOMIC | EPI_OUTF: epi_block<false, false, false, true, false, true>(E, stg, lane, row_base, nrow, col, bias_v, lo); break;
-          default: epi_block_generic(E, stg, lane, row_base, nrow, col, bias_v, lo);
-        }
-      }
-      __syncwarp();
+      if (lane == 0) mbar_arrive(&accum_empty[ab]);
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, BN);
+  if (warp == 1) tmem_dealloc(tmem_base, 2 * BN);
 }
 
 // ---- host side -----------------------------------------------------------------------------------------------
@@ -312,7 +346,7 @@ int make_tensor_map_bf16(CUtensorMap* out, const void* ptr, int64_t rows, int64_
 template <int BN, bool A_MN, bool B_MN, int NP>
 static int launch_cfg(const UmmaProblem* probs, int n_probs, cudaStream_t st) {
   static thread_local UmmaDevBatchT<NP> dev;      // large for the batched variant: keep it off the stack (launches are serialised per thread by the callers)
-  int max_tiles = 0, max_split = 1, max_kb = 1;
+  int total_tiles = 0, max_kb = 1;
   for (int i = 0; i < n_probs; ++i) {
     const UmmaProblem& P = probs[i];
     UmmaDevProblem& D = dev.p[i];
@@ -329,17 +363,27 @@ static int launch_cfg(const UmmaProblem* probs, int n_probs, cudaStream_t st) {
     split = (kb_total + D.kblocks_per_split - 1) / D.kblocks_per_split;
     if (split > 1 && !(P.epi.atomic && P.epi.out_f32 && !P.epi.out_bf16)) return IISAN_EINVAL;
     const int tiles = ((P.M + UBM - 1) / UBM) * ((P.N + BN - 1) / BN);
-    if (tiles > max_tiles) max_tiles = tiles;
-    if (split > max_split) max_split = split;
+    D.tile_start = total_tiles;
+    total_tiles += tiles * split;
     if (D.kblocks_per_split > max_kb) max_kb = D.kblocks_per_split;
   }
+  dev.n_probs = n_probs; dev.total_tiles = total_tiles;
   static bool attr_set = false;
   if (!attr_set) {
     IISAN_CUDA_OK(cudaFuncSetAttribute(umma_gemm_kernel<BN, A_MN, B_MN, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaSmem<BN>::total(USTAGES)));
     attr_set = true;
   }
-  dev.stages = max_kb < 1 ? 1 : (max_kb > USTAGES ? USTAGES : max_kb);
-  dim3 grid(max_tiles, max_split, n_probs);
+  // one CTA per SM: the stage count no longer has to leave room for a second CTA (the ring runs across tile boundaries); the
+  // full-size ring also keeps a second CTA (and its 2 * BN TMEM columns) off the SM
+  dev.stages = USTAGES;
+  (void)max_kb;
+  static int n_sm = 0;
+  if (n_sm == 0) {
+    int devid = 0;
+    IISAN_CUDA_OK(cudaGetDevice(&devid));
+    IISAN_CUDA_OK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, devid));
+  }
+  const int grid = total_tiles < n_sm ? total_tiles : n_sm;
   { LaunchScope ls_(IISAN_K_GEMM, st); umma_gemm_kernel<BN, A_MN, B_MN, NP><<<grid, UTHREADS, UmmaSmem<BN>::total(dev.stages), st>>>(dev); }
   IISAN_LAUNCH_OK();
   return IISAN_OK;
@@ -356,10 +400,10 @@ int launch_umma_gemm(const UmmaBatch& b, cudaStream_t st) {
   }
   if (a_mn != b_mn) return IISAN_EUNSUPPORTED;
   int bn = maxN <= 64 ? 64 : (maxN <= 128 ? 128 : 256);
-  if (bn == 256) {   // short grids: 128-wide tiles keep two to three CTAs per SM busy instead of one partial wave of wide tiles
-    int64_t ctas = 0;
-    for (int i = 0; i < b.n; ++i) ctas += (int64_t)((b.p[i].M + UBM - 1) / UBM) * ((b.p[i].N + 255) / 256) * (b.p[i].splitk < 1 ? 1 : b.p[i].splitk);
-    if (ctas < 2 * 148 * 2) bn = 128;
+  if (bn == 256) {   // fewer 256-wide tiles than SMs: 128-wide tiles spread the work over more of them
+    int64_t tiles = 0;
+    for (int i = 0; i < b.n; ++i) tiles += (int64_t)((b.p[i].M + UBM - 1) / UBM) * ((b.p[i].N + 255) / 256) * (b.p[i].splitk < 1 ? 1 : b.p[i].splitk);
+    if (tiles < 148) bn = 128;
   }
   if (!a_mn) {
     if (bn == 64) return launch_cfg<64, false, false, kUmmaMaxProbs>(b.p, b.n, st);
