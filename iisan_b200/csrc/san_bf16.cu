@@ -35,6 +35,21 @@ struct CastBatch { CastJob j[kCastJobs]; int n; };
 
 __global__ void __launch_bounds__(256) cast_transpose_kernel(const CastBatch batch) {
   const CastJob& J = batch.j[blockIdx.y];
+  if (!J.dstT) {                               // plain cast: 128-bit loads, 64-bit stores
+    const int64_t n = (int64_t)J.rows * J.cols;
+    if ((n & 3) == 0 && ((reinterpret_cast<uintptr_t>(J.src) & 15) == 0) && ((reinterpret_cast<uintptr_t>(J.dst) & 7) == 0)) {
+      for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n / 4; i += (int64_t)gridDim.x * 256) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(J.src) + i);
+        uint2 q;
+        *reinterpret_cast<__nv_bfloat162*>(&q.x) = __floats2bfloat162_rn(v.x, v.y);
+        *reinterpret_cast<__nv_bfloat162*>(&q.y) = __floats2bfloat162_rn(v.z, v.w);
+        reinterpret_cast<uint2*>(J.dst)[i] = q;
+      }
+    } else {
+      for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) J.dst[i] = __float2bfloat16_rn(J.src[i]);
+    }
+    return;
+  }
   __shared__ float tile[32][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
   const int tiles_c = (J.cols + 31) / 32, tiles_r = (J.rows + 31) / 32;
@@ -214,6 +229,16 @@ static UmmaProblem mk_linear(const bf16* x, int64_t ldx, const bf16* w, int M, i
   return p;
 }
 
+// dx[M,N] = dy[M,K] W[K,N]   (data gradient: the nn.Linear weight [out = K, in = N] is read in place as an MN-major B operand)
+static UmmaProblem mk_dgrad(const bf16* dy, int64_t lddy, const bf16* w, int M, int N, int K) {
+  UmmaProblem p{};
+  p.A = UmmaOperand{dy, M, K, lddy};
+  p.B = UmmaOperand{w, K, N, N};
+  p.a_mn_major = 0; p.b_mn_major = 1;
+  p.M = M; p.N = N; p.K = K; p.splitk = 1;
+  return p;
+}
+
 static int pick_split(int M, int N, int K, int nprob) {
   const int bn = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
   const int tiles = ((M + 127) / 128) * ((N + bn - 1) / bn) * (nprob < 1 ? 1 : nprob);
@@ -275,7 +300,7 @@ static int san_forward_bf16_t(const iisan_san_desc* D, const iisan_san_params* P
   // ---- bf16 weight copies (the fp32 nn.Parameters stay the source of truth) ----
   {
     CastList c(st);
-    for (int s = 0; s < D->n_stages; ++s) {
+    for (int s = 0; s < (chain ? 0 : D->n_stages); ++s) {      // layered path only: the chain kernels read the packed copies below
       const int ta = D->text_adapter[s], ia = D->img_adapter[s], mi = D->mm_index[s];
       if (ta >= 0) { c.add(P->text[ta].w_down, L.t_down[ta].w, L.t_down[ta].wt, D->r_text, D->d_text); c.add(P->text[ta].w_up, L.t_up[ta].w, L.t_up[ta].wt, D->d_text, D->r_text); }
       if (ia >= 0) { c.add(P->img[ia].w_down, L.i_down[ia].w, L.i_down[ia].wt, D->r_img, D->d_img); c.add(P->img[ia].w_up, L.i_up[ia].w, L.i_up[ia].wt, D->d_img, D->r_img); }
@@ -293,10 +318,11 @@ static int san_forward_bf16_t(const iisan_san_desc* D, const iisan_san_params* P
         c.add(P->mm[mi].w_down, L.wd_pack[2] + off, nullptr, D->r_mm, D->d_mm); c.add(P->mm[mi].w_up, L.wu_pack[2] + off, nullptr, D->d_mm, D->r_mm);
       }
     }
-    c.add(P->fc_text.w, L.fc_t.w, L.fc_t.wt, ft, D->d_text); c.add(P->fc_img.w, L.fc_i.w, L.fc_i.wt, fi, D->d_img);
-    c.add(P->fc_mm.w, L.fc_m.w, L.fc_m.wt, fm, D->d_mm);
-    c.add(P->pre_text.w, L.pre_t.w, L.pre_t.wt, E, ft); c.add(P->pre_img.w, L.pre_i.w, L.pre_i.wt, E, fi);
-    c.add(P->mm_down.w, L.pre_m.w, L.pre_m.wt, E, fm);
+    // heads: plain casts (their data gradients read the [out, in] copies in place as MN-major operands)
+    c.add(P->fc_text.w, L.fc_t.w, nullptr, ft, D->d_text); c.add(P->fc_img.w, L.fc_i.w, nullptr, fi, D->d_img);
+    c.add(P->fc_mm.w, L.fc_m.w, nullptr, fm, D->d_mm);
+    c.add(P->pre_text.w, L.pre_t.w, nullptr, E, ft); c.add(P->pre_img.w, L.pre_i.w, nullptr, E, fi);
+    c.add(P->mm_down.w, L.pre_m.w, nullptr, E, fm);
     c.flush();
     IISAN_TRY(c.status);
   }
@@ -442,9 +468,9 @@ static int san_backward_bf16_t(const iisan_san_desc* D, const iisan_san_params* 
     c.p[2] = {d_out + 2 * E, D->out_ld, N, E, G->mm_down.b};
     IISAN_TRY(launch_colsum(c, st));
     UmmaBatch dh{}; dh.n = 3;  // d head = d_out W_pre
-    dh.p[0] = mk_linear(do_i, ldo, L.pre_i.wt, N, fi, E); dh.p[0].epi.out_bf16 = L.dhead_i; dh.p[0].epi.ld_bf16 = fi;
-    dh.p[1] = mk_linear(do_t, ldo, L.pre_t.wt, N, ft, E); dh.p[1].epi.out_bf16 = L.dhead_t; dh.p[1].epi.ld_bf16 = ft;
-    dh.p[2] = mk_linear(do_m, ldo, L.pre_m.wt, N, fm, E); dh.p[2].epi.out_bf16 = L.dhead_m; dh.p[2].epi.ld_bf16 = fm;
+    dh.p[0] = mk_dgrad(do_i, ldo, L.pre_i.w, N, fi, E); dh.p[0].epi.out_bf16 = L.dhead_i; dh.p[0].epi.ld_bf16 = fi;
+    dh.p[1] = mk_dgrad(do_t, ldo, L.pre_t.w, N, ft, E); dh.p[1].epi.out_bf16 = L.dhead_t; dh.p[1].epi.ld_bf16 = ft;
+    dh.p[2] = mk_dgrad(do_m, ldo, L.pre_m.w, N, fm, E); dh.p[2].epi.out_bf16 = L.dhead_m; dh.p[2].epi.ld_bf16 = fm;
     IISAN_TRY(launch_umma_gemm(dh, st));
     UmmaBatch wf{}; wf.n = 3;  // d fc weights [f, d] += dhead^T last
     wf.p[0] = mk_wgrad(L.dhead_i, fi, fi, L.last_i[ls_i], D->d_img, D->d_img, N, G->fc_img.w, 3);
@@ -458,9 +484,9 @@ static int san_backward_bf16_t(const iisan_san_desc* D, const iisan_san_params* 
     IISAN_TRY(launch_colsum(cf, st));
     UmmaBatch dl{}; dl.n = 3;  // d last = d head W_fc
     const size_t lastoff = (size_t)(D->n_stages - 1) * chain_n_pad(N) * D->d_mm;
-    dl.p[0] = mk_linear(L.dhead_i, fi, L.fc_i.wt, N, D->d_img, fi);
-    dl.p[1] = mk_linear(L.dhead_t, ft, L.fc_t.wt, N, D->d_text, ft);
-    dl.p[2] = mk_linear(L.dhead_m, fm, L.fc_m.wt, N, D->d_mm, fm);
+    dl.p[0] = mk_dgrad(L.dhead_i, fi, L.fc_i.w, N, D->d_img, fi);
+    dl.p[1] = mk_dgrad(L.dhead_t, ft, L.fc_t.w, N, D->d_text, ft);
+    dl.p[2] = mk_dgrad(L.dhead_m, fm, L.fc_m.w, N, D->d_mm, fm);
     if (chain) {      // the fused backward takes d last_{A-1} as bf16 from the per-stage gradient stash
       dl.p[0].epi.out_bf16 = L.dys[1] + lastoff; dl.p[0].epi.ld_bf16 = D->d_img;
       dl.p[1].epi.out_bf16 = L.dys[0] + lastoff; dl.p[1].epi.ld_bf16 = D->d_text;

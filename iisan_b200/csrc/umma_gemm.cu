@@ -398,12 +398,17 @@ int launch_umma_gemm(const UmmaBatch& b, cudaStream_t st) {
     if ((b.p[i].a_mn_major != 0) != a_mn || (b.p[i].b_mn_major != 0) != b_mn) return IISAN_EINVAL;
     if (b.p[i].N > maxN) maxN = b.p[i].N;
   }
-  if (a_mn != b_mn) return IISAN_EUNSUPPORTED;
+  if (a_mn && !b_mn) return IISAN_EUNSUPPORTED;
   int bn = maxN <= 64 ? 64 : (maxN <= 128 ? 128 : 256);
   if (bn == 256) {   // fewer 256-wide tiles than SMs: 128-wide tiles spread the work over more of them
     int64_t tiles = 0;
     for (int i = 0; i < b.n; ++i) tiles += (int64_t)((b.p[i].M + UBM - 1) / UBM) * ((b.p[i].N + 255) / 256) * (b.p[i].splitk < 1 ? 1 : b.p[i].splitk);
     if (tiles < 148) bn = 128;
+  }
+  if (!a_mn && b_mn) {       // data gradient x W with the nn.Linear weight [out, in] read in place as a [K, N] operand
+    if (bn == 64) return launch_cfg<64, false, true, kUmmaMaxProbs>(b.p, b.n, st);
+    if (bn == 128) return launch_cfg<128, false, true, kUmmaMaxProbs>(b.p, b.n, st);
+    return launch_cfg<256, false, true, kUmmaMaxProbs>(b.p, b.n, st);
   }
   if (!a_mn) {
     if (bn == 64) return launch_cfg<64, false, false, kUmmaMaxProbs>(b.p, b.n, st);
