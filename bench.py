@@ -214,7 +214,7 @@ def run_ours(a):
         for p in model.parameters():                                 # same initial replica on every rank (DDP does this at wrap time)
             dist.broadcast(p.data, 0)
     use_graph = not a.no_graph
-    opt = FusedAdam(param_groups(model, args))            # iisan_adam_step: Adam over the reference's 5 LR groups, 2 launches
+    opt = FusedAdam(param_groups(model, args))            # iisan_adam_step: Adam over the reference's 5 LR groups, one launch
     gen = torch.Generator(device=device).manual_seed(SEED + rank)
     B = a.batch
     n_rot = 3                                               # 3 x 225 MB (bf16) rotating inputs >> 126 MB L2

@@ -435,34 +435,31 @@ __global__ void __launch_bounds__(256) ce_prepass_cast_kernel(const float* __res
   for (int64_t c = i0; c < C; c += stride) debias[c] = logf(pop[ids_cols[c]]);
 }
 
-// one thread per (row-user, 32-column word): bit k = col-pad masked OR id of column in the user's S ids
+// one CTA per row-user, one warp per 32-column word (lane k = column 32 w + k: coalesced id loads, the word is a ballot):
+// bit k = col-pad masked OR id of column in the user's S ids
 __global__ void __launch_bounds__(256) ce_maskbits_kernel(const int64_t* __restrict__ ids_rows, const int64_t* __restrict__ ids_cols,
                                                           const float* __restrict__ lm_cols, int B, int S, int L, int C, int Cw,
                                                           uint32_t* __restrict__ bits) {
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (int64_t)B * Cw) return;
-  const int i = (int)(idx / Cw), w = (int)(idx % Cw);
+  const int i = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int64_t rid[17];
 #pragma unroll
-  for (int k = 0; k < 17; ++k) rid[k] = (k < S) ? ids_rows[(int64_t)i * S + k] : ids_rows[(int64_t)i * S];
-  uint32_t word = 0;
-  for (int k = 0; k < 32; ++k) {
-    const int c = w * 32 + k;
-    bool m = true;                                   // columns beyond C: masked (never read as real columns)
+  for (int k = 0; k < 17; ++k) rid[k] = (k < S) ? __ldg(ids_rows + (int64_t)i * S + k) : __ldg(ids_rows + (int64_t)i * S);
+  for (int w = warp; w < Cw; w += 8) {
+    const int c = w * 32 + lane;
+    bool m = true;                                     // columns beyond C: masked (never read as real columns)
     if (c < C) {
-      const int p = c % S;
-      m = (p < L) && (lm_cols[(int64_t)(c / S) * L + p] == 0.f);
+      const int u = c / S, p = c - u * S;
+      m = (p < L) && (lm_cols[(int64_t)u * L + p] == 0.f);
       const int64_t id = ids_cols[c];
-      if (!m) {
-        bool hit = false;
+      bool hit = false;
 #pragma unroll
-        for (int q = 0; q < 17; ++q) if (q < S) hit |= (rid[q] == id);
-        m = hit;
-      }
+      for (int q = 0; q < 17; ++q) hit |= (rid[q] == id);  // slots >= S repeat slot 0
+      m = m || hit;
     }
-    word |= (m ? 1u : 0u) << k;
+    const uint32_t word = __ballot_sync(0xffffffffu, m);
+    if (lane == 0) bits[(int64_t)i * Cw + w] = word;
   }
-  bits[idx] = word;
 }
 
 __global__ void __launch_bounds__(256) ce_combine_kernel(const float* __restrict__ part_m, const float* __restrict__ part_s,
@@ -599,9 +596,8 @@ static int run_prepass(const iisan_ce_desc& d, const CeFastLayout& W, const floa
   }
   IISAN_LAUNCH_OK();
   {
-    const int64_t n = (int64_t)d.row_users * Cw;
     LaunchScope ls_(IISAN_K_CE, st);
-    ce_maskbits_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ids_rows, ids_cols, lm_cols, d.row_users, S, d.seq_len, C, Cw, W.maskbits);
+    ce_maskbits_kernel<<<(unsigned)d.row_users, 256, 0, st>>>(ids_rows, ids_cols, lm_cols, d.row_users, S, d.seq_len, C, Cw, W.maskbits);
   }
   IISAN_LAUNCH_OK();
   return IISAN_OK;

@@ -49,7 +49,7 @@ def param_groups(model, args):
 
 class FusedAdam(torch.optim.Optimizer):
     """torch.optim.Adam semantics (betas, eps; weight_decay 0, amsgrad off -- what the reference uses, Code_Cached/run.py:301-307)
-    through iisan_adam_step: two launches for the 146 tensors of the base model instead of one multi-tensor launch per
+    through iisan_adam_step: one launch for the 146 tensors of the base model instead of one multi-tensor launch per
     learning-rate group, step counter on the device (CUDA-graph capturable).  ``param_groups`` as for torch.optim.Adam."""
 
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):

@@ -280,7 +280,7 @@ int iisan_gather_states(const void* table, int32_t dtype, int64_t n_table_items,
  * default hyper-parameters semantics (weight_decay 0, amsgrad off).  `step_dev` is a device fp32 scalar holding the step count;
  * with advance_step != 0 it is incremented (stream-ordered) before the update, so the call is CUDA-graph safe.
  * ------------------------------------------------------------------------------------------- */
-#define IISAN_ADAM_MAX_TENSORS 80
+#define IISAN_ADAM_MAX_TENSORS 192
 typedef struct iisan_adam_tensor {
   float* param; const float* grad; float* exp_avg; float* exp_avg_sq;
   int64_t numel;

@@ -8,7 +8,7 @@ pytestmark = pytest.mark.gpu
 def test_fused_adam_matches_torch():
     from iisan_b200.optim import FusedAdam
     g = torch.Generator(device="cuda").manual_seed(1)
-    shapes = [(768, 768), (64, 768), (768,), (1,), (256, 64), (10, 64), (5000,), (3, 5, 7)] * 12        # 96 tensors: two launches
+    shapes = [(768, 768), (64, 768), (768,), (1,), (256, 64), (10, 64), (5000,), (3, 5, 7)] * 25        # 200 tensors: two launches (IISAN_ADAM_MAX_TENSORS = 192)
     ref = [torch.randn(s, device="cuda", generator=g).requires_grad_(True) for s in shapes]
     ours = [p.detach().clone().requires_grad_(True) for p in ref]
     lrs = [2e-4, 1e-4, 5e-5]
