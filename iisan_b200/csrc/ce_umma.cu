@@ -16,7 +16,9 @@
 //               turn S into masked logits / softmax weights; for the backward the bf16 weight tile goes back to shared
 //               memory (128B-swizzled K-major A operand) and a second tcgen05.mma accumulates W x T (the streamed tile is
 //               reused as an MN-major B operand) into a TMEM accumulator that is flushed once per CTA.
-//   warp roles: warp 0 TMA producer, warp 1 TMEM allocator + MMA issuer, warps 2..9 epilogue.
+//   warp roles: warp 0 TMA producer, warp 1 TMEM allocator + MMA issuer, warps 2..17 epilogue (the epilogue is ALU / latency
+//               bound -- K = 64 makes the MMAs negligible -- so every TMEM lane quadrant gets four warps, one per 32-column
+//               quarter of the streamed tile).
 #include "common.cuh"
 #include "launch.cuh"
 #include "umma.cuh"
@@ -34,8 +36,9 @@ constexpr float kNegMaskF = -1e4f;
 constexpr int CT = 128;            // tile extent on both sides
 constexpr int CE_E = 64;           // embedding width handled by this kernel (one 128-byte swizzle atom of bf16)
 constexpr int CE_NST = 3;          // streamed-tile ring
-constexpr int CE_THREADS = 320;    // 10 warps
-constexpr int CE_EPI_THREADS = 256;
+constexpr int CE_EPI_WARPS = 16;
+constexpr int CE_THREADS = 64 + 32 * CE_EPI_WARPS;    // 18 warps
+constexpr int CE_EPI_THREADS = 32 * CE_EPI_WARPS;
 constexpr int CE_TILE_BYTES = CT * CE_E * 2;     // 16 KB
 constexpr int CE_A2_BYTES = CT * CT * 2;         // 32 KB
 constexpr int CE_TMEM_COLS = 512;
@@ -66,10 +69,10 @@ struct CeSmem {
   static constexpr int kA2 = kT + CE_NST * CE_TILE_BYTES;
   static constexpr int kBar = kA2 + 2 * CE_A2_BYTES;
   static constexpr int kAttr = kBar + 256;
-  static constexpr int kTotal = kAttr + 2 * CT * 16 + 1024;   // attributes (double buffered, 16 B per entity) + align slack
+  static constexpr int kTotal = kAttr + 2 * CT * 40 + 1024;   // attributes (double buffered) / forward combine scratch (9 x 128 floats) + align slack
 };
 
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(CE_EPI_THREADS) : "memory"); }
 
 __device__ __forceinline__ float ce_scale_dev(const float* g_sum, const float* g_mean, const int32_t* n_valid) {
   float s = 0.f;
@@ -120,9 +123,9 @@ __global__ void __launch_bounds__(CE_THREADS, 1) ce_tile_kernel(const __grid_con
     tma_prefetch_desc(map_o); tma_prefetch_desc(map_t);
     mbar_init(o_full, 1);
     for (int s = 0; s < CE_NST; ++s) { mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&s_full[b], 1); mbar_init(&s_empty[b], 8); mbar_init(&a2_full[b], 8); mbar_init(&a2_empty[b], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&s_full[b], 1); mbar_init(&s_empty[b], CE_EPI_WARPS); mbar_init(&a2_full[b], CE_EPI_WARPS); mbar_init(&a2_empty[b], 1); }
     mbar_init(acc_full, 1);
-    for (int b = 0; b < 2; ++b) { mbar_init(&dsc_full[b], 1); mbar_init(&dsc_empty[b], 8); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&dsc_full[b], 1); mbar_init(&dsc_empty[b], CE_EPI_WARPS); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, CE_TMEM_COLS);
@@ -200,10 +203,10 @@ __global__ void __launch_bounds__(CE_THREADS, 1) ce_tile_kernel(const __grid_con
     }
   } else {
     // ===================== epilogue warps =====================
-    const int ew = warp - 2;                  // 0..7
+    const int ew = warp - 2;                  // 0..15
     const int quad = warp & 3;                // TMEM lane quadrant this warp may touch
-    const int half = ew >> 2;                 // which 64 of the 128 streamed entities
-    const int et = threadIdx.x - 64;          // 0..255
+    const int half = ew >> 2;                 // which 32 of the 128 streamed entities (0..3)
+    const int et = threadIdx.x - 64;          // 0..511
     const int o = o0 + quad * 32 + lane;      // owner entity of this thread
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
     const float scale = BWD ? ce_scale_dev(a.g_sum, a.g_mean, a.n_valid) : 0.f;
@@ -230,17 +233,17 @@ __global__ void __launch_bounds__(CE_THREADS, 1) ce_tile_kernel(const __grid_con
       const int b = t & 1; const uint32_t bph = (uint32_t)(t >> 1) & 1u;
       mbar_wait(&dsc_full[b], bph);
       tc_fence_after();
-      uint32_t raw[32];
-      tmem_ld_32x32(tmem_base + lane_addr + (uint32_t)(CE_DSC_COL + b * CE_E + half * 32), raw);
+      uint32_t raw[16];
+      tmem_ld_32x16(tmem_base + lane_addr + (uint32_t)(CE_DSC_COL + b * CE_E + half * 16), raw);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&dsc_empty[b]);
       const int col = (t_beg + t) * CT + quad * 32 + lane;
       if (col < a.C) {
-        float* op = a.d_out2 + (int64_t)col * CE_E + half * 32;
+        float* op = a.d_out2 + (int64_t)col * CE_E + half * 16;
 #pragma unroll
-        for (int q = 0; q < 8; ++q)
+        for (int q = 0; q < 4; ++q)
           red_add_v4(op + 4 * q, __uint_as_float(raw[4 * q]), __uint_as_float(raw[4 * q + 1]), __uint_as_float(raw[4 * q + 2]),
                      __uint_as_float(raw[4 * q + 3]));
       }
@@ -271,9 +274,8 @@ __global__ void __launch_bounds__(CE_THREADS, 1) ce_tile_kernel(const __grid_con
       tc_fence_after();
       if (BWD) mbar_wait(&a2_empty[b], bph ^ 1u);
       uint8_t* a2 = smem + CeSmem::kA2 + b * CE_A2_BYTES;
-#pragma unroll 1
-      for (int ch = 0; ch < 2; ++ch) {
-        const int k0 = half * 64 + ch * 32;                               // offset of this chunk inside the tile
+      {
+        const int k0 = half * 32;                                         // offset of this warp's 32 streamed entities inside the tile
         uint32_t raw[32];
         tmem_ld_32x32(tmem_base + lane_addr + (uint32_t)(b * CT + k0), raw);
         tmem_ld_wait();
@@ -377,32 +379,43 @@ __global__ void __launch_bounds__(CE_THREADS, 1) ce_tile_kernel(const __grid_con
     if (FUSED) flush_dsc(n_tiles - 1);
 
     if (!BWD) {
-      // combine the two column halves of each row, then write the split's partial
-      float* xm = attr_f;                 // reuse: [2][128] m, s, lab  (tile attributes are dead)
+      // combine the four column quarters of each row, then write the split's partial
+      float* xm = attr_f;                 // reuse: [3 quarters][m | s | lab][128]  (tile attributes are dead)
       epi_bar_sync();
-      if (half == 1) { xm[quad * 32 + lane] = run_m; xm[CT + quad * 32 + lane] = run_s; xm[2 * CT + quad * 32 + lane] = lab_val; }
+      if (half > 0) {
+        float* q = xm + (half - 1) * 3 * CT + quad * 32 + lane;
+        q[0] = run_m; q[CT] = run_s; q[2 * CT] = lab_val;
+      }
       epi_bar_sync();
       if (half == 0 && o < a.R) {
-        const float m2 = xm[quad * 32 + lane], s2 = xm[CT + quad * 32 + lane];
-        const float nm = fmaxf(run_m, m2);
-        float s = 0.f;
+        float nm = run_m;
+#pragma unroll
+        for (int h = 0; h < 3; ++h) nm = fmaxf(nm, xm[h * 3 * CT + quad * 32 + lane]);
+        float s = 0.f, lab = lab_val;
         if (run_m > -INFINITY) s += run_s * __expf(run_m - nm);
-        if (m2 > -INFINITY) s += s2 * __expf(m2 - nm);
+#pragma unroll
+        for (int h = 0; h < 3; ++h) {
+          const float* q = xm + h * 3 * CT + quad * 32 + lane;
+          if (q[0] > -INFINITY) s += q[CT] * __expf(q[0] - nm);
+          lab += q[2 * CT];
+        }
         const int64_t idx = (int64_t)blockIdx.y * a.R + o;
-        a.part_m[idx] = nm; a.part_s[idx] = s; a.part_lab[idx] = lab_val + xm[2 * CT + quad * 32 + lane];
+        a.part_m[idx] = nm; a.part_s[idx] = s; a.part_lab[idx] = lab;
       }
     } else {
-      // flush the accumulator: thread owns entity o, 32 of the 64 output features
+      // flush the accumulator: thread owns entity o, 16 of the 64 output features
       mbar_wait(acc_full, 0);
       tc_fence_after();
-      uint32_t raw[32];
-      tmem_ld_32x32(tmem_base + lane_addr + (uint32_t)(CE_ACC_COL + half * 32), raw);
+      uint32_t raw[16];
+      tmem_ld_32x16(tmem_base + lane_addr + (uint32_t)(CE_ACC_COL + half * 16), raw);
       tmem_ld_wait();
       const int limit = OWNER_ROWS ? a.R : a.C;
       if (o < limit) {
-        float* op = a.d_out + (int64_t)o * CE_E + half * 32;
+        float* op = a.d_out + (int64_t)o * CE_E + half * 16;
 #pragma unroll
-        for (int k = 0; k < 32; ++k) atomicAdd(op + k, __uint_as_float(raw[k]));
+        for (int q = 0; q < 4; ++q)
+          red_add_v4(op + 4 * q, __uint_as_float(raw[4 * q]), __uint_as_float(raw[4 * q + 1]), __uint_as_float(raw[4 * q + 2]),
+                     __uint_as_float(raw[4 * q + 3]));
       }
     }
   }

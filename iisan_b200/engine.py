@@ -45,8 +45,11 @@ class TrainStep:
             self._flat = torch.empty(sum(g.numel() for g in grads), dtype=torch.float32, device=grads[0].device)
         flat = self._flat
         torch._foreach_copy_(list(torch.split(flat, [g.numel() for g in grads])), [g.reshape(-1) for g in grads])
-        dist.all_reduce(flat, group=self.group)
-        flat.div_(self.world)
+        if dist.get_backend(self.group) == "nccl":
+            dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=self.group)       # mean inside the collective
+        else:
+            dist.all_reduce(flat, group=self.group)
+            flat.div_(self.world)
         torch._foreach_copy_([g.reshape(-1) for g in grads], list(torch.split(flat, [g.numel() for g in grads])))
 
     def _snapshot(self):

@@ -75,9 +75,9 @@ def global_negative_loss(prec, score, ids, log_mask, pop, group=None, compute=0,
     ids_all = _gather_plain(ids.view(b, -1), group)
     lm_all = _gather_plain(log_mask, group)
     ce = ce_fn or _cuda_ce
-    loss_sum, n_valid = ce(prec, score_all, ids.view(b, -1), ids_all, log_mask, lm_all, pop, rank * b, compute)
-    n_total = n_valid.clone().to(torch.int64) if n_valid.dtype != torch.int64 else n_valid.clone()
-    dist.all_reduce(n_total, group=group)
+    loss_sum, _n_valid = ce(prec, score_all, ids.view(b, -1), ids_all, log_mask, lm_all, pop, rank * b, compute)
+    # global number of valid rows: every rank already holds all log-masks, so no further collective is needed
+    n_total = (lm_all != 0).sum()
     scale = float(world) if grad_average else 1.0
     return loss_sum * scale / n_total.to(loss_sum.dtype).reshape(())
 
