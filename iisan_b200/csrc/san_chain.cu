@@ -104,11 +104,11 @@ struct ChainBars {
     z_full = u_empty + 2; z_ready = z_full + 1;
     tmem_slot = reinterpret_cast<uint32_t*>(z_ready + 1);
   }
-  __device__ void init() {
+  __device__ void init(int epi_warps = 8) {
     for (int i = 0; i < CH_NW; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
-    for (int i = 0; i < CH_NH; ++i) { mbar_init(&h_full[i], 1); mbar_init(&h_empty[i], 8); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&xk_full[i], 8); mbar_init(&xk_empty[i], 1); mbar_init(&u_full[i], 1); mbar_init(&u_empty[i], 8); }
-    mbar_init(z_full, 1); mbar_init(z_ready, 8);
+    for (int i = 0; i < CH_NH; ++i) { mbar_init(&h_full[i], 1); mbar_init(&h_empty[i], epi_warps); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&xk_full[i], epi_warps); mbar_init(&xk_empty[i], 1); mbar_init(&u_full[i], 1); mbar_init(&u_empty[i], epi_warps); }
+    mbar_init(z_full, 1); mbar_init(z_ready, epi_warps);
     fence_barrier_init();
   }
 };
@@ -116,7 +116,13 @@ struct ChainBars {
 // ================================================================================================================
 // forward
 // ================================================================================================================
-__global__ void __launch_bounds__(CH_THREADS, 1) san_chain_fwd_kernel(const __grid_constant__ ChainArgs a) {
+// 16 epilogue warps: four per TMEM lane quadrant, each thread owns one row and 16 of the chunk's 64 columns (the epilogue is
+// latency bound: twice the warps in flight hide the mbarrier / TMEM / shared-memory round trips of each other)
+constexpr int CF_EPI_WARPS = 16;
+constexpr int CF_THREADS = 96 + 32 * CF_EPI_WARPS;
+constexpr int CF_NCOL = 64 / (CF_EPI_WARPS / 4);     // columns per thread
+
+__global__ void __launch_bounds__(CF_THREADS, 1) san_chain_fwd_kernel(const __grid_constant__ ChainArgs a) {
   const ChainTower& T = a.tower[blockIdx.y];
   const bool is_mm = (T.mode == 1);
   const int NC = a.d / CH_CW;
@@ -132,7 +138,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) san_chain_fwd_kernel(const __gr
     tma_prefetch_desc(&T.map_wd); tma_prefetch_desc(&T.map_wu); tma_prefetch_desc(&T.map_h); tma_prefetch_desc(&T.map_x);
     tma_prefetch_desc(&T.map_last); tma_prefetch_desc(&T.map_z);
     if (is_mm) tma_prefetch_desc(&T.map_h2);
-    B.init();
+    B.init(CF_EPI_WARPS);
   }
   if (warp == 1) tmem_alloc(B.tmem_slot, CH_TMEM_COLS);
   tc_fence_before();
@@ -258,9 +264,10 @@ __global__ void __launch_bounds__(CH_THREADS, 1) san_chain_fwd_kernel(const __gr
     }
   } else {
     // ===================== epilogue warps =====================
-    const int ew = warp - 3;                  // 0..7
+    constexpr int NCOL = CF_NCOL, NQ = NCOL / 8;   // NQ 16-byte groups of 8 bf16 per thread and tile
+    const int ew = warp - 3;                  // 0..15
     const int quad = warp & 3;                // TMEM lane quadrant
-    const int hf = ew >> 2;                   // which 32 of the chunk's 64 columns
+    const int cq = ew >> 2;                   // which NCOL of the chunk's 64 columns
     const int m = quad * 32 + lane;           // row inside the tile
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
     const int sw_row = (m >> 3) * 1024 + (m & 7) * 128;      // byte offset of row m inside a swizzled [128 x 64] bf16 tile
@@ -269,47 +276,54 @@ __global__ void __launch_bounds__(CH_THREADS, 1) san_chain_fwd_kernel(const __gr
     auto put_tile = [&](uint8_t* tile_base, const float* v) {
       uint8_t* tile = tile_base + sw_row;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4*>(tile + (((hf * 4 + q) ^ (m & 7)) << 4)) = pack8(v + q * 8);
+      for (int q = 0; q < NQ; ++q) *reinterpret_cast<uint4*>(tile + (((cq * NQ + q) ^ (m & 7)) << 4)) = pack8(v + q * 8);
     };
-    // x chunk (and optionally the last chunk) -> swizzled shared memory; signals the MMA / store thread
-    auto emit = [&](const float (&xv)[32], const float (&lv)[32], bool has_x, bool has_l) {
+    // x chunk (or, in the final stage, the last chunk) -> swizzled shared memory; signals the MMA / store thread
+    auto emit = [&](const float (&xv)[NCOL], bool is_x) {
       const int b = n_x & 1; const uint32_t ph = (uint32_t)(n_x >> 1) & 1u;
       mbar_wait(&B.xk_empty[b], ph ^ 1u);
-      if (has_x) put_tile(smem + ChainSmem::kXk + b * CH_TILE_BYTES, xv);
-      if (has_l) put_tile(smem + ChainSmem::kLk + b * CH_TILE_BYTES, lv);
+      put_tile(smem + (is_x ? ChainSmem::kXk : ChainSmem::kLk) + b * CH_TILE_BYTES, xv);
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&B.xk_full[b]);
       ++n_x;
     };
     int h_slot = 0; uint32_t h_ph = 0;
-    auto read_h = [&](float* hv) {            // this thread's 32 columns of the next ring tile
+    auto read_h = [&](float* hv) {            // this thread's NCOL columns of the next ring tile
       mbar_wait(&B.h_full[h_slot], h_ph);
       const uint8_t* tile = smem + ChainSmem::kH + h_slot * CH_TILE_BYTES + sw_row;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) unpack8(*reinterpret_cast<const uint4*>(tile + (((hf * 4 + q) ^ (m & 7)) << 4)), hv + q * 8);
+      for (int q = 0; q < NQ; ++q) unpack8(*reinterpret_cast<const uint4*>(tile + (((cq * NQ + q) ^ (m & 7)) << 4)), hv + q * 8);
       __syncwarp();
       if (lane == 0) mbar_arrive(&B.h_empty[h_slot]);
       if (++h_slot == CH_NH) { h_slot = 0; h_ph ^= 1u; }
     };
+    auto tmem_cols = [&](uint32_t col0, float* out) {      // NCOL accumulator columns of this thread's row
+      uint32_t raw[NCOL];
+      tmem_ld_32x16(tmem_base + lane_addr + col0 + (uint32_t)(cq * NCOL), raw);
+      tmem_ld_wait();
+#pragma unroll
+      for (int k = 0; k < NCOL; ++k) out[k] = __uint_as_float(raw[k]);
+    };
+    static_assert(NCOL == 16, "tmem_ld_32x16");
 
     // ---- x_0 = fuse(h_0, 0) ----
     {
       const float g = gate_value(T.gate[0]);
       const float omg = 1.0f - g;
       for (int c = 0; c < NC; ++c) {
-        float hv[32], xv[32];
+        float hv[NCOL], xv[NCOL];
         read_h(hv);
         if (is_mm) {
-          float h2[32];
+          float h2[NCOL];
           read_h(h2);
 #pragma unroll
-          for (int k = 0; k < 32; ++k) xv[k] = fmaf(g, hv[k], omg * h2[k]);
+          for (int k = 0; k < NCOL; ++k) xv[k] = fmaf(g, hv[k], omg * h2[k]);
         } else {
 #pragma unroll
-          for (int k = 0; k < 32; ++k) xv[k] = g * hv[k];
+          for (int k = 0; k < NCOL; ++k) xv[k] = g * hv[k];
         }
-        emit(xv, xv, true, false);
+        emit(xv, true);
       }
     }
     for (int s = 0; s < A; ++s) {
@@ -318,16 +332,14 @@ __global__ void __launch_bounds__(CH_THREADS, 1) san_chain_fwd_kernel(const __gr
       {
         mbar_wait(B.z_full, (uint32_t)s & 1u);
         tc_fence_after();
-        uint32_t raw[32];
-        tmem_ld_32x32(tmem_base + lane_addr + (uint32_t)(CH_ZACC + hf * 32), raw);
-        tmem_ld_wait();
-        float zv[32];
-        const float4* bd = reinterpret_cast<const float4*>(T.b_down[s] + hf * 32);
+        float zv[NCOL];
+        tmem_cols(CH_ZACC, zv);
+        const float4* bd = reinterpret_cast<const float4*>(T.b_down[s] + cq * NCOL);
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
+        for (int q = 0; q < NCOL / 4; ++q) {
           const float4 bq = __ldg(bd + q);
-          zv[4 * q] = fmaxf(__uint_as_float(raw[4 * q]) + bq.x, 0.f); zv[4 * q + 1] = fmaxf(__uint_as_float(raw[4 * q + 1]) + bq.y, 0.f);
-          zv[4 * q + 2] = fmaxf(__uint_as_float(raw[4 * q + 2]) + bq.z, 0.f); zv[4 * q + 3] = fmaxf(__uint_as_float(raw[4 * q + 3]) + bq.w, 0.f);
+          zv[4 * q] = fmaxf(zv[4 * q] + bq.x, 0.f); zv[4 * q + 1] = fmaxf(zv[4 * q + 1] + bq.y, 0.f);
+          zv[4 * q + 2] = fmaxf(zv[4 * q + 2] + bq.z, 0.f); zv[4 * q + 3] = fmaxf(zv[4 * q + 3] + bq.w, 0.f);
         }
         put_tile(smem + ChainSmem::kZ, zv);
         tc_fence_before();
@@ -337,47 +349,44 @@ __global__ void __launch_bounds__(CH_THREADS, 1) san_chain_fwd_kernel(const __gr
       }
       const float g = more ? gate_value(T.gate[s + 1]) : 0.f;
       const float omg = 1.0f - g;
-      const bool keep_last = !more || T.store_last != 0;
       for (int c = 0; c < NC; ++c) {
-        float4 bq[8];                          // bias chunk first: its global-load latency hides behind the ring / MMA waits
+        float4 bq[NCOL / 4];                   // bias chunk first: its global-load latency hides behind the ring / MMA waits
         {
-          const float4* bu = reinterpret_cast<const float4*>(T.b_up[s] + c * CH_CW + hf * 32);
+          const float4* bu = reinterpret_cast<const float4*>(T.b_up[s] + c * CH_CW + cq * NCOL);
 #pragma unroll
-          for (int q = 0; q < 8; ++q) bq[q] = __ldg(bu + q);
+          for (int q = 0; q < NCOL / 4; ++q) bq[q] = __ldg(bu + q);
         }
-        float xr[32];
+        float xr[NCOL];
         read_h(xr);                            // residual x_s[c]
         const int b = n_u & 1; const uint32_t uph = (uint32_t)(n_u >> 1) & 1u;
         mbar_wait(&B.u_full[b], uph);
         tc_fence_after();
-        uint32_t raw[32];
-        tmem_ld_32x32(tmem_base + lane_addr + (uint32_t)(CH_UACC + b * 64 + hf * 32), raw);
-        tmem_ld_wait();
+        float lv[NCOL];
+        tmem_cols((uint32_t)(CH_UACC + b * 64), lv);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&B.u_empty[b]);
         ++n_u;
-        float lv[32];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          lv[4 * q] = __uint_as_float(raw[4 * q]) + bq[q].x + xr[4 * q]; lv[4 * q + 1] = __uint_as_float(raw[4 * q + 1]) + bq[q].y + xr[4 * q + 1];
-          lv[4 * q + 2] = __uint_as_float(raw[4 * q + 2]) + bq[q].z + xr[4 * q + 2]; lv[4 * q + 3] = __uint_as_float(raw[4 * q + 3]) + bq[q].w + xr[4 * q + 3];
+        for (int q = 0; q < NCOL / 4; ++q) {
+          lv[4 * q] += bq[q].x + xr[4 * q]; lv[4 * q + 1] += bq[q].y + xr[4 * q + 1];
+          lv[4 * q + 2] += bq[q].z + xr[4 * q + 2]; lv[4 * q + 3] += bq[q].w + xr[4 * q + 3];
         }
         if (more) {
-          float hv[32], xv[32];
+          float hv[NCOL], xv[NCOL];
           read_h(hv);
           if (is_mm) {
-            float h2[32];
+            float h2[NCOL];
             read_h(h2);
 #pragma unroll
-            for (int k = 0; k < 32; ++k) xv[k] = fmaf(omg, h2[k], fmaf(g, hv[k], lv[k]));
+            for (int k = 0; k < NCOL; ++k) xv[k] = fmaf(omg, h2[k], fmaf(g, hv[k], lv[k]));
           } else {
 #pragma unroll
-            for (int k = 0; k < 32; ++k) xv[k] = fmaf(g, hv[k], omg * lv[k]);
+            for (int k = 0; k < NCOL; ++k) xv[k] = fmaf(g, hv[k], omg * lv[k]);
           }
-          emit(xv, lv, true, keep_last);
+          emit(xv, true);
         } else {
-          emit(lv, lv, false, true);
+          emit(lv, false);
         }
       }
     }
@@ -690,7 +699,7 @@ int launch_san_chain_fwd(const ChainArgs& args, int n_towers, cudaStream_t st) {
     attr_set = true;
   }
   const int tiles = (args.n_items + CH_ROWS - 1) / CH_ROWS;
-  { LaunchScope ls_(IISAN_K_CHAIN, st); san_chain_fwd_kernel<<<dim3(tiles, n_towers), CH_THREADS, ChainSmem::kTotal, st>>>(args); }
+  { LaunchScope ls_(IISAN_K_CHAIN, st); san_chain_fwd_kernel<<<dim3(tiles, n_towers), CF_THREADS, ChainSmem::kTotal, st>>>(args); }
   IISAN_LAUNCH_OK();
   return IISAN_OK;
 }
