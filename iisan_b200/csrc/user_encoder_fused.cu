@@ -410,6 +410,22 @@ __device__ __forceinline__ void cta_load_rows(const FuArgs& a, int u0, float* s,
   }
 }
 
+// asynchronous variant (cp.async, 16 B per request): issued as soon as the destination buffer is free, completed by
+// cp_async_wait_all() + __syncthreads() right before the first use, so that the stash reloads overlap the preceding phases
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+template <int W, int SW>
+__device__ __forceinline__ void cta_load_rows_async(const FuArgs& a, int u0, float* s, const float* g) {
+  for (int idx = threadIdx.x; idx < FR * W / 4; idx += FTHREADS) {
+    const int r = idx / (W / 4), c4 = idx % (W / 4);
+    const int u = u0 + r / FL;
+    if (u < a.users) cp_async16(s + r * SW + 4 * c4, g + ((int64_t)u * FL + r % FL) * W + 4 * c4);
+    else reinterpret_cast<float4*>(s + r * SW)[c4] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
 template <bool TC>
 __global__ void __launch_bounds__(FTHREADS, 1) ue_fused_fwd_kernel(const __grid_constant__ FuArgs a) {
   using S = FuSmem<TC>;
@@ -540,9 +556,28 @@ __device__ __forceinline__ void cta_ln_bwd(const FuArgs& a, const DropRt& dr, in
       *reinterpret_cast<float4*>(dfs + r * SX + 4 * l) = make_float4(dp[0], dp[1], dp[2], dp[3]);
     }
   }
-  // gamma / beta partials of this half-warp -> shared accumulators
+  // gamma / beta partials: fold the two half-warps, then one row per warp (summed by ln_partials_flush: no atomics)
 #pragma unroll
-  for (int i = 0; i < 4; ++i) { atomicAdd(dgamma_s + 4 * l + i, ag[i]); atomicAdd(dbeta_s + 4 * l + i, ab[i]); }
+  for (int i = 0; i < 4; ++i) {
+    ag[i] += __shfl_xor_sync(0xffffffffu, ag[i], 16);
+    ab[i] += __shfl_xor_sync(0xffffffffu, ab[i], 16);
+  }
+  if ((threadIdx.x & 31) < 16) {
+    const int w = threadIdx.x >> 5;
+    *reinterpret_cast<float4*>(dgamma_s + w * FE + 4 * l) = make_float4(ag[0], ag[1], ag[2], ag[3]);
+    *reinterpret_cast<float4*>(dbeta_s + w * FE + 4 * l) = make_float4(ab[0], ab[1], ab[2], ab[3]);
+  }
+}
+// after a __syncthreads(): d gamma / d beta of the CTA's rows -> global (one red.add per feature)
+__device__ __forceinline__ void ln_partials_flush(const float* dgamma_s, const float* dbeta_s, float* g_w, float* g_b) {
+  if (threadIdx.x < 2 * FE) {
+    const int e = threadIdx.x & (FE - 1);
+    const float* src = (threadIdx.x < FE) ? dgamma_s : dbeta_s;
+    float sum = 0.f;
+#pragma unroll
+    for (int w = 0; w < FTHREADS / 32; ++w) sum += src[w * FE + e];
+    atomicAdd(((threadIdx.x < FE) ? g_w : g_b) + e, sum);
+  }
 }
 
 template <bool TC>
@@ -555,7 +590,7 @@ __global__ void __launch_bounds__(FTHREADS, 1) ue_fused_bwd_kernel(const __grid_
   float* sC = fsm + S::kC; float* sM = fsm + S::kM; float* sP = fsm + S::kP;
   float* sH = fsm + S::kH;      // h1
   float* sD = fsm + S::kD;      // d h1
-  __shared__ float sgam[FE], sbet[FE];
+  __shared__ __align__(16) float sgam[(FTHREADS / 32) * FE], sbet[(FTHREADS / 32) * FE];   // per-warp LayerNorm gamma / beta partials
   const int u0 = blockIdx.x * FUPC;
   const int H = a.H, dk = FE / H;
   const float temp = sqrtf((float)dk);
@@ -567,13 +602,16 @@ __global__ void __launch_bounds__(FTHREADS, 1) ue_fused_bwd_kernel(const __grid_
     const iisan_ue_block_ptrs& bp = a.P.blocks[b];
     const iisan_ue_block_ptrs& bg = a.G.blocks[b];
     const UeBlockBufs& X = a.W.b[b];
+    // ---- stash reloads whose buffers are free now: h1 -> sH, xmid -> sK, ctx -> sV, x_in -> sX (asynchronous) ----
+    cta_load_rows_async<FF, SH>(a, u0, sH, X.h1);
+    cta_load_rows_async<FE, SX>(a, u0, sK, X.xmid);
+    cta_load_rows_async<FE, SX>(a, u0, sV, X.ctx);
+    cta_load_rows_async<FE, SX>(a, u0, sX, X.x_in);
     // ---- LN2 backward: sC = dY -> sM = d pre2 (residual to xmid), sQ = df (w2 branch) ----
-    if (threadIdx.x < FE) { sgam[threadIdx.x] = 0.f; sbet[threadIdx.x] = 0.f; }
-    cta_load_rows<FF, SH>(a, u0, sH, X.h1);
-    __syncthreads();
     cta_ln_bwd<1, SX>(a, drt, u0, sC, X.pre2, X.stat2, bp.ln2_w, sgam, sbet, sM, sQ, 3u + 4u * b);
+    cp_async_wait_all();
     __syncthreads();
-    if (threadIdx.x < FE) { atomicAdd(bg.ln2_w + threadIdx.x, sgam[threadIdx.x]); atomicAdd(bg.ln2_b + threadIdx.x, sbet[threadIdx.x]); }
+    ln_partials_flush(sgam, sbet, bg.ln2_w, bg.ln2_b);
     // ---- W2: dW2 += df^T h1 ; db2 ; d h1 = (df W2) * (h1 > 0) ----
     cta_wgrad<TC, FF, FE>(bg.w2, bg.b2, sQ, sH);
     cta_linear_t<TC, FF, FE>(bp.w2, sQ, sD, false);
@@ -582,25 +620,22 @@ __global__ void __launch_bounds__(FTHREADS, 1) ue_fused_bwd_kernel(const __grid_
       const int o = (idx / FF) * SH + idx % FF;
       if (!(sH[o] > 0.f)) sD[o] = 0.f;
     }
-    cta_load_rows<FE, SX>(a, u0, sK, X.xmid);          // xmid for dW1
     __syncthreads();
     // ---- W1: dW1 += dh1^T xmid ; db1 ; d xmid = d pre2 + dh1 W1 ----
     cta_wgrad<TC, FE, FF>(bg.w1, bg.b1, sD, sK);
     cta_linear_t<TC, FE, FF>(bp.w1, sD, sM, true);
     __syncthreads();
+    cta_load_rows_async<FE, SX>(a, u0, sK, X.k);       // xmid is dead
     // ---- LN1 backward: sM = d xmid -> sC = d pre1 (residual to x_in), sQ = df (fc branch) ----
-    if (threadIdx.x < FE) { sgam[threadIdx.x] = 0.f; sbet[threadIdx.x] = 0.f; }
-    cta_load_rows<FE, SX>(a, u0, sV, X.ctx);
-    __syncthreads();
     cta_ln_bwd<1, SX>(a, drt, u0, sM, X.pre1, X.stat1, bp.ln1_w, sgam, sbet, sC, sQ, 2u + 4u * b);
     __syncthreads();
-    if (threadIdx.x < FE) { atomicAdd(bg.ln1_w + threadIdx.x, sgam[threadIdx.x]); atomicAdd(bg.ln1_b + threadIdx.x, sbet[threadIdx.x]); }
+    ln_partials_flush(sgam, sbet, bg.ln1_w, bg.ln1_b);
     // ---- fc: dWfc += df^T ctx ; d ctx = df Wfc -> sM ----
     cta_wgrad<TC, FE, FE>(bg.w_fc, nullptr, sQ, sV);
     cta_linear_t<TC, FE, FE>(bp.w_fc, sQ, sM, false);
     __syncthreads();
     // ---- attention backward: q,k,v,p from the stash, d ctx in sM -> dq, dk, dv ----
-    cta_load_rows<FE, SX>(a, u0, sQ, X.q); cta_load_rows<FE, SX>(a, u0, sK, X.k); cta_load_rows<FE, SX>(a, u0, sV, X.v);
+    cta_load_rows_async<FE, SX>(a, u0, sQ, X.q); cta_load_rows_async<FE, SX>(a, u0, sV, X.v);      // k is already on its way
     float* sPd = sH;                               // dropout(p)      [FUPC][H][FL][FL]   (h1 is dead)
     float* sDs = sH + FUPC * FMAXH * FL * FL;      // d scores / temp
     for (int idx = threadIdx.x; idx < FUPC * H * FL * FL; idx += FTHREADS) {
@@ -610,13 +645,18 @@ __global__ void __launch_bounds__(FTHREADS, 1) ue_fused_bwd_kernel(const __grid_
       if (u < a.users) { p = X.p[gi]; pd = drop1(drt, 1u + 4u * b, (uint64_t)gi, p); }
       sP[idx] = p; sPd[idx] = pd;
     }
+    cp_async_wait_all();
     __syncthreads();
     for (int idx = threadIdx.x; idx < FUPC * H * FL * FL; idx += FTHREADS) {       // d(dropout(p)) = dctx_i . v_j, then mask * scale
       const int ul = idx / (H * FL * FL), rem = idx % (H * FL * FL), u = u0 + ul;
       const int h = rem / (FL * FL), i = (rem / FL) % FL, j = rem % FL;
-      const float* dr = sM + (ul * FL + i) * SX + h * dk; const float* vr = sV + (ul * FL + j) * SX + h * dk;
+      const float4* dr = reinterpret_cast<const float4*>(sM + (ul * FL + i) * SX + h * dk);
+      const float4* vr = reinterpret_cast<const float4*>(sV + (ul * FL + j) * SX + h * dk);
       float acc = 0.f;
-      for (int c = 0; c < dk; ++c) acc = fmaf(dr[c], vr[c], acc);
+      for (int c = 0; c < dk / 4; ++c) {
+        const float4 d4 = dr[c], v4 = vr[c];
+        acc = fmaf(d4.x, v4.x, acc); acc = fmaf(d4.y, v4.y, acc); acc = fmaf(d4.z, v4.z, acc); acc = fmaf(d4.w, v4.w, acc);
+      }
       const int64_t gi = (int64_t)u * H * FL * FL + rem;
       sDs[idx] = (u < a.users) ? drop1(drt, 1u + 4u * b, (uint64_t)gi, acc) : 0.f;
     }
@@ -640,7 +680,6 @@ __global__ void __launch_bounds__(FTHREADS, 1) ue_fused_bwd_kernel(const __grid_
       }
       sDq[r * SX + e] = aq; sDk[r * SX + e] = ak; sDv[r * SX + e] = av;
     }
-    cta_load_rows<FE, SX>(a, u0, sX, X.x_in);
     __syncthreads();
     // ---- q/k/v projections: dW += d^T x_in ; d x_in = d pre1 + dq Wq + dk Wk + dv Wv (accumulated into sC) ----
     cta_wgrad<TC, FE, FE>(bg.w_q, nullptr, sDq, sX);
@@ -654,11 +693,9 @@ __global__ void __launch_bounds__(FTHREADS, 1) ue_fused_bwd_kernel(const __grid_
     __syncthreads();
   }
   // ---- entry LN + position embedding ----
-  if (threadIdx.x < FE) { sgam[threadIdx.x] = 0.f; sbet[threadIdx.x] = 0.f; }
-  __syncthreads();
   cta_ln_bwd<0, SX>(a, drt, u0, sC, a.W.pre0, a.W.stat0, a.P.ln_w, sgam, sbet, nullptr, sQ, 0u);
   __syncthreads();
-  if (threadIdx.x < FE) { atomicAdd(a.G.ln_w + threadIdx.x, sgam[threadIdx.x]); atomicAdd(a.G.ln_b + threadIdx.x, sbet[threadIdx.x]); }
+  ln_partials_flush(sgam, sbet, a.G.ln_w, a.G.ln_b);
   for (int idx = threadIdx.x; idx < FL * FE; idx += FTHREADS) {       // d pos[t] = sum over the CTA's users
     const int t = idx / FE, e = idx % FE;
     float s = 0.f;
