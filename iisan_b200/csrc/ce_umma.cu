@@ -81,6 +81,13 @@ __device__ __forceinline__ float ce_scale_dev(const float* g_sum, const float* g
   return s;
 }
 
+constexpr float kLog2e = 1.4426950408889634f;
+// 2^x, flush-to-zero approximation (one MUFU; exp(x) = 2^(x log2 e) folds the scale and the max / lse subtraction into one FMA)
+__device__ __forceinline__ float ex2_ftz(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
@@ -212,7 +219,7 @@ __global__ void __launch_bounds__(CE_THREADS, 1) ce_tile_kernel(const __grid_con
     const float scale = BWD ? ce_scale_dev(a.g_sum, a.g_mean, a.n_valid) : 0.f;
 
     // ---- owner attributes ----
-    bool o_ok; int o_label = -1; bool o_lab_masked = false; float o_lse = 0.f; float o_debias = 0.f;
+    bool o_ok; int o_label = -1; bool o_lab_masked = false; float o_lse = 0.f; float o_lse_l2 = 0.f; float o_debias = 0.f;
     const uint32_t* o_mask = nullptr;         // OWNER_ROWS: mask words of the row's user
     if (OWNER_ROWS) {
       o_ok = (o < a.R) && (a.lm_rows[o] != 0.f);
@@ -221,7 +228,7 @@ __global__ void __launch_bounds__(CE_THREADS, 1) ce_tile_kernel(const __grid_con
       o_label = (int)((a.user_offset + i) * a.S + j + 1);
       o_lab_masked = (j + 1 < a.L) && (a.lm_cols[(a.user_offset + i) * a.L + j + 1] == 0.f);
       o_mask = a.maskbits + (int64_t)i * a.Cw;
-      if (BWD) o_lse = o_ok ? a.lse[oc] : INFINITY;
+      if (BWD) { o_lse = o_ok ? a.lse[oc] : INFINITY; o_lse_l2 = -o_lse * kLog2e; }
     } else {
       o_ok = (o < a.C);
       o_debias = o_ok ? a.debias[o] : 0.f;
@@ -253,11 +260,12 @@ __global__ void __launch_bounds__(CE_THREADS, 1) ce_tile_kernel(const __grid_con
       const int b = t & 1; const uint32_t bph = (uint32_t)(t >> 1) & 1u;
       const int tt0 = (t_beg + t) * CT;                                  // first streamed entity of this tile
       // ---- stage streamed-side attributes (one entity per thread of the first 128) ----
-      float2* at = reinterpret_cast<float2*>(attr_f) + b * CT;          // OWNER_ROWS: .x = debias ; else (.x, .y) = (lse, label code)
+      float2* at = reinterpret_cast<float2*>(attr_f) + b * CT;          // !OWNER_ROWS: (.x, .y) = (lse, label code)
+      float* atf = attr_f + b * 2 * CT;                                 // OWNER_ROWS: debias of the tile's 128 columns (same buffer)
       if (et < CT) {
         const int e = tt0 + et;
         if (OWNER_ROWS) {
-          at[et] = make_float2((e < a.C) ? a.debias[e] : 0.f, 0.f);
+          atf[et] = (e < a.C) ? a.debias[e] : 0.f;
         } else {
           // streamed rows: lse (+inf for invalid rows => weight 0) and the label column with bit 30 = "label column is pad-masked"
           // (-1 for invalid rows: never equal to a column index)
@@ -281,43 +289,45 @@ __global__ void __launch_bounds__(CE_THREADS, 1) ce_tile_kernel(const __grid_con
         tmem_ld_wait();
         float v[32];
         if (OWNER_ROWS) {
-          const int c0 = tt0 + k0;                                        // 32 consecutive columns, c0 % 32 == 0
+          // 32 consecutive columns, c0 % 32 == 0.  Columns >= C carry mask bits (ce_maskbits_kernel) and a zero debias: they
+          // become -1e4 like every masked entry, whose softmax weight underflows to exactly 0 against any real logit of the row.
+          const int c0 = tt0 + k0;
           const uint32_t mw = (c0 < a.C) ? __ldg(o_mask + (c0 >> 5)) : 0xffffffffu;
-          const int rem = a.C - c0;                                       // columns beyond C do not exist
+          const float4* deb4 = reinterpret_cast<const float4*>(atf + k0);
 #pragma unroll
-          for (int k = 0; k < 32; ++k) {
-            const bool masked = (mw >> k) & 1u;
-            v[k] = masked ? kNegMaskF : __uint_as_float(raw[k]) - at[k0 + k].x;
+          for (int q = 0; q < 8; ++q) {
+            const float4 d = deb4[q];
+            v[4 * q] = ((mw >> (4 * q)) & 1u) ? kNegMaskF : __uint_as_float(raw[4 * q]) - d.x;
+            v[4 * q + 1] = ((mw >> (4 * q + 1)) & 1u) ? kNegMaskF : __uint_as_float(raw[4 * q + 1]) - d.y;
+            v[4 * q + 2] = ((mw >> (4 * q + 2)) & 1u) ? kNegMaskF : __uint_as_float(raw[4 * q + 2]) - d.z;
+            v[4 * q + 3] = ((mw >> (4 * q + 3)) & 1u) ? kNegMaskF : __uint_as_float(raw[4 * q + 3]) - d.w;
           }
-          if (o_label >= c0 && o_label < c0 + 32) {                       // the label column escapes the reject mask
+          const bool has_label = o_label >= c0 && o_label < c0 + 32;
+          if (has_label) {                                                // the label column escapes the reject mask
             const int kl = o_label - c0;
 #pragma unroll
             for (int k = 0; k < 32; ++k)
-              if (k == kl) v[k] = o_lab_masked ? kNegMaskF : __uint_as_float(raw[k]) - at[k0 + k].x;
+              if (k == kl) v[k] = o_lab_masked ? kNegMaskF : __uint_as_float(raw[k]) - atf[k0 + k];
           }
           if (!BWD) {
-            float cm = -INFINITY;
+            float cm = v[0];
 #pragma unroll
-            for (int k = 0; k < 32; ++k) if (k < rem) cm = fmaxf(cm, v[k]);
-            if (cm > -INFINITY) {
-              const float nm = fmaxf(run_m, cm);
-              float s = run_s * __expf(run_m - nm);
+            for (int k = 1; k < 32; ++k) cm = fmaxf(cm, v[k]);
+            const float nm = fmaxf(run_m, cm);
+            const float nml = -nm * kLog2e;
+            float s = run_s * ex2_ftz(fmaf(run_m, kLog2e, nml));           // run_m = -inf at the start: 0 * 2^-inf = 0
 #pragma unroll
-              for (int k = 0; k < 32; ++k) if (k < rem) s += __expf(v[k] - nm);
-              run_m = nm; run_s = s;
-            }
-            if (o_label >= c0 && o_label < c0 + 32) {
+            for (int k = 0; k < 32; ++k) s += ex2_ftz(fmaf(v[k], kLog2e, nml));
+            run_m = nm; run_s = s;
+            if (has_label) {
               const int kl = o_label - c0;
 #pragma unroll
               for (int k = 0; k < 32; ++k) if (k == kl) lab_val = v[k];
             }
           } else {
 #pragma unroll
-            for (int k = 0; k < 32; ++k) {
-              float w = (k < rem) ? __expf(v[k] - o_lse) : 0.f;            // o_lse = +inf for invalid rows -> 0
-              v[k] = w * scale;
-            }
-            if (o_ok && o_label >= c0 && o_label < c0 + 32) {
+            for (int k = 0; k < 32; ++k) v[k] = ex2_ftz(fmaf(v[k], kLog2e, o_lse_l2)) * scale;   // o_lse = +inf for invalid rows -> 0
+            if (o_ok && has_label) {
               const int kl = o_label - c0;
 #pragma unroll
               for (int k = 0; k < 32; ++k) if (k == kl) v[k] -= scale;
