@@ -1,6 +1,7 @@
 // C-ABI plumbing: version/status/error reporting, the dense layer (com_dense) and the cached-state gather.
 #include "common.cuh"
 #include "gemm_simt.cuh"
+#include "linear_tf32.cuh"
 #include "launch.cuh"
 #include "umma_gemm.cuh"
 
@@ -120,8 +121,9 @@ extern "C" const char* iisan_last_cuda_error_string(void) { return cudaGetErrorS
 
 extern "C" int iisan_linear_forward(int32_t rows, int32_t out_features, int32_t in_features, const float* x, int64_t ldx,
                                     const float* w, const float* b, float* y, int64_t ldy, int32_t compute, iisan_stream_t stream) {
-  (void)compute;
   if (!x || !w || !y || rows <= 0 || out_features <= 0 || in_features <= 0) return IISAN_EINVAL;
+  if (compute == IISAN_COMPUTE_BF16 && linear_tf32_supported(rows, out_features, in_features, x, ldx, w, ldy, y))
+    return linear_tf32_forward(rows, out_features, in_features, x, ldx, w, b, y, ldy, as_stream(stream));
   GemmBatch g{}; g.n = 1;
   g.p[0] = prob_linear(x, ldx, w, b, y, ldy, rows, out_features, in_features);
   return launch_gemm(g, as_stream(stream));
@@ -130,9 +132,11 @@ extern "C" int iisan_linear_forward(int32_t rows, int32_t out_features, int32_t 
 extern "C" int iisan_linear_backward(int32_t rows, int32_t out_features, int32_t in_features, const float* x, int64_t ldx,
                                      const float* w, const float* dy, int64_t lddy, float* dx, int64_t lddx, float* dw, float* db,
                                      int32_t compute, iisan_stream_t stream) {
-  (void)compute;
   if (!x || !w || !dy || rows <= 0 || out_features <= 0 || in_features <= 0) return IISAN_EINVAL;
   cudaStream_t st = as_stream(stream);
+  if (compute == IISAN_COMPUTE_BF16 && dw && linear_tf32_supported(rows, out_features, in_features, x, ldx, w, lddy, dy) &&
+      (!dx || (lddx % 4 == 0 && (reinterpret_cast<uintptr_t>(dx) & 15) == 0)))
+    return linear_tf32_backward(rows, out_features, in_features, x, ldx, w, dy, lddy, dx, lddx, dw, db, st);
   if (dx) {
     GemmBatch g{}; g.n = 1;
     g.p[0] = prob_dgrad(dy, lddy, w, dx, lddx, rows, out_features, in_features);

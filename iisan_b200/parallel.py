@@ -46,6 +46,34 @@ class AllGatherRows(torch.autograd.Function):
         return out, None
 
 
+class AllGatherPool(torch.autograd.Function):
+    """(score [n, E] fp32, ids [b, S] int64, log_mask [b, L] fp32) of every rank in ONE collective: the three tensors are
+    packed into one fp32 row per rank (the int64 ids travel as raw bit pairs).  Returns the rank-major global pool
+    (score_all [W*n, E], ids_all [W*b, S], lm_all [W*b, L]).  Backward: reduce-scatter(sum) of d score_all."""
+
+    @staticmethod
+    def forward(ctx, score, ids, log_mask, group):
+        ctx.group = group
+        world = dist.get_world_size(group)
+        n, e = score.shape
+        b = log_mask.shape[0]
+        parts = [score.contiguous().view(-1), ids.contiguous().view(torch.float32).view(-1), log_mask.contiguous().view(-1)]
+        sizes = [p.numel() for p in parts]
+        packed = torch.cat(parts)
+        out = torch.empty(world, packed.numel(), dtype=torch.float32, device=score.device)
+        dist.all_gather_into_tensor(out.view(-1), packed, group=group)
+        o0, o1 = sizes[0], sizes[0] + sizes[1]
+        score_all = out[:, :o0].reshape(world * n, e)
+        ids_all = out[:, o0:o1].contiguous().view(torch.int64).view(world * b, -1)
+        lm_all = out[:, o1:].reshape(world * b, -1)
+        ctx.mark_non_differentiable(ids_all, lm_all)
+        return score_all, ids_all, lm_all
+
+    @staticmethod
+    def backward(ctx, g, _gi, _gl):
+        return AllGatherRows.backward(ctx, g)[0], None, None, None
+
+
 def _gather_plain(x, group):
     world = dist.get_world_size(group)
     x = x.contiguous()
@@ -71,9 +99,12 @@ def global_negative_loss(prec, score, ids, log_mask, pop, group=None, compute=0,
     group = group if group is not None else dist.group.WORLD
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     b = log_mask.shape[0]
-    score_all = AllGatherRows.apply(score, group)
-    ids_all = _gather_plain(ids.view(b, -1), group)
-    lm_all = _gather_plain(log_mask, group)
+    if score.dtype == torch.float32 and log_mask.dtype == torch.float32 and ids.dtype == torch.int64:
+        score_all, ids_all, lm_all = AllGatherPool.apply(score, ids.view(b, -1), log_mask, group)      # one collective
+    else:
+        score_all = AllGatherRows.apply(score, group)
+        ids_all = _gather_plain(ids.view(b, -1), group)
+        lm_all = _gather_plain(log_mask, group)
     ce = ce_fn or _cuda_ce
     loss_sum, _n_valid = ce(prec, score_all, ids.view(b, -1), ids_all, log_mask, lm_all, pop, rank * b, compute)
     # global number of valid rows: every rank already holds all log-masks, so no further collective is needed

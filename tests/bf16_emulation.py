@@ -110,7 +110,11 @@ def train_step_grads_emul(params_np, batch, pop_prob, cfg, ce_bf16=False, fused_
     image = torch.as_tensor(batch["image"]); text = torch.as_tensor(batch["text"])
     debias = torch.log(torch.from_numpy(pop_prob)[torch.from_numpy(ids.reshape(-1))])
     e_cv, e_tx, e_mm = san_forward_emul(P, image, text, cfg, fused_chain=fused_chain)
-    score = F.linear(torch.cat([e_cv, e_tx, e_mm], dim=1), P["com_dense.weight"], P["com_dense.bias"])
+    cat = torch.cat([e_cv, e_tx, e_mm], dim=1)
+    if cat.shape[1] % 16 == 0 and cfg.embedding_dim % 16 == 0:      # linear_tf32_supported: com_dense runs as TF32 tiles
+        score = F.linear(rt(cat), rt(P["com_dense.weight"]), P["com_dense.bias"])
+    else:
+        score = F.linear(cat, P["com_dense.weight"], P["com_dense.bias"])
     embs = score.view(B, S, cfg.embedding_dim)
     tf32_ue = cfg.embedding_dim == 64 and S - 1 == 10 and cfg.heads <= 4          # ue_fused_supported (user_encoder_fused.cu)
     ue = user_encoder_forward_emul if tf32_ue else O.user_encoder_forward

@@ -54,3 +54,15 @@ def test_umma_gemm_mn_major_splitk(M, N, K):
 
 def test_umma_gemm_relu_bias():
     _gemm(512, 64, 768, False, False, bias=True, relu=True, out_bf16=True)
+
+
+@pytest.mark.parametrize("M,N,K", [(5632, 768, 768), (5632, 768, 64), (130, 256, 192), (128, 64, 64), (300, 24, 96)])
+def test_umma_gemm_data_gradient_majors(M, N, K):
+    """A K-major x B MN-major: dx = dy W with the nn.Linear weight [out = K, in = N] read in place."""
+    _gemm(M, N, K, False, True, out_bf16=True)
+
+
+def test_umma_gemm_persistent_many_tiles():
+    """More tiles than SMs: every CTA walks several tiles through its two TMEM accumulators."""
+    _gemm(8192, 1024, 256, False, False, bias=True, out_bf16=True)
+    _gemm(4096, 2048, 128, True, True, splitk=2)
