@@ -47,6 +47,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-store", action="store_true", help="skip the HBM-resident store e2e measurement")
     ap.add_argument("--no-graph", action="store_true", help="run the step eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--negatives", default="global", choices=["global", "local"],
+                    help="N > 1: in-batch negative pool (global = item-embedding all-gather, BASELINE configs[2]; local = the reference's DDP semantics)")
     return ap.parse_args()
 
 
@@ -210,7 +212,7 @@ def run_ours(a):
     model, args, cfg = build_model(device, a.compute)
     model.train()
     if world > 1:
-        model.negatives = "global"                                   # BASELINE configs[2]: item-embedding all-gather
+        model.negatives = a.negatives                                # "global": BASELINE configs[2], item-embedding all-gather
         for p in model.parameters():                                 # same initial replica on every rank (DDP does this at wrap time)
             dist.broadcast(p.data, 0)
     use_graph = not a.no_graph
@@ -403,7 +405,7 @@ def run_ours(a):
         "config": {"workload": f"IISAN(Cached) Instrument shape: item_num {ITEM_NUM}, B={B} users/GPU x 11 slots, BERT-base+ViT-B/16 "
                                f"cached states [13,768] stored {str(state_dtype).split('.')[-1]}, 7 of 13 layers, r=64, E=64, random-init adapters, "
                                f"dense batch, fwd+bwd+Adam",
-                   "negatives": "global (all-gather)" if world > 1 else "local",
+                   "negatives": ("global (all-gather)" if a.negatives == "global" else "local (reference DDP semantics)") if world > 1 else "local",
                    "l2_policy": f"inputs rotate over {n_rot} resident batches of {2 * B * 11 * 13 * 768 * elt / 1e6:.0f} MB (> 126 MB L2)",
                    "step_runner": "CUDA graph replay (iisan_b200.engine.TrainStep)" if use_graph else "eager",
                    "parallelism": f"dp{world}"},

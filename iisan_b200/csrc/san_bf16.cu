@@ -462,11 +462,6 @@ static int san_backward_bf16_t(const iisan_san_desc* D, const iisan_san_params* 
     w.p[1] = mk_wgrad(do_t, ldo, E, L.head_t, ft, ft, N, G->pre_text.w, 3);
     w.p[2] = mk_wgrad(do_m, ldo, E, L.head_m, fm, fm, N, G->mm_down.w, 3);
     IISAN_TRY(launch_umma_gemm(w, st));
-    ColsumBatch c{}; c.n = 3;
-    c.p[0] = {d_out, D->out_ld, N, E, G->pre_img.b};
-    c.p[1] = {d_out + E, D->out_ld, N, E, G->pre_text.b};
-    c.p[2] = {d_out + 2 * E, D->out_ld, N, E, G->mm_down.b};
-    IISAN_TRY(launch_colsum(c, st));
     UmmaBatch dh{}; dh.n = 3;  // d head = d_out W_pre
     dh.p[0] = mk_dgrad(do_i, ldo, L.pre_i.w, N, fi, E); dh.p[0].epi.out_bf16 = L.dhead_i; dh.p[0].epi.ld_bf16 = fi;
     dh.p[1] = mk_dgrad(do_t, ldo, L.pre_t.w, N, ft, E); dh.p[1].epi.out_bf16 = L.dhead_t; dh.p[1].epi.ld_bf16 = ft;
@@ -477,10 +472,13 @@ static int san_backward_bf16_t(const iisan_san_desc* D, const iisan_san_params* 
     wf.p[1] = mk_wgrad(L.dhead_t, ft, ft, L.last_t[ls_t], D->d_text, D->d_text, N, G->fc_text.w, 3);
     wf.p[2] = mk_wgrad(L.dhead_m, fm, fm, L.last_m[ls_m], D->d_mm, D->d_mm, N, G->fc_mm.w, 3);
     IISAN_TRY(launch_umma_gemm(wf, st));
-    ColsumBatch cf{}; cf.n = 3;
+    ColsumBatch cf{}; cf.n = 6;   // bias gradients of both head layers in one launch
     cf.p[0] = {nullptr, fi, N, fi, G->fc_img.b, L.dhead_i};
     cf.p[1] = {nullptr, ft, N, ft, G->fc_text.b, L.dhead_t};
     cf.p[2] = {nullptr, fm, N, fm, G->fc_mm.b, L.dhead_m};
+    cf.p[3] = {d_out, D->out_ld, N, E, G->pre_img.b, nullptr};
+    cf.p[4] = {d_out + E, D->out_ld, N, E, G->pre_text.b, nullptr};
+    cf.p[5] = {d_out + 2 * E, D->out_ld, N, E, G->mm_down.b, nullptr};
     IISAN_TRY(launch_colsum(cf, st));
     UmmaBatch dl{}; dl.n = 3;  // d last = d head W_fc
     const size_t lastoff = (size_t)(D->n_stages - 1) * chain_n_pad(N) * D->d_mm;
@@ -519,7 +517,7 @@ static int san_backward_bf16_t(const iisan_san_desc* D, const iisan_san_params* 
       static thread_local UmmaBatchBig wg;
       wg.n = 0;
       const int np = 6 * D->n_stages;
-      for (int s = D->n_stages - 1; s >= 0; --s) {
+      for (int s = 0; s < D->n_stages; ++s) {       // the chain backward ends with stage 0: its stashes are the hottest in L2
         const int ta = D->text_adapter[s], ia = D->img_adapter[s], mi = D->mm_index[s];
         const size_t off = (size_t)s * chain_n_pad(N) * D->d_mm;
         wg.p[wg.n++] = mk_wgrad(L.dys[0] + off, D->d_text, D->d_text, L.z_t[s], D->r_text, D->r_text, N, G->text[ta].w_up, np);
