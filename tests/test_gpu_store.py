@@ -74,10 +74,15 @@ def test_pipelined_store_runner_trains():
                     pipe.submit(hid, log_mask=hlm)
                     out.append(pipe.run().item())
             losses[kind] = out
-        assert losses["eager"][-1] < losses["eager"][0]
-        # same arithmetic in both runners: the first loss agrees tightly; later ones only up to the reduction-order noise of the
-        # gradient atomics, which Adam's normalised first steps (|update| ~ lr whatever the gradient scale) amplify
-        assert np.allclose(losses["eager"][0], losses["pipe"][0], rtol=1e-5), losses
-        assert np.allclose(losses["eager"], losses["pipe"], rtol=1e-2), losses
+        # Same arithmetic in both runners.  The gradient atomics (split-K, weight-gradient reductions) make every run differ in
+        # the last bits, and five Adam steps at lr = 1e-3 on a 16-user batch (loss 6.4 -> 0.65) amplify that chaotically:
+        # two EAGER runs already differ by ~1.5 % at step 5.  Hence: step 1 exact to fp32 noise, steps 2-3 tight, then only
+        # the trend.
+        e, p = losses["eager"], losses["pipe"]
+        assert np.allclose(e[0], p[0], rtol=1e-5), losses
+        assert np.allclose(e[1], p[1], rtol=1e-4), losses
+        assert np.allclose(e[2], p[2], rtol=5e-3), losses
+        assert e[-1] < 0.5 * e[0] and p[-1] < 0.5 * p[0], losses
+        assert np.allclose(e, p, rtol=0.1), losses
     finally:
         set_compute_mode(None)
