@@ -53,7 +53,9 @@ class FusedAdam(torch.optim.Optimizer):
     learning-rate group, step counter on the device (CUDA-graph capturable).  ``param_groups`` as for torch.optim.Adam."""
 
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
-        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, capturable=True))
+        # the full key set of torch.optim.Adam's param groups, so that a saved state loads into either optimizer
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=0, amsgrad=False, maximize=False, foreach=None,
+                                      capturable=True, differentiable=False, fused=None, decoupled_weight_decay=False))
         self._table = None
         self._key = None
         self._step_dev = None
@@ -81,6 +83,27 @@ class FusedAdam(torch.optim.Optimizer):
                 arr[i].numel, arr[i].lr = p.numel(), lr
             self._table, self._key, self._keep = arr, key, [e[1] for e in entries]
         return len(entries)
+
+    # ---- checkpoint hand-over with torch.optim.Adam (Code_Cached/run.py:234-243 restores `optimizer` from epoch-N.pt,
+    #      data_utils/utils.py:104-110 saves it): same state_dict layout -- exp_avg, exp_avg_sq and a per-parameter `step` ----
+    def state_dict(self):
+        sd = super().state_dict()
+        step = float(self._step_dev.item()) if self._step_dev is not None else 0.0
+        for st in sd["state"].values():
+            st["step"] = torch.tensor(step, dtype=torch.float32)
+        return sd
+
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+        step = None
+        for p, st in self.state.items():
+            if "step" in st:
+                v = st.pop("step")
+                step = float(v.item() if torch.is_tensor(v) else v) if step is None else step
+        if step is not None:
+            dev = self.param_groups[0]["params"][0].device
+            self._step_dev = torch.full((1,), step, dtype=torch.float32, device=dev)
+        self._key = None                    # rebuild the pointer table (the moment tensors were replaced)
 
     @torch.no_grad()
     def step(self, closure=None):

@@ -298,6 +298,18 @@ int iisan_adam_step(const iisan_adam_tensor* tensors, int32_t n, float beta1, fl
 int iisan_stage_states_h2d(const void* host_src, void* dev_dst, int64_t n_rows, int32_t layers, int32_t d, int32_t dtype,
                            const int32_t* sel, int32_t n_sel, iisan_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Evaluation scoring: 1-based rank of each user's held-out item among the catalogue.
+ * Replaces the per-user Python loop of CC/data_utils/metrics.py:212-222 + metrics_topK (:59-67):
+ *   scores = prec . item_embs^T over ids 0..item_num ; scores[history] = -inf ; id 0 dropped ; rank = position of the target
+ *   in the descending order = 1 + #{ i in 1..item_num, i not in history : score_i > score_target }.
+ * prec fp32 [users, emb]; item_embs fp32 [n_items1 = item_num + 1, emb] (16-byte aligned, emb % 4 == 0, emb <= 256);
+ * targets int64 [users] (ids in 1..item_num); history int64 [users, hist_len], padded with 0 (may be NULL when hist_len == 0,
+ * duplicates allowed); ranks int32 [users].  Hit@K = [rank <= K], nDCG@K = 1 / log2(rank + 1).
+ * ------------------------------------------------------------------------------------------- */
+int iisan_eval_ranks(const float* prec, const float* item_embs, const int64_t* targets, const int64_t* history, int32_t users,
+                     int32_t n_items1, int32_t emb, int32_t hist_len, int32_t* ranks, iisan_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
