@@ -248,6 +248,61 @@ __global__ void __launch_bounds__(UTHREADS, 1) umma_gemm_kernel(const __grid_con
           }
           continue;
         }
+        // ---- direct path (one output, no mask / residual): the thread owns 32 consecutive columns of its row, i.e. a 64 B (bf16)
+        //      or 128 B (fp32) contiguous segment -> 128-bit stores / vector reductions instead of 32 two-byte stores per lane ----
+        if ((features == EPI_OUTB || features == EPI_OUTF || features == (EPI_ATOMIC | EPI_OUTF)) && n0 + c0 + 32 <= P.N) {
+          const int row = row_base + lane;
+          if (row < P.M) {
+            float v[32];
+            const bool add_bias = E.bias && (!E.atomic || first_split);
+            const float lo = E.relu ? 0.f : -INFINITY;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (add_bias) b4 = __ldg(reinterpret_cast<const float4*>(E.bias + n0 + c0) + q);
+              v[4 * q] = fmaxf(__uint_as_float(raw[4 * q]) + b4.x, lo); v[4 * q + 1] = fmaxf(__uint_as_float(raw[4 * q + 1]) + b4.y, lo);
+              v[4 * q + 2] = fmaxf(__uint_as_float(raw[4 * q + 2]) + b4.z, lo); v[4 * q + 3] = fmaxf(__uint_as_float(raw[4 * q + 3]) + b4.w, lo);
+            }
+            if (features == EPI_OUTB) {
+              __nv_bfloat16* ob = E.out_bf16 + (int64_t)row * E.ld_bf16 + n0 + c0;
+              if ((reinterpret_cast<uintptr_t>(ob) & 15) == 0) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  uint4 pk;
+                  __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+                  for (int z = 0; z < 4; ++z) h2[z] = __floats2bfloat162_rn(v[8 * q + 2 * z], v[8 * q + 2 * z + 1]);
+                  reinterpret_cast<uint4*>(ob)[q] = pk;
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) ob[j] = __float2bfloat16_rn(v[j]);
+              }
+            } else {
+              float* of = E.out_f32 + (int64_t)row * E.ld_f32 + n0 + c0;
+              const bool al = (reinterpret_cast<uintptr_t>(of) & 15) == 0;
+              if (features == EPI_OUTF) {
+                if (al) {
+#pragma unroll
+                  for (int q = 0; q < 8; ++q) reinterpret_cast<float4*>(of)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 32; ++j) of[j] = v[j];
+                }
+              } else if (al) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(of + 4 * q), "f"(v[4 * q]), "f"(v[4 * q + 1]), "f"(v[4 * q + 2]),
+                               "f"(v[4 * q + 3])
+                               : "memory");
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) atomicAdd(of + j, v[j]);
+              }
+            }
+          }
+          continue;
+        }
 #pragma unroll
         for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = __uint_as_float(raw[j]);
         __syncwarp();
