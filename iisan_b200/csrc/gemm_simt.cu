@@ -146,26 +146,49 @@ int launch_gemm(const GemmBatch& b, cudaStream_t st) {
   return IISAN_OK;
 }
 
+// out[n] += sum_m Y[m, n]: a thread owns 8 consecutive columns (one 128-bit load per row for bf16, two for fp32), a warp 256
+// columns, the 8 warps of a CTA take alternate rows of a 256-row block; partial sums meet in shared memory, one red.add per
+// column and CTA.
 __global__ void __launch_bounds__(256) colsum_kernel(const ColsumBatch batch, int rows_per_cta) {
   const ColsumProb& P = batch.p[blockIdx.z];
-  const int col = blockIdx.x * 32 + (threadIdx.x % 32);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int col = blockIdx.x * 256 + lane * 8;
   const int r0 = blockIdx.y * rows_per_cta;
-  if (r0 >= P.M) return;
+  if (r0 >= P.M || blockIdx.x * 256 >= P.N) return;
   const int r1 = min(P.M, r0 + rows_per_cta);
-  float s = 0.f;
-  if (col < P.N)
-  {
-    if (P.Y) { for (int r = r0 + threadIdx.x / 32; r < r1; r += 8) s += __ldg(P.Y + (int64_t)r * P.ld + col); }
-    else { for (int r = r0 + threadIdx.x / 32; r < r1; r += 8) s += __bfloat162float(P.Yb[(int64_t)r * P.ld + col]); }
+  float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const bool vec = (col + 8 <= P.N) && (P.ld % 8 == 0) &&
+                   ((reinterpret_cast<uintptr_t>(P.Y ? (const void*)P.Y : (const void*)P.Yb) & 15) == 0);
+  if (col < P.N) {
+    if (vec && !P.Y) {
+      for (int r = r0 + warp; r < r1; r += 8) {
+        const uint4 q = __ldg(reinterpret_cast<const uint4*>(P.Yb + (int64_t)r * P.ld + col));
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { const float2 f = __bfloat1622float2(h[i]); s[2 * i] += f.x; s[2 * i + 1] += f.y; }
+      }
+    } else if (vec) {
+      for (int r = r0 + warp; r < r1; r += 8) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(P.Y + (int64_t)r * P.ld + col));
+        const float4 c = __ldg(reinterpret_cast<const float4*>(P.Y + (int64_t)r * P.ld + col) + 1);
+        s[0] += a.x; s[1] += a.y; s[2] += a.z; s[3] += a.w; s[4] += c.x; s[5] += c.y; s[6] += c.z; s[7] += c.w;
+      }
+    } else {
+      for (int r = r0 + warp; r < r1; r += 8)
+        for (int i = 0; i < 8; ++i)
+          if (col + i < P.N) s[i] += P.Y ? __ldg(P.Y + (int64_t)r * P.ld + col + i) : __bfloat162float(P.Yb[(int64_t)r * P.ld + col + i]);
+    }
   }
-  __shared__ float red[8][33];
-  red[threadIdx.x / 32][threadIdx.x % 32] = s;
+  __shared__ float red[8][257];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) red[warp][lane * 8 + i] = s[i];
   __syncthreads();
-  if (threadIdx.x < 32) {
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c < P.N) {
     float t = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
-    if (col < P.N) atomicAdd(P.out + col, t);
+    atomicAdd(P.out + c, t);
   }
 }
 
@@ -173,8 +196,8 @@ int launch_colsum(const ColsumBatch& b, cudaStream_t st) {
   if (b.n <= 0) return IISAN_OK;
   int maxN = 0, maxM = 0;
   for (int i = 0; i < b.n; ++i) { maxN = max(maxN, b.p[i].N); maxM = max(maxM, b.p[i].M); }
-  const int rows_per_cta = 256;
-  dim3 grid((maxN + 31) / 32, (maxM + rows_per_cta - 1) / rows_per_cta, b.n);
+  const int rows_per_cta = 128;
+  dim3 grid((maxN + 255) / 256, (maxM + rows_per_cta - 1) / rows_per_cta, b.n);
   { LaunchScope ls_(IISAN_K_MISC, st); colsum_kernel<<<grid, 256, 0, st>>>(b, rows_per_cta); }
   IISAN_LAUNCH_OK();
   return IISAN_OK;
