@@ -30,7 +30,7 @@ UNIT = "samples/s"
 ITEM_NUM = 19246          # Instrument catalogue
 SEED = 12345              # reference seed (Code_Cached/scripts/run_IISAN.py:44)
 # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed ncu --set full capture (profiles/), per launch
-TRAFFIC_NCU = {"fwd": 299.3e6, "bwd": 432.6e6}   # profiles/r01c_chain_ncu_full.txt
+TRAFFIC_NCU = {"fwd": 296.7e6, "bwd": 433.2e6}   # profiles/r01d_chain_ncu_full.txt
 LRS = dict(lr=2e-4, adapter_cv_lr=1e-4, adapter_bert_lr=1e-4, fine_tune_lr_image=1e-4, fine_tune_lr_text=5e-5)
 
 
