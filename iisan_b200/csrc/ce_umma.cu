@@ -9,9 +9,8 @@
 //   prepass   : bf16 copies of prec / score (the MMA operands), debias[c] = log(pop[id_c]) and ONE mask bit per
 //               (row-user, column): col-pad OR id membership, by exact int64 compares (bit-exact with the reference's
 //               masks; 10x fewer compares than per (row, column) because the 10 rows of a user share their reject set).
-//   tile pass : one CTA owns 128 "owner" entities (TMEM lanes) and streams 128-wide tiles of the other side:
-//                 OWNER_ROWS : lanes = loss rows,   tiles = item columns  -> forward (online log-sum-exp) and d_prec
-//                 !OWNER_ROWS: lanes = item columns, tiles = loss rows     -> d_score
+//   tile pass : one CTA owns 128 loss rows (TMEM lanes) and streams 128-wide tiles of item columns: forward (online
+//               log-sum-exp) or backward (d_prec in the CTA's accumulator AND the per-tile d_score partial)
 //               S = O x T^T (K = E = 64) by tcgen05.mma into a double-buffered TMEM accumulator; the 8 epilogue warps
 //               turn S into masked logits / softmax weights; for the backward the bf16 weight tile goes back to shared
 //               memory (128B-swizzled K-major A operand) and a second tcgen05.mma accumulates W x T (the streamed tile is
@@ -92,13 +91,13 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-// MODE 0: forward partial log-sum-exp (OWNER_ROWS) ; MODE 1: d_prec (OWNER_ROWS) ; MODE 2: d_score (!OWNER_ROWS)
-// MODE 3: d_prec AND d_score in one pass (OWNER_ROWS): the bf16 weight tile W [128 rows x 128 columns] that feeds
+// MODE 0: forward partial log-sum-exp
+// MODE 3: d_prec AND d_score in one pass: the bf16 weight tile W [128 rows x 128 columns] that feeds
 //         acc_prec += W x T is read a second time as an MN-major A operand, dsc = W^T x O (K = the CTA's 128 rows), and the
 //         [128 columns x 64] partial is added to d_score by vector reductions once per streamed tile.
 template <int MODE>
 __global__ void __launch_bounds__(CE_THREADS, 1) ce_tile_kernel(const __grid_constant__ CeTileArgs a) {
-  constexpr bool OWNER_ROWS = (MODE != 2);
+  static_assert(MODE == 0 || MODE == 3, "forward or fused backward");
   constexpr bool BWD = (MODE != 0);
   constexpr bool FUSED = (MODE == 3);
   extern __shared__ uint8_t smem_raw[];
@@ -123,8 +122,8 @@ __global__ void __launch_bounds__(CE_THREADS, 1) ce_tile_kernel(const __grid_con
   const int t_end = min(a.tiles_stream, t_beg + a.tiles_per_split);
   const int n_tiles = t_end - t_beg;
   if (n_tiles <= 0) return;
-  const CUtensorMap* map_o = OWNER_ROWS ? &a.map_prec : &a.map_score;
-  const CUtensorMap* map_t = OWNER_ROWS ? &a.map_score : &a.map_prec;
+  const CUtensorMap* map_o = &a.map_prec;
+  const CUtensorMap* map_t = &a.map_score;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(map_o); tma_prefetch_desc(map_t);
@@ -218,21 +217,15 @@ __global__ void __launch_bounds__(CE_THREADS, 1) ce_tile_kernel(const __grid_con
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
     const float scale = BWD ? ce_scale_dev(a.g_sum, a.g_mean, a.n_valid) : 0.f;
 
-    // ---- owner attributes ----
-    bool o_ok; int o_label = -1; bool o_lab_masked = false; float o_lse = 0.f; float o_lse_l2 = 0.f; float o_debias = 0.f;
-    const uint32_t* o_mask = nullptr;         // OWNER_ROWS: mask words of the row's user
-    if (OWNER_ROWS) {
-      o_ok = (o < a.R) && (a.lm_rows[o] != 0.f);
-      const int oc = o < a.R ? o : 0;
-      const int i = oc / a.L, j = oc % a.L;
-      o_label = (int)((a.user_offset + i) * a.S + j + 1);
-      o_lab_masked = (j + 1 < a.L) && (a.lm_cols[(a.user_offset + i) * a.L + j + 1] == 0.f);
-      o_mask = a.maskbits + (int64_t)i * a.Cw;
-      if (BWD) { o_lse = o_ok ? a.lse[oc] : INFINITY; o_lse_l2 = -o_lse * kLog2e; }
-    } else {
-      o_ok = (o < a.C);
-      o_debias = o_ok ? a.debias[o] : 0.f;
-    }
+    // ---- attributes of this thread's loss row ----
+    float o_lse_l2 = 0.f;
+    const bool o_ok = (o < a.R) && (a.lm_rows[o] != 0.f);
+    const int oc = o < a.R ? o : 0;
+    const int o_i = oc / a.L, o_j = oc % a.L;
+    const int o_label = (int)((a.user_offset + o_i) * a.S + o_j + 1);
+    const bool o_lab_masked = (o_j + 1 < a.L) && (a.lm_cols[(a.user_offset + o_i) * a.L + o_j + 1] == 0.f);
+    const uint32_t* o_mask = a.maskbits + (int64_t)o_i * a.Cw;       // mask words of the row's user
+    if (BWD) o_lse_l2 = -(o_ok ? a.lse[oc] : INFINITY) * kLog2e;
     float run_m = -INFINITY, run_s = 0.f, lab_val = 0.f;
 
     // MODE 3: add the d_score partial of streamed tile t (TMEM lanes = its 128 columns) to global memory
@@ -259,23 +252,11 @@ __global__ void __launch_bounds__(CE_THREADS, 1) ce_tile_kernel(const __grid_con
     for (int t = 0; t < n_tiles; ++t) {
       const int b = t & 1; const uint32_t bph = (uint32_t)(t >> 1) & 1u;
       const int tt0 = (t_beg + t) * CT;                                  // first streamed entity of this tile
-      // ---- stage streamed-side attributes (one entity per thread of the first 128) ----
-      float2* at = reinterpret_cast<float2*>(attr_f) + b * CT;          // !OWNER_ROWS: (.x, .y) = (lse, label code)
-      float* atf = attr_f + b * 2 * CT;                                 // OWNER_ROWS: debias of the tile's 128 columns (same buffer)
+      // ---- stage the debias of the tile's 128 columns (one per thread of the first 128; double buffered) ----
+      float* atf = attr_f + b * 2 * CT;
       if (et < CT) {
         const int e = tt0 + et;
-        if (OWNER_ROWS) {
-          atf[et] = (e < a.C) ? a.debias[e] : 0.f;
-        } else {
-          // streamed rows: lse (+inf for invalid rows => weight 0) and the label column with bit 30 = "label column is pad-masked"
-          // (-1 for invalid rows: never equal to a column index)
-          const bool ok = (e < a.R) && (a.lm_rows[e] != 0.f);
-          const int ec = e < a.R ? e : 0;
-          const int i = ec / a.L, j = ec % a.L;
-          const bool lmk = (j + 1 < a.L) && (a.lm_cols[(a.user_offset + i) * a.L + j + 1] == 0.f);
-          const int code = ok ? ((int)((a.user_offset + i) * a.S + j + 1) | (lmk ? 0x40000000 : 0)) : -1;
-          at[et] = make_float2(ok ? a.lse[ec] : INFINITY, __int_as_float(code));
-        }
+        atf[et] = (e < a.C) ? a.debias[e] : 0.f;
       }
       epi_bar_sync();
       mbar_wait(&s_full[b], bph);
@@ -288,7 +269,7 @@ __global__ void __launch_bounds__(CE_THREADS, 1) ce_tile_kernel(const __grid_con
         tmem_ld_32x32(tmem_base + lane_addr + (uint32_t)(b * CT + k0), raw);
         tmem_ld_wait();
         float v[32];
-        if (OWNER_ROWS) {
+        {
           // 32 consecutive columns, c0 % 32 == 0.  Columns >= C carry mask bits (ce_maskbits_kernel) and a zero debias: they
           // become -1e4 like every masked entry, whose softmax weight underflows to exactly 0 against any real logit of the row.
           const int c0 = tt0 + k0;
@@ -331,30 +312,6 @@ __global__ void __launch_bounds__(CE_THREADS, 1) ce_tile_kernel(const __grid_con
               const int kl = o_label - c0;
 #pragma unroll
               for (int k = 0; k < 32; ++k) if (k == kl) v[k] -= scale;
-            }
-          }
-        } else {
-          // lanes = columns, chunk = 32 consecutive rows of the tile; the mask bit of (row-user, this column) changes only when
-          // the row's user changes (every L rows): one warp-uniform 32-bit load per user
-          const int cw = (o0 + quad * 32) >> 5;                           // mask word of this warp's 32 columns
-          const bool cw_ok = (o0 + quad * 32) < a.C;
-          int r_user = (tt0 + k0) / a.L, r_rem = (tt0 + k0) % a.L;
-          bool mbit = true;
-          if (cw_ok && r_user < a.B) mbit = (__ldg(a.maskbits + (int64_t)r_user * a.Cw + cw) >> lane) & 1u;
-#pragma unroll
-          for (int k = 0; k < 32; ++k) {
-            const float2 ra = at[k0 + k];
-            const int code = __float_as_int(ra.y);
-            const bool is_label = (code >= 0) && ((code & 0x3fffffff) == o);
-            const bool masked = is_label ? ((code & 0x40000000) != 0) : mbit;
-            const float lg = masked ? kNegMaskF : __uint_as_float(raw[k]) - o_debias;
-            float w = __expf(lg - ra.x);                                   // lse = +inf for invalid rows -> 0
-            if (is_label) w -= 1.f;
-            v[k] = o_ok ? w * scale : 0.f;
-            if (++r_rem == a.L) {                                          // next row belongs to the next user (warp-uniform)
-              r_rem = 0; ++r_user;
-              mbit = true;
-              if (cw_ok && r_user < a.B) mbit = (__ldg(a.maskbits + (int64_t)r_user * a.Cw + cw) >> lane) & 1u;
             }
           }
         }
@@ -419,8 +376,7 @@ __global__ void __launch_bounds__(CE_THREADS, 1) ce_tile_kernel(const __grid_con
       uint32_t raw[16];
       tmem_ld_32x16(tmem_base + lane_addr + (uint32_t)(CE_ACC_COL + half * 16), raw);
       tmem_ld_wait();
-      const int limit = OWNER_ROWS ? a.R : a.C;
-      if (o < limit) {
+      if (o < a.R) {
         float* op = a.d_out + (int64_t)o * CE_E + half * 16;
 #pragma unroll
         for (int q = 0; q < 4; ++q)
@@ -656,21 +612,10 @@ int ce_fast_backward(const iisan_ce_desc& d, const float* lm_rows, const float* 
   IISAN_TRY(fill_args(d, W, &A, lm_rows, lm_cols));
   A.g_sum = g_sum; A.g_mean = g_mean; A.n_valid = n_valid;
   const int row_tiles = (R + CT - 1) / CT, col_tiles = (C + CT - 1) / CT;
-  static const bool split_bwd = [] { const char* e = getenv("IISAN_B200_CE_SPLIT_BWD"); return e && e[0] == '1'; }();
-  if (!split_bwd) {      // one pass: d_prec in the CTA's accumulator, d_score by per-tile reductions
+  {      // one pass: d_prec in the CTA's accumulator, d_score by per-tile reductions
     const int splits = ce_fast_splits(row_tiles, col_tiles);
     A.tiles_stream = col_tiles; A.tiles_per_split = (col_tiles + splits - 1) / splits; A.d_out = d_prec; A.d_out2 = d_score;
-    return launch_tile<3>(A, row_tiles, splits, st);
-  }
-  {
-    const int splits = ce_fast_splits(row_tiles, col_tiles);
-    A.tiles_stream = col_tiles; A.tiles_per_split = (col_tiles + splits - 1) / splits; A.d_out = d_prec;
-    IISAN_TRY(launch_tile<1>(A, row_tiles, splits, st));
-  }
-  {
-    const int splits = ce_fast_splits(col_tiles, row_tiles);
-    A.tiles_stream = row_tiles; A.tiles_per_split = (row_tiles + splits - 1) / splits; A.d_out = d_score;
-    IISAN_TRY(launch_tile<2>(A, col_tiles, splits, st));
+    IISAN_TRY(launch_tile<3>(A, row_tiles, splits, st));
   }
   return IISAN_OK;
 }
