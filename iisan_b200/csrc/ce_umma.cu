@@ -424,27 +424,43 @@ __global__ void __launch_bounds__(256) ce_maskbits_kernel(const int64_t* __restr
   int64_t rid[17];
 #pragma unroll
   for (int k = 0; k < 17; ++k) rid[k] = (k < S) ? __ldg(ids_rows + (int64_t)i * S + k) : __ldg(ids_rows + (int64_t)i * S);
-  for (int w = warp; w < Cw; w += 8) {
-    const int c = w * 32 + lane;
-    bool m = true;                                     // columns beyond C: masked (never read as real columns)
-    if (c < C) {
-      const int u = c / S, p = c - u * S;
-      m = (p < L) && (lm_cols[(int64_t)u * L + p] == 0.f);
-      const int64_t id = ids_cols[c];
-      bool hit = false;
+  for (int w0 = warp; w0 < Cw; w0 += 32) {              // four independent words per iteration: their loads overlap
+    int64_t id[4]; float lmv[4]; int pp[4];
 #pragma unroll
-      for (int q = 0; q < 17; ++q) hit |= (rid[q] == id);  // slots >= S repeat slot 0
-      m = m || hit;
+    for (int q = 0; q < 4; ++q) {
+      const int c = (w0 + 8 * q) * 32 + lane;
+      id[q] = 0; lmv[q] = 1.f; pp[q] = L;
+      if (w0 + 8 * q < Cw && c < C) {
+        const int u = c / S, p = c - u * S;
+        pp[q] = p;
+        id[q] = ids_cols[c];
+        if (p < L) lmv[q] = lm_cols[(int64_t)u * L + p];
+      }
     }
-    const uint32_t word = __ballot_sync(0xffffffffu, m);
-    if (lane == 0) bits[(int64_t)i * Cw + w] = word;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int w = w0 + 8 * q;
+      if (w >= Cw) break;                                  // warp-uniform
+      const int c = w * 32 + lane;
+      bool m = true;                                       // columns beyond C: masked (never read as real columns)
+      if (c < C) {
+        m = (pp[q] < L) && (lmv[q] == 0.f);
+        bool hit = false;
+#pragma unroll
+        for (int k = 0; k < 17; ++k) hit |= (rid[k] == id[q]);   // slots >= S repeat slot 0
+        m = m || hit;
+      }
+      const uint32_t word = __ballot_sync(0xffffffffu, m);
+      if (lane == 0) bits[(int64_t)i * Cw + w] = word;
+    }
   }
 }
 
 __global__ void __launch_bounds__(256) ce_combine_kernel(const float* __restrict__ part_m, const float* __restrict__ part_s,
                                                          const float* __restrict__ part_lab, int splits, int R,
                                                          const float* __restrict__ lm_rows, float* __restrict__ lse_out,
-                                                         double* __restrict__ acc_sum, int* __restrict__ acc_cnt) {
+                                                         double* __restrict__ acc_sum, int* __restrict__ acc_cnt, float* loss_sum,
+                                                         int32_t* n_valid, float* loss) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   float contrib = 0.f; int cnt = 0;
   if (r < R) {
@@ -474,14 +490,18 @@ __global__ void __launch_bounds__(256) ce_combine_kernel(const float* __restrict
     double t = 0.0; int n = 0;
     for (int k = 0; k < 8; ++k) { t += rs[k]; n += rc[k]; }
     if (n) { atomicAdd(acc_sum, t); atomicAdd(acc_cnt, n); }
+    // the CTA that takes the last ticket sees every partial: it writes the results (no separate finalize launch)
+    __threadfence();
+    int* done = acc_cnt + 1;
+    if (atomicAdd(done, 1) == (int)gridDim.x - 1) {
+      __threadfence();
+      const double s = *reinterpret_cast<volatile double*>(acc_sum);
+      const int nn = *reinterpret_cast<volatile int*>(acc_cnt);
+      if (loss_sum) *loss_sum = (float)s;
+      if (n_valid) *n_valid = nn;
+      if (loss) *loss = (float)(s / (double)nn);
+    }
   }
-}
-
-__global__ void ce_finalize2_kernel(const double* acc_sum, const int* acc_cnt, float* loss_sum, int32_t* n_valid, float* loss) {
-  const double s = *acc_sum; const int n = *acc_cnt;
-  if (loss_sum) *loss_sum = (float)s;
-  if (n_valid) *n_valid = n;
-  if (loss) *loss = (float)(s / (double)n);
 }
 
 // expand the mask bits into the probe format of iisan_inbatch_ce_masks (bit0 masked, bit2 label, bit3 row valid)
@@ -514,7 +534,7 @@ struct CeFastLayout {
     Arena a(ws);
     const size_t R = (size_t)d.row_users * d.seq_len, S = d.seq_len + 1, C = (size_t)d.col_users * S, Cw = (C + 31) / 32;
     lse = a.take<float>(R);
-    acc_sum = a.take<double>(1); acc_cnt = a.take<int>(1);
+    acc_sum = a.take<double>(1); acc_cnt = a.take<int>(2);      // acc_cnt[1]: ticket counter of ce_combine_kernel
     prec_b = a.take<bf16>(R * d.emb); score_b = a.take<bf16>(C * d.emb);
     debias = a.take<float>(C); maskbits = a.take<uint32_t>((size_t)d.row_users * Cw);
     splits_fwd = ce_fast_splits((int)((R + CT - 1) / CT), (int)((C + CT - 1) / CT));
@@ -587,7 +607,7 @@ int ce_fast_forward(const iisan_ce_desc& d, const float* prec, const float* scor
                     float* loss, cudaStream_t st) {
   CeFastLayout W(d, ws);
   const int R = d.row_users * d.seq_len, S = d.seq_len + 1, C = d.col_users * S;
-  IISAN_CUDA_OK(cudaMemsetAsync(W.acc_sum, 0, 256 + sizeof(int), st));
+  IISAN_CUDA_OK(cudaMemsetAsync(W.acc_sum, 0, 256 + 2 * sizeof(int), st));
   IISAN_TRY(run_prepass(d, W, prec, score, ids_rows, ids_cols, lm_cols, pop, st));
   CeTileArgs A;
   IISAN_TRY(fill_args(d, W, &A, lm_rows, lm_cols));
@@ -595,9 +615,7 @@ int ce_fast_forward(const iisan_ce_desc& d, const float* prec, const float* scor
   A.tiles_stream = (C + CT - 1) / CT;
   A.tiles_per_split = (A.tiles_stream + W.splits_fwd - 1) / W.splits_fwd;
   IISAN_TRY(launch_tile<0>(A, owner_tiles, W.splits_fwd, st));
-  { LaunchScope ls_(IISAN_K_CE, st); ce_combine_kernel<<<(R + 255) / 256, 256, 0, st>>>(W.part_m, W.part_s, W.part_lab, W.splits_fwd, R, lm_rows, W.lse, W.acc_sum, W.acc_cnt); }
-  IISAN_LAUNCH_OK();
-  { LaunchScope ls_(IISAN_K_CE, st); ce_finalize2_kernel<<<1, 1, 0, st>>>(W.acc_sum, W.acc_cnt, loss_sum, n_valid, loss); }
+  { LaunchScope ls_(IISAN_K_CE, st); ce_combine_kernel<<<(R + 255) / 256, 256, 0, st>>>(W.part_m, W.part_s, W.part_lab, W.splits_fwd, R, lm_rows, W.lse, W.acc_sum, W.acc_cnt, loss_sum, n_valid, loss); }
   IISAN_LAUNCH_OK();
   return IISAN_OK;
 }

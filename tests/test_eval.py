@@ -22,6 +22,21 @@ def test_oracle_matches_reference_metrics_topk():
         assert abs(ndcg - z["hit_ndcg"][u, 1]) < 1e-6
 
 
+def test_host_helpers_follow_the_reference_dataset():
+    """pad_sequences == BuildMMEvalDataset.__getitem__ (dataset.py:185-191); hit_ndcg == metrics_topK's outputs from a rank."""
+    from iisan_b200.eval import hit_ndcg, pad_sequences
+    tok, lm, tgt = pad_sequences([[5, 7, 9], [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11], [4, 2]], 10)
+    assert tok[0].tolist() == [0] * 8 + [5, 7] and lm[0].tolist() == [0.0] * 8 + [1.0, 1.0] and int(tgt[0]) == 9
+    assert tok[1].tolist() == list(range(1, 11)) and lm[1].sum() == 10 and int(tgt[1]) == 11
+    assert tok[2].tolist() == [0] * 9 + [4] and int(tgt[2]) == 2
+    z = np.load(GOLD)
+    from oracle import eval_oracle as EO
+    ranks = [EO.rank_from_scores(z["scores"][u], int(z["targets"][u]), z["history"][u][z["history"][u] > 0]) for u in range(len(z["targets"]))]
+    hit, ndcg = hit_ndcg(torch.tensor(ranks), int(z["topk"]))
+    assert np.array_equal(hit.numpy(), z["hit_ndcg"][:, 0])
+    assert np.allclose(ndcg.numpy(), z["hit_ndcg"][:, 1], atol=1e-6)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("users,item_num,emb,hmax", [(64, 300, 64, 12), (257, 5000, 64, 40), (33, 1000, 32, 0), (8, 19246, 64, 11)])
 def test_eval_ranks_match_oracle(users, item_num, emb, hmax):
