@@ -12,9 +12,58 @@ the table) and the model consumes the packed [N, A, d] tensors directly (``packe
 """
 from __future__ import annotations
 
+import os
+from concurrent.futures import ThreadPoolExecutor
+
 import torch
 
 from . import ops
+
+
+def load_state_files(directory, item_id_to_keys, item_num, prefix, dtype=torch.bfloat16, workers=16):
+    """One-time repack of the reference's per-item cache files into one [item_num + 1, layers, d] tensor (host memory).
+
+    File layout of the reference (Code_Cached/preprocess_vectors.py:27-31 writes, data_utils/dataset.py:29-34 reads):
+    ``<directory>/<prefix>_<KEY>.pt`` = ``torch.save`` of a CPU tensor [n_layers + 1, d] (fp32; fp16 for the LLaMA / EVA-CLIP
+    files of Code_Cached_Asym), KEY = ``item_id_to_keys[item_id]`` (bytes or str, dataset.py:80-81).  Row 0 stays zero (the
+    padding item, dataset.py:87-88).  A missing file raises, like the reference's ``torch.stack`` on ``None`` does."""
+    def key(i):
+        k = item_id_to_keys[i]
+        return k.decode("utf-8") if isinstance(k, (bytes, bytearray)) else str(k)
+
+    def load(i):
+        path = os.path.join(directory, f"{prefix}_{key(i)}.pt")
+        if not os.path.exists(path):
+            raise FileNotFoundError(f"cached hidden states of item {i} not found: {path}")
+        t = torch.load(path, map_location="cpu")
+        if t.dim() != 2:
+            raise ValueError(f"{path}: expected a [layers, d] tensor, got {tuple(t.shape)}")
+        return i, t
+
+    first = load(1)[1]
+    table = torch.zeros(item_num + 1, first.shape[0], first.shape[1], dtype=dtype)
+    with ThreadPoolExecutor(max_workers=workers) as ex:
+        for i, t in ex.map(load, range(1, item_num + 1)):
+            if t.shape != first.shape:
+                raise ValueError(f"item {i}: shape {tuple(t.shape)} differs from {tuple(first.shape)}")
+            table[i] = t.to(dtype)
+    return table
+
+
+def build_id_batch(seqs, max_seq_len):
+    """(ids int64 [B, max_seq_len + 1], log_mask fp32 [B, max_seq_len]) of a list of user sequences, exactly as
+    Build_MM_Dataset.__getitem__ lays them out (dataset.py:65-72): left padding with id 0, log_mask = [0]*pad + [1]*(len - 1).
+    With the HBM-resident store this is the whole train batch."""
+    S = max_seq_len + 1
+    ids = torch.zeros(len(seqs), S, dtype=torch.int64)
+    log_mask = torch.zeros(len(seqs), max_seq_len, dtype=torch.float32)
+    for u, seq in enumerate(seqs):
+        seq = list(seq)[-S:]
+        n = len(seq)
+        ids[u, S - n:] = torch.as_tensor(seq, dtype=torch.int64)
+        if n > 1:
+            log_mask[u, max_seq_len - (n - 1):] = 1.0
+    return ids, log_mask
 
 
 class CachedStateStore:
