@@ -157,6 +157,37 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def bind_to_gpu_numa_node(local):
+    """Pin this rank's host threads (and hence its first-touch / pinned allocations) to the CPUs of the NUMA node the GPU hangs
+    off: with one process per GPU the pinned staging buffers otherwise land on an arbitrary socket and the H2D copies of 8 ranks
+    share the inter-socket link.  Reads sysfs; silently does nothing when the topology is not exposed."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local)
+        if hasattr(pr, "pci_bus_id") and hasattr(pr, "pci_domain_id"):
+            bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        else:                                                   # e.g. "00000000:1B:00.0"
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = vis.split(",")[local] if vis else str(local)
+            out = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", idx], capture_output=True, text=True).stdout
+            dom, bus, rest = out.strip().lower().split(":")
+            bdf = f"{dom[-4:]}:{bus}:{rest}"
+        txt = open(f"/sys/bus/pci/devices/{bdf}/local_cpulist").read().strip()
+        cpus = set()
+        for part in txt.split(","):
+            if "-" in part:
+                a, b = part.split("-"); cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read().strip()), len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def build_model(device, compute):
     import torch
     from torch import nn
@@ -206,6 +237,7 @@ def run_ours(a):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
+    numa = bind_to_gpu_numa_node(local) if world > 1 else None      # N = 1 keeps every core for the cpu_baseline leg
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
     state_dtype = torch.bfloat16 if a.compute == "bf16" else torch.float32
@@ -408,7 +440,7 @@ def run_ours(a):
                    "negatives": ("global (all-gather)" if a.negatives == "global" else "local (reference DDP semantics)") if world > 1 else "local",
                    "l2_policy": f"inputs rotate over {n_rot} resident batches of {2 * B * 11 * 13 * 768 * elt / 1e6:.0f} MB (> 126 MB L2)",
                    "step_runner": "CUDA graph replay (iisan_b200.engine.TrainStep)" if use_graph else "eager",
-                   "parallelism": f"dp{world}"},
+                   "parallelism": f"dp{world}", "host_numa_binding": numa},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / e2e_steps, "host_link_gbs": h2d / (ms_e2e / e2e_steps / 1e3) / 1e9,
                 "note": "PipelinedTrainStep.submit/run with pinned HOST batch tensors of the reference shapes [B,11,13,768]: every timed "
