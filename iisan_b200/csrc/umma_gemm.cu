@@ -6,6 +6,7 @@
 //   warps 2-9: epilogue       (tcgen05.ld 32 lanes x 32 columns -> bias / ReLU / mask / residual -> global)
 #include "umma_gemm.cuh"
 
+#include <cstdlib>
 #include <mutex>
 #include <unordered_map>
 
@@ -24,7 +25,7 @@ constexpr int UEPI_WARPS = 8;
 constexpr int USTG_FLOATS = 32 * 33;   // per-warp transpose staging (padded: conflict-free both ways)
 
 struct UmmaDevProblem {
-  CUtensorMap map_a, map_b;
+  CUtensorMap map_a, map_b;   // MC: map_b boxes cover HALF of the column tile (each CTA of the pair loads one half for both)
   int M, N, K;
   int kblocks_per_split;
   int tile_start;             // first tile of this problem in the launch-wide tile list (tiles: split-major, then m, then n)
@@ -38,16 +39,19 @@ struct UmmaDevBatchT {
 };
 
 struct UmmaTile { int prob, m0, n0, kb_beg, kb_end, split; };
-template <int BN, int NP>
-__device__ __forceinline__ UmmaTile umma_decode_tile(const UmmaDevBatchT<NP>& batch, int tile) {
+// MC (multicast cluster of two CTAs): the list holds PAIRS of row tiles that share a column tile; CTA `crank` of the cluster
+// takes row tile 2 * pair + crank (a pair past the last row tile computes on zero-filled rows and stores nothing)
+template <int BN, int NP, bool MC>
+__device__ __forceinline__ UmmaTile umma_decode_tile(const UmmaDevBatchT<NP>& batch, int tile, int crank) {
   int p = 0;
   while (p + 1 < batch.n_probs && tile >= batch.p[p + 1].tile_start) ++p;
   const UmmaDevProblem& P = batch.p[p];
-  const int tiles_n = (P.N + BN - 1) / BN, tiles_m = (P.M + UBM - 1) / UBM;
+  const int tiles_n = (P.N + BN - 1) / BN;
+  const int tiles_m = MC ? ((P.M + UBM - 1) / UBM + 1) / 2 : (P.M + UBM - 1) / UBM;
   const int l = tile - P.tile_start;
   const int split = l / (tiles_m * tiles_n), r = l % (tiles_m * tiles_n);
   UmmaTile t;
-  t.prob = p; t.split = split; t.m0 = (r / tiles_n) * UBM; t.n0 = (r % tiles_n) * BN;
+  t.prob = p; t.split = split; t.m0 = ((r / tiles_n) * (MC ? 2 : 1) + crank) * UBM; t.n0 = (r % tiles_n) * BN;
   const int kb_total = (P.K + UBK - 1) / UBK;
   t.kb_beg = split * P.kblocks_per_split;
   t.kb_end = min(kb_total, t.kb_beg + P.kblocks_per_split);
@@ -121,9 +125,34 @@ __device__ __noinline__ void epi_block_generic(const UmmaEpilogue& E, const floa
 
 enum : int { EPI_MASK = 1, EPI_RESB = 2, EPI_RESF = 4, EPI_OUTF = 8, EPI_OUTB = 16, EPI_ATOMIC = 32 };
 
-template <int BN, bool A_MN, bool B_MN, int NP>
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA load that lands at the same shared-memory offset of every CTA in `mask` and completes bytes on each one's mbarrier
+__device__ __forceinline__ void tma_load_2d_mc(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+// all MMAs issued so far by this thread arrive on the mbarrier at this offset in every CTA of `mask`
+__device__ __forceinline__ void mma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"(mask)
+               : "memory");
+}
+
+// MC: the kernel runs as clusters of two CTAs that work on two row tiles of the same column tile: each CTA loads its own A tile
+// and ONE HALF of the B tile, multicast into both CTAs (operand traffic from L2 per row tile: A + B/2 instead of A + B; the
+// 768 x 768 heads are L2-bandwidth bound: 396 tiles x 589 KB).  A ring slot is refilled only when BOTH consumers released it.
+template <int BN, bool A_MN, bool B_MN, int NP, bool MC>
 __global__ void __launch_bounds__(UTHREADS, 1) umma_gemm_kernel(const __grid_constant__ UmmaDevBatchT<NP> batch) {
   const int NSTG = batch.stages;
+  const int crank = MC ? (int)cluster_ctarank() : 0;
+  const int tile_first = MC ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int tile_step = MC ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   using S = UmmaSmem<BN>;
@@ -136,21 +165,22 @@ __global__ void __launch_bounds__(UTHREADS, 1) umma_gemm_kernel(const __grid_con
 
   const int warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < NSTG; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < NSTG; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], MC ? 2 : 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&accum_full[b], 1); mbar_init(&accum_empty[b], UEPI_WARPS); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 2 * BN);
   tc_fence_before();
   __syncthreads();
+  if (MC) cluster_sync_all();          // the peer's barriers exist before any multicast traffic / remote commit
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
     if (elect_one()) {
       int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < batch.total_tiles; tile += gridDim.x) {
-        const UmmaTile t = umma_decode_tile<BN, NP>(batch, tile);
+      for (int tile = tile_first; tile < batch.total_tiles; tile += tile_step) {
+        const UmmaTile t = umma_decode_tile<BN, NP, MC>(batch, tile, crank);
         const UmmaDevProblem& P = batch.p[t.prob];
         for (int kb = t.kb_beg; kb < t.kb_end; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
@@ -164,7 +194,17 @@ __global__ void __launch_bounds__(UTHREADS, 1) umma_gemm_kernel(const __grid_con
           } else {
             tma_load_2d(sa, &P.map_a, &full[stage], k0, t.m0);
           }
-          if (B_MN) {
+          if (MC) {          // this CTA's half of the column tile, into both CTAs
+            if (B_MN) {
+#pragma unroll
+              for (int i = 0; i < BN / 128; ++i) {
+                const int bi = crank * (BN / 128) + i;
+                tma_load_2d_mc(sb + bi * (64 * UBK * 2), &P.map_b, &full[stage], t.n0 + bi * 64, k0, (uint16_t)3);
+              }
+            } else {
+              tma_load_2d_mc(sb + crank * (BN / 2) * UBK * 2, &P.map_b, &full[stage], k0, t.n0 + crank * (BN / 2), (uint16_t)3);
+            }
+          } else if (B_MN) {
 #pragma unroll
             for (int i = 0; i < BN / 64; ++i) tma_load_2d(sb + i * (64 * UBK * 2), &P.map_b, &full[stage], t.n0 + i * 64, k0);
           } else {
@@ -179,8 +219,8 @@ __global__ void __launch_bounds__(UTHREADS, 1) umma_gemm_kernel(const __grid_con
       constexpr uint32_t idesc = instr_desc_bf16(UBM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
       int stage = 0; uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < batch.total_tiles; tile += gridDim.x, ++it) {
-        const UmmaTile t = umma_decode_tile<BN, NP>(batch, tile);
+      for (int tile = tile_first; tile < batch.total_tiles; tile += tile_step, ++it) {
+        const UmmaTile t = umma_decode_tile<BN, NP, MC>(batch, tile, crank);
         const int ab = it & 1; const uint32_t aph = (uint32_t)(it >> 1) & 1u;
         mbar_wait(&accum_empty[ab], aph ^ 1u);           // the epilogue has drained this accumulator
         tc_fence_after();
@@ -197,7 +237,8 @@ __global__ void __launch_bounds__(UTHREADS, 1) umma_gemm_kernel(const __grid_con
             const uint64_t bd = B_MN ? smem_desc_sw128(sb + k * 2048, 64 * UBK * 2, 1024) : smem_desc_sw128(sb + k * 32, 16, 1024);
             mma_bf16_ss(tm, ad, bd, idesc, (kb > t.kb_beg || k > 0) ? 1u : 0u);
           }
-          mma_commit(&empty[stage]);                 // frees the smem slot when these MMAs retire
+          if (MC) mma_commit_mc(&empty[stage], (uint16_t)3);   // both CTAs' producers write into this slot of both CTAs
+          else mma_commit(&empty[stage]);            // frees the smem slot when these MMAs retire
           if (++stage == NSTG) { stage = 0; phase ^= 1; }
         }
         mma_commit(&accum_full[ab]);
@@ -213,8 +254,8 @@ __global__ void __launch_bounds__(UTHREADS, 1) umma_gemm_kernel(const __grid_con
     const int lane = threadIdx.x & 31;
     float* stg = staging + ew * USTG_FLOATS;
     int it = 0;
-    for (int tile = blockIdx.x; tile < batch.total_tiles; tile += gridDim.x, ++it) {
-      const UmmaTile t = umma_decode_tile<BN, NP>(batch, tile);
+    for (int tile = tile_first; tile < batch.total_tiles; tile += tile_step, ++it) {
+      const UmmaTile t = umma_decode_tile<BN, NP, MC>(batch, tile, crank);
       const UmmaDevProblem& P = batch.p[t.prob];
       const int m0 = t.m0, n0 = t.n0;
       const int ab = it & 1; const uint32_t aph = (uint32_t)(it >> 1) & 1u;
@@ -333,6 +374,7 @@ __global__ void __launch_bounds__(UTHREADS, 1) umma_gemm_kernel(const __grid_con
   }
   tc_fence_before();
   __syncthreads();
+  if (MC) cluster_sync_all();          // no CTA leaves while its peer may still multicast into it / arrive on its barriers
   if (warp == 1) tmem_dealloc(tmem_base, 2 * BN);
 }
 
@@ -398,7 +440,9 @@ int make_tensor_map_bf16(CUtensorMap* out, const void* ptr, int64_t rows, int64_
   return IISAN_OK;
 }
 
-template <int BN, bool A_MN, bool B_MN, int NP>
+static const bool g_no_multicast = [] { const char* e = getenv("IISAN_B200_NO_MULTICAST"); return e && e[0] == '1'; }();
+
+template <int BN, bool A_MN, bool B_MN, int NP, bool MC = false>
 static int launch_cfg(const UmmaProblem* probs, int n_probs, cudaStream_t st) {
   static thread_local UmmaDevBatchT<NP> dev;      // large for the batched variant: keep it off the stack (launches are serialised per thread by the callers)
   int total_tiles = 0, max_kb = 1;
@@ -410,14 +454,15 @@ static int launch_cfg(const UmmaProblem* probs, int n_probs, cudaStream_t st) {
     if (A_MN) IISAN_TRY(make_tensor_map_bf16(&D.map_a, P.A.ptr, P.A.rows, P.A.cols, P.A.pitch, 64, UBK));
     else IISAN_TRY(make_tensor_map_bf16(&D.map_a, P.A.ptr, P.A.rows, P.A.cols, P.A.pitch, UBK, UBM));
     if (B_MN) IISAN_TRY(make_tensor_map_bf16(&D.map_b, P.B.ptr, P.B.rows, P.B.cols, P.B.pitch, 64, UBK));
-    else IISAN_TRY(make_tensor_map_bf16(&D.map_b, P.B.ptr, P.B.rows, P.B.cols, P.B.pitch, UBK, BN));
+    else IISAN_TRY(make_tensor_map_bf16(&D.map_b, P.B.ptr, P.B.rows, P.B.cols, P.B.pitch, UBK, MC ? BN / 2 : BN));
     D.M = P.M; D.N = P.N; D.K = P.K; D.epi = P.epi;
     const int kb_total = (P.K + UBK - 1) / UBK;
     int split = P.splitk < 1 ? 1 : (P.splitk > kb_total ? kb_total : P.splitk);
     D.kblocks_per_split = (kb_total + split - 1) / split;
     split = (kb_total + D.kblocks_per_split - 1) / D.kblocks_per_split;
     if (split > 1 && !(P.epi.atomic && P.epi.out_f32 && !P.epi.out_bf16)) return IISAN_EINVAL;
-    const int tiles = ((P.M + UBM - 1) / UBM) * ((P.N + BN - 1) / BN);
+    const int tiles_m = (P.M + UBM - 1) / UBM;
+    const int tiles = (MC ? (tiles_m + 1) / 2 : tiles_m) * ((P.N + BN - 1) / BN);
     D.tile_start = total_tiles;
     total_tiles += tiles * split;
     if (D.kblocks_per_split > max_kb) max_kb = D.kblocks_per_split;
@@ -425,7 +470,7 @@ static int launch_cfg(const UmmaProblem* probs, int n_probs, cudaStream_t st) {
   dev.n_probs = n_probs; dev.total_tiles = total_tiles;
   static bool attr_set = false;
   if (!attr_set) {
-    IISAN_CUDA_OK(cudaFuncSetAttribute(umma_gemm_kernel<BN, A_MN, B_MN, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaSmem<BN>::total(USTAGES)));
+    IISAN_CUDA_OK(cudaFuncSetAttribute(umma_gemm_kernel<BN, A_MN, B_MN, NP, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaSmem<BN>::total(USTAGES)));
     attr_set = true;
   }
   // one CTA per SM: the stage count no longer has to leave room for a second CTA (the ring runs across tile boundaries); the
@@ -438,8 +483,20 @@ static int launch_cfg(const UmmaProblem* probs, int n_probs, cudaStream_t st) {
     IISAN_CUDA_OK(cudaGetDevice(&devid));
     IISAN_CUDA_OK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, devid));
   }
+  if (MC) {
+    const int pairs = total_tiles < n_sm / 2 ? total_tiles : n_sm / 2;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(UTHREADS); cfg.dynamicSmemBytes = UmmaSmem<BN>::total(dev.stages); cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    { LaunchScope ls_(IISAN_K_GEMM, st); IISAN_CUDA_OK(cudaLaunchKernelEx(&cfg, umma_gemm_kernel<BN, A_MN, B_MN, NP, MC>, dev)); }
+    IISAN_LAUNCH_OK();
+    return IISAN_OK;
+  }
   const int grid = total_tiles < n_sm ? total_tiles : n_sm;
-  { LaunchScope ls_(IISAN_K_GEMM, st); umma_gemm_kernel<BN, A_MN, B_MN, NP><<<grid, UTHREADS, UmmaSmem<BN>::total(dev.stages), st>>>(dev); }
+  { LaunchScope ls_(IISAN_K_GEMM, st); umma_gemm_kernel<BN, A_MN, B_MN, NP, MC><<<grid, UTHREADS, UmmaSmem<BN>::total(dev.stages), st>>>(dev); }
   IISAN_LAUNCH_OK();
   return IISAN_OK;
 }
@@ -460,19 +517,29 @@ int launch_umma_gemm(const UmmaBatch& b, cudaStream_t st) {
     for (int i = 0; i < b.n; ++i) tiles += (int64_t)((b.p[i].M + UBM - 1) / UBM) * ((b.p[i].N + 255) / 256) * (b.p[i].splitk < 1 ? 1 : b.p[i].splitk);
     if (tiles < 148) bn = 128;
   }
+  // Large launches of 256-wide tiles (>= 4 tiles per SM: operand traffic from L2 is what bounds them): clusters of two CTAs share
+  // the column tile by TMA multicast.  Measured: 8192^3 1250 -> 1297 TFLOP/s; the 396-tile head GEMMs of the base config are
+  // unchanged within noise (0.282 vs 0.286 ms for the whole GEMM class), so they keep the simpler single-CTA schedule.
+  bool mc = (bn == 256) && !g_no_multicast;
+  int64_t tiles256 = 0;
+  for (int i = 0; i < b.n; ++i) {
+    mc = mc && (b.p[i].M > UBM);
+    tiles256 += (int64_t)((b.p[i].M + UBM - 1) / UBM) * ((b.p[i].N + 255) / 256) * (b.p[i].splitk < 1 ? 1 : b.p[i].splitk);
+  }
+  mc = mc && tiles256 >= 4 * 148;
   if (!a_mn && b_mn) {       // data gradient x W with the nn.Linear weight [out, in] read in place as a [K, N] operand
     if (bn == 64) return launch_cfg<64, false, true, kUmmaMaxProbs>(b.p, b.n, st);
     if (bn == 128) return launch_cfg<128, false, true, kUmmaMaxProbs>(b.p, b.n, st);
-    return launch_cfg<256, false, true, kUmmaMaxProbs>(b.p, b.n, st);
+    return mc ? launch_cfg<256, false, true, kUmmaMaxProbs, true>(b.p, b.n, st) : launch_cfg<256, false, true, kUmmaMaxProbs>(b.p, b.n, st);
   }
   if (!a_mn) {
     if (bn == 64) return launch_cfg<64, false, false, kUmmaMaxProbs>(b.p, b.n, st);
     if (bn == 128) return launch_cfg<128, false, false, kUmmaMaxProbs>(b.p, b.n, st);
-    return launch_cfg<256, false, false, kUmmaMaxProbs>(b.p, b.n, st);
+    return mc ? launch_cfg<256, false, false, kUmmaMaxProbs, true>(b.p, b.n, st) : launch_cfg<256, false, false, kUmmaMaxProbs>(b.p, b.n, st);
   }
   if (bn == 64) return launch_cfg<64, true, true, kUmmaMaxProbs>(b.p, b.n, st);
   if (bn == 128) return launch_cfg<128, true, true, kUmmaMaxProbs>(b.p, b.n, st);
-  return launch_cfg<256, true, true, kUmmaMaxProbs>(b.p, b.n, st);
+  return mc ? launch_cfg<256, true, true, kUmmaMaxProbs, true>(b.p, b.n, st) : launch_cfg<256, true, true, kUmmaMaxProbs>(b.p, b.n, st);
 }
 
 int launch_umma_gemm_big(const UmmaBatchBig& b, cudaStream_t st) {
