@@ -66,3 +66,10 @@ def test_umma_gemm_persistent_many_tiles():
     """More tiles than SMs: every CTA walks several tiles through its two TMEM accumulators."""
     _gemm(8192, 1024, 256, False, False, bias=True, out_bf16=True)
     _gemm(4096, 2048, 128, True, True, splitk=2)
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, True)])
+def test_umma_gemm_multicast_clusters(a_mn, b_mn):
+    """>= 4 tiles of 128 x 256 per SM: clusters of two CTAs, the column tile is multicast (odd row-tile count included)."""
+    _gemm(8192, 2560, 128, a_mn, b_mn, bias=not a_mn, out_bf16=not a_mn)
+    _gemm(8064, 2560, 192, a_mn, b_mn)          # 63 row tiles: the last pair has a phantom tile
