@@ -45,7 +45,9 @@ enum iisan_status {
 enum iisan_dtype { IISAN_F32 = 0, IISAN_BF16 = 1, IISAN_F16 = 2 };
 
 /* arithmetic mode: FP32 = fp32 FMA everywhere (<=1e-5 rel vs the reference run in fp32);
- * BF16 = bf16 tensor-core (tcgen05) GEMMs with fp32 accumulation (<=1e-2 rel). */
+ * BF16 = the fast mode (<=1e-2 rel on loss / embeddings): bf16 tensor-core (tcgen05) operands for the side-adapter network and
+ * the in-batch loss, TF32 tensor-core (mma.sync) operands -- the mantissa of the reference's fp16 autocast GEMMs -- for the
+ * SASRec user encoder (emb 64, seq_len 10) and the dense layer; fp32 accumulation, LayerNorm, softmax, log-sum-exp. */
 enum iisan_compute { IISAN_COMPUTE_FP32 = 0, IISAN_COMPUTE_BF16 = 1 };
 
 int iisan_abi_version(void);
