@@ -40,6 +40,22 @@ CASES = {
     "asym_equal": ("Code_Cached_Asym", dict(asym=True, d_text=64, d_img=64, layers_text=7, layers_img=7,
                                             bert_list="1,3,5", vit_list="1,3,5", r_cv=16, r_bert=16,
                                             embedding_dim=32, item_num=500), 5, "dense", 606),
+    # --- BASELINE.json configs[3] / configs[4] at their REAL widths and layer counts (small B: the widths, layer pitches,
+    #     stage plans and the dim-alignment GEMM are what these cases pin; tests/test_gpu_versa_shapes.py) ---
+    # BERT-large text + ViT-large image, group layer-drop 13 text vs 7 image adapters: 6 text-only stages, then 7 paired
+    # (list options CA/script/run_IISAN.py:48-53)
+    "versa_bertlarge_vitlarge": ("Code_Cached_Asym", dict(asym=True, d_text=1024, d_img=1024, layers_text=25, layers_img=25,
+                                                          bert_list="1,3,5,7,9,11,13,15,17,19,21,23", vit_list="1,3,5,7,9,11",
+                                                          r_cv=64, r_bert=64, embedding_dim=64, item_num=22785), 3, "realistic", 707),
+    # BERT-large text + ViT-base image: group layer-drop AND down_project 1024 -> 768 (CA/model/model.py:406-411)
+    "versa_bertlarge_vitbase": ("Code_Cached_Asym", dict(asym=True, d_text=1024, d_img=768, layers_text=25, layers_img=13,
+                                                         bert_list="1,3,5,7,9,11,13,15,17,19,21,23", vit_list="1,3,5,7,9,11",
+                                                         r_cv=64, r_bert=64, embedding_dim=64, item_num=22785), 3, "realistic", 808),
+    # LLaMA-3-70B-shaped text [81, 8192] + EVA-CLIP-18B-shaped image [49, 5120], down_project 8192 -> 5120
+    # (CA/script/run_IISAN_eva.py:56-65)
+    "versa_llama70b_evaclip": ("Code_Cached_Asym", dict(asym=True, d_text=8192, d_img=5120, layers_text=81, layers_img=49,
+                                                        bert_list="4,19,34,49,64,79", vit_list="2,11,20,29,38,47",
+                                                        r_cv=64, r_bert=64, embedding_dim=64, item_num=22785), 2, "dense", 909),
 }
 
 SAMPLE_MAX = 2048
