@@ -47,6 +47,11 @@ CASES = {
     "versa_bertlarge_vitlarge": ("Code_Cached_Asym", dict(asym=True, d_text=1024, d_img=1024, layers_text=25, layers_img=25,
                                                           bert_list="1,3,5,7,9,11,13,15,17,19,21,23", vit_list="1,3,5,7,9,11",
                                                           r_cv=64, r_bert=64, embedding_dim=64, item_num=22785), 3, "realistic", 707),
+    # the same widths with equal adapter counts (list option "3,7,11,15,19,23", CA/script/run_IISAN.py:49): with bf16 states this is
+    # the configuration the fused chain kernels serve at d = 1024
+    "versa_large_sym": ("Code_Cached_Asym", dict(asym=True, d_text=1024, d_img=1024, layers_text=25, layers_img=25,
+                                                 bert_list="3,7,11,15,19,23", vit_list="3,7,11,15,19,23",
+                                                 r_cv=64, r_bert=64, embedding_dim=64, item_num=22785), 4, "realistic", 717),
     # BERT-large text + ViT-base image: group layer-drop AND down_project 1024 -> 768 (CA/model/model.py:406-411)
     "versa_bertlarge_vitbase": ("Code_Cached_Asym", dict(asym=True, d_text=1024, d_img=768, layers_text=25, layers_img=13,
                                                          bert_list="1,3,5,7,9,11,13,15,17,19,21,23", vit_list="1,3,5,7,9,11",

@@ -109,3 +109,53 @@ def test_stage_plan_matches_oracle_plan():
         plan = make_plan(make_args(cfg), cfg.asym)
         exp = [tuple(-1 if v is None else v for v in st) for st in stage_plan(cfg)]
         assert plan.stages == exp
+
+
+def _versa_cfgs():
+    from golden_util import VERSA_CASES, load_case
+    from oracle.synthetic import PathConfig
+    return {name: PathConfig(**load_case(name)[1]["cfg"]) for name in VERSA_CASES}
+
+
+def test_versa_real_shapes_parameter_abi_plan_and_descriptors():
+    """BASELINE configs[3]/[4] at their real widths: parameter names / shapes / order == the reference's (the fixtures were
+    generated after asserting param_shapes == the reference's named_parameters()), the stage plan == the oracle's, and the C
+    ABI accepts the descriptors of both arithmetic modes (host-side validation + workspace size only: no kernel launch)."""
+    from oracle.iisan_oracle import stage_plan
+    from oracle.synthetic import make_args, param_shapes
+    from iisan_b200 import _lib, model_asym as pkg
+    from iisan_b200.plan import SanBinder
+    lib = _lib.load()
+    expected_params = {"versa_llama70b_evaclip": 337_800_000}
+    for name, cfg in _versa_cfgs().items():
+        args = make_args(cfg)
+
+        class Img(nn.Module):
+            def __init__(self):
+                super().__init__()
+                self.classifier = nn.Linear(cfg.d_img, cfg.embedding_dim)
+
+        with torch.device("meta"):                         # shapes only: the LLaMA/EVA case has 338 M parameters
+            m = pkg.ModelMM(args, cfg.item_num, True, Img(), nn.Identity(), [1.0] * 4)
+            m.mm_encoder = pkg.IISANAdaptedMModel(m.mm_encoder, args)
+        got = [(n, tuple(p.shape)) for n, p in m.named_parameters()]
+        assert got == list(param_shapes(cfg).items()), name
+        total = sum(p.numel() for p in m.parameters())
+        if name in expected_params:
+            assert abs(total - expected_params[name]) < 0.01 * expected_params[name], total     # SURVEY 8a row a9 [probe]
+        plan = m.mm_encoder.plan
+        assert plan.stages == [tuple(-1 if v is None else v for v in st) for st in stage_plan(cfg)], name
+        binder = SanBinder(plan, [n for n, _ in m.mm_encoder.named_parameters()])
+        n_items = 22
+        for dtype in (torch.float32, torch.bfloat16, torch.float16):
+            image = torch.empty(n_items, cfg.layers_img, cfg.d_img, dtype=dtype, device="meta")
+            text = torch.empty(n_items, cfg.layers_text, cfg.d_text, dtype=dtype, device="meta")
+            for compute in (_lib.COMPUTE_FP32, _lib.COMPUTE_BF16):
+                d = binder.desc(image, text, compute)
+                assert d.n_stages == len(plan.stages) and d.d_mm == min(cfg.d_text, cfg.d_img)
+                nbytes = lib.iisan_san_workspace_bytes(ctypes.byref(d))
+                assert 0 < nbytes < (4 << 30), (name, dtype, compute, nbytes)
+        # a selected layer outside the cached states is refused on the host
+        with pytest.raises(_lib.IisanLibraryError):
+            binder.desc(torch.empty(n_items, 3, cfg.d_img, device="meta"), torch.empty(n_items, 3, cfg.d_text, device="meta"),
+                        _lib.COMPUTE_FP32)

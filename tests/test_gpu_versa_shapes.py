@@ -1,0 +1,191 @@
+"""IISAN-Versa at the REAL widths / layer counts of BASELINE.json configs[3] and configs[4], small batches:
+
+  versa_bertlarge_vitlarge   text [25,1024] / image [25,1024], 13 vs 7 adapters: 6 text-only stages, then 7 paired
+  versa_large_sym            the same widths with 7 / 7 adapters: with bf16 states this runs the fused chain kernels at d = 1024
+  versa_bertlarge_vitbase    text [25,1024] / image [13,768]: group layer-drop + down_project 1024 -> 768
+  versa_llama70b_evaclip     text [81,8192] / image [49,5120] (fp16 in the reference's cache files): down_project 8192 -> 5120
+
+Frozen outputs of the reference's own Code_Cached_Asym model (tests/golden/versa_*.npz, oracle/make_golden.py) are the
+fp32 bar; the fast mode is held to north_star's tolerance (loss and embeddings <= 1e-2 relative to the fp32 reference) and
+its gradients to the rounding-point emulation, exactly as tests/test_gpu_parity.py does for the small-width fixtures.
+Every test prints its measured errors before asserting and appends them to gpurun_out/versa_shapes.jsonl.
+"""
+import functools
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from golden_util import VERSA_CASES, check_grads, golden_masked, load_case, rebuild_inputs
+from product_util import build_product, run_step
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+# fp32 mode: north_star asks 1e-5 relative on the loss; embeddings / gradients are compared norm-wise (error relative to the
+# largest reference entry of the tensor) because a contraction over 8192 terms reorders ~1e-6 of absolute noise per element.
+FP32_LOSS_RTOL = 1e-5
+FP32_EMB_RTOL = 1e-4
+FP32_GRAD_RTOL = 1e-3
+# fast mode: same bars as tests/test_gpu_parity.py
+BF16_LOSS_RTOL = 1e-2
+BF16_EMB_RTOL = 1e-2
+BF16_GRAD_L2 = 5e-2
+BF16_GRAD_L2_MEDIAN = 2.5e-2
+BF16_GATE_RTOL = 0.10
+BF16_GRAD_COS = 0.97
+
+
+def _log(rec):
+    try:
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", "versa_shapes.jsonl"), "a") as f:
+            f.write(json.dumps(rec) + "\n")
+    except OSError:
+        pass
+    print(json.dumps(rec), flush=True)
+
+
+@functools.lru_cache(maxsize=4)
+def _inputs(name):
+    z, meta = load_case(name)
+    return (z, meta) + tuple(rebuild_inputs(meta))
+
+
+def _round_to(a, dt):
+    return torch.from_numpy(a).to(dt).float().numpy()
+
+
+def _maxrel(a, b):
+    return float(np.abs(np.asarray(a, np.float64) - np.asarray(b, np.float64)).max() / (np.abs(b).max() + 1e-30))
+
+
+@pytest.mark.parametrize("name", VERSA_CASES)
+def test_versa_fp32_matches_reference_fixture(name):
+    from iisan_b200.precision import set_compute_mode
+    z, meta, cfg, batch, params, pop = _inputs(name)
+    set_compute_mode("fp32")
+    try:
+        model = build_product(cfg, params, pop).eval()
+        loss, grads = run_step(model, batch)
+        image = torch.from_numpy(batch["image"]).cuda(); text = torch.from_numpy(batch["text"]).cuda()
+        with torch.no_grad():
+            score = model.item_embeddings(image, text)
+            cv, (tx, mm) = model.mm_encoder(image, text)
+            E = cfg.embedding_dim
+            prec = model.user_encoder(score.view(-1, 11, E)[:, :-1], torch.from_numpy(batch["log_mask"]).cuda(), "cuda")
+    finally:
+        set_compute_mode(None)
+    rec = {"test": "fp32", "case": name, "loss": float(loss), "ref_loss": float(z["loss"]),
+           "loss_rel": abs(float(loss) - float(z["loss"])) / abs(float(z["loss"])),
+           "score": _maxrel(score.cpu().numpy(), z["score_embs"]), "e_cv": _maxrel(cv.cpu().numpy(), z["e_cv"]),
+           "e_text": _maxrel(tx.cpu().numpy(), z["e_text"]), "e_mm": _maxrel(mm.cpu().numpy(), z["e_mm"]),
+           "prec": _maxrel(prec.reshape(-1, E).cpu().numpy(), z["prec_vec"])}
+    # gradient digests: worst error of the strided samples relative to the largest reference entry of the tensor
+    worst, worst_name = 0.0, ""
+    for key in z.files:
+        if key.startswith("gradnone/"):
+            n = key[len("gradnone/"):]
+            assert grads.get(n) is None or not np.any(grads[n]), n
+        if not key.endswith("/sample"):
+            continue
+        n = key[len("grad/"):-len("/sample")]
+        assert grads[n] is not None, n
+        got = np.asarray(grads[n], np.float32).reshape(-1)[::int(z[f"grad/{n}/step"])]
+        e = _maxrel(got, z[key])
+        if e > worst:
+            worst, worst_name = e, n
+    rec["grad_worst"], rec["grad_worst_name"] = worst, worst_name
+    _log(rec)
+    assert rec["loss_rel"] <= FP32_LOSS_RTOL, rec
+    for k in ("score", "e_cv", "e_text", "e_mm", "prec"):
+        assert rec[k] <= FP32_EMB_RTOL, (k, rec)
+    assert worst <= FP32_GRAD_RTOL, rec
+    check_grads(z, grads, rtol=FP32_GRAD_RTOL)          # also the norms of the full tensors
+
+
+@pytest.mark.parametrize("name", VERSA_CASES)
+def test_versa_masks_and_labels_bit_exact(name):
+    from iisan_b200.ops import inbatch_ce_masks
+    from oracle import iisan_oracle as O
+    z, meta, cfg, batch, _, _ = _inputs(name)
+    ids = torch.from_numpy(batch["ids"]).cuda(); lm = torch.from_numpy(batch["log_mask"]).cuda()
+    rows = O.valid_rows(batch["log_mask"])
+    for fast in (False, True):
+        bits = inbatch_ce_masks(ids, ids, lm, lm, fast=fast).cpu().numpy()
+        if fast:       # bit0 = masked (column pad or reject, label excepted), bit2 = label, bit3 = row valid
+            masked = ((bits & 1) != 0)[rows]
+        else:
+            masked = ((bits & 3) != 0)[rows]
+        assert np.array_equal(np.nonzero(bits[:, 0] & 8)[0], rows)
+        assert np.array_equal(masked, golden_masked(z))
+        assert np.array_equal(np.argmax((bits & 4) != 0, axis=1)[rows], z["labels_valid"])
+
+
+def _state_dtypes(name):
+    # the reference's LLaMA / EVA-CLIP cache files hold fp16 tensors (CA/preprocess_llama-3-70b_off.py:63,
+    # CA/process_eva_clip_vectors.py:86,113)
+    return ["float32", "bfloat16", "float16"] if "llama" in name else ["float32", "bfloat16"]
+
+
+@pytest.mark.parametrize("name,state_dtype", [(n, d) for n in VERSA_CASES for d in _state_dtypes(n)])
+def test_versa_bf16_mode(name, state_dtype):
+    from bf16_emulation import train_step_grads_emul
+    from iisan_b200.precision import set_compute_mode
+    from oracle import iisan_oracle as O
+    z, meta, cfg, batch, params, pop = _inputs(name)
+    dt = getattr(torch, state_dtype)
+    if dt != torch.float32:                      # the references see exactly the stored (rounded) states
+        batch = dict(batch, image=_round_to(batch["image"], dt), text=_round_to(batch["text"], dt))
+    ref_out, ref_grads = O.train_step_grads(params, batch, pop, cfg)
+    plan = O.stage_plan(cfg)
+    fused = (dt == torch.bfloat16 and cfg.d_text == cfg.d_img and cfg.d_text % 64 == 0 and cfg.r_cv == 64 and cfg.r_bert == 64 and
+             cfg.remove_first != "TRUE" and len(plan) <= 8 and all(None not in st for st in plan))       # san_chain_eligible
+    emu_out, emu_grads = train_step_grads_emul(params, batch, pop, cfg, ce_bf16=(cfg.embedding_dim == 64), fused_chain=fused)
+    set_compute_mode("bf16")
+    try:
+        model = build_product(cfg, params, pop).eval()
+        loss, grads = run_step(model, batch, dtype=dt)
+        with torch.no_grad():
+            score = model.item_embeddings(torch.from_numpy(batch["image"]).cuda().to(dt),
+                                          torch.from_numpy(batch["text"]).cuda().to(dt)).cpu().numpy()
+    finally:
+        set_compute_mode(None)
+    ref_loss, ref_score = float(ref_out["loss"]), ref_out["score_embs"]
+    errs, names, dot, n1, n2 = [], [], 0.0, 0.0, 0.0
+    gate_ref, gate_got = [], []
+    for n, g in emu_grads.items():
+        if g is None:
+            assert grads[n] is None or not np.any(grads[n]), n
+            continue
+        assert grads[n] is not None and np.isfinite(grads[n]).all(), n
+        err = float(np.linalg.norm((grads[n] - g).astype(np.float64)) / (np.linalg.norm(g.astype(np.float64)) + 1e-30))
+        if g.size == 1:
+            gate_ref.append(float(g.ravel()[0])); gate_got.append(float(grads[n].ravel()[0]))
+        else:
+            errs.append(err); names.append(n)
+        r = ref_grads[n].astype(np.float64).ravel(); o = grads[n].astype(np.float64).ravel()
+        s = 1.0 / (np.linalg.norm(r) + 1e-30)
+        dot += float(np.dot(r, o)) * s * s; n1 += float(np.dot(r, r)) * s * s; n2 += float(np.dot(o, o)) * s * s
+    order = np.argsort(errs)[::-1]
+    rec = {"test": "bf16", "case": name, "states": state_dtype, "fused_chain": bool(fused), "loss": float(loss), "ref_loss": ref_loss,
+           "loss_rel_vs_fp32": abs(float(loss) - ref_loss) / abs(ref_loss),
+           "score_vs_fp32": _maxrel(score, ref_score),
+           "loss_rel_vs_emul": abs(float(loss) - float(emu_out["loss"])) / abs(ref_loss),
+           "score_vs_emul": float(np.abs(score - emu_out["score_embs"]).max() / np.abs(ref_score).max()),
+           "grad_l2_worst": float(max(errs)), "grad_l2_median": float(np.median(errs)),
+           "grad_l2_top": [(names[i], round(errs[i], 4)) for i in order[:5]],
+           "gate_err": float(np.linalg.norm(np.array(gate_got) - np.array(gate_ref)) / np.linalg.norm(gate_ref)),
+           "cos_vs_fp32": float(dot / np.sqrt(n1 * n2))}
+    _log(rec)
+    assert rec["loss_rel_vs_fp32"] <= BF16_LOSS_RTOL, rec
+    assert rec["score_vs_fp32"] <= BF16_EMB_RTOL, rec
+    assert rec["cos_vs_fp32"] >= BF16_GRAD_COS, rec
+    assert rec["loss_rel_vs_emul"] <= 3e-4, rec
+    assert rec["score_vs_emul"] <= 2e-3, rec
+    assert rec["grad_l2_worst"] <= BF16_GRAD_L2, rec
+    assert rec["grad_l2_median"] <= BF16_GRAD_L2_MEDIAN, rec
+    assert rec["gate_err"] <= BF16_GATE_RTOL, rec
