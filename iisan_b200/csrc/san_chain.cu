@@ -25,8 +25,6 @@
 // whose depth of ~2 chunks is far below the 12 chunks between a write and its re-read).
 //
 // warp roles: 0 weight TMA producer | 1 TMEM allocator + MMA issuer + TMA stores | 2 data TMA producer | 3..10 epilogue
-#include <cstdlib>
-
 #include "common.cuh"
 #include "launch.cuh"
 #include "san_chain.cuh"
@@ -47,8 +45,6 @@ constexpr int CH_TILE_BYTES = CH_ROWS * CH_CW * 2;   // 16 KB
 constexpr int CH_W_BYTES = CH_CW * CH_R * 2;         // 8 KB
 constexpr int CH_TMEM_COLS = 256;
 constexpr int CH_ZACC = 0, CH_UACC = 64;     // TMEM columns: z (dz) accumulator, two chunk accumulators
-constexpr int CH_XRES = 192;                 // forward, resid_chunks > 0: first column of the resident x chunks (32 columns each)
-constexpr int CH_XRES_MAX = (512 - CH_XRES) / 32;   // 10 chunks fit beside the accumulators
 
 struct ChainSmem {
   static constexpr int kZ = 0;                                   // z / dz operand [128 x 64]
@@ -126,7 +122,6 @@ constexpr int CF_EPI_WARPS = 16;
 constexpr int CF_THREADS = 96 + 32 * CF_EPI_WARPS;
 constexpr int CF_NCOL = 64 / (CF_EPI_WARPS / 4);     // columns per thread
 
-template <bool kResid>      // kResid = false: the measured default (NRES folds to 0 and the code is the one that was profiled)
 __global__ void __launch_bounds__(CF_THREADS, 1) san_chain_fwd_kernel(const __grid_constant__ ChainArgs a) {
   const ChainTower& T = a.tower[blockIdx.y];
   const bool is_mm = (T.mode == 1);
@@ -134,10 +129,6 @@ __global__ void __launch_bounds__(CF_THREADS, 1) san_chain_fwd_kernel(const __gr
   const int A = a.n_stages;
   const int m0 = blockIdx.x * CH_ROWS;
   const int NP = a.n_pad;
-  // EXPERIMENTAL (off unless IISAN_B200_CHAIN_TMEM_RESID is set): chunks c < NRES of the running x_s stay in TMEM as packed
-  // bf16 (the same rounded values the stash receives), so their residual does not come back through the TMA ring
-  const int NRES = kResid ? a.resid_chunks : 0;
-  const uint32_t tmem_ncols = NRES > 0 ? 512u : (uint32_t)CH_TMEM_COLS;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -149,7 +140,7 @@ __global__ void __launch_bounds__(CF_THREADS, 1) san_chain_fwd_kernel(const __gr
     if (is_mm) tma_prefetch_desc(&T.map_h2);
     B.init(CF_EPI_WARPS);
   }
-  if (warp == 1) tmem_alloc(B.tmem_slot, tmem_ncols);
+  if (warp == 1) tmem_alloc(B.tmem_slot, CH_TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -190,7 +181,7 @@ __global__ void __launch_bounds__(CF_THREADS, 1) san_chain_fwd_kernel(const __gr
       }
       for (int s = 0; s < A; ++s) {
         for (int c = 0; c < NC; ++c) {
-          if (c >= NRES) load(&T.map_x, c * CH_CW, s * NP + m0);
+          load(&T.map_x, c * CH_CW, s * NP + m0);
           if (s + 1 < A) {
             load(&T.map_h, T.layer[s + 1] * a.d + c * CH_CW, m0);
             if (is_mm) load(&T.map_h2, T.layer2[s + 1] * a.d + c * CH_CW, m0);
@@ -288,18 +279,10 @@ __global__ void __launch_bounds__(CF_THREADS, 1) san_chain_fwd_kernel(const __gr
       for (int q = 0; q < NQ; ++q) *reinterpret_cast<uint4*>(tile + (((cq * NQ + q) ^ (m & 7)) << 4)) = pack8(v + q * 8);
     };
     // x chunk (or, in the final stage, the last chunk) -> swizzled shared memory; signals the MMA / store thread
-    auto xres_addr = [&](int c) { return tmem_base + lane_addr + (uint32_t)(CH_XRES + c * 32 + cq * (NCOL / 2)); };
-    // c_res >= 0 (warp-uniform): also keep the packed chunk in TMEM as the residual of the next stage
-    auto emit = [&](const float (&xv)[NCOL], bool is_x, int c_res) {
+    auto emit = [&](const float (&xv)[NCOL], bool is_x) {
       const int b = n_x & 1; const uint32_t ph = (uint32_t)(n_x >> 1) & 1u;
       mbar_wait(&B.xk_empty[b], ph ^ 1u);
       put_tile(smem + (is_x ? ChainSmem::kXk : ChainSmem::kLk) + b * CH_TILE_BYTES, xv);
-      if (c_res >= 0) {
-        uint32_t w[NCOL / 2];
-        const uint4 p0 = pack8(xv), p1 = pack8(xv + 8);
-        w[0] = p0.x; w[1] = p0.y; w[2] = p0.z; w[3] = p0.w; w[4] = p1.x; w[5] = p1.y; w[6] = p1.z; w[7] = p1.w;
-        tmem_st_32x8(xres_addr(c_res), w);
-      }
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&B.xk_full[b]);
@@ -340,7 +323,7 @@ __global__ void __launch_bounds__(CF_THREADS, 1) san_chain_fwd_kernel(const __gr
 #pragma unroll
           for (int k = 0; k < NCOL; ++k) xv[k] = g * hv[k];
         }
-        emit(xv, true, c < NRES ? c : -1);
+        emit(xv, true);
       }
     }
     for (int s = 0; s < A; ++s) {
@@ -374,16 +357,7 @@ __global__ void __launch_bounds__(CF_THREADS, 1) san_chain_fwd_kernel(const __gr
           for (int q = 0; q < NCOL / 4; ++q) bq[q] = __ldg(bu + q);
         }
         float xr[NCOL];
-        if (c < NRES) {                        // residual x_s[c] from TMEM (stored by this thread one stage earlier)
-          uint32_t w[NCOL / 2];
-          tmem_st_wait();
-          tmem_ld_32x8(xres_addr(c), w);
-          tmem_ld_wait();
-          unpack8(make_uint4(w[0], w[1], w[2], w[3]), xr);
-          unpack8(make_uint4(w[4], w[5], w[6], w[7]), xr + 8);
-        } else {
-          read_h(xr);                          // residual x_s[c] through the ring
-        }
+        read_h(xr);                            // residual x_s[c]
         const int b = n_u & 1; const uint32_t uph = (uint32_t)(n_u >> 1) & 1u;
         mbar_wait(&B.u_full[b], uph);
         tc_fence_after();
@@ -410,22 +384,21 @@ __global__ void __launch_bounds__(CF_THREADS, 1) san_chain_fwd_kernel(const __gr
 #pragma unroll
             for (int k = 0; k < NCOL; ++k) xv[k] = fmaf(g, hv[k], omg * lv[k]);
           }
-          emit(xv, true, c < NRES ? c : -1);
+          emit(xv, true);
         } else {
-          emit(lv, false, -1);
+          emit(lv, false);
         }
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, tmem_ncols);
+  if (warp == 1) tmem_dealloc(tmem_base, CH_TMEM_COLS);
 }
 
 // ================================================================================================================
 // backward
 // ================================================================================================================
-template <bool kResid>      // kResid = false: the measured default
 __global__ void __launch_bounds__(CH_THREADS, 1) san_chain_bwd_kernel(const __grid_constant__ ChainBwdArgs a) {
   const ChainBwdTower& T = a.tower[blockIdx.y];
   const bool is_mm = (T.mode == 1);
@@ -433,10 +406,6 @@ __global__ void __launch_bounds__(CH_THREADS, 1) san_chain_bwd_kernel(const __gr
   const int A = a.n_stages;
   const int m0 = blockIdx.x * CH_ROWS;
   const int NP = a.n_pad;
-  // EXPERIMENTAL: chunks c < NRES of d last_s (bf16, as stashed) stay in TMEM from the stage that emits them (or the prologue,
-  // for s = A-1) to the stage that adds them to dx, instead of coming back through the TMA ring
-  const int NRES = kResid ? a.resid_chunks : 0;
-  const uint32_t tmem_ncols = NRES > 0 ? 512u : (uint32_t)CH_TMEM_COLS;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -447,7 +416,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) san_chain_bwd_kernel(const __gr
     tma_prefetch_desc(&T.map_aux); tma_prefetch_desc(&T.map_dz);
     B.init();
   }
-  if (warp == 1) tmem_alloc(B.tmem_slot, tmem_ncols);
+  if (warp == 1) tmem_alloc(B.tmem_slot, CH_TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -485,7 +454,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) san_chain_bwd_kernel(const __gr
       for (int c = 0; c < NC; ++c) load(&T.map_dy, c * CH_CW, (A - 1) * NP + m0);
       for (int s = A - 1; s >= 0; --s) {
         for (int c = 0; c < NC; ++c) {
-          if (c >= NRES) load(&T.map_dy, c * CH_CW, s * NP + m0);
+          load(&T.map_dy, c * CH_CW, s * NP + m0);
           load(&T.map_h, T.layer[s] * a.d + c * CH_CW, m0);
           if (is_mm) load(&T.map_aux, T.layer2[s] * a.d + c * CH_CW, m0);
           else if (s > 0) load(&T.map_aux, c * CH_CW, s * NP + m0);          // x_s (the forward's stash)
@@ -579,21 +548,10 @@ __global__ void __launch_bounds__(CH_THREADS, 1) san_chain_bwd_kernel(const __gr
       if (lane == 0) mbar_arrive(&B.h_empty[h_slot]);
       if (++h_slot == CH_NH) { h_slot = 0; h_ph ^= 1u; }
     };
-    auto xres_addr = [&](int c) { return tmem_base + lane_addr + (uint32_t)(CH_XRES + c * 32 + hf * 16); };
-    // bf16 chunk -> A operand (the MMA thread stores it to the stash); c_res >= 0 (warp-uniform): also kept in TMEM
-    auto emit = [&](const float* xv, int c_res) {
+    auto emit = [&](const float* xv) {                // bf16 chunk -> A operand (the MMA thread stores it to the stash)
       const int b = n_x & 1; const uint32_t ph = (uint32_t)(n_x >> 1) & 1u;
       mbar_wait(&B.xk_empty[b], ph ^ 1u);
       put_tile(smem + ChainSmem::kXk + b * CH_TILE_BYTES, xv);
-      if (c_res >= 0) {
-        uint32_t w[16];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const uint4 p = pack8(xv + q * 8);
-          w[4 * q] = p.x; w[4 * q + 1] = p.y; w[4 * q + 2] = p.z; w[4 * q + 3] = p.w;
-        }
-        tmem_st_32x16(xres_addr(c_res), w);
-      }
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&B.xk_full[b]);
@@ -604,7 +562,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) san_chain_bwd_kernel(const __gr
     for (int c = 0; c < NC; ++c) {
       float dv[32];
       read_tile(dv);
-      emit(dv, c < NRES ? c : -1);
+      emit(dv);
     }
     for (int s = A - 1; s >= 0; --s) {
       const int j = A - 1 - s;
@@ -638,16 +596,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) san_chain_bwd_kernel(const __gr
       float gpart = 0.f;
       for (int c = 0; c < NC; ++c) {
         float dy[32], hv[32], av[32];
-        if (c < NRES) {                        // d last_s[c] from TMEM (rows past N were stored as zeros)
-          uint32_t w[16];
-          tmem_st_wait();
-          tmem_ld_32x16(xres_addr(c), w);
-          tmem_ld_wait();
-#pragma unroll
-          for (int q = 0; q < 4; ++q) unpack8(make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]), dy + q * 8);
-        } else {
-          read_tile(dy);
-        }
+        read_tile(dy);
         read_tile(hv);
         const bool has_aux = is_mm || more;
         if (has_aux) read_tile(av);
@@ -673,7 +622,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) san_chain_bwd_kernel(const __gr
 #pragma unroll
             for (int k = 0; k < 32; ++k) dx[k] *= omg;
           }
-          emit(dx, c < NRES ? c : -1);
+          emit(dx);
         }
         const float cs = warp_colsum32(dy, lane);                        // db_up
         atomicAdd(T.g_b_up[s] + c * CH_CW + hf * 32 + lane, cs);
@@ -688,7 +637,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) san_chain_bwd_kernel(const __gr
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, tmem_ncols);
+  if (warp == 1) tmem_dealloc(tmem_base, CH_TMEM_COLS);
 }
 
 // ================================================================================================================
@@ -734,23 +683,11 @@ int chain_fill_bwd_tower(ChainBwdTower* T, int mode, const void* h, int64_t n_it
 int launch_san_chain_bwd(const ChainBwdArgs& args, int n_towers, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    IISAN_CUDA_OK(cudaFuncSetAttribute(san_chain_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ChainSmem::kTotal));
-    IISAN_CUDA_OK(cudaFuncSetAttribute(san_chain_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ChainSmem::kTotal));
+    IISAN_CUDA_OK(cudaFuncSetAttribute(san_chain_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ChainSmem::kTotal));
     attr_set = true;
   }
   const int tiles = (args.n_items + CH_ROWS - 1) / CH_ROWS;
-  const char* env = getenv("IISAN_B200_CHAIN_TMEM_RESID_BWD");     // EXPERIMENTAL switch, read per launch
-  const int want = env ? atoi(env) : 0;
-  if (want > 0) {
-    ChainBwdArgs a2 = args;
-    const int nc = args.d / CH_CW;
-    a2.resid_chunks = want > CH_XRES_MAX ? CH_XRES_MAX : want;
-    if (a2.resid_chunks > nc) a2.resid_chunks = nc;
-    { LaunchScope ls_(IISAN_K_CHAIN_BWD, st); san_chain_bwd_kernel<true><<<dim3(tiles, n_towers), CH_THREADS, ChainSmem::kTotal, st>>>(a2); }
-    IISAN_LAUNCH_OK();
-    return IISAN_OK;
-  }
-  { LaunchScope ls_(IISAN_K_CHAIN_BWD, st); san_chain_bwd_kernel<false><<<dim3(tiles, n_towers), CH_THREADS, ChainSmem::kTotal, st>>>(args); }
+  { LaunchScope ls_(IISAN_K_CHAIN_BWD, st); san_chain_bwd_kernel<<<dim3(tiles, n_towers), CH_THREADS, ChainSmem::kTotal, st>>>(args); }
   IISAN_LAUNCH_OK();
   return IISAN_OK;
 }
@@ -758,24 +695,11 @@ int launch_san_chain_bwd(const ChainBwdArgs& args, int n_towers, cudaStream_t st
 int launch_san_chain_fwd(const ChainArgs& args, int n_towers, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    IISAN_CUDA_OK(cudaFuncSetAttribute(san_chain_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ChainSmem::kTotal));
-    IISAN_CUDA_OK(cudaFuncSetAttribute(san_chain_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ChainSmem::kTotal));
+    IISAN_CUDA_OK(cudaFuncSetAttribute(san_chain_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ChainSmem::kTotal));
     attr_set = true;
   }
   const int tiles = (args.n_items + CH_ROWS - 1) / CH_ROWS;
-  // EXPERIMENTAL switch, read per launch (a CUDA-graph capture bakes the value in): IISAN_B200_CHAIN_TMEM_RESID=<chunks>
-  const char* env = getenv("IISAN_B200_CHAIN_TMEM_RESID");
-  const int want = env ? atoi(env) : 0;
-  if (want > 0) {
-    ChainArgs a2 = args;
-    const int nc = args.d / CH_CW;
-    a2.resid_chunks = want > CH_XRES_MAX ? CH_XRES_MAX : want;
-    if (a2.resid_chunks > nc) a2.resid_chunks = nc;
-    { LaunchScope ls_(IISAN_K_CHAIN, st); san_chain_fwd_kernel<true><<<dim3(tiles, n_towers), CF_THREADS, ChainSmem::kTotal, st>>>(a2); }
-    IISAN_LAUNCH_OK();
-    return IISAN_OK;
-  }
-  { LaunchScope ls_(IISAN_K_CHAIN, st); san_chain_fwd_kernel<false><<<dim3(tiles, n_towers), CF_THREADS, ChainSmem::kTotal, st>>>(args); }
+  { LaunchScope ls_(IISAN_K_CHAIN, st); san_chain_fwd_kernel<<<dim3(tiles, n_towers), CF_THREADS, ChainSmem::kTotal, st>>>(args); }
   IISAN_LAUNCH_OK();
   return IISAN_OK;
 }

@@ -29,8 +29,6 @@ struct ChainTower {
 struct ChainArgs {
   ChainTower tower[3];
   int n_items, n_pad, d, n_stages;
-  int resid_chunks;         // EXPERIMENTAL (0 = off, the measured default): the first resid_chunks 64-column chunks of the running
-                            // x_s stay in TMEM as packed bf16 for the residual instead of coming back through the TMA ring
 };
 
 struct ChainBwdTower {
@@ -51,8 +49,6 @@ struct ChainBwdTower {
 struct ChainBwdArgs {
   ChainBwdTower tower[3];
   int n_items, n_pad, d, n_stages;
-  int resid_chunks;         // EXPERIMENTAL (0 = off): the first resid_chunks chunks of d last_s stay in TMEM between the stage that
-                            // produces them and the stage that adds them to dx (IISAN_B200_CHAIN_TMEM_RESID_BWD)
 };
 
 int chain_n_pad(int n_items);
