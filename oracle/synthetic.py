@@ -265,3 +265,26 @@ def make_params(cfg: PathConfig, seed: int, perturb: bool = True):
             v = v + rng.standard_normal(shape) * 0.05
         out[name] = np.ascontiguousarray(v, dtype=np.float32)
     return out
+
+
+# ----------------------------------------------------------------------------------------------
+# cache files of the data loader (Code_Cached/preprocess_vectors.py:27-31 writes them, data_utils/dataset.py:29-34 reads them)
+# ----------------------------------------------------------------------------------------------
+
+def make_cache_case(seed: int = 4242, item_num: int = 12, layers: int = 13, d: int = 16):
+    """Seeded stand-in for one dataset: ``item_id_to_keys`` (bytes ASINs, as the lmdb key table holds them), per-item
+    [layers, d] fp32 states for both modalities and train sequences (``u2seq``: user -> item ids, lengths 2..11, one user
+    with a repeated item)."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    keys = {i: f"B{seed % 1000:03d}{i:06d}".encode() for i in range(1, item_num + 1)}
+    bert = {i: torch.randn(layers, d, generator=g) for i in range(1, item_num + 1)}
+    vit = {i: torch.randn(layers, d, generator=g) for i in range(1, item_num + 1)}
+    rng = np.random.default_rng(seed)
+    u2seq = {}
+    for u, n in enumerate([2, 3, 5, 11, 7, 11, 4, 9]):
+        seq = [int(v) for v in rng.integers(1, item_num + 1, size=n)]
+        if u == 4:
+            seq[2] = seq[0]
+        u2seq[u] = seq
+    return keys, bert, vit, u2seq

@@ -6,7 +6,7 @@ import os
 import numpy as np
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-_ALL = sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz") and not f.startswith("eval_"))   # eval_*: tests/test_eval.py
+_ALL = sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz") and not f.startswith(("eval_", "data_")))   # eval_*: tests/test_eval.py, data_*: tests/test_store_cpu.py
 CASES = [c for c in _ALL if not c.startswith("versa_")]          # small widths: every parity test runs on all of them
 VERSA_CASES = [c for c in _ALL if c.startswith("versa_")]         # BASELINE configs[3]/[4] at their real widths / layer counts
 
