@@ -103,3 +103,25 @@ def test_loss_invariant_under_user_permutation():
         a = model(ids.view(-1), image, text, lm, 0)
         b = model(ids[perm].reshape(-1), image[perm].contiguous(), text[perm].contiguous(), lm[perm].contiguous(), 0)
     assert abs(float(a) - float(b)) <= 2e-6 * abs(float(a))
+
+
+@pytest.mark.parametrize("n_items", [44, 176, 5632])
+def test_forward_never_reads_workspace_it_did_not_write(n_items, monkeypatch):
+    """The fused chain kernels re-read their own stash (x_s one stage after writing it) through the TMA ring, ordered by distance
+    (san_chain.cu header) rather than by a completion barrier.  With every workspace byte poisoned (0xFF = bf16 / fp32 NaN) a read
+    that overtakes its store, or any read of memory the launch did not write, turns the embeddings into NaN / Inf; with a clean
+    workspace the result must be the same, bit for bit.  (This probe is what exposed the ordering hazard of the TMEM-residual
+    experiment, profiles/r01e_chain_tmem_residual_experiment.md; partial tiles 44 / 176 and the full benchmark size 5632.)"""
+    from iisan_b200 import ops
+    model = _model()
+    g = torch.Generator(device="cuda").manual_seed(n_items)
+    img = torch.randn(n_items, 13, 768, device="cuda", generator=g).bfloat16()
+    txt = torch.randn(n_items, 13, 768, device="cuda", generator=g).bfloat16()
+    with torch.no_grad():
+        clean = model.mm_encoder.embed(img, txt).clone()
+    monkeypatch.setattr(ops, "_workspace",
+                        lambda nbytes, device: torch.full((max(int(nbytes), 256),), 0xFF, dtype=torch.uint8, device=device))
+    with torch.no_grad():
+        poisoned = model.mm_encoder.embed(img, txt)
+    assert torch.isfinite(poisoned).all()
+    assert torch.equal(clean, poisoned)
