@@ -159,7 +159,8 @@ int iisan_linear_backward(int32_t rows, int32_t out_features, int32_t in_feature
  * parity tests can pin it in isolation.  D[M,N] = act(A x B + bias), fp32 accumulate.
  *   a_mn_major = 0: A stored [M,K] row-major (pitch a_pitch) ; 1: A stored [K,M] row-major
  *   b_mn_major = 0: B stored [N,K] row-major (nn.Linear weight) ; 1: B stored [K,N] row-major
- * (a_mn_major must equal b_mn_major).  out_f32 / out_bf16: either may be null.  splitk > 1 accumulates
+ * Built combinations: K/K (forward), K/MN (data gradients: the weight is read in place), MN/MN (weight gradients); MN/K is
+ * not.  out_f32 / out_bf16: either may be null.  splitk > 1 accumulates
  * atomically into a caller-zeroed out_f32.  N % 8 == 0, pitches % 8 == 0, 16-byte aligned pointers. */
 int iisan_gemm_bf16(int32_t M, int32_t N, int32_t K, const void* A, int64_t a_pitch, int32_t a_mn_major,
                     const void* B, int64_t b_pitch, int32_t b_mn_major, float* out_f32, int64_t ld_f32,

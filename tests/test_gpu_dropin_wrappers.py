@@ -75,9 +75,11 @@ def process_group():
     import torch.distributed as dist
     created = False
     if not dist.is_initialized():
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("MASTER_PORT", "29617")
-        dist.init_process_group("nccl", rank=0, world_size=1)
+        import socket
+        with socket.socket() as sock:                    # a free port: the box may run other rendezvous at the same time
+            sock.bind(("127.0.0.1", 0))
+            port = sock.getsockname()[1]
+        dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=0, world_size=1)
         created = True
     yield
     if created:
