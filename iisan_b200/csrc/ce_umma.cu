@@ -576,10 +576,11 @@ static int fill_args(const iisan_ce_desc& d, const CeFastLayout& W, CeTileArgs* 
 
 template <int MODE>
 static int launch_tile(const CeTileArgs& A, int owner_tiles, int splits, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static std::atomic<uint64_t> attr_done{0};      // devices on which the attribute has been set
+  const uint64_t dev_bit = device_bit();
+  if (!(attr_done.load(std::memory_order_acquire) & dev_bit)) {
     IISAN_CUDA_OK(cudaFuncSetAttribute(ce_tile_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, CeSmem::kTotal));
-    attr_set = true;
+    attr_done.fetch_or(dev_bit, std::memory_order_release);
   }
   { LaunchScope ls_(IISAN_K_CE, st); ce_tile_kernel<MODE><<<dim3(owner_tiles, splits), CE_THREADS, CeSmem::kTotal, st>>>(A); }
   IISAN_LAUNCH_OK();

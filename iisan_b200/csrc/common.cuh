@@ -5,6 +5,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 #include "../../include/iisan_b200.h"
 
 namespace iisan {
@@ -36,6 +38,14 @@ inline int cuda_fail(cudaError_t e) {
   } while (0)
 
 inline cudaStream_t as_stream(iisan_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// cudaFuncSetAttribute applies to the CURRENT device only.  Each launcher keeps one std::atomic<uint64_t> of the devices it has
+// configured (one process per GPU is the normal deployment, but one process driving several GPUs must work too).
+inline uint64_t device_bit() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+  return 1ull << (dev & 63);
+}
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 

@@ -681,10 +681,11 @@ int chain_fill_bwd_tower(ChainBwdTower* T, int mode, const void* h, int64_t n_it
 }
 
 int launch_san_chain_bwd(const ChainBwdArgs& args, int n_towers, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static std::atomic<uint64_t> attr_done{0};      // devices on which the attribute has been set
+  const uint64_t dev_bit = device_bit();
+  if (!(attr_done.load(std::memory_order_acquire) & dev_bit)) {
     IISAN_CUDA_OK(cudaFuncSetAttribute(san_chain_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ChainSmem::kTotal));
-    attr_set = true;
+    attr_done.fetch_or(dev_bit, std::memory_order_release);
   }
   const int tiles = (args.n_items + CH_ROWS - 1) / CH_ROWS;
   { LaunchScope ls_(IISAN_K_CHAIN_BWD, st); san_chain_bwd_kernel<<<dim3(tiles, n_towers), CH_THREADS, ChainSmem::kTotal, st>>>(args); }
@@ -693,10 +694,11 @@ int launch_san_chain_bwd(const ChainBwdArgs& args, int n_towers, cudaStream_t st
 }
 
 int launch_san_chain_fwd(const ChainArgs& args, int n_towers, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static std::atomic<uint64_t> attr_done{0};      // devices on which the attribute has been set
+  const uint64_t dev_bit = device_bit();
+  if (!(attr_done.load(std::memory_order_acquire) & dev_bit)) {
     IISAN_CUDA_OK(cudaFuncSetAttribute(san_chain_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ChainSmem::kTotal));
-    attr_set = true;
+    attr_done.fetch_or(dev_bit, std::memory_order_release);
   }
   const int tiles = (args.n_items + CH_ROWS - 1) / CH_ROWS;
   { LaunchScope ls_(IISAN_K_CHAIN, st); san_chain_fwd_kernel<<<dim3(tiles, n_towers), CF_THREADS, ChainSmem::kTotal, st>>>(args); }

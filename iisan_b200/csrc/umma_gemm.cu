@@ -468,10 +468,11 @@ static int launch_cfg(const UmmaProblem* probs, int n_probs, cudaStream_t st) {
     if (D.kblocks_per_split > max_kb) max_kb = D.kblocks_per_split;
   }
   dev.n_probs = n_probs; dev.total_tiles = total_tiles;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static std::atomic<uint64_t> attr_done{0};      // devices on which the attribute has been set
+  const uint64_t dev_bit = device_bit();
+  if (!(attr_done.load(std::memory_order_acquire) & dev_bit)) {
     IISAN_CUDA_OK(cudaFuncSetAttribute(umma_gemm_kernel<BN, A_MN, B_MN, NP, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaSmem<BN>::total(USTAGES)));
-    attr_set = true;
+    attr_done.fetch_or(dev_bit, std::memory_order_release);
   }
   // one CTA per SM: the stage count no longer has to leave room for a second CTA (the ring runs across tile boundaries); the
   // full-size ring also keeps a second CTA (and its 2 * BN TMEM columns) off the SM

@@ -710,11 +710,12 @@ bool ue_fused_supported(const iisan_ue_desc& D) {
 
 template <bool TC>
 static int fused_forward_t(const FuArgs& a, int grid, cudaStream_t st) {
-  static bool attr_set = false;
+  static std::atomic<uint64_t> attr_done{0};      // devices on which the attribute has been set
   const size_t smem = FuSmem<TC>::kFwdFloats * sizeof(float);
-  if (!attr_set) {
+  const uint64_t dev_bit = device_bit();
+  if (!(attr_done.load(std::memory_order_acquire) & dev_bit)) {
     IISAN_CUDA_OK(cudaFuncSetAttribute(ue_fused_fwd_kernel<TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
+    attr_done.fetch_or(dev_bit, std::memory_order_release);
   }
   { LaunchScope ls_(IISAN_K_USER, st); ue_fused_fwd_kernel<TC><<<grid, FTHREADS, smem, st>>>(a); }
   IISAN_LAUNCH_OK();
@@ -722,11 +723,12 @@ static int fused_forward_t(const FuArgs& a, int grid, cudaStream_t st) {
 }
 template <bool TC>
 static int fused_backward_t(const FuArgs& a, int grid, cudaStream_t st) {
-  static bool attr_set = false;
+  static std::atomic<uint64_t> attr_done{0};      // devices on which the attribute has been set
   const size_t smem = FuSmem<TC>::kBwdFloats * sizeof(float);
-  if (!attr_set) {
+  const uint64_t dev_bit = device_bit();
+  if (!(attr_done.load(std::memory_order_acquire) & dev_bit)) {
     IISAN_CUDA_OK(cudaFuncSetAttribute(ue_fused_bwd_kernel<TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
+    attr_done.fetch_or(dev_bit, std::memory_order_release);
   }
   { LaunchScope ls_(IISAN_K_USER, st); ue_fused_bwd_kernel<TC><<<grid, FTHREADS, smem, st>>>(a); }
   IISAN_LAUNCH_OK();
