@@ -159,3 +159,45 @@ def test_versa_real_shapes_parameter_abi_plan_and_descriptors():
         with pytest.raises(_lib.IisanLibraryError):
             binder.desc(torch.empty(n_items, 3, cfg.d_img, device="meta"), torch.empty(n_items, 3, cfg.d_text, device="meta"),
                         _lib.COMPUTE_FP32)
+
+
+@pytest.mark.parametrize("tree", ["Code_Cached", "Code_Cached_Asym"])
+def test_state_dict_equals_reference_checkpoint_layout(tree, tmp_path):
+    """SURVEY 8f-4 / 8b "Parameter ABI": ``state_dict()`` of the drop-in model has the keys, shapes, dtypes and order of the
+    reference model's (tests/golden/state_dict_keys.json, frozen from the reference's own ModelMM + IISANAdaptedMModel by
+    oracle/make_golden_statedict.py), so an ``epoch-N.pt`` (utils.py:104-110: model_state_dict / optimizer / rng_state /
+    cuda_rng_state) written by either side loads into the other (run.py:234-243)."""
+    import json
+    from oracle.synthetic import PathConfig, make_args
+    z = json.load(open(os.path.join(ROOT, "tests", "golden", "state_dict_keys.json")))[tree]
+    cfg = PathConfig(**z["cfg"])
+    if cfg.asym:
+        from iisan_b200 import model_asym as pkg
+    else:
+        from iisan_b200 import model as pkg
+    args = make_args(cfg)
+
+    class Img(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.classifier = nn.Linear(cfg.d_img, cfg.embedding_dim)
+
+    def build():
+        m = pkg.ModelMM(args, 50, True, Img(), nn.Identity(), [1.0] * 51)
+        m.mm_encoder = pkg.IISANAdaptedMModel(m.mm_encoder, args)
+        return m
+
+    m = build()
+    got = [[k, list(v.shape), str(v.dtype)] for k, v in m.state_dict().items()]
+    assert got == z["entries"]
+    # the reference's checkpoint dict, written here and loaded the way run.py:234-243 does (strict key matching)
+    opt = torch.optim.Adam(m.parameters(), lr=1e-3)
+    path = tmp_path / "epoch-3.pt"
+    torch.save({"model_state_dict": m.state_dict(), "optimizer": opt.state_dict(), "rng_state": torch.get_rng_state(),
+                "cuda_rng_state": torch.ByteTensor(8)}, path)
+    ck = torch.load(path, map_location=torch.device("cpu"))
+    m2 = build()
+    missing, unexpected = m2.load_state_dict(ck["model_state_dict"])
+    assert not missing and not unexpected
+    for (k, a), (_, b) in zip(m.state_dict().items(), m2.state_dict().items()):
+        assert torch.equal(a, b), k
