@@ -201,3 +201,35 @@ def test_state_dict_equals_reference_checkpoint_layout(tree, tmp_path):
     assert not missing and not unexpected
     for (k, a), (_, b) in zip(m.state_dict().items(), m2.state_dict().items()):
         assert torch.equal(a, b), k
+
+
+@pytest.mark.parametrize("tree", ["Code_Cached", "Code_Cached_Asym"])
+def test_lr_groups_equal_reference_routing(tree):
+    """the learning rate of every parameter as routed by the reference's own training script (the substring tests
+    of Code_Cached/run.py:260-307, executed from /root/reference by oracle/make_golden_lr_groups.py over the reference model's
+    parameter names and frozen in tests/golden/lr_groups.json) equals what iisan_b200.optim.param_groups assigns -- the groups
+    FusedAdam / torch.optim.Adam are built from."""
+    import argparse
+    import json
+    from iisan_b200.optim import param_groups
+    z = json.load(open(os.path.join(ROOT, "tests", "golden", "lr_groups.json")))[tree]
+    names = list(z["lr_of"].keys())
+
+    class Param:
+        requires_grad = True
+
+    params = {n: Param() for n in names}
+
+    class Named:
+        def named_parameters(self):
+            return list(params.items())
+
+    groups = param_groups(Named(), argparse.Namespace(**z["lrs"]))
+    assert [len(g["params"]) for g in groups] == z["group_sizes"]
+    got = {}
+    for g in groups:
+        for p in g["params"]:
+            name = next(n for n, q in params.items() if q is p)
+            assert name not in got
+            got[name] = g["lr"]
+    assert got == z["lr_of"]
