@@ -313,6 +313,17 @@ int iisan_stage_states_h2d(const void* host_src, void* dev_dst, int64_t n_rows, 
 int iisan_eval_ranks(const float* prec, const float* item_embs, const int64_t* targets, const int64_t* history, int32_t users,
                      int32_t n_items1, int32_t emb, int32_t hist_len, int32_t* ranks, iisan_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Measurement probe (not on the product path; scripts/probe_tile_stream.py): issues the TMA box loads of the fused chain
+ * kernels' hidden-state tiles and nothing else.  base: bf16 [n_rows, layers, d] (contiguous == 0: the reference layout, a
+ * tile = 128 segments of 128 B at the row pitch layers*d*2) or the same number of [128, 64] tiles stored back to back
+ * (contiguous != 0).  One CTA per 128 rows walks sel[0..n_sel) x d/64 chunks `repeat` times through a ring of `slots` tiles.
+ * sink: 8 writable device bytes.  Replaces nothing in the reference: it measures the ceiling of streaming
+ * CC/run.py:373-374's [B, 11, 13, 768] tensors in place.
+ * ------------------------------------------------------------------------------------------- */
+int iisan_probe_tile_stream(const void* base, int64_t n_rows, int32_t layers, int32_t d, const int32_t* sel, int32_t n_sel,
+                            int32_t slots, int32_t repeat, int32_t contiguous, void* sink, iisan_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
