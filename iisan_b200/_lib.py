@@ -17,7 +17,8 @@ K_STREAM, K_GEMM, K_USER, K_CE, K_MISC, K_CHAIN, K_CHAIN_BWD = range(7)
 KERNEL_CLASSES = ("stream", "gemm", "user", "ce", "misc", "chain", "chain_bwd")
 COMPUTE_FP32, COMPUTE_BF16 = 0, 1
 
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libiisan_b200.so")
+# IISAN_B200_LIB: load an instrumented build variant instead (iisan_b200/build.py; debugging aid, same ABI)
+_LIB_PATH = os.environ.get("IISAN_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libiisan_b200.so")
 
 vp = C.c_void_p
 

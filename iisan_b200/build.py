@@ -16,13 +16,18 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
-OBJDIR = os.path.join(HERE, "build")
-LIB = os.path.join(LIBDIR, "libiisan_b200.so")
+# Build variants (debug aids; the product is the default variant).  IISAN_B200_BUILD_VARIANT=trace compiles the chain kernels
+# with wait-time accounting (-DIISAN_CHAIN_TRACE, san_chain.cu) into lib/libiisan_b200_trace.so; load it with
+# IISAN_B200_LIB=<path> (iisan_b200/_lib.py), see scripts/chain_trace.py.
+VARIANT = os.environ.get("IISAN_B200_BUILD_VARIANT", "")
+VARIANT_FLAGS = {"": [], "trace": ["-DIISAN_CHAIN_TRACE"]}[VARIANT]
+OBJDIR = os.path.join(HERE, "build" + ("_" + VARIANT if VARIANT else ""))
+LIB = os.path.join(LIBDIR, "libiisan_b200" + ("_" + VARIANT if VARIANT else "") + ".so")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-         "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--expt-relaxed-constexpr", "-I", INCLUDE]
+         "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--expt-relaxed-constexpr", "-I", INCLUDE, *VARIANT_FLAGS]
 
 
 def sources():

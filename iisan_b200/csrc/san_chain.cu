@@ -46,6 +46,38 @@ constexpr int CH_W_BYTES = CH_CW * CH_R * 2;         // 8 KB
 constexpr int CH_TMEM_COLS = 256;
 constexpr int CH_ZACC = 0, CH_UACC = 64;     // TMEM columns: z (dz) accumulator, two chunk accumulators
 
+// ---- optional wait-time accounting (build variant "trace": -DIISAN_CHAIN_TRACE, see iisan_b200/build.py and
+// scripts/chain_trace.py).  The middle CTA of every tower adds, per role and wait site, the cycles spent in the wait and the
+// number of waits.  Roles: 0 weight producer, 1 MMA / store thread, 2 data producer, 3 one epilogue thread.  In the default
+// build the macros vanish and the kernels are unchanged. ----
+#ifdef IISAN_CHAIN_TRACE
+constexpr int CH_TR_ROLES = 4, CH_TR_SITES = 16;
+__device__ unsigned long long g_chain_trace[2][3][CH_TR_ROLES][CH_TR_SITES][2];   // [fwd|bwd][tower][role][site]{cycles, count}
+#define CH_T0() const long long ch_t0_ = clock64()
+#define CH_T1(pass, role, site)                                                                   \
+  do {                                                                                            \
+    if (blockIdx.x == gridDim.x / 2) {                                                            \
+      g_chain_trace[pass][blockIdx.y][role][site][0] += (unsigned long long)(clock64() - ch_t0_); \
+      g_chain_trace[pass][blockIdx.y][role][site][1] += 1ull;                                     \
+    }                                                                                             \
+  } while (0)
+#define CH_T1E(pass, site) do { if (threadIdx.x == 96) CH_T1(pass, 3, site); } while (0)        /* first epilogue thread */
+#define CH_TT0() const long long ch_tt0_ = clock64()
+#define CH_TT1(pass, role)                                                                                       \
+  do {                                                                                                           \
+    if (blockIdx.x == gridDim.x / 2) {                                                                           \
+      g_chain_trace[pass][blockIdx.y][role][CH_TR_SITES - 1][0] += (unsigned long long)(clock64() - ch_tt0_);    \
+      g_chain_trace[pass][blockIdx.y][role][CH_TR_SITES - 1][1] += 1ull;                                         \
+    }                                                                                                            \
+  } while (0)
+#else
+#define CH_TT0() do {} while (0)
+#define CH_TT1(pass, role) do {} while (0)
+#define CH_T0() do {} while (0)
+#define CH_T1(pass, role, site) do {} while (0)
+#define CH_T1E(pass, site) do {} while (0)
+#endif
+
 struct ChainSmem {
   static constexpr int kZ = 0;                                   // z / dz operand [128 x 64]
   static constexpr int kXk = kZ + CH_TILE_BYTES;                 // 2 chunk operands (x_{s+1}[c], resp. dy_{s-1}[c])
@@ -156,7 +188,7 @@ __global__ void __launch_bounds__(CF_THREADS, 1) san_chain_fwd_kernel(const __gr
         const int sv = u / NC - 1, c = u % NC;
         const int slot = u % CH_NW; const uint32_t ph = (uint32_t)(u / CH_NW) & 1u;
         const bool has_wu = sv >= 0, has_wd = sv + 1 < A;
-        mbar_wait(&B.w_empty[slot], ph ^ 1u);
+        { CH_T0(); mbar_wait(&B.w_empty[slot], ph ^ 1u); CH_T1(0, 0, 0); }
         uint8_t* dst = smem + ChainSmem::kW + slot * 2 * CH_W_BYTES;
         mbar_expect_tx(&B.w_full[slot], (has_wu ? CH_W_BYTES : 0) + (has_wd ? CH_W_BYTES : 0));
         if (has_wu) tma_load_2d(dst, &T.map_wu, &B.w_full[slot], 0, sv * a.d + c * CH_CW);                 // Wu_sv rows [c*64, +64), all r
@@ -168,7 +200,7 @@ __global__ void __launch_bounds__(CF_THREADS, 1) san_chain_fwd_kernel(const __gr
     if (elect_one()) {
       int slot = 0; uint32_t ph = 0;
       auto load = [&](const CUtensorMap* m, int col, int row) {
-        mbar_wait(&B.h_empty[slot], ph ^ 1u);
+        { CH_T0(); mbar_wait(&B.h_empty[slot], ph ^ 1u); CH_T1(0, 2, 0); }
         mbar_expect_tx(&B.h_full[slot], CH_TILE_BYTES);
         tma_load_2d(smem + ChainSmem::kH + slot * CH_TILE_BYTES, m, &B.h_full[slot], col, row);
         if (++slot == CH_NH) { slot = 0; ph ^= 1u; }
@@ -192,6 +224,7 @@ __global__ void __launch_bounds__(CF_THREADS, 1) san_chain_fwd_kernel(const __gr
   } else if (warp == 1) {
     // ===================== MMA issuer + TMA stores =====================
     if (elect_one()) {
+      CH_TT0();
       constexpr uint32_t idesc = instr_desc_bf16(CH_ROWS, 64, 0, 0);   // [128 x 64] (+)= A (K-major) x B^T (K-major), K = 64
       const uint32_t sz = smem_u32(smem + ChainSmem::kZ);
       int n_x = 0, n_u = 0;
@@ -199,7 +232,7 @@ __global__ void __launch_bounds__(CF_THREADS, 1) san_chain_fwd_kernel(const __gr
       auto down = [&](int unit, int c, int sx, bool with_last) {
         const int b = n_x & 1; const uint32_t ph = (uint32_t)(n_x >> 1) & 1u;
         const int slot = unit % CH_NW;
-        mbar_wait(&B.xk_full[b], ph);
+        { CH_T0(); mbar_wait(&B.xk_full[b], ph); CH_T1(0, 1, 0); }
         tc_fence_after();
         const uint8_t* xk = smem + ChainSmem::kXk + b * CH_TILE_BYTES;
         tma_store_2d(&T.map_x, xk, c * CH_CW, sx * NP + m0);
@@ -210,16 +243,15 @@ __global__ void __launch_bounds__(CF_THREADS, 1) san_chain_fwd_kernel(const __gr
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           mma_bf16_ss(tmem_base + CH_ZACC, smem_desc_sw128(sx_a + k * 32, 16, 1024), smem_desc_sw128(sw + k * 32, 16, 1024), idesc, (c > 0 || k > 0) ? 1u : 0u);
-        bulk_wait_read0();                           // the stores have read their tiles: the buffers are free once the MMAs retire
-        bulk_wait_3();                               // stores older than 3 chunks are complete in memory (re-read 9+ chunks later)
-        mma_commit(&B.xk_empty[b]);
-        mma_commit(&B.w_empty[slot]);
+        { CH_T0(); bulk_wait_read0(); CH_T1(0, 1, 1); }   // the stores have read their tiles: the buffers are free once the MMAs retire
+        { CH_T0(); bulk_wait_3(); CH_T1(0, 1, 2); }       // stores older than 3 chunks are complete in memory (re-read 9+ chunks later)
+        { CH_T0(); mma_commit(&B.xk_empty[b]); mma_commit(&B.w_empty[slot]); CH_T1(0, 1, 3); }
         ++n_x;
       };
       // final stage: only last_{A-1}[c] sits in lk[b]
       auto flush_last = [&](int c) {
         const int b = n_x & 1; const uint32_t ph = (uint32_t)(n_x >> 1) & 1u;
-        mbar_wait(&B.xk_full[b], ph);
+        { CH_T0(); mbar_wait(&B.xk_full[b], ph); CH_T1(0, 1, 4); }
         tma_store_2d(&T.map_last, smem + ChainSmem::kLk + b * CH_TILE_BYTES, c * CH_CW, (A - 1) * NP + m0);
         bulk_commit();
         bulk_wait_read0();
@@ -228,21 +260,21 @@ __global__ void __launch_bounds__(CF_THREADS, 1) san_chain_fwd_kernel(const __gr
       };
       for (int c = 0; c < NC; ++c) {                 // x_0 chunks arrive from the epilogue warps
         const int unit = c; const uint32_t wph = (uint32_t)(unit / CH_NW) & 1u;
-        mbar_wait(&B.w_full[unit % CH_NW], wph);
+        { CH_T0(); mbar_wait(&B.w_full[unit % CH_NW], wph); CH_T1(0, 1, 5); }
         down(unit, c, 0, false);
       }
       mma_commit(B.z_full);
       for (int s = 0; s < A; ++s) {
         const bool more = s + 1 < A;
-        mbar_wait(B.z_ready, (uint32_t)s & 1u);
+        { CH_T0(); mbar_wait(B.z_ready, (uint32_t)s & 1u); CH_T1(0, 1, 6); }
         tc_fence_after();
         tma_store_2d(&T.map_z, smem + ChainSmem::kZ, 0, s * NP + m0);   // z_s stash
         bulk_commit();
         for (int c = 0; c < NC; ++c) {
           const int unit = (s + 1) * NC + c; const int slot = unit % CH_NW; const uint32_t wph = (uint32_t)(unit / CH_NW) & 1u;
           const int b = n_u & 1; const uint32_t uph = (uint32_t)(n_u >> 1) & 1u;
-          mbar_wait(&B.w_full[slot], wph);
-          mbar_wait(&B.u_empty[b], uph ^ 1u);
+          { CH_T0(); mbar_wait(&B.w_full[slot], wph); CH_T1(0, 1, 5); }
+          { CH_T0(); mbar_wait(&B.u_empty[b], uph ^ 1u); CH_T1(0, 1, 7); }
           tc_fence_after();
           const uint32_t sw = smem_u32(smem + ChainSmem::kW + slot * 2 * CH_W_BYTES);
 #pragma unroll
@@ -261,10 +293,12 @@ __global__ void __launch_bounds__(CF_THREADS, 1) san_chain_fwd_kernel(const __gr
         else flush_last(NC - 1);
       }
       bulk_wait_0();
+      CH_TT1(0, 1);
     }
   } else {
     // ===================== epilogue warps =====================
     constexpr int NCOL = CF_NCOL, NQ = NCOL / 8;   // NQ 16-byte groups of 8 bf16 per thread and tile
+    CH_TT0();
     const int ew = warp - 3;                  // 0..15
     const int quad = warp & 3;                // TMEM lane quadrant
     const int cq = ew >> 2;                   // which NCOL of the chunk's 64 columns
@@ -281,7 +315,7 @@ __global__ void __launch_bounds__(CF_THREADS, 1) san_chain_fwd_kernel(const __gr
     // x chunk (or, in the final stage, the last chunk) -> swizzled shared memory; signals the MMA / store thread
     auto emit = [&](const float (&xv)[NCOL], bool is_x) {
       const int b = n_x & 1; const uint32_t ph = (uint32_t)(n_x >> 1) & 1u;
-      mbar_wait(&B.xk_empty[b], ph ^ 1u);
+      { CH_T0(); mbar_wait(&B.xk_empty[b], ph ^ 1u); CH_T1E(0, 0); }
       put_tile(smem + (is_x ? ChainSmem::kXk : ChainSmem::kLk) + b * CH_TILE_BYTES, xv);
       fence_proxy_async_smem();
       __syncwarp();
@@ -290,7 +324,7 @@ __global__ void __launch_bounds__(CF_THREADS, 1) san_chain_fwd_kernel(const __gr
     };
     int h_slot = 0; uint32_t h_ph = 0;
     auto read_h = [&](float* hv) {            // this thread's NCOL columns of the next ring tile
-      mbar_wait(&B.h_full[h_slot], h_ph);
+      { CH_T0(); mbar_wait(&B.h_full[h_slot], h_ph); CH_T1E(0, 1); }
       const uint8_t* tile = smem + ChainSmem::kH + h_slot * CH_TILE_BYTES + sw_row;
 #pragma unroll
       for (int q = 0; q < NQ; ++q) unpack8(*reinterpret_cast<const uint4*>(tile + (((cq * NQ + q) ^ (m & 7)) << 4)), hv + q * 8);
@@ -330,7 +364,7 @@ __global__ void __launch_bounds__(CF_THREADS, 1) san_chain_fwd_kernel(const __gr
       const bool more = s + 1 < A;
       // ---- z_s = relu(zacc + bd) -> A operand (the MMA thread also stores it to the stash) ----
       {
-        mbar_wait(B.z_full, (uint32_t)s & 1u);
+        { CH_T0(); mbar_wait(B.z_full, (uint32_t)s & 1u); CH_T1E(0, 2); }
         tc_fence_after();
         float zv[NCOL];
         tmem_cols(CH_ZACC, zv);
@@ -359,7 +393,7 @@ __global__ void __launch_bounds__(CF_THREADS, 1) san_chain_fwd_kernel(const __gr
         float xr[NCOL];
         read_h(xr);                            // residual x_s[c]
         const int b = n_u & 1; const uint32_t uph = (uint32_t)(n_u >> 1) & 1u;
-        mbar_wait(&B.u_full[b], uph);
+        { CH_T0(); mbar_wait(&B.u_full[b], uph); CH_T1E(0, 3); }
         tc_fence_after();
         float lv[NCOL];
         tmem_cols((uint32_t)(CH_UACC + b * 64), lv);
@@ -390,6 +424,7 @@ __global__ void __launch_bounds__(CF_THREADS, 1) san_chain_fwd_kernel(const __gr
         }
       }
     }
+    if (threadIdx.x == 96) CH_TT1(0, 3);
   }
   tc_fence_before();
   __syncthreads();
@@ -434,7 +469,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) san_chain_bwd_kernel(const __gr
         const int sv = A - 1 - j;                         // j = -1 -> A
         const int slot = u % CH_NW; const uint32_t ph = (uint32_t)(u / CH_NW) & 1u;
         const bool has_wd = j >= 0, has_wu = sv - 1 >= 0;
-        mbar_wait(&B.w_empty[slot], ph ^ 1u);
+        { CH_T0(); mbar_wait(&B.w_empty[slot], ph ^ 1u); CH_T1(1, 0, 0); }
         uint8_t* dst = smem + ChainSmem::kW + slot * 2 * CH_W_BYTES;
         mbar_expect_tx(&B.w_full[slot], (has_wd ? CH_W_BYTES : 0) + (has_wu ? CH_W_BYTES : 0));
         if (has_wd) tma_load_2d(dst, &T.map_wd, &B.w_full[slot], c * CH_CW, sv * CH_R);                       // Wd_sv[:, chunk] : [r, 64]
@@ -446,7 +481,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) san_chain_bwd_kernel(const __gr
     if (elect_one()) {
       int slot = 0; uint32_t ph = 0;
       auto load = [&](const CUtensorMap* m, int col, int row) {
-        mbar_wait(&B.h_empty[slot], ph ^ 1u);
+        { CH_T0(); mbar_wait(&B.h_empty[slot], ph ^ 1u); CH_T1(1, 2, 0); }
         mbar_expect_tx(&B.h_full[slot], CH_TILE_BYTES);
         tma_load_2d(smem + ChainSmem::kH + slot * CH_TILE_BYTES, m, &B.h_full[slot], col, row);
         if (++slot == CH_NH) { slot = 0; ph ^= 1u; }
@@ -464,6 +499,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) san_chain_bwd_kernel(const __gr
   } else if (warp == 1) {
     // ===================== MMA issuer + TMA stores =====================
     if (elect_one()) {
+      CH_TT0();
       constexpr uint32_t idesc = instr_desc_bf16(CH_ROWS, 64, 0, 1);   // A K-major, B MN-major ([K, N] row-major weight tiles)
       const uint32_t sz = smem_u32(smem + ChainSmem::kZ);
       int n_x = 0, n_u = 0;
@@ -471,7 +507,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) san_chain_bwd_kernel(const __gr
       auto dzacc_step = [&](int unit, int c, int sp, bool store) {
         const int b = n_x & 1; const uint32_t ph = (uint32_t)(n_x >> 1) & 1u;
         const int slot = unit % CH_NW;
-        mbar_wait(&B.xk_full[b], ph);
+        { CH_T0(); mbar_wait(&B.xk_full[b], ph); CH_T1(1, 1, 0); }
         tc_fence_after();
         const uint8_t* xk = smem + ChainSmem::kXk + b * CH_TILE_BYTES;
         if (store) { tma_store_2d(&T.map_dy, xk, c * CH_CW, sp * NP + m0); bulk_commit(); }
@@ -480,29 +516,28 @@ __global__ void __launch_bounds__(CH_THREADS, 1) san_chain_bwd_kernel(const __gr
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           mma_bf16_ss(tmem_base + CH_ZACC, smem_desc_sw128(sx + k * 32, 16, 1024), smem_desc_sw128(sw + k * 2048, 8192, 1024), idesc, (c > 0 || k > 0) ? 1u : 0u);
-        if (store) { bulk_wait_read0(); bulk_wait_3(); }
-        mma_commit(&B.xk_empty[b]);
-        mma_commit(&B.w_empty[slot]);
+        if (store) { { CH_T0(); bulk_wait_read0(); CH_T1(1, 1, 1); } { CH_T0(); bulk_wait_3(); CH_T1(1, 1, 2); } }
+        { CH_T0(); mma_commit(&B.xk_empty[b]); mma_commit(&B.w_empty[slot]); CH_T1(1, 1, 3); }
         ++n_x;
       };
       for (int c = 0; c < NC; ++c) {
         const int unit = c; const uint32_t wph = (uint32_t)(unit / CH_NW) & 1u;
-        mbar_wait(&B.w_full[unit % CH_NW], wph);
+        { CH_T0(); mbar_wait(&B.w_full[unit % CH_NW], wph); CH_T1(1, 1, 5); }
         dzacc_step(unit, c, A - 1, false);
       }
       mma_commit(B.z_full);
       for (int j = 0; j < A; ++j) {
         const int s = A - 1 - j;
         const bool more = s > 0;
-        mbar_wait(B.z_ready, (uint32_t)j & 1u);
+        { CH_T0(); mbar_wait(B.z_ready, (uint32_t)j & 1u); CH_T1(1, 1, 6); }
         tc_fence_after();
         tma_store_2d(&T.map_dz, smem + ChainSmem::kZ, 0, s * NP + m0);   // dz_s stash (wgrad operand)
         bulk_commit();
         for (int c = 0; c < NC; ++c) {
           const int unit = (j + 1) * NC + c; const int slot = unit % CH_NW; const uint32_t wph = (uint32_t)(unit / CH_NW) & 1u;
           const int b = n_u & 1; const uint32_t uph = (uint32_t)(n_u >> 1) & 1u;
-          mbar_wait(&B.w_full[slot], wph);
-          mbar_wait(&B.u_empty[b], uph ^ 1u);
+          { CH_T0(); mbar_wait(&B.w_full[slot], wph); CH_T1(1, 1, 5); }
+          { CH_T0(); mbar_wait(&B.u_empty[b], uph ^ 1u); CH_T1(1, 1, 7); }
           tc_fence_after();
           const uint32_t sw = smem_u32(smem + ChainSmem::kW + slot * 2 * CH_W_BYTES);
 #pragma unroll
@@ -516,9 +551,11 @@ __global__ void __launch_bounds__(CH_THREADS, 1) san_chain_bwd_kernel(const __gr
         if (more) { dzacc_step((j + 1) * NC + NC - 1, NC - 1, s - 1, true); mma_commit(B.z_full); }
       }
       bulk_wait_0();
+      CH_TT1(1, 1);
     }
   } else {
     // ===================== epilogue warps =====================
+    CH_TT0();
     const int ew = warp - 3;
     const int quad = warp & 3;
     const int hf = ew >> 2;
@@ -536,7 +573,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) san_chain_bwd_kernel(const __gr
       for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4*>(tile + (((hf * 4 + q) ^ (m & 7)) << 4)) = pack8(v + q * 8);
     };
     auto read_tile = [&](float* hv) {                 // this thread's 32 columns of the next ring tile (zeros for rows past N)
-      mbar_wait(&B.h_full[h_slot], h_ph);
+      { CH_T0(); mbar_wait(&B.h_full[h_slot], h_ph); CH_T1E(1, 1); }
       const uint8_t* tile = smem + ChainSmem::kH + h_slot * CH_TILE_BYTES + sw_row;
 #pragma unroll
       for (int q = 0; q < 4; ++q) unpack8(*reinterpret_cast<const uint4*>(tile + (((hf * 4 + q) ^ (m & 7)) << 4)), hv + q * 8);
@@ -550,7 +587,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) san_chain_bwd_kernel(const __gr
     };
     auto emit = [&](const float* xv) {                // bf16 chunk -> A operand (the MMA thread stores it to the stash)
       const int b = n_x & 1; const uint32_t ph = (uint32_t)(n_x >> 1) & 1u;
-      mbar_wait(&B.xk_empty[b], ph ^ 1u);
+      { CH_T0(); mbar_wait(&B.xk_empty[b], ph ^ 1u); CH_T1E(1, 0); }
       put_tile(smem + ChainSmem::kXk + b * CH_TILE_BYTES, xv);
       fence_proxy_async_smem();
       __syncwarp();
@@ -569,7 +606,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) san_chain_bwd_kernel(const __gr
       const bool more = s > 0;
       // ---- dz_s = dz_acc * (z_s > 0) ----
       {
-        mbar_wait(B.z_full, (uint32_t)j & 1u);
+        { CH_T0(); mbar_wait(B.z_full, (uint32_t)j & 1u); CH_T1E(1, 2); }
         tc_fence_after();
         uint32_t raw[32];
         tmem_ld_32x32(tmem_base + lane_addr + (uint32_t)(CH_ZACC + hf * 32), raw);
@@ -601,7 +638,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) san_chain_bwd_kernel(const __gr
         const bool has_aux = is_mm || more;
         if (has_aux) read_tile(av);
         const int b = n_u & 1; const uint32_t uph = (uint32_t)(n_u >> 1) & 1u;
-        mbar_wait(&B.u_full[b], uph);
+        { CH_T0(); mbar_wait(&B.u_full[b], uph); CH_T1E(1, 3); }
         tc_fence_after();
         uint32_t raw[32];
         tmem_ld_32x32(tmem_base + lane_addr + (uint32_t)(CH_UACC + b * 64 + hf * 32), raw);
@@ -634,6 +671,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) san_chain_bwd_kernel(const __gr
       const float gfac = (!is_mm && more) ? g / 0.1f : g * omg / 0.1f;
       if (lane == 0) atomicAdd(T.g_gate[s], gpart * gfac);
     }
+    if (threadIdx.x == 96) CH_TT1(1, 3);
   }
   tc_fence_before();
   __syncthreads();
@@ -707,3 +745,19 @@ int launch_san_chain_fwd(const ChainArgs& args, int n_towers, cudaStream_t st) {
 }
 
 }  // namespace iisan
+
+#ifdef IISAN_CHAIN_TRACE
+// trace build only (not declared in include/iisan_b200.h): copy the wait-time counters to the host, optionally clearing them.
+// layout: [fwd|bwd][tower text|img|mm][role][site]{cycles, count}, site 15 = lifetime of the role's thread
+extern "C" int iisan_debug_chain_trace_read(unsigned long long* host_out, int reset) {
+  using namespace iisan;
+  if (!host_out) return IISAN_EINVAL;
+  IISAN_CUDA_OK(cudaDeviceSynchronize());
+  IISAN_CUDA_OK(cudaMemcpyFromSymbol(host_out, g_chain_trace, sizeof(g_chain_trace)));
+  if (reset) {
+    static unsigned long long zeros[sizeof(g_chain_trace) / sizeof(unsigned long long)];
+    IISAN_CUDA_OK(cudaMemcpyToSymbol(g_chain_trace, zeros, sizeof(g_chain_trace)));
+  }
+  return IISAN_OK;
+}
+#endif
