@@ -18,3 +18,8 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-store --no-graph > gpurun_out/r2a_ncu_bench.log 2>&1; echo "ncu list rc=$?"
 ncu --set full --clock-control none --import-source on -k regex:ce_tile -s 6 -c 2 -o gpurun_out/r2a_ce \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-store --no-graph > gpurun_out/r2a_ncu_ce.log 2>&1; echo "ncu ce rc=$?"
+# 6. (only if the trace variant was built before the call: IISAN_B200_BUILD_VARIANT=trace python -m iisan_b200.build)
+#    measurement #2 of DESIGN.md 4.1: where the chain kernels wait, per role and wait site
+if [ -f iisan_b200/lib/libiisan_b200_trace.so ]; then
+  IISAN_B200_LIB=$PWD/iisan_b200/lib/libiisan_b200_trace.so python scripts/chain_trace.py 512 > gpurun_out/r2a_chain_trace.json 2> gpurun_out/r2a_chain_trace.err; echo "trace rc=$?"
+fi
