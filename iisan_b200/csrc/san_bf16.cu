@@ -98,8 +98,10 @@ struct CastList {
 // ------------------------------------------------------------------------------------------------
 // The fused chain kernel (san_chain.cu) covers the symmetric configurations: equal widths, r = 64, bf16 cached states, every
 // tower active in every stage (no group layer-drop), towers starting from zero.
+// d >= 640 (ten 64-column chunks): the kernels re-read their own stash one stage after writing it, ordered by the distance
+// between the write and the re-read (san_chain.cu header); narrower states fall back to the layered path.
 static bool san_chain_eligible(const iisan_san_desc& D) {
-  if (D.d_text != D.d_img || D.d_text % 64 || D.r_text != 64 || D.r_img != 64 || D.r_mm != 64) return false;
+  if (D.d_text != D.d_img || D.d_text % 64 || D.d_text < 640 || D.r_text != 64 || D.r_img != 64 || D.r_mm != 64) return false;
   if (D.state_dtype != IISAN_BF16 || D.remove_first || D.n_stages > kChainMaxStages) return false;
   for (int s = 0; s < D.n_stages; ++s)
     if (D.text_adapter[s] < 0 || D.img_adapter[s] < 0 || D.mm_index[s] < 0) return false;

@@ -191,8 +191,8 @@ class PipelinedTrainStep:
         self.n_run = 0
         enc = getattr(model, "mm_encoder", None)
         plan = getattr(enc, "plan", None)
-        self.sel_img = list(plan.layers_img_sel) if plan is not None else None
-        self.sel_text = list(plan.layers_text_sel) if plan is not None else None
+        self.sel_img = list(plan.layers_img_read) if plan is not None else None      # incl. layer 0 under remove_first
+        self.sel_text = list(plan.layers_text_read) if plan is not None else None
 
     def submit(self, ids, image=None, text=None, log_mask=None):
         """With a store attached the batch is ``submit(ids, log_mask=log_mask)``: only ids and mask cross the host link."""

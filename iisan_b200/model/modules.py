@@ -65,7 +65,7 @@ class TransformerEncoder(nn.Module):
         self._cfg = (d_model, n_heads, n_layers, float(dropout))
         self._binder = None
         self._step_dev = None
-        self.dropout_seed = 0x5EED1154
+        self.dropout_seed = None         # derived on first use from torch's seed and the rank (see _dropout_stream)
 
     def _bind(self):
         if self._binder is None:
@@ -74,19 +74,44 @@ class TransformerEncoder(nn.Module):
             self._binder = UserEncoderBinder(names, d_model, n_heads, n_layers, p)
         return self._binder
 
+    # ---- dropout stream: Philox keyed by (seed, step counter) ----
+    def _dropout_stream(self, device):
+        """Seed = torch's global seed (torch.manual_seed, i.e. the reference's setup_seed, run.py:465-472) mixed with the rank, so
+        that seeding the run seeds the masks and the ranks of a data-parallel job draw different masks.  The step counter lives on
+        the device (advanced by a stream-ordered add: valid eagerly and under CUDA-graph replay)."""
+        if self.dropout_seed is None:
+            rank = 0
+            if torch.distributed.is_available() and torch.distributed.is_initialized():
+                rank = torch.distributed.get_rank()
+            self.dropout_seed = (0x5EED1154 ^ int(torch.initial_seed()) ^ (rank * 0x9E3779B97F4A7C15)) & ((1 << 62) - 1)
+        if self._step_dev is None or self._step_dev.device != device:
+            self._step_dev = torch.zeros(1, dtype=torch.int64, device=device)
+        return self._step_dev
+
+    def dropout_state(self):
+        """(seed, step) of the dropout stream, for checkpoints (kept OUT of state_dict(): its keys are the reference's)."""
+        return {"seed": self.dropout_seed, "step": None if self._step_dev is None else int(self._step_dev.item())}
+
+    def load_dropout_state(self, st, device=None):
+        self.dropout_seed = st.get("seed")
+        if st.get("step") is not None:
+            dev = device if device is not None else next(self.parameters()).device
+            self._step_dev = torch.full((1,), int(st["step"]), dtype=torch.int64, device=dev)
+
     def forward(self, input_embs, log_mask, att_mask=None):
         # att_mask is implied by log_mask (causal + key padding, encoders.py:54-57) and rebuilt in-kernel.
         params = tuple(self.parameters())
         d_model, n_heads, n_layers, p = self._cfg
-        offset = 0
+        offset, seed = 0, 0
         if self.training and p > 0:
-            # Philox offset = a device-side step counter, advanced by a stream-ordered add: the same code path is valid
-            # eagerly and under CUDA-graph replay (a host counter would be frozen into the captured kernel arguments).
-            if self._step_dev is None or self._step_dev.device != input_embs.device:
-                self._step_dev = torch.zeros(1, dtype=torch.int64, device=input_embs.device)
-            self._step_dev += 1
-            offset = self._step_dev
-        return UserEncoderFn.apply(self._bind(), input_embs, log_mask, self.training, self.dropout_seed, offset,
+            # Each forward gets its OWN copy of the advanced counter; the backward regenerates the masks from that copy, so a
+            # second training forward before the first backward (gradient accumulation, two model calls per step) cannot change
+            # the masks of the first (the clone is a stream-ordered device copy: capturable).
+            ctr = self._dropout_stream(input_embs.device)
+            ctr += 1
+            offset = ctr.clone()
+            seed = self.dropout_seed
+        return UserEncoderFn.apply(self._bind(), input_embs, log_mask, self.training, seed, offset,
                                    compute_mode(), *params)
 
 

@@ -47,6 +47,17 @@ class SanPlan:
     def d_mm(self):
         return min(self.d_text, self.d_img)
 
+    # Layers the kernels READ: the selected ones plus, with remove_first, cached layer 0 -- the towers then start from the
+    # embedding output instead of zero (CC/model/model.py:305-308) although layer 0 feeds no adapter stage.  Stores and
+    # partial host-to-device copies must carry these, not just the selected layers.
+    @property
+    def layers_text_read(self):
+        return sorted(set(self.layers_text_sel) | ({0} if self.remove_first else set()))
+
+    @property
+    def layers_img_read(self):
+        return sorted(set(self.layers_img_sel) | ({0} if self.remove_first else set()))
+
 
 def make_plan(args, asym: bool) -> SanPlan:
     """Validate the configuration and lay out the stages.  Unsupported reference options are rejected at
@@ -214,11 +225,11 @@ class SanBinder(_BinderBase):
             raise L.IisanLibraryError("image and text batches disagree on the number of items")
         if di != pl.d_img or dt != pl.d_text:
             raise L.IisanLibraryError(f"hidden widths ({dt},{di}) do not match the module ({pl.d_text},{pl.d_img})")
-        rank_i = {l: k for k, l in enumerate(sorted(set(pl.layers_img_sel)))}
-        rank_t = {l: k for k, l in enumerate(sorted(set(pl.layers_text_sel)))}
+        rank_i = {l: k for k, l in enumerate(pl.layers_img_read)}        # with remove_first layer 0 is packed too (rank 0)
+        rank_t = {l: k for k, l in enumerate(pl.layers_text_read)}
         if packed:
             if li != len(rank_i) or lt != len(rank_t):
-                raise L.IisanLibraryError(f"packed states must hold exactly the selected layers ({len(rank_i)} image, {len(rank_t)} text)")
+                raise L.IisanLibraryError(f"packed states must hold exactly the layers the towers read ({len(rank_i)} image, {len(rank_t)} text)")
         elif max(pl.layers_img_sel) >= li or max(pl.layers_text_sel) >= lt:
             raise L.IisanLibraryError("a selected layer index is outside the cached states")
         key = (n, li, lt, image.dtype, compute, bool(packed))

@@ -80,7 +80,7 @@ class CachedStateStore:
     @classmethod
     def for_model(cls, model, image_states, text_states, **kw):
         plan = model.mm_encoder.plan
-        return cls(image_states, text_states, plan.layers_img_sel, plan.layers_text_sel, **kw)
+        return cls(image_states, text_states, plan.layers_img_read, plan.layers_text_read, **kw)
 
     @staticmethod
     def _pack(states, sel, device, dtype):

@@ -125,3 +125,34 @@ def test_forward_never_reads_workspace_it_did_not_write(n_items, monkeypatch):
         poisoned = model.mm_encoder.embed(img, txt)
     assert torch.isfinite(poisoned).all()
     assert torch.equal(clean, poisoned)
+
+
+@pytest.mark.parametrize("d", [128, 256, 512, 640])
+def test_narrow_equal_widths_poisoned_workspace(d, monkeypatch):
+    """Equal-width Versa configurations with bf16 states and r = 64 below ten 64-column chunks: the fused chain
+    kernels' distance-based stash ordering is not provable there, so san_chain_eligible sends d < 640 to the layered path; d = 640
+    is the narrowest width the chain kernels take.  Either way: poisoned workspace == clean workspace, bit for bit, and the
+    embeddings agree with the oracle within the fast-mode bar."""
+    from iisan_b200 import ops
+    from oracle import iisan_oracle as O
+    from oracle.synthetic import PathConfig, make_params, make_pop_prob
+    from product_util import build_product
+    cfg = PathConfig(item_num=50, asym=True, d_img=d, d_text=d)
+    params = make_params(cfg, 5, perturb=True)
+    model = build_product(cfg, params, make_pop_prob(cfg, 5)).eval()
+    n_items = 300
+    g = torch.Generator(device="cuda").manual_seed(d)
+    img = torch.randn(n_items, 13, d, device="cuda", generator=g).bfloat16()
+    txt = torch.randn(n_items, 13, d, device="cuda", generator=g).bfloat16()
+    with torch.no_grad():
+        clean = model.mm_encoder.embed(img, txt).clone()
+        e_cv, e_tx, e_mm = O.san_forward(O.params_to_torch(params, requires_grad=False), img.float().cpu(), txt.float().cpu(), cfg)
+    ref = torch.cat([e_cv, e_tx, e_mm], dim=1)
+    err = float((clean.cpu() - ref).abs().max() / ref.abs().max())
+    assert err <= 1e-2, err
+    monkeypatch.setattr(ops, "_workspace",
+                        lambda nbytes, device: torch.full((max(int(nbytes), 256),), 0xFF, dtype=torch.uint8, device=device))
+    with torch.no_grad():
+        poisoned = model.mm_encoder.embed(img, txt)
+    assert torch.isfinite(poisoned).all()
+    assert torch.equal(clean, poisoned)

@@ -86,3 +86,61 @@ def test_pipelined_store_runner_trains():
         assert np.allclose(e, p, rtol=0.1), losses
     finally:
         set_compute_mode(None)
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_remove_first_through_store_and_host_pipeline(mode):
+    """remove_first == "TRUE": the towers start from cached layer 0 (CC/model/model.py:305-308) although no adapter stage reads
+    it, so the packed store and the partial H2D copy must carry layer 0 as well (plan.layers_*_read).  Checked against the
+    oracle and against the dense [B, 11, 13, 768] path, with the layers nobody reads poisoned."""
+    from iisan_b200.engine import PipelinedTrainStep
+    from iisan_b200.optim import FusedAdam
+    from iisan_b200.precision import set_compute_mode
+    from iisan_b200.store import CachedStateStore
+    from oracle import iisan_oracle as O
+    from oracle.synthetic import PathConfig, make_ids, make_params, make_pop_prob
+    item_num, B, seed = 120, 12, 17
+    cfg = PathConfig(item_num=item_num, remove_first="TRUE", bert_list="0,2,4,6,8,10")
+    ids, lm = make_ids(B, cfg, seed, "realistic")
+    params = make_params(cfg, seed, perturb=True)
+    pop = make_pop_prob(cfg, seed)
+    g = torch.Generator().manual_seed(seed)
+    img = torch.randn(item_num + 1, 13, 768, generator=g).bfloat16()
+    txt = torch.randn(item_num + 1, 13, 768, generator=g).bfloat16()
+    img[0] = 0; txt[0] = 0
+    idt = torch.from_numpy(ids).view(-1)
+    batch = {"ids": ids, "log_mask": lm, "image": img[idt].view(B, 11, 13, 768).float().numpy(),
+             "text": txt[idt].view(B, 11, 13, 768).float().numpy()}
+    with torch.no_grad():
+        ref = float(O.model_forward(O.params_to_torch(params, requires_grad=False), batch, pop, cfg)["loss"])
+    set_compute_mode(mode)
+    try:
+        model = build_product(cfg, params, pop).eval()
+        plan = model.mm_encoder.plan
+        assert 0 in plan.layers_img_read and 0 in plan.layers_text_read and 0 not in plan.layers_img_sel
+        idc = idt.cuda(); lmc = torch.from_numpy(lm).cuda()
+        dense_i = img.cuda()[idc].view(-1, 11, 13, 768); dense_t = txt.cuda()[idc].view(-1, 11, 13, 768)
+        with torch.no_grad():
+            l_dense = model(idc, dense_i, dense_t, lmc, "cuda")
+            store = CachedStateStore.for_model(model, img, txt)
+            pi, pt = store.gather(idc)
+            assert pi.shape[1] == len(plan.layers_img_read) and pt.shape[1] == len(plan.layers_text_read)
+            l_store = model(idc, pi, pt, lmc, "cuda", packed=True)
+        assert torch.equal(l_dense, l_store)
+        tol = 1e-5 if mode == "fp32" else 1e-2
+        assert abs(float(l_dense) - ref) <= tol * abs(ref), (float(l_dense), ref)
+        # host pipeline: only the read layers cross the link; everything else on the device is NaN
+        opt = FusedAdam(model.parameters(), lr=1e-3)
+        pipe = PipelinedTrainStep(model, opt, use_graph=False)
+        host = (idt.pin_memory(), img[idt].view(B, 11, 13, 768).contiguous().pin_memory(),
+                txt[idt].view(B, 11, 13, 768).contiguous().pin_memory(), torch.from_numpy(lm).pin_memory())
+        pipe.submit(*host)
+        torch.cuda.synchronize()
+        for t, rd in ((pipe.bufs[0][1], plan.layers_img_read), (pipe.bufs[0][2], plan.layers_text_read)):
+            for l in range(13):
+                if l not in rd:
+                    t[:, :, l] = float("nan")
+        l_pipe = pipe.run()
+        assert torch.equal(l_pipe, l_dense), (float(l_pipe), float(l_dense))
+    finally:
+        set_compute_mode(None)

@@ -112,3 +112,43 @@ def test_fused_tensor_core_mode_matches_oracle(B):
     assert rel(xs.grad.cpu(), xr.grad) <= 5e-2
     for n, p in enc.named_parameters():
         assert rel(p.grad.cpu(), P["user_encoder." + n].grad) <= 5e-2, n
+
+
+def test_dropout_masks_survive_a_second_forward_before_backward():
+    """Each training forward snapshots its own dropout counter: the gradient of forward #1 must not depend on
+    whether forward #2 ran before its backward (gradient accumulation, two model calls per step)."""
+    from iisan_b200.precision import set_compute_mode
+    set_compute_mode("fp32")
+    enc = _encoder(0.25).train()
+    te = enc.transformer_encoder
+    x, lm = _inputs(8)
+    w = torch.randn(8, 10, 64, device="cuda") * lm[..., None]
+
+    def grads(interleave):
+        te.load_dropout_state({"seed": 1234, "step": 3})
+        enc.zero_grad(set_to_none=True)
+        xs = x.clone().requires_grad_(True)
+        out1 = enc(xs[:, :-1], lm, "cuda")
+        if interleave:
+            out2 = enc(x[:, :-1], lm, "cuda")                    # advances the live counter
+            assert (out2 - out1).abs().max() > 1e-3              # a different mask
+        (out1 * w).sum().backward()
+        return out1.detach().clone(), xs.grad.clone(), {n: p.grad.clone() for n, p in enc.named_parameters()}
+
+    o_a, gx_a, gp_a = grads(False)
+    o_b, gx_b, gp_b = grads(True)
+    assert torch.equal(o_a, o_b)
+    assert torch.allclose(gx_a, gx_b, rtol=1e-5, atol=1e-7)
+    for n in gp_a:
+        assert torch.allclose(gp_a[n], gp_b[n], rtol=1e-4, atol=1e-6), n
+    assert te.dropout_state()["step"] == 5
+    # seeding: torch.manual_seed decides the stream of a fresh encoder
+    torch.manual_seed(77); e1 = _encoder(0.25, seed=77).train()
+    torch.manual_seed(77); e2 = _encoder(0.25, seed=77).train()
+    torch.manual_seed(78); e3 = _encoder(0.25, seed=77).train()
+    torch.manual_seed(77)
+    y1 = e1(x[:, :-1], lm, "cuda")
+    y2 = e2(x[:, :-1], lm, "cuda")
+    torch.manual_seed(78)
+    y3 = e3(x[:, :-1], lm, "cuda")
+    assert torch.equal(y1, y2) and not torch.equal(y1, y3)
