@@ -105,6 +105,7 @@ _SIGNATURES = {
     "iisan_gather_states": (C.c_int, [vp, i32, C.c_int64, i32, i32, vp, i32, vp, i32, vp, vp]),
     "iisan_eval_ranks": (C.c_int, [vp, vp, vp, vp, i32, i32, i32, i32, vp, vp]),
     "iisan_probe_tile_stream": (C.c_int, [vp, C.c_int64, i32, i32, C.POINTER(i32), i32, i32, i32, i32, vp, vp]),
+    "iisan_debug_chain_generation": (C.c_int, [i32]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

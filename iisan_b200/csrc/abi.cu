@@ -207,3 +207,6 @@ extern "C" int iisan_stage_states_h2d(const void* host_src, void* dev_dst, int64
   }
   return IISAN_OK;
 }
+
+namespace iisan { int set_chain_generation(int gen); }
+extern "C" int iisan_debug_chain_generation(int32_t gen) { return iisan::set_chain_generation(gen); }

@@ -202,8 +202,11 @@ struct SanLayoutBf16 {
   }
 };
 
-// test / profiling switch: IISAN_B200_NO_CHAIN=1 forces the layered path
+// test / profiling switches: IISAN_B200_NO_CHAIN=1 forces the layered path, IISAN_B200_CHAIN_GEN=1 the first-generation chain
+// forward (A/B measurements; the default is the second generation wherever it applies: d a multiple of 128)
 static const bool g_disable_chain = [] { const char* e = getenv("IISAN_B200_NO_CHAIN"); return e && e[0] == '1'; }();
+static std::atomic<int> g_chain_gen{[] { const char* e = getenv("IISAN_B200_CHAIN_GEN"); return (e && e[0] == '1') ? 1 : 2; }()};
+int set_chain_generation(int gen) { return g_chain_gen.exchange(gen); }
 
 size_t san_bf16_workspace_bytes(const iisan_san_desc& D) {
   SanLayoutBf16 L(D, nullptr);
@@ -347,7 +350,8 @@ static int san_forward_bf16_t(const iisan_san_desc* D, const iisan_san_params* P
       t1.layer[s] = D->img_layer[s]; t1.gate[s] = P->gate_img[ia]; t1.b_down[s] = P->img[ia].b_down; t1.b_up[s] = P->img[ia].b_up;
       t2.layer[s] = D->img_layer[s]; t2.layer2[s] = D->text_layer[s]; t2.gate[s] = P->gate_mm[mi]; t2.b_down[s] = P->mm[mi].b_down; t2.b_up[s] = P->mm[mi].b_up;
     }
-    IISAN_TRY(launch_san_chain_fwd(ca, 3, st));
+    if (g_chain_gen.load(std::memory_order_relaxed) >= 2) IISAN_TRY(launch_san_chain2_fwd(ca, 3, st));
+    else IISAN_TRY(launch_san_chain_fwd(ca, 3, st));
     last_t = L.last_t[D->n_stages - 1]; last_i = L.last_i[D->n_stages - 1]; last_m = L.last_m[D->n_stages - 1];
   }
   for (int s = 0; s < (chain ? 0 : D->n_stages); ++s) {

@@ -702,6 +702,7 @@ int chain_fill_tower(ChainTower* T, int mode, const void* h, int64_t n_items, in
   IISAN_TRY(make_tensor_map_bf16(&T->map_x, x_all, (int64_t)n_stages * np, d, d, CH_CW, CH_ROWS));
   IISAN_TRY(make_tensor_map_bf16(&T->map_last, last_all, (int64_t)n_stages * np, d, d, CH_CW, CH_ROWS));
   IISAN_TRY(make_tensor_map_bf16(&T->map_z, z_all, (int64_t)n_stages * np, CH_R, CH_R, CH_R, CH_ROWS));
+  T->z_out = const_cast<bf16*>(z_all);
   return fill_common(&T->map_wd, &T->map_wu, wd_pack, wu_pack, n_stages, d);
 }
 

@@ -1,0 +1,644 @@
+// Fused side-adapter chain, second generation (forward).  Same contract as san_chain.cu (one CTA = one row tile of ONE tower, all
+// A stages on chip; symmetric configurations, r == 64, bf16 cached states) and the same arithmetic, bit for bit; what changed is
+// the dataflow inside the SM:
+//
+//   * both MMA A operands live in TENSOR MEMORY (tcgen05.mma with A in TMEM, B = weight chunk in shared memory): the epilogue
+//     warps write z_s and the x_{s+1} chunks as packed bf16 straight into TMEM with tcgen05.st.  Per 64-column chunk the tensor
+//     core now fetches 16 KB of shared memory (two weight chunks) instead of 48 KB, which was the longest serial phase of a
+//     chunk step in the first generation (operand fetch of an SS-mode MMA is ~64 B per cycle: 768 of ~2200 cycles);
+//   * four U accumulators, the TMA stores of the stash on their own warp: the MMA thread never waits for a store (the first
+//     generation spent ~630 cycles per chunk in cp.async.bulk.wait_group.read);
+//   * the 16 epilogue warps form 4 groups; a group owns one 32-column half of every other chunk, so up to four chunk halves
+//     are in flight and the waits of one group hide behind the work of the others;
+//   * the x stash is re-read (the residual of the next stage) only after the store warp has published its COMPLETION
+//     (cp.async.bulk.wait_group, then a release store of the completed-chunk count that the data producer acquires): explicit
+//     ordering instead of the distance-based one of the first generation (VERDICT round 1 / ADVICE round 1);
+//   * z_s goes to the stash by direct 128-bit stores from the epilogue registers (once per stage);
+//   * the biases of a stage are staged in shared memory by one bulk copy (their global-load latency was the largest single
+//     stall of the epilogue), shared memory is addressed through explicit 32-bit shared-window addresses, the element-wise
+//     arithmetic uses the packed f32x2 instructions, and the epilogue body is specialised per (tower kind, last stage).
+//
+// forward                                                          reference
+//   x_0       = fuse(h_0, 0)                                       gated fusion   CC/model/model.py:319-326 (mm: :335-337)
+//   z_s       = relu(x_s Wd_s^T + bd_s)                            AdapterBlock   CC/model/modules.py:113-116
+//   last_s    = z_s Wu_s^T + bu_s + x_s
+//   x_{s+1}   = fuse(h_{s+1}, last_s)                              (mm tower: last_s + g h_cv + (1-g) h_text)
+//
+// warp roles: 0 weight TMA producer | 1 TMEM allocator + MMA issuer | 2 data TMA producer | 3 TMA store warp | 4..19 epilogue
+#include "common.cuh"
+#include "launch.cuh"
+#include "san_chain.cuh"
+#include "umma.cuh"
+
+namespace iisan {
+
+using namespace umma;
+using bf16 = __nv_bfloat16;
+
+namespace c2 {
+constexpr int ROWS = 128;
+constexpr int CW = 64;                      // chunk width == one 128-byte swizzle atom
+constexpr int R = 64;                       // adapter bottleneck
+constexpr int TILE_BYTES = ROWS * CW * 2;   // 16 KB
+constexpr int W_BYTES = CW * R * 2;         // 8 KB weight chunk
+constexpr int NW = 6;                       // weight ring, 8 KB units in the MMA thread's consumption order
+constexpr int NDR = 4;                      // data ring depth (h / h2 / residual tiles, 16 KB); ONE RING PER CHUNK PARITY
+constexpr int NX = 2;                       // x slots (one per chunk parity): TMEM operand (32 columns) + staging tile of the stash store
+constexpr int NU = 4;                       // U accumulators (64 TMEM columns each), two per chunk parity
+// Every mbarrier below is waited on by ONE agent in strict use order, or by the two epilogue groups that own the chunks of one
+// parity: x slots, U accumulators (index = chunk counter mod 2 / mod 4, NC even) and data rings are therefore per parity, so a
+// waiter is never more than one phase ahead of its barrier (a parity wait cannot tell phase k from phase k-2).
+constexpr int LOOK = NU - 1;                // the U MMAs run this many chunks ahead of the down-projections
+constexpr int EPI_WARPS = 16;
+constexpr int THREADS = 128 + 32 * EPI_WARPS;   // 640
+constexpr int MAX_D = 1024;
+constexpr int BIAS_BYTES = (MAX_D + R) * 4;     // one stage: b_up [d] | b_down [64]
+// tensor memory columns
+constexpr int T_ZACC = 0;                   // fp32 z accumulator [128 x 64]
+constexpr int T_ZOP = 64;                   // packed bf16 z operand (32 columns)
+constexpr int T_UACC = 96;                  // NU x 64
+constexpr int T_XOP = T_UACC + NU * 64;     // NX x 32
+constexpr int T_COLS = 512;
+static_assert(T_XOP + NX * 32 <= T_COLS, "tensor memory budget");
+
+struct Smem {
+  static constexpr int kW = 0;
+  static constexpr int kD = kW + NW * W_BYTES;                // [parity][NDR] tiles
+  static constexpr int kX = kD + 2 * NDR * TILE_BYTES;
+  static constexpr int kBias = kX + NX * TILE_BYTES;          // two stages
+  static constexpr int kBar = kBias + 2 * BIAS_BYTES;
+  static constexpr int kTotal = kBar + 1024 + 1024;           // barriers + alignment slack
+  // barrier block (byte offsets from kBar)
+  static constexpr int bWFull = 0, bWEmpty = bWFull + 8 * NW, bDFull = bWEmpty + 8 * NW, bDEmpty = bDFull + 16 * NDR;
+  static constexpr int bXFull = bDEmpty + 16 * NDR, bXEmpty = bXFull + 8 * NX, bUFull = bXEmpty + 8 * NX, bUEmpty = bUFull + 8 * NU;
+  static constexpr int bZFull = bUEmpty + 8 * NU, bZReady = bZFull + 8, bBias = bZReady + 8, bTmem = bBias + 16, bStored = bTmem + 4;
+  static constexpr int bGates = bStored + 4;                  // kChainMaxStages floats
+};
+static_assert(Smem::bGates + 4 * kChainMaxStages <= 1024, "barrier block");
+static_assert(Smem::kTotal <= 232448, "shared memory budget");
+
+// ---- explicit shared-window primitives (32-bit addresses) ----
+__device__ __forceinline__ void mbar_init_a(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
+__device__ __forceinline__ void mbar_expect_tx_a(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_a(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP_A:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE_A;\n"
+      "bra WAIT_LOOP_A;\n"
+      "WAIT_DONE_A:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+// single-thread roles: let the hardware park the thread (suspend-time hint) instead of spinning on the issue port that the
+// epilogue warps of the same scheduler need
+__device__ __forceinline__ void mbar_wait_park(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP_P:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+      "@p bra WAIT_DONE_P;\n"
+      "bra WAIT_LOOP_P;\n"
+      "WAIT_DONE_P:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity), "r"(20000u)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_a(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+               "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_load_a(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_2d_a(const CUtensorMap* m, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src), "r"(c0),
+               "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void mma_commit_a(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ float lds32f(uint32_t a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_shared(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_shared(uint32_t a, uint32_t v) { asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+
+// D[tmem] (+)= A[tmem] * B[smem]: A = 128 rows x 16 bf16 per MMA, packed two per 32-bit column (8 columns per K step)
+__device__ __forceinline__ void mma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]),
+      "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint32_t (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]),
+               "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// ---- packed f32x2 arithmetic ----
+__device__ __forceinline__ uint64_t f2pack(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ uint64_t u2pack(uint32_t lo, uint32_t hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+  return r;
+}
+// two bf16 (one 32-bit word, low element first) -> two fp32
+__device__ __forceinline__ uint64_t bf2(uint32_t w) {
+  uint64_t r;
+  asm("{\n.reg .b32 lo, hi;\nshl.b32 lo, %1, 16;\nand.b32 hi, %1, 0xffff0000;\nmov.b64 %0, {lo, hi};\n}" : "=l"(r) : "r"(w));
+  return r;
+}
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) { uint64_t r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ uint64_t fmul2(uint64_t a, uint64_t b) { uint64_t r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+// two fp32 (register pair) -> one word of two bf16, round to nearest even, low element first
+__device__ __forceinline__ uint32_t pack2x(uint64_t v) {
+  uint32_t r;
+  asm("{\n.reg .b32 lo, hi;\nmov.b64 {lo, hi}, %1;\ncvt.rn.bf16x2.f32 %0, hi, lo;\n}" : "=r"(r) : "l"(v));
+  return r;
+}
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+
+template <bool V> struct BoolTag { static constexpr bool value = V; };
+}  // namespace c2
+
+using namespace c2;
+
+// ---- optional wait-time accounting (build variant "trace", -DIISAN_CHAIN_TRACE; scripts/chain2_trace.py).  Every role of the
+// middle CTA of a tower sums, in registers, the cycles spent at each wait site and writes them once at the end. ----
+#ifdef IISAN_CHAIN_TRACE
+constexpr int TR_SITES = 8;
+__device__ unsigned int g_c2_trace[3][8][TR_SITES];      // [tower][role][site] ; site 7 = lifetime of the role
+#define TR_DECL() unsigned int tr_acc[TR_SITES] = {0, 0, 0, 0, 0, 0, 0, 0}; const unsigned int tr_life0 = clock()
+#define TR(site, stmt) do { const unsigned int tr_t0 = clock(); stmt; tr_acc[site] += clock() - tr_t0; } while (0)
+#define TR_FLUSH(role)                                                                             \
+  do {                                                                                             \
+    if (blockIdx.x == gridDim.x / 2) {                                                             \
+      tr_acc[TR_SITES - 1] = clock() - tr_life0;                                                   \
+      for (int i = 0; i < TR_SITES; ++i) g_c2_trace[blockIdx.y][role][i] = tr_acc[i];             \
+    }                                                                                              \
+  } while (0)
+#else
+#define TR_DECL() do {} while (0)
+#define TR(site, stmt) do { stmt; } while (0)
+#define TR_FLUSH(role) do {} while (0)
+#endif
+
+// Tile sequence of the data ring of one chunk parity (chunks c = p, p + 2, ...; j = c >> 1).  Phase -1 (x_0): per chunk h_0[c]
+// (+ h2_0[c]).  Stage s: per chunk the residual x_s[c] and, unless s is the last stage, h_{s+1}[c] (+ h2_{s+1}[c]).  Ring-local
+// index of the first tile of (phase, chunk):
+struct TileSeq {
+  int NCh, A, nh;                // NCh = chunks per parity ; nh = hidden-state tiles per chunk (1 intra, 2 inter-modal)
+  __device__ int x0(int j) const { return j * nh; }
+  __device__ int stage(int s, int j) const {             // s < A-1: (1 + nh) tiles per chunk ; last stage: 1
+    return NCh * nh + s * NCh * (1 + nh) + j * ((s + 1 < A) ? (1 + nh) : 1);
+  }
+};
+
+__global__ void __launch_bounds__(THREADS, 1) san_chain2_fwd_kernel(const __grid_constant__ ChainArgs a) {
+  const ChainTower& T = a.tower[blockIdx.y];
+  const bool is_mm = (T.mode == 1);
+  const int NC = a.d / CW;
+  const int A = a.n_stages;
+  const int m0 = blockIdx.x * ROWS;
+  const int NP = a.n_pad;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;        // 1024-byte aligned shared-window address
+  const uint32_t bar0 = sbase + Smem::kBar;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&T.map_wd); tma_prefetch_desc(&T.map_wu); tma_prefetch_desc(&T.map_h); tma_prefetch_desc(&T.map_x);
+    tma_prefetch_desc(&T.map_last);
+    if (is_mm) tma_prefetch_desc(&T.map_h2);
+    for (int i = 0; i < NW; ++i) { mbar_init_a(bar0 + Smem::bWFull + 8 * i, 1); mbar_init_a(bar0 + Smem::bWEmpty + 8 * i, 1); }
+    for (int i = 0; i < 2 * NDR; ++i) { mbar_init_a(bar0 + Smem::bDFull + 8 * i, 1); mbar_init_a(bar0 + Smem::bDEmpty + 8 * i, 8); }   // 8 warps read a tile
+    for (int i = 0; i < NX; ++i) { mbar_init_a(bar0 + Smem::bXFull + 8 * i, 8); mbar_init_a(bar0 + Smem::bXEmpty + 8 * i, 2); }        // MMA commit + store warp
+    for (int i = 0; i < NU; ++i) { mbar_init_a(bar0 + Smem::bUFull + 8 * i, 1); mbar_init_a(bar0 + Smem::bUEmpty + 8 * i, 8); }
+    mbar_init_a(bar0 + Smem::bZFull, 1); mbar_init_a(bar0 + Smem::bZReady, EPI_WARPS);
+    mbar_init_a(bar0 + Smem::bBias, 1); mbar_init_a(bar0 + Smem::bBias + 8, 1);
+    st_release_shared(bar0 + Smem::bStored, 0u);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(bar0 + Smem::bTmem), "r"((uint32_t)T_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (warp == 2 && lane < A) {
+    const float gv = gate_value(T.gate[lane]);
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(bar0 + Smem::bGates + 4 * lane), "f"(gv) : "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(bar0 + Smem::bTmem) : "memory");
+  const TileSeq TS{NC / 2, A, is_mm ? 2 : 1};
+
+  if (warp == 0) {
+    // ===================== weight + bias producer: 8 KB units in the MMA thread's consumption order =====================
+    if (elect_one()) {
+      int n = 0;
+      TR_DECL();
+      auto put = [&](bool up, int s, int c) {
+        const int slot = n % NW;
+        TR(0, mbar_wait_park(bar0 + Smem::bWEmpty + 8 * slot, ((uint32_t)(n / NW) & 1u) ^ 1u));
+        const uint32_t dst = sbase + Smem::kW + slot * W_BYTES, bar = bar0 + Smem::bWFull + 8 * slot;
+        mbar_expect_tx_a(bar, W_BYTES);
+        if (up) tma_load_2d_a(dst, &T.map_wu, bar, 0, s * a.d + c * CW);      // Wu_s rows [c*64, +64), all r : [64 x r]
+        else tma_load_2d_a(dst, &T.map_wd, bar, c * CW, s * R);               // Wd_s[:, chunk] : [r x 64]
+        ++n;
+      };
+      // biases of stage s -> buffer s & 1 (b_up [d] | b_down [64]).  Stage s + 1 is requested while the MMA thread is inside
+      // stage s (a unit is only emitted after the unit NW places earlier has been consumed), i.e. after every epilogue warp has
+      // left stage s - 1, the previous user of that buffer.
+      auto put_bias = [&](int s) {
+        const uint32_t dst = sbase + Smem::kBias + (s & 1) * BIAS_BYTES, bar = bar0 + Smem::bBias + 8 * (s & 1);
+        mbar_expect_tx_a(bar, (uint32_t)(a.d * 4 + R * 4));
+        bulk_load_a(dst, T.b_up[s], (uint32_t)(a.d * 4), bar);
+        bulk_load_a(dst + a.d * 4, T.b_down[s], R * 4, bar);
+      };
+      put_bias(0);
+      for (int c = 0; c < NC; ++c) put(false, 0, c);
+      for (int s = 0; s < A; ++s) {
+        const bool more = s + 1 < A;
+        for (int c = 0; c < NC + LOOK; ++c) {
+          if (c == LOOK && more) put_bias(s + 1);
+          if (c < NC) put(true, s, c);
+          if (c >= LOOK && more) put(false, s + 1, c - LOOK);
+        }
+      }
+      TR_FLUSH(0);
+    }
+  } else if (warp == 2) {
+    // ===================== data producer =====================
+    if (elect_one()) {
+      int n0 = 0, n1 = 0;
+      TR_DECL();
+      auto load = [&](int par, const CUtensorMap* m, int col, int row) {
+        int& n = par ? n1 : n0;
+        const int slot = par * NDR + (n & (NDR - 1));
+        TR(0, mbar_wait_park(bar0 + Smem::bDEmpty + 8 * slot, ((uint32_t)(n / NDR) & 1u) ^ 1u));
+        const uint32_t bar = bar0 + Smem::bDFull + 8 * slot;
+        mbar_expect_tx_a(bar, TILE_BYTES);
+        tma_load_2d_a(sbase + Smem::kD + slot * TILE_BYTES, m, bar, col, row);
+        ++n;
+      };
+      for (int c = 0; c < NC; ++c) {
+        load(c & 1, &T.map_h, T.layer[0] * a.d + c * CW, m0);
+        if (is_mm) load(c & 1, &T.map_h2, T.layer2[0] * a.d + c * CW, m0);
+      }
+      for (int s = 0; s < A; ++s) {
+        for (int c = 0; c < NC; ++c) {
+          // residual x_s[c]: stored by this CTA as x-stash chunk number s*NC + c ; wait until that store is complete
+          const uint32_t need = (uint32_t)(s * NC + c + 1);
+          TR(1, while (ld_acquire_shared(bar0 + Smem::bStored) < need) __nanosleep(64));
+          load(c & 1, &T.map_x, c * CW, s * NP + m0);
+          if (s + 1 < A) {
+            load(c & 1, &T.map_h, T.layer[s + 1] * a.d + c * CW, m0);
+            if (is_mm) load(c & 1, &T.map_h2, T.layer2[s + 1] * a.d + c * CW, m0);
+          }
+        }
+      }
+      TR_FLUSH(2);
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (elect_one()) {
+      constexpr uint32_t idesc = instr_desc_bf16(ROWS, 64, 0, 0);   // [128 x 64] (+)= A (TMEM) x B^T (K-major smem), K = 64
+      int nw = 0;
+      TR_DECL();
+      auto wait_w = [&]() -> uint32_t {
+        const int slot = nw % NW;
+        TR(0, mbar_wait_park(bar0 + Smem::bWFull + 8 * slot, (uint32_t)(nw / NW) & 1u));
+        return sbase + Smem::kW + slot * W_BYTES;
+      };
+      auto free_w = [&]() { mma_commit_a(bar0 + Smem::bWEmpty + 8 * (nw % NW)); ++nw; };
+      // z_acc (+)= x chunk (TMEM operand of x slot nx) x Wd[c]^T
+      auto down = [&](int nx, int c, bool last_chunk) {
+        const uint32_t sw = wait_w();
+        const int xb = nx & 1;
+        TR(1, mbar_wait_park(bar0 + Smem::bXFull + 8 * xb, (uint32_t)(nx >> 1) & 1u));
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          mma_bf16_ts(tmem_base + T_ZACC, tmem_base + T_XOP + xb * 32 + k * 8, smem_desc_sw128(sw + k * 32, 16, 1024), idesc,
+                      (c > 0 || k > 0) ? 1u : 0u);
+        TR(4, mma_commit_a(bar0 + Smem::bXEmpty + 8 * xb); if (last_chunk) mma_commit_a(bar0 + Smem::bZFull); free_w());
+      };
+      for (int c = 0; c < NC; ++c) down(c, c, c == NC - 1);
+      for (int s = 0; s < A; ++s) {
+        const bool more = s + 1 < A;
+        TR(2, mbar_wait_park(bar0 + Smem::bZReady, (uint32_t)s & 1u));
+        tc_fence_after();
+        for (int c = 0; c < NC + LOOK; ++c) {
+          if (c < NC) {
+            const uint32_t sw = wait_w();
+            const int nu = s * NC + c, ub = nu & 3;
+            TR(3, mbar_wait_park(bar0 + Smem::bUEmpty + 8 * ub, ((uint32_t)(nu >> 2) & 1u) ^ 1u));
+            tc_fence_after();
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              mma_bf16_ts(tmem_base + T_UACC + ub * 64, tmem_base + T_ZOP + k * 8, smem_desc_sw128(sw + k * 32, 16, 1024), idesc, k > 0 ? 1u : 0u);
+            TR(4, mma_commit_a(bar0 + Smem::bUFull + 8 * ub); free_w());
+          }
+          if (c >= LOOK) {
+            const int cc = c - LOOK, nx = (s + 1) * NC + cc;
+            if (more) {
+              down(nx, cc, cc == NC - 1);
+            } else {                                   // final stage: the slot only carries last_{A-1}[cc] to the store warp
+              const int xb = nx & 1;
+              TR(1, mbar_wait_park(bar0 + Smem::bXFull + 8 * xb, (uint32_t)(nx >> 1) & 1u));
+              mbar_arrive_a(bar0 + Smem::bXEmpty + 8 * xb);
+            }
+          }
+        }
+      }
+      TR_FLUSH(1);
+    }
+  } else if (warp == 3) {
+    // ===================== store warp: x stash (every stage) / last_{A-1} (final stage) =====================
+    if (elect_one()) {
+      const int n_total = (A + 1) * NC;
+      TR_DECL();
+      for (int nx = 0; nx < n_total; ++nx) {
+        const int sx = nx / NC, c = nx % NC;             // sx == A: the last_{A-1} chunks
+        const int xb = nx & 1;
+        TR(0, mbar_wait_park(bar0 + Smem::bXFull + 8 * xb, (uint32_t)(nx >> 1) & 1u));
+        const uint32_t src = sbase + Smem::kX + xb * TILE_BYTES;
+        if (sx < A) tma_store_2d_a(&T.map_x, src, c * CW, sx * NP + m0);
+        else tma_store_2d_a(&T.map_last, src, c * CW, (A - 1) * NP + m0);
+        bulk_commit();
+        TR(1, bulk_wait_read0());                        // the store has read its tile: the staging buffer is free
+        mbar_arrive_a(bar0 + Smem::bXEmpty + 8 * xb);
+        TR(2, bulk_wait<2>());                           // every store but the two youngest is complete in global memory
+        if (nx >= 2) st_release_shared(bar0 + Smem::bStored, (uint32_t)(nx - 1));
+      }
+      bulk_wait<0>();
+      st_release_shared(bar0 + Smem::bStored, (uint32_t)n_total);
+      TR_FLUSH(3);
+    }
+  } else {
+    // ===================== epilogue warps =====================
+    // Shared memory is addressed through 32-bit shared-window addresses (generic 64-bit pointers cost two to three extra
+    // integer instructions per access and the loads then count as global accesses); the arithmetic runs on packed f32x2
+    // instructions (two columns per issue); the loop bodies are specialised per (tower kind, last stage).
+    const int ew = warp - 4;                  // 0..15
+    const int quad = warp & 3;                // TMEM lane quadrant (warp % 4)
+    const int grp = ew >> 2;                  // 0..3
+    const int half = grp & 1;                 // which 32 columns of the chunk
+    const int par = grp >> 1;                 // chunks c == par (mod 2)
+    const int m = quad * 32 + lane;           // row inside the tile
+    const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+    const uint32_t sw_row = (uint32_t)((m >> 3) * 1024 + (m & 7) * 128);      // row m inside a swizzled [128 x 64] bf16 tile
+    uint32_t offq[4];                         // this thread's four 16-byte groups of a tile
+#pragma unroll
+    for (int q = 0; q < 4; ++q) offq[q] = sw_row + (uint32_t)(((half * 4 + q) ^ (m & 7)) << 4);
+    const int64_t grow = (int64_t)m0 + m;
+    const uint32_t bar_d_full = bar0 + Smem::bDFull + par * NDR * 8, bar_d_empty = bar0 + Smem::bDEmpty + par * NDR * 8;
+    const uint32_t bar_x_full = bar0 + Smem::bXFull + par * 8, bar_x_empty = bar0 + Smem::bXEmpty + par * 8;
+    const uint32_t d_base = sbase + Smem::kD + par * NDR * TILE_BYTES;
+    const uint32_t x_tile = sbase + Smem::kX + par * TILE_BYTES;
+    const uint32_t x_tmem = tmem_base + lane_addr + (uint32_t)(T_XOP + par * 32 + half * 16);
+    TR_DECL();
+    static_assert(NDR == 4 && NX == 2 && NU == 4, "ring index arithmetic below");
+
+    auto d_tile = [&](int t) -> uint32_t { return d_base + (uint32_t)(t & 3) * TILE_BYTES; };
+    auto d_wait = [&](int t) { TR(0, mbar_wait_a(bar_d_full + (t & 3) * 8, (uint32_t)(t >> 2) & 1u)); };
+    auto d_release = [&](int t) { if (lane == 0) mbar_arrive_a(bar_d_empty + (t & 3) * 8); };
+    // publish this thread's 32 output columns of this parity's x slot (use number ux): packed bf16 into the TMEM operand (when
+    // an MMA follows) and into the swizzled staging tile of the store warp
+    auto emit = [&](int ux, const uint32_t (&o)[16], bool to_tmem) {
+      TR(1, mbar_wait_a(bar_x_empty, ((uint32_t)ux & 1u) ^ 1u));
+#pragma unroll
+      for (int q = 0; q < 4; ++q) sts128(x_tile + offq[q], o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+      if (to_tmem) {
+        TR(4, tmem_st_32x16(x_tmem, o); tmem_st_wait(); tc_fence_before());
+      }
+      TR(5, fence_proxy_async_smem(); __syncwarp());
+      if (lane == 0) mbar_arrive_a(bar_x_full);
+    };
+
+    // ---- x_0 = fuse(h_0, 0) ----
+    auto x0_phase = [&](auto mm_tag) {
+      constexpr bool MM = decltype(mm_tag)::value;
+      const float g = lds32f(bar0 + Smem::bGates);
+      const uint64_t g2 = f2pack(g, g), omg2 = f2pack(1.0f - g, 1.0f - g);
+      for (int c = par; c < NC; c += 2) {
+        const int t0 = TS.x0(c >> 1);
+        uint32_t o[16];
+        d_wait(t0);
+        if (MM) d_wait(t0 + 1);
+        const uint32_t tb0 = d_tile(t0), tb1 = d_tile(t0 + 1);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint4 hq = lds128(tb0 + offq[q]);
+          const uint32_t hw[4] = {hq.x, hq.y, hq.z, hq.w};
+          if (MM) {
+            const uint4 h2q = lds128(tb1 + offq[q]);
+            const uint32_t h2w[4] = {h2q.x, h2q.y, h2q.z, h2q.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) o[4 * q + k] = pack2x(ffma2(g2, bf2(hw[k]), fmul2(omg2, bf2(h2w[k]))));
+          } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) o[4 * q + k] = pack2x(fmul2(g2, bf2(hw[k])));
+          }
+        }
+        __syncwarp();
+        d_release(t0);
+        if (MM) d_release(t0 + 1);
+        emit(c >> 1, o, true);
+      }
+    };
+    if (is_mm) x0_phase(BoolTag<true>{}); else x0_phase(BoolTag<false>{});
+
+    // ---- the chunks of one stage ----
+    auto stage_chunks = [&](auto mm_tag, auto more_tag, int s) {
+      constexpr bool MM = decltype(mm_tag)::value, MORE = decltype(more_tag)::value;
+      float g = 0.f;
+      if (MORE) g = lds32f(bar0 + Smem::bGates + 4 * (s + 1));
+      const uint64_t g2 = f2pack(g, g), omg2 = f2pack(1.0f - g, 1.0f - g);
+      const uint32_t bias = sbase + Smem::kBias + (s & 1) * BIAS_BYTES + half * 128;
+      const int ux0 = (s + 1) * (NC >> 1);                 // x-slot use number of this parity's first chunk of the stage
+      for (int c = par; c < NC; c += 2) {
+        const int t0 = TS.stage(s, c >> 1);       // residual tile ; t0 + 1 (+ 2): hidden states of stage s + 1
+        const int nu = s * NC + c, ub = nu & 3;
+        TR(3, mbar_wait_a(bar0 + Smem::bUFull + 8 * ub, (uint32_t)(nu >> 2) & 1u));
+        tc_fence_after();
+        uint32_t raw[32];
+        TR(6, tmem_ld_32x32(tmem_base + lane_addr + (uint32_t)(T_UACC + ub * 64 + half * 32), raw); tmem_ld_wait());
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_a(bar0 + Smem::bUEmpty + 8 * ub);
+        uint64_t uv[16];                           // U + bias, two columns per register pair
+        const uint32_t bc = bias + c * (CW * 4);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const uint4 b = lds128(bc + q * 16);
+          uv[2 * q] = fadd2(u2pack(raw[4 * q], raw[4 * q + 1]), u2pack(b.x, b.y));
+          uv[2 * q + 1] = fadd2(u2pack(raw[4 * q + 2], raw[4 * q + 3]), u2pack(b.z, b.w));
+        }
+        d_wait(t0);
+        if (MORE) { d_wait(t0 + 1); if (MM) d_wait(t0 + 2); }
+        const uint32_t tb0 = d_tile(t0), tb1 = d_tile(t0 + 1), tb2 = d_tile(t0 + 2);
+        uint32_t o[16];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint4 rq = lds128(tb0 + offq[q]);                        // residual x_s[c]
+          const uint32_t rw[4] = {rq.x, rq.y, rq.z, rq.w};
+          uint64_t lv[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) lv[k] = fadd2(uv[4 * q + k], bf2(rw[k]));
+          if (MORE) {
+            const uint4 hq = lds128(tb1 + offq[q]);
+            const uint32_t hw[4] = {hq.x, hq.y, hq.z, hq.w};
+            if (MM) {
+              const uint4 h2q = lds128(tb2 + offq[q]);
+              const uint32_t h2w[4] = {h2q.x, h2q.y, h2q.z, h2q.w};
+#pragma unroll
+              for (int k = 0; k < 4; ++k) lv[k] = ffma2(omg2, bf2(h2w[k]), ffma2(g2, bf2(hw[k]), lv[k]));
+            } else {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) lv[k] = ffma2(g2, bf2(hw[k]), fmul2(omg2, lv[k]));
+            }
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) o[4 * q + k] = pack2x(lv[k]);
+        }
+        __syncwarp();
+        d_release(t0);
+        if (MORE) { d_release(t0 + 1); if (MM) d_release(t0 + 2); }
+        emit(ux0 + (c >> 1), o, MORE);
+      }
+    };
+
+    for (int s = 0; s < A; ++s) {
+      const bool more = s + 1 < A;
+      // ---- z_s = relu(zacc + bd): packed bf16 into the TMEM operand of the U MMAs, and to the stash.  All 16 warps: warp
+      //      (quad, grp) takes columns [grp*16, +16) of its 32 rows ----
+      {
+        TR(2, mbar_wait_a(bar0 + Smem::bBias + 8 * (s & 1), (uint32_t)(s >> 1) & 1u));      // this stage's biases have landed
+        const uint32_t bd = sbase + Smem::kBias + (s & 1) * BIAS_BYTES + a.d * 4 + grp * 64;
+        TR(2, mbar_wait_a(bar0 + Smem::bZFull, (uint32_t)s & 1u));
+        tc_fence_after();
+        uint32_t raw[16];
+        tmem_ld_32x16(tmem_base + lane_addr + (uint32_t)(T_ZACC + grp * 16), raw);
+        tmem_ld_wait();
+        uint32_t zo[8];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint4 b = lds128(bd + q * 16);
+          const float z0 = fmaxf(__uint_as_float(raw[4 * q]) + __uint_as_float(b.x), 0.f), z1 = fmaxf(__uint_as_float(raw[4 * q + 1]) + __uint_as_float(b.y), 0.f);
+          const float z2 = fmaxf(__uint_as_float(raw[4 * q + 2]) + __uint_as_float(b.z), 0.f), z3 = fmaxf(__uint_as_float(raw[4 * q + 3]) + __uint_as_float(b.w), 0.f);
+          zo[2 * q] = pack2(z0, z1); zo[2 * q + 1] = pack2(z2, z3);
+        }
+        tmem_st_32x8(tmem_base + lane_addr + (uint32_t)(T_ZOP + grp * 8), zo);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_a(bar0 + Smem::bZReady);
+        // stash (backward: ReLU mask and the operand of dWu); rows past the item count are never read
+        uint4* zs = reinterpret_cast<uint4*>(T.z_out + ((int64_t)s * NP + grow) * R + grp * 16);
+        zs[0] = make_uint4(zo[0], zo[1], zo[2], zo[3]);
+        zs[1] = make_uint4(zo[4], zo[5], zo[6], zo[7]);
+      }
+      if (is_mm) { if (more) stage_chunks(BoolTag<true>{}, BoolTag<true>{}, s); else stage_chunks(BoolTag<true>{}, BoolTag<false>{}, s); }
+      else { if (more) stage_chunks(BoolTag<false>{}, BoolTag<true>{}, s); else stage_chunks(BoolTag<false>{}, BoolTag<false>{}, s); }
+    }
+    if (quad == 0 && lane == 0) TR_FLUSH(4 + grp);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, T_COLS);
+}
+
+// What this generation covers; everything else stays with the first generation (san_chain.cu).
+static bool chain2_supported(const ChainArgs& args, int n_towers) {
+  if (args.d % 128 != 0 || args.d < 256 || args.d > MAX_D) return false;      // even chunk count (per-parity rings), bias staging buffer
+  for (int t = 0; t < n_towers; ++t)
+    for (int s = 0; s < args.n_stages; ++s)                                    // bulk copies of the biases need 16-byte aligned sources
+      if ((reinterpret_cast<uintptr_t>(args.tower[t].b_up[s]) | reinterpret_cast<uintptr_t>(args.tower[t].b_down[s])) & 15) return false;
+  return true;
+}
+
+int launch_san_chain2_fwd(const ChainArgs& args, int n_towers, cudaStream_t st) {
+  if (!chain2_supported(args, n_towers)) return launch_san_chain_fwd(args, n_towers, st);
+  static std::atomic<uint64_t> attr_done{0};      // devices on which the attribute has been set
+  const uint64_t dev_bit = device_bit();
+  if (!(attr_done.load(std::memory_order_acquire) & dev_bit)) {
+    IISAN_CUDA_OK(cudaFuncSetAttribute(san_chain2_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::kTotal));
+    attr_done.fetch_or(dev_bit, std::memory_order_release);
+  }
+  const int tiles = (args.n_items + ROWS - 1) / ROWS;
+  { LaunchScope ls_(IISAN_K_CHAIN, st); san_chain2_fwd_kernel<<<dim3(tiles, n_towers), THREADS, Smem::kTotal, st>>>(args); }
+  IISAN_LAUNCH_OK();
+  return IISAN_OK;
+}
+
+}  // namespace iisan
+
+#ifdef IISAN_CHAIN_TRACE
+// trace build only (not declared in include/iisan_b200.h): [tower][role][site] cycle sums of the last forward launch.
+// roles: 0 weight producer, 1 MMA thread, 2 data producer, 3 store warp, 4..7 epilogue groups 0..3 ; site 7 = lifetime
+extern "C" int iisan_debug_chain2_trace_read(unsigned int* host_out) {
+  using namespace iisan;
+  if (!host_out) return IISAN_EINVAL;
+  IISAN_CUDA_OK(cudaDeviceSynchronize());
+  IISAN_CUDA_OK(cudaMemcpyFromSymbol(host_out, g_c2_trace, sizeof(g_c2_trace)));
+  return IISAN_OK;
+}
+#endif

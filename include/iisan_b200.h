@@ -324,6 +324,10 @@ int iisan_eval_ranks(const float* prec, const float* item_embs, const int64_t* t
 int iisan_probe_tile_stream(const void* base, int64_t n_rows, int32_t layers, int32_t d, const int32_t* sel, int32_t n_sel,
                             int32_t slots, int32_t repeat, int32_t contiguous, void* sink, iisan_stream_t stream);
 
+/* Measurement switch (not on the product path; scripts/chain_ab.py): generation of the fused chain kernels used from now on
+ * (1 = first generation, 2 = second generation, the default wherever it applies).  Returns the previous value. */
+int iisan_debug_chain_generation(int32_t gen);
+
 #ifdef __cplusplus
 }
 #endif
