@@ -27,10 +27,21 @@ sys.path.insert(0, ROOT)
 
 METRIC = "iisan_cached_train_samples_per_s"
 UNIT = "samples/s"
-ITEM_NUM = 19246          # Instrument catalogue
+ITEM_NUM = 19246          # Instrument catalogue (BASELINE configs[1]); N > 1 uses the Office catalogue (configs[2])
+ITEM_NUM_OFFICE = 22785
 SEED = 12345              # reference seed (Code_Cached/scripts/run_IISAN.py:44)
-# dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed ncu --set full capture (profiles/), per launch
-TRAFFIC_NCU = {"fwd": 296.7e6, "bwd": 433.2e6}   # profiles/r01d_chain_ncu_full.txt
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the chain kernels: read from the newest committed ncu summary that
+# names them (profiles/*_chain_traffic.json, written by scripts/ncu_traffic.py from an `ncu --set full` capture of this commit's
+# kernels); the file name travels into the JSON line.  None when no such file exists.
+def ncu_traffic():
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_chain_traffic.json")))
+    if not files:
+        return {}, None
+    try:
+        return json.load(open(files[-1])), os.path.relpath(files[-1], ROOT)
+    except Exception:
+        return {}, None
 LRS = dict(lr=2e-4, adapter_cv_lr=1e-4, adapter_bert_lr=1e-4, fine_tune_lr_image=1e-4, fine_tune_lr_text=5e-5)
 
 
@@ -48,13 +59,28 @@ def parse():
     ap.add_argument("--no-store", action="store_true", help="skip the HBM-resident store e2e measurement")
     ap.add_argument("--no-graph", action="store_true", help="run the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--negatives", default="global", choices=["global", "local"],
-                    help="N > 1: in-batch negative pool (global = item-embedding all-gather, BASELINE configs[2]; local = the reference's DDP semantics)")
+                    help="N > 1: in-batch negative pool of the headline value (global = item-embedding all-gather, BASELINE configs[2]; "
+                         "local = the reference's DDP semantics); the other mode is measured too and reported under its own key")
+    ap.add_argument("--reps", type=int, default=10, help="repetitions of the timed --steps block; the median is reported")
+    ap.add_argument("--item-num", type=int, default=0, help="catalogue size (default: Instrument 19,246 at N=1, Office 22,785 at N>1)")
     return ap.parse_args()
 
 
 # ----------------------------------------------------------------------------------------------------------------
 # CPU arm: the reference algorithm (oracle port) on the host cores
 # ----------------------------------------------------------------------------------------------------------------
+def cpu_reference_loss(params_np, batch_np, pop, item_num):
+    """Forward of the oracle on GIVEN parameters / batch (the GPU arm's initial replica and its first batch): the self-check of
+    the bench line (loss_ref_step0 vs loss_gpu_step0)."""
+    import torch
+    from oracle import iisan_oracle as O
+    from oracle.synthetic import PathConfig
+    cfg = PathConfig(item_num=item_num)
+    with torch.no_grad():
+        out = O.model_forward(O.params_to_torch(params_np, requires_grad=False), batch_np, pop, cfg)
+    return float(out["loss"])
+
+
 def cpu_reference_steps(batch, steps, warmup):
     """fwd + bwd + Adam of the oracle restatement (fp32, all host threads).  Returns (samples/s, s/step, cores)."""
     import numpy as np
@@ -86,8 +112,9 @@ def cpu_reference_steps(batch, steps, warmup):
     return sps, sum(times) / len(times), cores, float(out["loss"].item())
 
 
-def workload_name(batch, stored):
-    return (f"IISAN(Cached) Instrument shape: item_num {ITEM_NUM}, B={batch} users/GPU x 11 slots, BERT-base+ViT-B/16 "
+def workload_name(batch, stored, item_num=ITEM_NUM):
+    shape = {ITEM_NUM: "Instrument", ITEM_NUM_OFFICE: "Office"}.get(item_num, "custom")
+    return (f"IISAN(Cached) {shape} shape: item_num {item_num}, B={batch} users/GPU x 11 slots, BERT-base+ViT-B/16 "
             f"cached states [13,768] stored {stored}, 7 of 13 layers, r=64, E=64, random-init adapters, "
             f"dense batch, fwd+bwd+Adam")
 
@@ -197,7 +224,7 @@ def bind_to_gpu_numa_node(local):
     return None
 
 
-def build_model(device, compute):
+def build_model(device, compute, item_num=ITEM_NUM):
     import torch
     from torch import nn
     from iisan_b200 import model as pkg
@@ -214,19 +241,19 @@ def build_model(device, compute):
 
     import numpy as np
     rng = np.random.default_rng(SEED)
-    counts = np.floor(1.0 + rng.pareto(1.2, size=ITEM_NUM) * 3.0)
+    counts = np.floor(1.0 + rng.pareto(1.2, size=item_num) * 3.0)
     pop = np.concatenate([[1.0], counts / counts.sum()]).astype("float32")
-    m = pkg.ModelMM(args, ITEM_NUM, True, ImgStub(), nn.Identity(), pop)
+    m = pkg.ModelMM(args, item_num, True, ImgStub(), nn.Identity(), pop)
     m.mm_encoder = pkg.IISANAdaptedMModel(m.mm_encoder, args)          # Code_Cached/run.py:182-183
     set_compute_mode(compute)
     return m.to(device), args, cfg
 
 
-def make_device_batches(n, B, device, dtype, gen):
+def make_device_batches(n, B, device, dtype, gen, item_num=ITEM_NUM):
     import torch
     out = []
     for _ in range(n):
-        ids = torch.randint(1, ITEM_NUM + 1, (B * 11,), device=device, generator=gen, dtype=torch.int64)
+        ids = torch.randint(1, item_num + 1, (B * 11,), device=device, generator=gen, dtype=torch.int64)
         image = torch.randn(B, 11, 13, 768, device=device, generator=gen, dtype=torch.float32).to(dtype)
         text = torch.randn(B, 11, 13, 768, device=device, generator=gen, dtype=torch.float32).to(dtype)
         lm = torch.ones(B, 10, device=device, dtype=torch.float32)
@@ -236,6 +263,7 @@ def make_device_batches(n, B, device, dtype, gen):
 
 def run_ours(a):
     import ctypes as C
+    import numpy as np
     import torch
     import torch.distributed as dist
     from iisan_b200 import _lib
@@ -249,11 +277,10 @@ def run_ours(a):
     numa = bind_to_gpu_numa_node(local) if world > 1 else None      # N = 1 keeps every core for the cpu_baseline leg
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
+    item_num = a.item_num or (ITEM_NUM if world == 1 else ITEM_NUM_OFFICE)
     state_dtype = torch.bfloat16 if a.compute == "bf16" else torch.float32
-    model, args, cfg = build_model(device, a.compute)
-    model.train()
+    model, args, cfg = build_model(device, a.compute, item_num)
     if world > 1:
-        model.negatives = a.negatives                                # "global": BASELINE configs[2], item-embedding all-gather
         for p in model.parameters():                                 # same initial replica on every rank (DDP does this at wrap time)
             dist.broadcast(p.data, 0)
     use_graph = not a.no_graph
@@ -261,68 +288,103 @@ def run_ours(a):
     gen = torch.Generator(device=device).manual_seed(SEED + rank)
     B = a.batch
     n_rot = 3                                               # 3 x 225 MB (bf16) rotating inputs >> 126 MB L2
-    batches = make_device_batches(n_rot, B, device, state_dtype, gen)
+    batches = make_device_batches(n_rot, B, device, state_dtype, gen, item_num)
     group = dist.group.WORLD if world > 1 else None
+    dbg = (lambda m: print(f"[bench rank {rank}] {m}", file=sys.stderr, flush=True)) if os.environ.get("IISAN_BENCH_DEBUG") else (lambda m: None)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(n, fn):
+    def timed(n, fn, reps=1):
+        """`reps` back-to-back blocks of `n` steps, each block between its own pair of CUDA events; barrier + synchronize on both
+        sides of the whole region; per block the MAX over ranks; returns (median block ms, all block ms, t0, t1, last result)."""
         barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
         t0 = time.time()
-        e0.record()
-        for i in range(n):
-            last = fn(i)
-        e1.record()
+        ev[0].record()
+        k = 0
+        for r in range(reps):
+            for _ in range(n):
+                last = fn(k); k += 1
+            ev[r + 1].record()
         barrier()
-        ms = e0.elapsed_time(e1)
+        t1 = time.time()
+        blocks = [ev[r].elapsed_time(ev[r + 1]) for r in range(reps)]
         if world > 1:
-            t = torch.tensor([ms], device=device)
+            t = torch.tensor(blocks, device=device)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms, t0, time.time(), last
+            blocks = [float(v) for v in t.tolist()]
+        return statistics.median(blocks), blocks, t0, t1, last
+
+    # ---- step 0 self-check: forward of the INITIAL replica on batch 0 (eval mode: no dropout), compared below with the CPU arm
+    #      run on the very same parameters / ids / states / popularity table ----
+    model.eval()
+    with torch.no_grad():
+        loss_gpu_step0 = float(model(*batches[0], device).item())
+    selfcheck = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        selfcheck = {"params": {n: p.detach().float().cpu().numpy() for n, p in model.named_parameters()},
+                     "batch": {"ids": batches[0][0].view(B, 11).cpu().numpy(), "log_mask": batches[0][3].cpu().numpy(),
+                               "image": batches[0][1].float().cpu().numpy(), "text": batches[0][2].float().cpu().numpy()},
+                     "pop": model.pop_prob_list.detach().float().cpu().numpy()}
+    model.train()
 
     # ---- launches per step, counted on one eager step ----
     eager = TrainStep(model, opt, use_graph=False, group=group)
+    if world > 1:
+        model.negatives = a.negatives
     eager(*batches[0])
     torch.cuda.synchronize()
     l0 = lib.iisan_launch_count(-1)
     eager(*batches[1])
     torch.cuda.synchronize()
     launches_per_step = lib.iisan_launch_count(-1) - l0
+    dbg("eager ok")
 
     # ---- the timed arm: inputs resident in HBM; one captured graph per resident batch (no staging copies) ----
-    dbg = (lambda m: print(f"[bench rank {rank}] {m}", file=sys.stderr, flush=True)) if os.environ.get("IISAN_BENCH_DEBUG") else (lambda m: None)
-    dbg("eager ok")
-    runners_ref = []
-    if use_graph:
-        runners = runners_ref = [TrainStep(model, opt, use_graph=True, group=group) for _ in range(n_rot)]
-        for r, bt in zip(runners, batches):
-            r.capture(*bt)
-            dbg("captured")
-        step = lambda i: runners[i % n_rot].replay()
-    else:
-        step = lambda i: eager(*batches[i % n_rot])
-    for i in range(max(a.warmup, 3)):
-        step(i)
+    keep = []                                                # graphs hold NCCL work: released explicitly at shutdown
+
+    def measure(negatives):
+        if world > 1:
+            model.negatives = negatives
+        if use_graph:
+            runners = [TrainStep(model, opt, use_graph=True, group=group) for _ in range(n_rot)]
+            keep.extend(runners)
+            for r, bt in zip(runners, batches):
+                r.capture(*bt)
+            step = lambda i: runners[i % n_rot].replay()
+        else:
+            step = lambda i: eager(*batches[i % n_rot])
+        for i in range(max(a.warmup, 3)):
+            step(i)
+        return step
+
     sampler = ClockSampler(local) if rank == 0 else None
+    step = measure(a.negatives)
     if sampler:
         sampler.start(); time.sleep(0.3)
     dbg("warm")
-    ms, t0, t1, last = timed(a.steps, step)
+    ms, blocks, t0, t1, last = timed(a.steps, step, a.reps)
     dbg("timed")
     if sampler:
         time.sleep(0.2); sampler.stop()
     clocks = sampler.summary(t0, t1) if sampler else None
     value = world * B * a.steps / (ms / 1e3)
     loss_val = float(last.item())
+    other = None
+    if world > 1:                                            # the other negative-pool definition, same run
+        om = "local" if a.negatives == "global" else "global"
+        ostep = measure(om)
+        oms, oblocks, _, _, _ = timed(a.steps, ostep, a.reps)
+        other = {"negatives": om, "value": world * B * a.steps / (oms / 1e3), "unit": UNIT, "ms_per_step": oms / a.steps,
+                 "block_ms_min_max": [min(oblocks), max(oblocks)]}
+        model.negatives = a.negatives
 
     # ---- per-kernel-class device time: K eager steps with CUDA events around every library launch ----
     lib.iisan_timing_enable(1)
-    ms_prof, _, _, _ = timed(a.steps, lambda i: eager(*batches[i % n_rot]))
+    ms_prof, _, _, _, _ = timed(a.steps, lambda i: eager(*batches[i % n_rot]))
     lib.iisan_timing_enable(0)
     classes = {}
     for k, name in enumerate(_lib.KERNEL_CLASSES):
@@ -330,34 +392,89 @@ def run_ours(a):
         lib.iisan_timing_read(k, C.byref(tot), C.byref(n))
         classes[name] = {"ms_per_step": tot.value / a.steps, "launches_per_step": n.value / a.steps}
 
-    # ---- end-to-end through the public API with HOST buffers: pinned batch -> H2D -> step -> loss read back ----
+    # ---- exposed communication (N > 1): the local-negatives step with and without its gradient all-reduce ----
+    exposed = None
+    if world > 1 and use_graph:
+        model.negatives = "local"
+        runners = [TrainStep(model, opt, use_graph=True, group=False) for _ in range(n_rot)]      # group=False: no collectives at all
+        for r, bt in zip(runners, batches):
+            r.capture(*bt)
+        for i in range(3):
+            runners[i % n_rot].replay()
+        nms, _, _, _, _ = timed(a.steps, lambda i: runners[i % n_rot].replay(), max(3, a.reps // 2))
+        local_ms = (ms if a.negatives == "local" else other["ms_per_step"] * a.steps) / a.steps
+        exposed = {"ms_per_step_no_collectives": nms / a.steps, "ms_per_step_local_negatives": local_ms,
+                   "exposed_comm_ms": local_ms - nms / a.steps,
+                   "note": "local in-batch negatives: captured step with the gradient all-reduce minus the same step without any collective"}
+        runners = None
+        model.negatives = a.negatives
     host = []
     for ids, image, text, lm in batches[:2]:
         host.append(tuple(t.cpu().pin_memory() for t in (ids, image, text, lm)))
-    h2d = sum(t.numel() * t.element_size() for t in host[0])
-    e2e_runner = PipelinedTrainStep(model, opt, group=group, use_graph=use_graph)
-    e2e_runner.submit(*host[0])
-    n_sel = len(set(model.mm_encoder.plan.layers_img_sel)) + len(set(model.mm_encoder.plan.layers_text_sel))
-    h2d = sum(t.numel() * t.element_size() for t in (host[0][0], host[0][3])) + B * 11 * n_sel * 768 * host[0][1].element_size()
-
-    def e2e_step(i):
-        e2e_runner.submit(*host[(i + 1) % len(host)])                    # H2D of the next batch (selected layers) on the copy stream
-        loss = e2e_runner.run()                                          # step on the batch submitted one call earlier
-        return loss.item()                                               # D2H read of the result (run.py:382,387)
-
-    for i in range(4):
-        e2e_step(i)
     e2e_steps = max(3, min(a.steps, 20))
-    ms_e2e, _, _, _ = timed(e2e_steps, e2e_step)
-    e2e_value = world * B * e2e_steps / (ms_e2e / 1e3)
+
+    # ---- end to end, the product path (north_star subsystem 1): the cached states of the whole catalogue are packed once into
+    #      HBM (selected layers only); a batch is (ids, log_mask) from pinned host memory, the per-item / per-layer gather runs on
+    #      the device inside the captured step; the loss is read back every step ----
+    e2e = None
+    if not a.no_store:
+        from iisan_b200.store import CachedStateStore
+        tab = lambda: torch.randn(item_num + 1, 13, 768, device=device, generator=gen, dtype=torch.float32).to(state_dtype)
+        store = CachedStateStore.for_model(model, tab(), tab(), device=device, dtype=state_dtype)
+        srunner = PipelinedTrainStep(model, opt, group=group, use_graph=use_graph, store=store)
+        hids = [(h[0], h[3]) for h in host]
+        srunner.submit(hids[0][0], log_mask=hids[0][1])
+
+        def store_step(i):
+            hi, hl = hids[(i + 1) % len(hids)]
+            srunner.submit(hi, log_mask=hl)                                  # H2D of the next batch's ids + log_mask
+            return srunner.run().item()                                      # step + D2H read of the loss
+
+        for i in range(4):
+            store_step(i)
+        ms_st, st_blocks, _, _, _ = timed(e2e_steps, store_step, min(a.reps, 5))
+        e2e = {"value": world * B * e2e_steps / (ms_st / 1e3), "unit": UNIT, "ms_per_step": ms_st / e2e_steps,
+               "h2d_bytes_per_step": sum(t.numel() * t.element_size() for t in hids[0]), "d2h_bytes_per_step": 4,
+               "path": "HBM-resident cached-state store",
+               "store_bytes_hbm": int(store.image.numel() * store.image.element_size() + store.text.numel() * store.text.element_size()),
+               "note": "PipelinedTrainStep(store=CachedStateStore), the public API of the cached hidden-state path: the 7+7 selected layers "
+                       "of the whole catalogue are resident in HBM; every timed step copies one batch of ids + log_mask from pinned HOST "
+                       "memory, gathers per item and layer on the device inside the captured step, and reads the loss back"}
+        srunner = None
+        keep.append(store)
+
+    # ---- end to end from HOST batches of the reference shapes [B,11,13,768] (Code_Cached/run.py:368-377 as is): bound by the
+    #      host link (the selected layers of one batch are 121 MB in bf16) ----
+    def host_batch_e2e(hb, label):
+        runner = PipelinedTrainStep(model, opt, group=group, use_graph=use_graph)
+        keep.append(runner)
+        runner.submit(*hb[0])
+        n_sel = len(set(model.mm_encoder.plan.layers_img_read)) + len(set(model.mm_encoder.plan.layers_text_read))
+        nbytes = sum(t.numel() * t.element_size() for t in (hb[0][0], hb[0][3])) + B * 11 * n_sel * 768 * hb[0][1].element_size()
+
+        def fn(i):
+            runner.submit(*hb[(i + 1) % len(hb)])                            # H2D of the next batch (selected layers) on the copy stream
+            return runner.run().item()                                       # step on the batch submitted one call earlier + loss read-back
+
+        for i in range(3):
+            fn(i)
+        ms_h, _, _, _, _ = timed(e2e_steps, fn, 3)
+        return {"value": world * B * e2e_steps / (ms_h / 1e3), "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": 4,
+                "ms_per_step": ms_h / e2e_steps, "host_link_gbs": nbytes / (ms_h / e2e_steps / 1e3) / 1e9, "host_dtype": label}
+
+    e2e_host = host_batch_e2e(host, str(state_dtype).split(".")[-1])
+    e2e_host["note"] = ("PipelinedTrainStep.submit/run with pinned HOST batch tensors of the reference shapes: every timed step issues the "
+                        "H2D copy of one batch (ids, log_mask, the 7+7 selected layers) and reads one loss back; the copy of batch i+1 "
+                        "overlaps the step of batch i")
+    if e2e is None:
+        e2e = dict(e2e_host, path="host batches")
 
     def shutdown():
         """Release the captured graphs (they hold NCCL work) before tearing the process group down; a process that still
         cannot finalise NCCL within 20 s exits anyway (the JSON line is already out)."""
         if world == 1:
             return
-        nonlocal runners_ref, e2e_runner
-        runners_ref.clear(); e2e_runner = None
+        keep.clear()
         torch.cuda.synchronize()
         sys.stdout.flush(); sys.stderr.flush()
         t = threading.Timer(20.0, lambda: os._exit(0))
@@ -368,32 +485,6 @@ def run_ours(a):
             dist.destroy_process_group()
         finally:
             t.cancel()
-
-    # ---- end-to-end with the HBM-resident cached-state store: a batch is (ids, log_mask) only, the layer-selecting gather runs on
-    #      the device inside the captured step (iisan_b200.store) ----
-    e2e_store = None
-    if not a.no_store:
-        from iisan_b200.store import CachedStateStore
-        tab = lambda: torch.randn(ITEM_NUM + 1, 13, 768, device=device, generator=gen, dtype=torch.float32).to(state_dtype)
-        store = CachedStateStore.for_model(model, tab(), tab(), device=device, dtype=state_dtype)
-        srunner = PipelinedTrainStep(model, opt, group=group, use_graph=use_graph, store=store)
-        hids = [(h[0], h[3]) for h in host]
-        srunner.submit(hids[0][0], log_mask=hids[0][1])
-
-        def store_step(i):
-            hi, hl = hids[(i + 1) % len(hids)]
-            srunner.submit(hi, log_mask=hl)
-            return srunner.run().item()
-
-        for i in range(4):
-            store_step(i)
-        ms_st, _, _, _ = timed(e2e_steps, store_step)
-        e2e_store = {"value": world * B * e2e_steps / (ms_st / 1e3), "unit": UNIT, "ms_per_step": ms_st / e2e_steps,
-                     "h2d_bytes_per_step": sum(t.numel() * t.element_size() for t in hids[0]), "d2h_bytes_per_step": 4,
-                     "store_bytes_hbm": int(store.image.numel() * store.image.element_size() + store.text.numel() * store.text.element_size()),
-                     "note": "PipelinedTrainStep(store=CachedStateStore): per step only ids + log_mask cross the host link; the 7+7 selected "
-                             "layers of the whole catalogue live in HBM and are gathered per item on the device inside the graph"}
-        srunner = None
 
     if rank != 0:
         shutdown()
@@ -411,18 +502,20 @@ def run_ours(a):
     # Algorithmic bytes per launch: forward = every selected layer of every item read once,
     # S * (A_i*D_i + A_t*D_t) * sizeof(elt) per sample; the backward re-streams the same layers once for the gate gradients.
     alg_bytes = B * 11 * (7 * 768 + 7 * 768) * elt
+    traffic, traffic_src = ncu_traffic()
 
-    def hbm_roof(cls, kname, traffic):
+    def hbm_roof(cls, kname, tkey):
         c = classes[cls]
         k_ms = c["ms_per_step"] / c["launches_per_step"] if c["launches_per_step"] > 0 else 0.0
         r = {"bound": "hbm", "kernel": kname, "achieved": alg_bytes / (k_ms / 1e3) / 1e9 if k_ms > 0 else None, "peak": hbm_peak,
-             "unit": "GB/s", "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": k_ms}
+             "unit": "GB/s", "traffic": traffic.get(tkey), "traffic_source": traffic_src, "peak_source": peak_src,
+             "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": k_ms}
         r["frac"] = (r["achieved"] / hbm_peak) if r["achieved"] else None
         return r
 
     if classes["chain"]["launches_per_step"] > 0:
-        roof = hbm_roof("chain", "san_chain_fwd_kernel (fused layer-select gather + gate fusion + adapter chain, forward)", TRAFFIC_NCU.get("fwd"))
-        roof_bwd = hbm_roof("chain_bwd", "san_chain_bwd_kernel (fused data/gate/bias gradients of the chain)", TRAFFIC_NCU.get("bwd"))
+        roof = hbm_roof("chain", "san_chain2_fwd_kernel (fused layer-select gather + gate fusion + adapter chain, forward)", "fwd")
+        roof_bwd = hbm_roof("chain_bwd", "chain backward kernel (fused data/gate/bias gradients of the chain)", "bwd")
     else:
         roof = hbm_roof("stream", "mix kernels (layer-select gather + gate fusion fwd, gate-grad re-stream bwd), summed", None)
         roof_bwd = None
@@ -433,34 +526,40 @@ def run_ours(a):
     roof_tensor["frac"] = (roof_tensor["achieved"] / tf_peak) if roof_tensor["achieved"] else None
 
     cpu = None
+    loss_ref_step0 = None
     if world == 1 and not a.no_cpu_baseline:
         sps, sec, cores, _ = cpu_reference_steps(a.cpu_batch, a.cpu_steps, 1)
         cpu = {"value": sps, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"{a.cpu_steps} full train steps of B={a.cpu_batch} dense users (fp32, torch CPU, oracle port of the reference "
                          f"algorithm with vectorised negative masks -- faster than the reference's per-user Python mask loop; {sec:.2f} s/step)"}
+        if selfcheck is not None:
+            loss_ref_step0 = cpu_reference_loss(selfcheck["params"], selfcheck["batch"], selfcheck["pop"], item_num)
 
+    n_timed = a.steps * a.reps
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
         "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": a.compute, "data": "synthetic",
-        "config": {"workload": workload_name(B, str(state_dtype).split('.')[-1]),
+        "timing": {"reps": a.reps, "statistic": "median over reps of the device time of one block of `steps` steps (max over ranks per block)",
+                   "block_ms_min_max": [min(blocks), max(blocks)], "timed_region_s": t1 - t0},
+        "config": {"workload": workload_name(B, str(state_dtype).split('.')[-1], item_num),
                    "negatives": ("global (all-gather)" if a.negatives == "global" else "local (reference DDP semantics)") if world > 1 else "local",
                    "l2_policy": f"inputs rotate over {n_rot} resident batches of {2 * B * 11 * 13 * 768 * elt / 1e6:.0f} MB (> 126 MB L2)",
                    "step_runner": "CUDA graph replay (iisan_b200.engine.TrainStep)" if use_graph else "eager",
                    "parallelism": f"dp{world}", "host_numa_binding": numa},
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                "ms_per_step": ms_e2e / e2e_steps, "host_link_gbs": h2d / (ms_e2e / e2e_steps / 1e3) / 1e9,
-                "note": "PipelinedTrainStep.submit/run with pinned HOST batch tensors of the reference shapes [B,11,13,768]: every timed "
-                        "step issues the H2D copy of one batch (ids, log_mask, the 7+7 selected layers) and reads one loss back; the copy "
-                        "of batch i+1 overlaps the step of batch i"},
-        "e2e_store": e2e_store,
-        "gpu_launches": int(launches_per_step * a.steps),
+        "e2e": e2e, "e2e_host_batches": e2e_host,
+        "gpu_launches": int(launches_per_step * n_timed),
         "gpu_launches_per_step": launches_per_step,
         "clocks": clocks,
         "roofline": roof, "roofline_chain_bwd": roof_bwd, "roofline_tensor": roof_tensor,
         "kernel_classes": classes, "ms_per_step_eager_with_kernel_events": ms_prof / a.steps,
         "cpu_baseline": cpu, "loss": loss_val,
+        "loss_gpu_step0": loss_gpu_step0, "loss_ref_step0": loss_ref_step0,
     }
+    if other is not None:
+        line["other_negatives"] = other
+    if exposed is not None:
+        line["exposed_comm"] = exposed
     print(json.dumps(line), flush=True)
     shutdown()
 

@@ -303,9 +303,7 @@ __global__ void __launch_bounds__(THREADS, 1) san_chain2_fwd_kernel(const __grid
         else tma_load_2d_a(dst, &T.map_wd, bar, c * CW, s * R);               // Wd_s[:, chunk] : [r x 64]
         ++n;
       };
-      // biases of stage s -> buffer s & 1 (b_up [d] | b_down [64]).  Stage s + 1 is requested while the MMA thread is inside
-      // stage s (a unit is only emitted after the unit NW places earlier has been consumed), i.e. after every epilogue warp has
-      // left stage s - 1, the previous user of that buffer.
+      // biases of stage s -> buffer s & 1 (b_up [d] | b_down [64]); see the request rule in the loop below
       auto put_bias = [&](int s) {
         const uint32_t dst = sbase + Smem::kBias + (s & 1) * BIAS_BYTES, bar = bar0 + Smem::bBias + 8 * (s & 1);
         mbar_expect_tx_a(bar, (uint32_t)(a.d * 4 + R * 4));
@@ -316,10 +314,18 @@ __global__ void __launch_bounds__(THREADS, 1) san_chain2_fwd_kernel(const __grid
       for (int c = 0; c < NC; ++c) put(false, 0, c);
       for (int s = 0; s < A; ++s) {
         const bool more = s + 1 < A;
+        const int n_u0 = n;                       // index of the unit U(s, 0)
+        bool bias_sent = !more;
         for (int c = 0; c < NC + LOOK; ++c) {
-          if (c == LOOK && more) put_bias(s + 1);
           if (c < NC) put(true, s, c);
           if (c >= LOOK && more) put(false, s + 1, c - LOOK);
+          // the last put waited for the release of unit n - 1 - NW: once that is U(s, 0) or younger the MMA thread has passed
+          // z_ready(s), i.e. every epilogue warp has left stage s - 1 and its bias buffer may be overwritten
+          if (!bias_sent && n - 1 - NW >= n_u0) { put_bias(s + 1); bias_sent = true; }
+        }
+        if (!bias_sent) {                         // short stages: wait for the release of U(s, 0) explicitly
+          mbar_wait_park(bar0 + Smem::bWEmpty + 8 * (n_u0 % NW), (uint32_t)(n_u0 / NW) & 1u);
+          put_bias(s + 1);
         }
       }
       TR_FLUSH(0);

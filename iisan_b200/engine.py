@@ -26,9 +26,12 @@ class TrainStep:
         self.opt = optimizer
         self.use_graph = bool(use_graph)
         self.group = group
-        self.world = dist.get_world_size(group) if (group is not None or (dist.is_available() and dist.is_initialized())) else 1
-        if self.world > 1 and group is None:
-            self.group = dist.group.WORLD
+        if group is False:            # explicit "no communication" (measurements: the step without its collectives)
+            self.group, self.world = None, 1
+        else:
+            self.world = dist.get_world_size(group) if (group is not None or (dist.is_available() and dist.is_initialized())) else 1
+            if self.world > 1 and group is None:
+                self.group = dist.group.WORLD
         self.warmup = int(warmup)
         self.graph = None
         self.static_in = None
