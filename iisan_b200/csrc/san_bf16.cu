@@ -517,7 +517,8 @@ static int san_backward_bf16_t(const iisan_san_desc* D, const iisan_san_params* 
       t1.layer[s] = D->img_layer[s]; t1.gate[s] = P->gate_img[ia]; t1.g_gate[s] = G->gate_img[ia]; t1.g_b_down[s] = G->img[ia].b_down; t1.g_b_up[s] = G->img[ia].b_up;
       t2.layer[s] = D->img_layer[s]; t2.layer2[s] = D->text_layer[s]; t2.gate[s] = P->gate_mm[mi]; t2.g_gate[s] = G->gate_mm[mi]; t2.g_b_down[s] = G->mm[mi].b_down; t2.g_b_up[s] = G->mm[mi].b_up;
     }
-    IISAN_TRY(launch_san_chain_bwd(ca, 3, st));
+    if (g_chain_gen.load(std::memory_order_relaxed) >= 2) IISAN_TRY(launch_san_chain2_bwd(ca, 3, st));
+    else IISAN_TRY(launch_san_chain_bwd(ca, 3, st));
     // ---- weight gradients: reductions over all items; the 6 x A split-K GEMMs over the stashes share ONE launch ----
     {
       static thread_local UmmaBatchBig wg;

@@ -716,6 +716,7 @@ int chain_fill_bwd_tower(ChainBwdTower* T, int mode, const void* h, int64_t n_it
   if (mode == 1) IISAN_TRY(make_tensor_map_bf16(&T->map_aux, h2, n_items, h2_pitch_cols, h2_pitch_cols, CH_CW, CH_ROWS));
   else IISAN_TRY(make_tensor_map_bf16(&T->map_aux, x_all, (int64_t)n_stages * np, d, d, CH_CW, CH_ROWS));
   IISAN_TRY(make_tensor_map_bf16(&T->map_dz, dz_all, (int64_t)n_stages * np, CH_R, CH_R, CH_R, CH_ROWS));
+  T->dz_out = const_cast<bf16*>(dz_all);
   return fill_common(&T->map_wd, &T->map_wu, wd_pack, wu_pack, n_stages, d);
 }
 

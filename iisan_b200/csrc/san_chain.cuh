@@ -45,6 +45,7 @@ struct ChainBwdTower {
   float* g_b_down[kChainMaxStages];
   float* g_b_up[kChainMaxStages];
   const __nv_bfloat16* z_stash;                   // [A * n_pad, r]
+  __nv_bfloat16* dz_out;                          // dz stash as a plain pointer (second-generation kernel: direct stores)
 };
 
 struct ChainBwdArgs {
@@ -60,7 +61,8 @@ int chain_fill_bwd_tower(ChainBwdTower* T, int mode, const void* h, int64_t n_it
                          int64_t h2_pitch_cols, const __nv_bfloat16* wd_pack, const __nv_bfloat16* wu_pack, const __nv_bfloat16* dy_all,
                          const __nv_bfloat16* last_all, const __nv_bfloat16* dz_all, int n_stages, int d);
 int launch_san_chain_fwd(const ChainArgs& args, int n_towers, cudaStream_t st);
-int launch_san_chain2_fwd(const ChainArgs& args, int n_towers, cudaStream_t st);   // san_chain2.cu (needs d % 128 == 0, d >= 256)
+int launch_san_chain2_fwd(const ChainArgs& args, int n_towers, cudaStream_t st);   // san_chain2.cu (falls back to generation 1 for shapes it does not cover)
+int launch_san_chain2_bwd(const ChainBwdArgs& args, int n_towers, cudaStream_t st);   // san_chain2_bwd.cu (same)
 int launch_san_chain_bwd(const ChainBwdArgs& args, int n_towers, cudaStream_t st);
 
 }  // namespace iisan
