@@ -252,43 +252,61 @@ __global__ void __launch_bounds__(CE_THREADS, 1) ce_tile_kernel(const __grid_con
     for (int t = 0; t < n_tiles; ++t) {
       const int b = t & 1; const uint32_t bph = (uint32_t)(t >> 1) & 1u;
       const int tt0 = (t_beg + t) * CT;                                  // first streamed entity of this tile
-      // ---- stage the debias of the tile's 128 columns (one per thread of the first 128; double buffered) ----
-      float* atf = attr_f + b * 2 * CT;
-      if (et < CT) {
-        const int e = tt0 + et;
-        atf[et] = (e < a.C) ? a.debias[e] : 0.f;
+      // ---- debias of this warp's 32 columns: straight from global memory (the 32 lanes read the same addresses: one L1
+      //      wavefront per load), issued before the wait for S so that its latency is hidden; no CTA-wide barrier per tile ----
+      const int k0 = half * 32;                                           // offset of this warp's 32 streamed entities inside the tile
+      const int c0 = tt0 + k0;
+      float4 deb[8];
+      if (c0 + 32 <= a.C) {
+        const float4* dp = reinterpret_cast<const float4*>(a.debias + c0);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) deb[q] = __ldg(dp + q);
+      } else {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          deb[q].x = (c0 + 4 * q < a.C) ? __ldg(a.debias + c0 + 4 * q) : 0.f;
+          deb[q].y = (c0 + 4 * q + 1 < a.C) ? __ldg(a.debias + c0 + 4 * q + 1) : 0.f;
+          deb[q].z = (c0 + 4 * q + 2 < a.C) ? __ldg(a.debias + c0 + 4 * q + 2) : 0.f;
+          deb[q].w = (c0 + 4 * q + 3 < a.C) ? __ldg(a.debias + c0 + 4 * q + 3) : 0.f;
+        }
       }
-      epi_bar_sync();
+      // 32 consecutive columns, c0 % 32 == 0.  Columns >= C carry mask bits (ce_maskbits_kernel) and a zero debias: they
+      // become -1e4 like every masked entry, whose softmax weight underflows to exactly 0 against any real logit of the row.
+      const uint32_t mw = (c0 < a.C) ? __ldg(o_mask + (c0 >> 5)) : 0xffffffffu;
       mbar_wait(&s_full[b], bph);
       tc_fence_after();
       if (BWD) mbar_wait(&a2_empty[b], bph ^ 1u);
       uint8_t* a2 = smem + CeSmem::kA2 + b * CE_A2_BYTES;
       {
-        const int k0 = half * 32;                                         // offset of this warp's 32 streamed entities inside the tile
         uint32_t raw[32];
         tmem_ld_32x32(tmem_base + lane_addr + (uint32_t)(b * CT + k0), raw);
         tmem_ld_wait();
         float v[32];
         {
-          // 32 consecutive columns, c0 % 32 == 0.  Columns >= C carry mask bits (ce_maskbits_kernel) and a zero debias: they
-          // become -1e4 like every masked entry, whose softmax weight underflows to exactly 0 against any real logit of the row.
-          const int c0 = tt0 + k0;
-          const uint32_t mw = (c0 < a.C) ? __ldg(o_mask + (c0 >> 5)) : 0xffffffffu;
-          const float4* deb4 = reinterpret_cast<const float4*>(atf + k0);
+          // masked entries are rare (the 11 items of the row's user, padded slots): when no lane of the warp has one in this
+          // block of 32 columns the per-logit selects are skipped altogether
+          if (!__any_sync(0xffffffffu, mw != 0u)) {
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const float4 d = deb4[q];
-            v[4 * q] = ((mw >> (4 * q)) & 1u) ? kNegMaskF : __uint_as_float(raw[4 * q]) - d.x;
-            v[4 * q + 1] = ((mw >> (4 * q + 1)) & 1u) ? kNegMaskF : __uint_as_float(raw[4 * q + 1]) - d.y;
-            v[4 * q + 2] = ((mw >> (4 * q + 2)) & 1u) ? kNegMaskF : __uint_as_float(raw[4 * q + 2]) - d.z;
-            v[4 * q + 3] = ((mw >> (4 * q + 3)) & 1u) ? kNegMaskF : __uint_as_float(raw[4 * q + 3]) - d.w;
+            for (int q = 0; q < 8; ++q) {
+              v[4 * q] = __uint_as_float(raw[4 * q]) - deb[q].x; v[4 * q + 1] = __uint_as_float(raw[4 * q + 1]) - deb[q].y;
+              v[4 * q + 2] = __uint_as_float(raw[4 * q + 2]) - deb[q].z; v[4 * q + 3] = __uint_as_float(raw[4 * q + 3]) - deb[q].w;
+            }
+          } else {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float4 d = deb[q];
+              v[4 * q] = ((mw >> (4 * q)) & 1u) ? kNegMaskF : __uint_as_float(raw[4 * q]) - d.x;
+              v[4 * q + 1] = ((mw >> (4 * q + 1)) & 1u) ? kNegMaskF : __uint_as_float(raw[4 * q + 1]) - d.y;
+              v[4 * q + 2] = ((mw >> (4 * q + 2)) & 1u) ? kNegMaskF : __uint_as_float(raw[4 * q + 2]) - d.z;
+              v[4 * q + 3] = ((mw >> (4 * q + 3)) & 1u) ? kNegMaskF : __uint_as_float(raw[4 * q + 3]) - d.w;
+            }
           }
           const bool has_label = o_label >= c0 && o_label < c0 + 32;
           if (has_label) {                                                // the label column escapes the reject mask
             const int kl = o_label - c0;
 #pragma unroll
             for (int k = 0; k < 32; ++k)
-              if (k == kl) v[k] = o_lab_masked ? kNegMaskF : __uint_as_float(raw[k]) - atf[k0 + k];
+              if (k == kl) v[k] = o_lab_masked ? kNegMaskF : __uint_as_float(raw[k]) - reinterpret_cast<const float*>(deb)[k];
           }
           if (!BWD) {
             float cm = v[0];

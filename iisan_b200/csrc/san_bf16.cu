@@ -207,6 +207,9 @@ struct SanLayoutBf16 {
 static const bool g_disable_chain = [] { const char* e = getenv("IISAN_B200_NO_CHAIN"); return e && e[0] == '1'; }();
 static std::atomic<int> g_chain_gen{[] { const char* e = getenv("IISAN_B200_CHAIN_GEN"); return (e && e[0] == '1') ? 1 : 2; }()};
 int set_chain_generation(int gen) { return g_chain_gen.exchange(gen); }
+// L2 prefetch distance (chunks) of the second-generation chain kernels; IISAN_B200_CHAIN_PF overrides (measurement switch)
+static const int g_chain_pf_fwd = [] { const char* e = getenv("IISAN_B200_CHAIN_PF"); return e ? atoi(e) : 0; }();
+static const int g_chain_pf_bwd = [] { const char* e = getenv("IISAN_B200_CHAIN_PF_BWD"); return e ? atoi(e) : 0; }();
 
 size_t san_bf16_workspace_bytes(const iisan_san_desc& D) {
   SanLayoutBf16 L(D, nullptr);
@@ -336,7 +339,7 @@ static int san_forward_bf16_t(const iisan_san_desc* D, const iisan_san_params* P
   if (chain) {
     // ---- all stages of all three towers in one launch (san_chain.cu) ----
     ChainArgs ca{};
-    ca.n_items = N; ca.n_pad = chain_n_pad(N); ca.d = D->d_mm; ca.n_stages = D->n_stages;
+    ca.n_items = N; ca.n_pad = chain_n_pad(N); ca.d = D->d_mm; ca.n_stages = D->n_stages; ca.pf = g_chain_pf_fwd;
     IISAN_TRY(chain_fill_tower(&ca.tower[0], 0, text, N, (int64_t)D->layers_text * D->d_text, nullptr, 0, L.wd_pack[0], L.wu_pack[0], L.x_t[0], L.last_t[0], L.z_t[0], D->n_stages, D->d_text));
     IISAN_TRY(chain_fill_tower(&ca.tower[1], 0, image, N, (int64_t)D->layers_img * D->d_img, nullptr, 0, L.wd_pack[1], L.wu_pack[1], L.x_i[0], L.last_i[0], L.z_i[0], D->n_stages, D->d_img));
     IISAN_TRY(chain_fill_tower(&ca.tower[2], 1, image, N, (int64_t)D->layers_img * D->d_img, text, (int64_t)D->layers_text * D->d_text, L.wd_pack[2], L.wu_pack[2], L.x_m[0], L.last_m[0], L.z_m[0], D->n_stages, D->d_mm));
@@ -505,7 +508,7 @@ static int san_backward_bf16_t(const iisan_san_desc* D, const iisan_san_params* 
   if (chain) {
     // ---- data / gate / bias gradients of all stages and towers in one launch (san_chain.cu) ----
     ChainBwdArgs ca{};
-    ca.n_items = N; ca.n_pad = chain_n_pad(N); ca.d = D->d_mm; ca.n_stages = D->n_stages;
+    ca.n_items = N; ca.n_pad = chain_n_pad(N); ca.d = D->d_mm; ca.n_stages = D->n_stages; ca.pf = g_chain_pf_bwd;
     IISAN_TRY(chain_fill_bwd_tower(&ca.tower[0], 0, text, N, (int64_t)D->layers_text * D->d_text, nullptr, 0, L.wd_pack[0], L.wu_pack[0], L.dys[0], L.x_t[0], L.dzs[0][0], D->n_stages, D->d_text));
     IISAN_TRY(chain_fill_bwd_tower(&ca.tower[1], 0, image, N, (int64_t)D->layers_img * D->d_img, nullptr, 0, L.wd_pack[1], L.wu_pack[1], L.dys[1], L.x_i[0], L.dzs[1][0], D->n_stages, D->d_img));
     IISAN_TRY(chain_fill_bwd_tower(&ca.tower[2], 1, image, N, (int64_t)D->layers_img * D->d_img, text, (int64_t)D->layers_text * D->d_text, L.wd_pack[2], L.wu_pack[2], L.dys[2], L.x_m[0], L.dzs[2][0], D->n_stages, D->d_mm));

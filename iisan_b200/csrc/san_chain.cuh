@@ -30,6 +30,7 @@ struct ChainTower {
 struct ChainArgs {
   ChainTower tower[3];
   int n_items, n_pad, d, n_stages;
+  int pf;                   // second generation: hidden-state tiles are requested into L2 this many chunks ahead (0: off)
 };
 
 struct ChainBwdTower {
@@ -51,6 +52,7 @@ struct ChainBwdTower {
 struct ChainBwdArgs {
   ChainBwdTower tower[3];
   int n_items, n_pad, d, n_stages;
+  int pf;
 };
 
 int chain_n_pad(int n_items);

@@ -144,12 +144,24 @@ __global__ void __launch_bounds__(THREADS, 1) san_chain2_fwd_kernel(const __grid
         tma_load_2d_a(sbase + Smem::kD + slot * TILE_BYTES, m, bar, col, row);
         ++n;
       };
+      // The ring holds about one chunk of look-ahead per parity, less than the DRAM latency of a strided tile under load: with
+      // a.pf > 0 the hidden-state tiles are requested into L2 a.pf chunks before their ring load.
+      const int PF = a.pf;
+      auto prefetch_h = [&](int k) {              // k-th hidden-state chunk of the whole launch: stage k / NC, chunk k % NC
+        const int sp = k / NC, c = k % NC;
+        if (sp >= A) return;
+        tma_prefetch_l2_2d(&T.map_h, T.layer[sp] * a.d + c * CW, m0);
+        if (is_mm) tma_prefetch_l2_2d(&T.map_h2, T.layer2[sp] * a.d + c * CW, m0);
+      };
+      if (PF > 0) for (int k = 0; k < PF; ++k) prefetch_h(k);
       for (int c = 0; c < NC; ++c) {
+        if (PF > 0) prefetch_h(c + PF);
         load(c & 1, &T.map_h, T.layer[0] * a.d + c * CW, m0);
         if (is_mm) load(c & 1, &T.map_h2, T.layer2[0] * a.d + c * CW, m0);
       }
       for (int s = 0; s < A; ++s) {
         for (int c = 0; c < NC; ++c) {
+          if (PF > 0) prefetch_h((s + 1) * NC + c + PF);
           // residual x_s[c]: stored by this CTA as x-stash chunk number s*NC + c ; wait until that store is complete
           const uint32_t need = (uint32_t)(s * NC + c + 1);
           TR(1, while (ld_acquire_shared(bar0 + Smem::bStored) < need) __nanosleep(64));

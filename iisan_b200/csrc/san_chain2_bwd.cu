@@ -153,10 +153,23 @@ __global__ void __launch_bounds__(THREADS, 1) san_chain2_bwd_kernel(const __grid
         tma_load_2d_a(sbase + S::kD + slot * TILE_BYTES, m, bar, col, row);
         ++n;
       };
+      // with a.pf > 0 the tiles that come from HBM (hidden states, the forward's x stash) are requested into L2 a.pf chunks
+      // before their ring load: three tiles per chunk leave the ring about one chunk of look-ahead
+      const int PF = a.pf;
+      auto prefetch = [&](int k) {                // k-th chunk of the stage loops: stage number k / NC, chunk k % NC
+        const int q = k / NC, c = k % NC;
+        if (q >= A) return;
+        const int s = A - 1 - q;
+        tma_prefetch_l2_2d(&T.map_h, T.layer[s] * a.d + c * CW, m0);
+        if (is_mm) tma_prefetch_l2_2d(&T.map_aux, T.layer2[s] * a.d + c * CW, m0);
+        else if (s > 0) tma_prefetch_l2_2d(&T.map_aux, c * CW, s * NP + m0);
+      };
+      if (PF > 0) for (int k = 0; k < PF; ++k) prefetch(k);
       for (int c = 0; c < NC; ++c) load(c & 1, &T.map_dy, c * CW, (A - 1) * NP + m0);
       for (int q = 0; q < A; ++q) {
         const int s = A - 1 - q;
         for (int c = 0; c < NC; ++c) {
+          if (PF > 0) prefetch(q * NC + c + PF);
           if (q > 0) {      // dy_s[c] was stored by this CTA as x-slot use q*NC + c: wait until that store is complete
             const uint32_t need = (uint32_t)(q * NC + c + 1);
             TR(1, while (ld_acquire_shared(bar0 + S::bStored) < need) __nanosleep(64));

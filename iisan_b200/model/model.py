@@ -132,12 +132,27 @@ class ModelMM(nn.Module):
         device = score_embs.device
         ids = sample_items_id.to(device).view(-1)
         log_mask = log_mask.to(device=device, dtype=torch.float32)
+        pool = deferred = None
+        if self.negatives == "global":
+            # start the pool all-gather now: the SASRec forward below only needs the local rows and hides the transfer; in the
+            # backward the reduce-scatter of d score_all is launched before the SASRec backward and joined after it
+            from .. import parallel as par
+            import torch.distributed as dist
+            group = self.process_group if self.process_group is not None else dist.group.WORLD
+            if score_embs.dtype == torch.float32 and dist.get_backend(group) != "gloo":
+                deferred = par._PendingScatter()
+                if score_embs.requires_grad:
+                    score_embs = par.JoinPoolGrad.apply(score_embs, deferred)
+                else:
+                    deferred = None
+                pool = par.start_pool_gather(score_embs, ids.view(log_mask.shape[0], -1), log_mask, group)
         input_embs = score_embs.view(-1, S, E)
         prec_vec = self.user_encoder(input_embs[:, :-1, :], log_mask, local_rank).reshape(-1, E)   # model.py:76-79
         pop = self._pop(device)
         if self.negatives == "global":
             from ..parallel import global_negative_loss
-            return global_negative_loss(prec_vec, score_embs, ids, log_mask, pop, self.process_group, compute_mode())
+            return global_negative_loss(prec_vec, score_embs, ids, log_mask, pop, self.process_group, compute_mode(), pool=pool,
+                                        deferred=deferred)
         _sum, _n, loss = InBatchCeFn.apply(prec_vec, score_embs, ids, ids, log_mask, log_mask, pop, 0, compute_mode())
         return loss
 

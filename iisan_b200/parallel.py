@@ -46,22 +46,58 @@ class AllGatherRows(torch.autograd.Function):
         return out, None
 
 
+class PoolGather:
+    """In-flight all-gather of the packed (score | ids | log_mask) rows of every rank, started with ``start_pool_gather`` as soon
+    as the local item embeddings exist, so that the transfer overlaps the SASRec forward (which only needs the local rows)."""
+
+    def __init__(self, out, work, sizes, shapes):
+        self.out, self.work, self.sizes, self.shapes = out, work, sizes, shapes
+
+    def wait(self):
+        if self.work is not None:
+            self.work.wait()             # the current stream waits for the collective (stream-ordered, capturable)
+            self.work = None
+        return self.out
+
+
+def start_pool_gather(score, ids, log_mask, group=None):
+    """Launch the ONE packed all-gather of the global negative pool asynchronously (fp32 score [n, E], int64 ids [b, S], fp32
+    log_mask [b, L]; the int64 ids travel as raw bit pairs).  Returns a PoolGather handle for ``global_negative_loss(pool=...)``."""
+    group = group if group is not None else dist.group.WORLD
+    world = dist.get_world_size(group)
+    b = log_mask.shape[0]
+    parts = [score.detach().contiguous().view(-1), ids.contiguous().view(b, -1).view(torch.float32).view(-1), log_mask.contiguous().view(-1)]
+    sizes = [p.numel() for p in parts]
+    packed = torch.cat(parts)
+    out = torch.empty(world, packed.numel(), dtype=torch.float32, device=score.device)
+    work = dist.all_gather_into_tensor(out.view(-1), packed, group=group, async_op=True)
+    return PoolGather(out, work, sizes, (tuple(score.shape), b))
+
+
+class _PendingScatter:
+    """Reduce-scatter of d score_all launched by AllGatherPool.backward and consumed by JoinPoolGrad.backward."""
+    out = None
+    work = None
+
+
 class AllGatherPool(torch.autograd.Function):
     """(score [n, E] fp32, ids [b, S] int64, log_mask [b, L] fp32) of every rank in ONE collective: the three tensors are
-    packed into one fp32 row per rank (the int64 ids travel as raw bit pairs).  Returns the rank-major global pool
-    (score_all [W*n, E], ids_all [W*b, S], lm_all [W*b, L]).  Backward: reduce-scatter(sum) of d score_all."""
+    packed into one fp32 row per rank.  Returns the rank-major global pool (score_all [W*n, E], ids_all [W*b, S], lm_all [W*b, L]).
+    ``pool``: a PoolGather started earlier (its collective is only waited for here).
+    Backward: reduce-scatter(sum) of d score_all.  With ``deferred`` (a _PendingScatter) the reduce-scatter is only LAUNCHED here
+    -- this node runs before the SASRec backward, which it then overlaps -- and its result joins the gradient of the local item
+    embeddings in JoinPoolGrad.backward."""
 
     @staticmethod
-    def forward(ctx, score, ids, log_mask, group):
-        ctx.group = group
+    def forward(ctx, score, ids, log_mask, group, pool, deferred):
+        ctx.group, ctx.deferred = group, deferred
         world = dist.get_world_size(group)
         n, e = score.shape
         b = log_mask.shape[0]
-        parts = [score.contiguous().view(-1), ids.contiguous().view(torch.float32).view(-1), log_mask.contiguous().view(-1)]
-        sizes = [p.numel() for p in parts]
-        packed = torch.cat(parts)
-        out = torch.empty(world, packed.numel(), dtype=torch.float32, device=score.device)
-        dist.all_gather_into_tensor(out.view(-1), packed, group=group)
+        if pool is None:
+            pool = start_pool_gather(score, ids, log_mask, group)
+        out = pool.wait()
+        sizes = pool.sizes
         o0, o1 = sizes[0], sizes[0] + sizes[1]
         score_all = out[:, :o0].reshape(world * n, e)
         ids_all = out[:, o0:o1].contiguous().view(torch.int64).view(world * b, -1)
@@ -71,7 +107,33 @@ class AllGatherPool(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g, _gi, _gl):
-        return AllGatherRows.backward(ctx, g)[0], None, None, None
+        if ctx.deferred is None or dist.get_backend(ctx.group) == "gloo":
+            return AllGatherRows.backward(ctx, g)[0], None, None, None, None, None
+        world = dist.get_world_size(ctx.group)
+        g = g.contiguous()
+        out = torch.empty((g.shape[0] // world,) + tuple(g.shape[1:]), dtype=g.dtype, device=g.device)
+        ctx.deferred.out = out
+        ctx.deferred.work = dist.reduce_scatter_tensor(out, g, op=dist.ReduceOp.SUM, group=ctx.group, async_op=True)
+        return None, None, None, None, None, None
+
+
+class JoinPoolGrad(torch.autograd.Function):
+    """Identity on the local item embeddings, placed before they fan out to the SASRec encoder and to the pool gather.  Its
+    backward runs after BOTH branches: it waits for the reduce-scatter launched by AllGatherPool.backward and adds its result."""
+
+    @staticmethod
+    def forward(ctx, score, deferred):
+        ctx.deferred = deferred
+        return score.view_as(score)
+
+    @staticmethod
+    def backward(ctx, g):
+        d = ctx.deferred
+        if d.work is not None:
+            d.work.wait()
+            g = g + d.out if g is not None else d.out
+            d.work, d.out = None, None
+        return g, None
 
 
 def _gather_plain(x, group):
@@ -88,19 +150,21 @@ def _cuda_ce(prec, score_all, ids, ids_all, lm, lm_all, pop, user_offset, comput
     return loss_sum, n_valid
 
 
-def global_negative_loss(prec, score, ids, log_mask, pop, group=None, compute=0, ce_fn=None, grad_average=True):
+def global_negative_loss(prec, score, ids, log_mask, pop, group=None, compute=0, ce_fn=None, grad_average=True, pool=None,
+                         deferred=None):
     """In-batch CE of the local rows against the all-gathered item pool.
 
     Returns ``W * loss_sum_local / n_valid_global`` when ``grad_average`` (so that DDP's mean over ranks
     of the parameter gradients equals the gradient of the single-process loss on the concatenated batch),
     else ``loss_sum_local / n_valid_global`` (use with a SUM all-reduce of gradients).
-    ``ce_fn`` is injectable for the CPU/gloo tests; the default is the CUDA kernel.
+    ``ce_fn`` is injectable for the CPU/gloo tests; the default is the CUDA kernel.  ``pool`` / ``deferred``: see
+    start_pool_gather / JoinPoolGrad (communication overlapped with the SASRec forward / backward).
     """
     group = group if group is not None else dist.group.WORLD
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     b = log_mask.shape[0]
     if score.dtype == torch.float32 and log_mask.dtype == torch.float32 and ids.dtype == torch.int64:
-        score_all, ids_all, lm_all = AllGatherPool.apply(score, ids.view(b, -1), log_mask, group)      # one collective
+        score_all, ids_all, lm_all = AllGatherPool.apply(score, ids.view(b, -1), log_mask, group, pool, deferred)      # one collective
     else:
         score_all = AllGatherRows.apply(score, group)
         ids_all = _gather_plain(ids.view(b, -1), group)
