@@ -44,6 +44,29 @@ def ncu_traffic():
         return {}, None
 LRS = dict(lr=2e-4, adapter_cv_lr=1e-4, adapter_bert_lr=1e-4, fine_tune_lr_image=1e-4, fine_tune_lr_text=5e-5)
 
+# Workloads (BASELINE.json configs).  "instrument" (configs[1] / [2]) is the default the driver runs; the IISAN-Versa ones
+# (Code_Cached_Asym) are selected with --workload.  layers = cached states per item (n_layers + 1); lists as in the reference's
+# launchers (Code_Cached_Asym/script/run_IISAN_eva.py:56-65 for LLaMA-3-70B + EVA-CLIP).
+WORKLOADS = {
+    "instrument": dict(asym=False, d_text=768, d_img=768, layers_text=13, layers_img=13, vit="1,3,5,7,9,11", bert="1,3,5,7,9,11",
+                       stored="bfloat16", batch=512, cpu_batch=512, label="BERT-base+ViT-B/16 cached states [13,768]"),
+    "versa_large": dict(asym=True, d_text=1024, d_img=1024, layers_text=25, layers_img=25, vit="1,3,5,7,9,11",
+                        bert="1,3,5,7,9,11,13,15,17,19,21,23", stored="bfloat16", batch=512, cpu_batch=64,
+                        label="IISAN-Versa BERT-large [25,1024] + ViT-large [25,1024], group layer-drop (13 text / 7 image adapters)"),
+    "llama_eva": dict(asym=True, d_text=8192, d_img=5120, layers_text=81, layers_img=49, vit="2,11,20,29,38,47",
+                      bert="4,19,34,49,64,79", stored="float16", batch=512, cpu_batch=8,
+                      label="IISAN-Versa LLaMA-3-70B-shaped text states [81,8192] + EVA-CLIP image states [49,5120], down_project 8192->5120"),
+}
+
+
+def workload_args(w):
+    from iisan_b200.config import default_args
+    over = dict(LRS, side_adapter_vit_list=w["vit"], side_adapter_bert_list=w["bert"])
+    if w["asym"]:
+        over.update(text_embedding_dim=w["d_text"], image_embedding_dim=w["d_img"], text_layers=w["layers_text"] - 1,
+                    image_layers=w["layers_img"] - 1, word_embedding_dim=w["d_text"])
+    return default_args(**over)
+
 
 def parse():
     ap = argparse.ArgumentParser()
@@ -51,9 +74,11 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=512)
+    ap.add_argument("--workload", default="instrument", choices=["instrument", "versa_large", "llama_eva"],
+                    help="instrument = BASELINE configs[1]/[2] (the default the driver runs); versa_large = configs[3]; llama_eva = configs[4]")
+    ap.add_argument("--batch", type=int, default=0, help="users per GPU (default: the workload's, 512)")
     ap.add_argument("--compute", default="bf16", choices=["bf16", "fp32"])
-    ap.add_argument("--cpu-batch", type=int, default=512)
+    ap.add_argument("--cpu-batch", type=int, default=0, help="users per CPU-arm step (default: the workload's bounded sample)")
     ap.add_argument("--cpu-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-store", action="store_true", help="skip the HBM-resident store e2e measurement")
@@ -69,31 +94,40 @@ def parse():
 # ----------------------------------------------------------------------------------------------------------------
 # CPU arm: the reference algorithm (oracle port) on the host cores
 # ----------------------------------------------------------------------------------------------------------------
-def cpu_reference_loss(params_np, batch_np, pop, item_num):
+def cpu_reference_loss(params_np, batch_np, pop, item_num, wname="instrument"):
     """Forward of the oracle on GIVEN parameters / batch (the GPU arm's initial replica and its first batch): the self-check of
     the bench line (loss_ref_step0 vs loss_gpu_step0)."""
     import torch
     from oracle import iisan_oracle as O
-    from oracle.synthetic import PathConfig
-    cfg = PathConfig(item_num=item_num)
+    cfg = oracle_config(wname, item_num)
     with torch.no_grad():
         out = O.model_forward(O.params_to_torch(params_np, requires_grad=False), batch_np, pop, cfg)
     return float(out["loss"])
 
 
-def cpu_reference_steps(batch, steps, warmup):
+def oracle_config(wname, item_num):
+    from oracle.synthetic import PathConfig
+    w = WORKLOADS[wname]
+    if not w["asym"]:
+        return PathConfig(item_num=item_num)
+    return PathConfig(item_num=item_num, asym=True, d_text=w["d_text"], d_img=w["d_img"], layers_text=w["layers_text"],
+                      layers_img=w["layers_img"], vit_list=w["vit"], bert_list=w["bert"])
+
+
+def cpu_reference_steps(batch, steps, warmup, wname="instrument"):
     """fwd + bwd + Adam of the oracle restatement (fp32, all host threads).  Returns (samples/s, s/step, cores)."""
     import numpy as np
     import torch
     from oracle import iisan_oracle as O
-    from oracle.synthetic import PathConfig, make_ids, make_params, make_pop_prob
+    from oracle.synthetic import make_ids, make_params, make_pop_prob
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    cfg = PathConfig(item_num=ITEM_NUM)
+    cfg = oracle_config(wname, ITEM_NUM)
+    w = WORKLOADS[wname]
     ids, lm = make_ids(batch, cfg, SEED, "dense")
     g = torch.Generator().manual_seed(SEED)
-    image = torch.randn(batch, 11, 13, 768, generator=g).numpy()
-    text = torch.randn(batch, 11, 13, 768, generator=g).numpy()
+    image = torch.randn(batch, 11, w["layers_img"], w["d_img"], generator=g).numpy()
+    text = torch.randn(batch, 11, w["layers_text"], w["d_text"], generator=g).numpy()
     b = {"ids": ids, "log_mask": lm, "image": image, "text": text}
     pop = make_pop_prob(cfg, SEED)
     P = O.params_to_torch(make_params(cfg, SEED, perturb=False))
@@ -112,18 +146,24 @@ def cpu_reference_steps(batch, steps, warmup):
     return sps, sum(times) / len(times), cores, float(out["loss"].item())
 
 
-def workload_name(batch, stored, item_num=ITEM_NUM):
+def workload_name(batch, stored, item_num=ITEM_NUM, wname="instrument"):
     shape = {ITEM_NUM: "Instrument", ITEM_NUM_OFFICE: "Office"}.get(item_num, "custom")
-    return (f"IISAN(Cached) {shape} shape: item_num {item_num}, B={batch} users/GPU x 11 slots, BERT-base+ViT-B/16 "
-            f"cached states [13,768] stored {stored}, 7 of 13 layers, r=64, E=64, random-init adapters, "
-            f"dense batch, fwd+bwd+Adam")
+    w = WORKLOADS[wname]
+    if wname == "instrument":
+        return (f"IISAN(Cached) {shape} shape: item_num {item_num}, B={batch} users/GPU x 11 slots, BERT-base+ViT-B/16 "
+                f"cached states [13,768] stored {stored}, 7 of 13 layers, r=64, E=64, random-init adapters, "
+                f"dense batch, fwd+bwd+Adam")
+    return (f"{w['label']}; {shape} catalogue (item_num {item_num}), B={batch} users/GPU x 11 slots, states stored {stored}, r=64, E=64, "
+            f"random-init adapters, dense batch, fwd+bwd+Adam")
 
 
 def run_reference_arm(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sps, sec, cores, loss = cpu_reference_steps(a.cpu_batch, a.steps, a.warmup)
+    cpu_batch = a.cpu_batch or WORKLOADS[a.workload]["cpu_batch"]
+    a.cpu_batch = cpu_batch
+    sps, sec, cores, loss = cpu_reference_steps(cpu_batch, a.steps, a.warmup, a.workload)
     sample = (f"{a.steps} full train steps (fwd+bwd+Adam) of B={a.cpu_batch} dense users, fp32, torch CPU, oracle port of the reference "
               f"algorithm (its negative masks are vectorised; the reference's own per-user Python mask loop, Code_Cached/model/model.py:92-100, "
               f"is slower: SURVEY 8a row a6)")
@@ -131,7 +171,7 @@ def run_reference_arm(a):
         "impl": "reference", "metric": METRIC, "value": sps, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": workload_name(a.cpu_batch, "float32"), "negatives": "local", "step_runner": "torch CPU eager, all host threads",
+        "config": {"workload": workload_name(a.cpu_batch, "float32", ITEM_NUM, a.workload), "negatives": "local", "step_runner": "torch CPU eager, all host threads",
                    "parallelism": "host cores of rank 0"},
         "cpu_baseline": {"value": sps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": sps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -224,20 +264,23 @@ def bind_to_gpu_numa_node(local):
     return None
 
 
-def build_model(device, compute, item_num=ITEM_NUM):
+def build_model(device, compute, item_num=ITEM_NUM, wname="instrument"):
     import torch
     from torch import nn
-    from iisan_b200 import model as pkg
-    from iisan_b200.config import default_args
     from iisan_b200.precision import set_compute_mode
-    args = default_args(**LRS)
+    w = WORKLOADS[wname]
+    if w["asym"]:
+        from iisan_b200 import model_asym as pkg
+    else:
+        from iisan_b200 import model as pkg
+    args = workload_args(w)
     cfg = args
     torch.manual_seed(SEED)
 
     class ImgStub(nn.Module):                                  # ViTForImageClassification head stand-in (run.py:44-49)
         def __init__(self):
             super().__init__()
-            self.classifier = nn.Linear(768, args.embedding_dim)
+            self.classifier = nn.Linear(w["d_img"], args.embedding_dim)
 
     import numpy as np
     rng = np.random.default_rng(SEED)
@@ -249,13 +292,21 @@ def build_model(device, compute, item_num=ITEM_NUM):
     return m.to(device), args, cfg
 
 
-def make_device_batches(n, B, device, dtype, gen, item_num=ITEM_NUM):
+def make_device_batches(n, B, device, dtype, gen, item_num=ITEM_NUM, wname="instrument"):
     import torch
+    w = WORKLOADS[wname]
     out = []
+
+    def states(layers, d):                                     # generated slot by slot: the fp32 staging of [B,11,81,8192] would be 15 GB
+        t = torch.empty(B, 11, layers, d, device=device, dtype=dtype)
+        for k in range(11):
+            t[:, k] = torch.randn(B, layers, d, device=device, generator=gen, dtype=torch.float32).to(dtype)
+        return t
+
     for _ in range(n):
         ids = torch.randint(1, item_num + 1, (B * 11,), device=device, generator=gen, dtype=torch.int64)
-        image = torch.randn(B, 11, 13, 768, device=device, generator=gen, dtype=torch.float32).to(dtype)
-        text = torch.randn(B, 11, 13, 768, device=device, generator=gen, dtype=torch.float32).to(dtype)
+        image = states(w["layers_img"], w["d_img"])
+        text = states(w["layers_text"], w["d_text"])
         lm = torch.ones(B, 10, device=device, dtype=torch.float32)
         out.append((ids, image, text, lm))
     return out
@@ -277,18 +328,19 @@ def run_ours(a):
     numa = bind_to_gpu_numa_node(local) if world > 1 else None      # N = 1 keeps every core for the cpu_baseline leg
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
-    item_num = a.item_num or (ITEM_NUM if world == 1 else ITEM_NUM_OFFICE)
-    state_dtype = torch.bfloat16 if a.compute == "bf16" else torch.float32
-    model, args, cfg = build_model(device, a.compute, item_num)
+    W = WORKLOADS[a.workload]
+    item_num = a.item_num or (ITEM_NUM if (world == 1 and a.workload == "instrument") else ITEM_NUM_OFFICE)
+    state_dtype = getattr(torch, W["stored"]) if a.compute == "bf16" else torch.float32
+    model, args, cfg = build_model(device, a.compute, item_num, a.workload)
     if world > 1:
         for p in model.parameters():                                 # same initial replica on every rank (DDP does this at wrap time)
             dist.broadcast(p.data, 0)
     use_graph = not a.no_graph
     opt = FusedAdam(param_groups(model, args))            # iisan_adam_step: Adam over the reference's 5 LR groups, one launch
     gen = torch.Generator(device=device).manual_seed(SEED + rank)
-    B = a.batch
+    B = a.batch or W["batch"]
     n_rot = 3                                               # 3 x 225 MB (bf16) rotating inputs >> 126 MB L2
-    batches = make_device_batches(n_rot, B, device, state_dtype, gen, item_num)
+    batches = make_device_batches(n_rot, B, device, state_dtype, gen, item_num, a.workload)
     group = dist.group.WORLD if world > 1 else None
     dbg = (lambda m: print(f"[bench rank {rank}] {m}", file=sys.stderr, flush=True)) if os.environ.get("IISAN_BENCH_DEBUG") else (lambda m: None)
 
@@ -324,7 +376,7 @@ def run_ours(a):
     with torch.no_grad():
         loss_gpu_step0 = float(model(*batches[0], device).item())
     selfcheck = None
-    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+    if rank == 0 and world == 1 and not a.no_cpu_baseline and a.workload == "instrument":
         selfcheck = {"params": {n: p.detach().float().cpu().numpy() for n, p in model.named_parameters()},
                      "batch": {"ids": batches[0][0].view(B, 11).cpu().numpy(), "log_mask": batches[0][3].cpu().numpy(),
                                "image": batches[0][1].float().cpu().numpy(), "text": batches[0][2].float().cpu().numpy()},
@@ -410,7 +462,10 @@ def run_ours(a):
         model.negatives = a.negatives
     host = []
     for ids, image, text, lm in batches[:2]:
-        host.append(tuple(t.cpu().pin_memory() for t in (ids, image, text, lm)))
+        if a.workload == "instrument":
+            host.append(tuple(t.cpu().pin_memory() for t in (ids, image, text, lm)))
+        else:                                                # only ids / log_mask are needed on the host (store path)
+            host.append((ids.cpu().pin_memory(), image, text, lm.cpu().pin_memory()))
     e2e_steps = max(3, min(a.steps, 20))
 
     # ---- end to end, the product path (north_star subsystem 1): the cached states of the whole catalogue are packed once into
@@ -419,8 +474,12 @@ def run_ours(a):
     e2e = None
     if not a.no_store:
         from iisan_b200.store import CachedStateStore
-        tab = lambda: torch.randn(item_num + 1, 13, 768, device=device, generator=gen, dtype=torch.float32).to(state_dtype)
-        store = CachedStateStore.for_model(model, tab(), tab(), device=device, dtype=state_dtype)
+        plan = model.mm_encoder.plan
+        # the catalogue tables are generated already packed (only the layers the towers read): the full [item_num+1, 81, 8192]
+        # table of the LLaMA workload would be 30 GB
+        tab = lambda n_l, d: torch.randn(item_num + 1, n_l, d, device=device, generator=gen, dtype=torch.float32).to(state_dtype)
+        store = CachedStateStore(tab(len(plan.layers_img_read), W["d_img"]), tab(len(plan.layers_text_read), W["d_text"]),
+                                 range(len(plan.layers_img_read)), range(len(plan.layers_text_read)), device=device, dtype=state_dtype)
         srunner = PipelinedTrainStep(model, opt, group=group, use_graph=use_graph, store=store)
         hids = [(h[0], h[3]) for h in host]
         srunner.submit(hids[0][0], log_mask=hids[0][1])
@@ -450,7 +509,9 @@ def run_ours(a):
         keep.append(runner)
         runner.submit(*hb[0])
         n_sel = len(set(model.mm_encoder.plan.layers_img_read)) + len(set(model.mm_encoder.plan.layers_text_read))
-        nbytes = sum(t.numel() * t.element_size() for t in (hb[0][0], hb[0][3])) + B * 11 * n_sel * 768 * hb[0][1].element_size()
+        pl = model.mm_encoder.plan
+        nbytes = (sum(t.numel() * t.element_size() for t in (hb[0][0], hb[0][3]))
+                  + B * 11 * (len(pl.layers_img_read) * W["d_img"] + len(pl.layers_text_read) * W["d_text"]) * hb[0][1].element_size())
 
         def fn(i):
             runner.submit(*hb[(i + 1) % len(hb)])                            # H2D of the next batch (selected layers) on the copy stream
@@ -462,12 +523,16 @@ def run_ours(a):
         return {"value": world * B * e2e_steps / (ms_h / 1e3), "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_h / e2e_steps, "host_link_gbs": nbytes / (ms_h / e2e_steps / 1e3) / 1e9, "host_dtype": label}
 
-    e2e_host = host_batch_e2e(host, str(state_dtype).split(".")[-1])
-    e2e_host["note"] = ("PipelinedTrainStep.submit/run with pinned HOST batch tensors of the reference shapes: every timed step issues the "
-                        "H2D copy of one batch (ids, log_mask, the 7+7 selected layers) and reads one loss back; the copy of batch i+1 "
-                        "overlaps the step of batch i")
-    if e2e is None:
-        e2e = dict(e2e_host, path="host batches")
+    e2e_host = None
+    if a.workload == "instrument" or e2e is None:          # (the pinned host copies of a LLaMA-shaped batch would be 2 x 10 GB)
+        if not host[0][1].is_pinned():
+            host = [tuple(t.cpu().pin_memory() for t in bt) for bt in batches[:2]]
+        e2e_host = host_batch_e2e(host, str(state_dtype).split(".")[-1])
+        e2e_host["note"] = ("PipelinedTrainStep.submit/run with pinned HOST batch tensors of the reference shapes: every timed step issues "
+                            "the H2D copy of one batch (ids, log_mask, the selected layers) and reads one loss back; the copy of batch i+1 "
+                            "overlaps the step of batch i")
+        if e2e is None:
+            e2e = dict(e2e_host, path="host batches")
 
     def shutdown():
         """Release the captured graphs (they hold NCCL work) before tearing the process group down; a process that still
@@ -497,11 +562,12 @@ def run_ours(a):
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     tf_peak = peaks.get("bf16_tflops_sustained", 1400.0)
     peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
-    elt = 2 if state_dtype == torch.bfloat16 else 4
+    elt = 4 if state_dtype == torch.float32 else 2
+    plan = model.mm_encoder.plan
     # Dominant kernels of the hidden-state path: the fused chain forward and backward (one launch each per step).
     # Algorithmic bytes per launch: forward = every selected layer of every item read once,
     # S * (A_i*D_i + A_t*D_t) * sizeof(elt) per sample; the backward re-streams the same layers once for the gate gradients.
-    alg_bytes = B * 11 * (7 * 768 + 7 * 768) * elt
+    alg_bytes = B * 11 * (len(plan.layers_img_read) * W["d_img"] + len(plan.layers_text_read) * W["d_text"]) * elt
     traffic, traffic_src = ncu_traffic()
 
     def hbm_roof(cls, kname, tkey):
@@ -520,20 +586,32 @@ def run_ours(a):
         roof = hbm_roof("stream", "mix kernels (layer-select gather + gate fusion fwd, gate-grad re-stream bwd), summed", None)
         roof_bwd = None
     gemm_ms = classes["gemm"]["ms_per_step"] + classes["chain"]["ms_per_step"] + classes["chain_bwd"]["ms_per_step"]
-    roof_tensor = {"bound": "tensor", "achieved": (B * 11 * 3 * 7987200 / (gemm_ms / 1e3) / 1e12) if gemm_ms > 0 else None,
-                   "peak": tf_peak, "unit": "TFLOP/s", "ms_per_step": gemm_ms,
-                   "note": "SAN adapter/head GEMM FLOPs (fwd+bwd = 3x 7.99 MFLOP/item) over the summed GEMM-class + chain kernel time"}
+    # forward GEMM FLOPs of the SAN per item: adapters (down + up per active tower and stage), dim-alignment GEMMs, heads
+    E = plan.emb
+    f_item = 0
+    for (ta, _tl, ia, _il, mi) in plan.stages:
+        if ta >= 0: f_item += 4 * plan.d_text * plan.r_text
+        if ia >= 0: f_item += 4 * plan.d_img * plan.r_img
+        if mi >= 0:
+            f_item += 4 * plan.d_mm * plan.r_mm
+            if plan.n_down_project: f_item += 2 * max(plan.d_text, plan.d_img) * plan.d_mm
+    ft, fi = (E, E) if plan.asym else (plan.d_text, plan.d_img)
+    f_item += 2 * plan.d_text * ft + 2 * ft * E + 2 * plan.d_img * fi + 2 * fi * E + 2 * plan.d_mm * plan.d_mm + 2 * plan.d_mm * E
+    roof_tensor = {"bound": "tensor", "achieved": (B * 11 * 3 * f_item / (gemm_ms / 1e3) / 1e12) if gemm_ms > 0 else None,
+                   "peak": tf_peak, "unit": "TFLOP/s", "ms_per_step": gemm_ms, "flop_per_item_forward": f_item,
+                   "note": "SAN adapter / alignment / head GEMM FLOPs (fwd+bwd = 3x forward) over the summed GEMM-class + chain kernel time"}
     roof_tensor["frac"] = (roof_tensor["achieved"] / tf_peak) if roof_tensor["achieved"] else None
 
     cpu = None
     loss_ref_step0 = None
     if world == 1 and not a.no_cpu_baseline:
-        sps, sec, cores, _ = cpu_reference_steps(a.cpu_batch, a.cpu_steps, 1)
+        a.cpu_batch = a.cpu_batch or W["cpu_batch"]
+        sps, sec, cores, _ = cpu_reference_steps(a.cpu_batch, a.cpu_steps, 1, a.workload)
         cpu = {"value": sps, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"{a.cpu_steps} full train steps of B={a.cpu_batch} dense users (fp32, torch CPU, oracle port of the reference "
                          f"algorithm with vectorised negative masks -- faster than the reference's per-user Python mask loop; {sec:.2f} s/step)"}
         if selfcheck is not None:
-            loss_ref_step0 = cpu_reference_loss(selfcheck["params"], selfcheck["batch"], selfcheck["pop"], item_num)
+            loss_ref_step0 = cpu_reference_loss(selfcheck["params"], selfcheck["batch"], selfcheck["pop"], item_num, a.workload)
 
     n_timed = a.steps * a.reps
     line = {
@@ -542,16 +620,18 @@ def run_ours(a):
         "dtype": a.compute, "data": "synthetic",
         "timing": {"reps": a.reps, "statistic": "median over reps of the device time of one block of `steps` steps (max over ranks per block)",
                    "block_ms_min_max": [min(blocks), max(blocks)], "timed_region_s": t1 - t0},
-        "config": {"workload": workload_name(B, str(state_dtype).split('.')[-1], item_num),
+        "config": {"workload": workload_name(B, str(state_dtype).split('.')[-1], item_num, a.workload), "workload_key": a.workload,
                    "negatives": ("global (all-gather)" if a.negatives == "global" else "local (reference DDP semantics)") if world > 1 else "local",
-                   "l2_policy": f"inputs rotate over {n_rot} resident batches of {2 * B * 11 * 13 * 768 * elt / 1e6:.0f} MB (> 126 MB L2)",
+                   "l2_policy": f"inputs rotate over {n_rot} resident batches of "
+                                f"{B * 11 * (W['layers_img'] * W['d_img'] + W['layers_text'] * W['d_text']) * elt / 1e6:.0f} MB (> 126 MB L2)",
                    "step_runner": "CUDA graph replay (iisan_b200.engine.TrainStep)" if use_graph else "eager",
                    "parallelism": f"dp{world}", "host_numa_binding": numa},
         "e2e": e2e, "e2e_host_batches": e2e_host,
         "gpu_launches": int(launches_per_step * n_timed),
         "gpu_launches_per_step": launches_per_step,
         "clocks": clocks,
-        "roofline": roof, "roofline_chain_bwd": roof_bwd, "roofline_tensor": roof_tensor,
+        "roofline": (roof_tensor if a.workload == "llama_eva" else roof), "roofline_hbm": roof, "roofline_chain_bwd": roof_bwd,
+        "roofline_tensor": roof_tensor,
         "kernel_classes": classes, "ms_per_step_eager_with_kernel_events": ms_prof / a.steps,
         "cpu_baseline": cpu, "loss": loss_val,
         "loss_gpu_step0": loss_gpu_step0, "loss_ref_step0": loss_ref_step0,

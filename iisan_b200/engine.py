@@ -37,23 +37,32 @@ class TrainStep:
         self.static_in = None
         self.static_loss = None
         self._params = [p for p in model.parameters() if p.requires_grad]
-        self._flat = None
 
     # ------------------------------------------------------------------------------------------------------------
     def _allreduce(self):
+        """Mean of the gradients over the ranks, in place and without staging copies: the gradients of the SAN (146 tensors) and of
+        the SASRec encoder are views of ONE flat buffer each (ops.SanFn / ops.UserEncoderFn hand views of their zero-initialised
+        gradient arena to autograd, which adopts them as ``.grad``), so all-reducing the distinct base buffers covers every
+        parameter with a handful of collectives."""
         if self.world == 1:
             return
-        grads = [p.grad for p in self._params if p.grad is not None]
-        if self._flat is None:
-            self._flat = torch.empty(sum(g.numel() for g in grads), dtype=torch.float32, device=grads[0].device)
-        flat = self._flat
-        torch._foreach_copy_(list(torch.split(flat, [g.numel() for g in grads])), [g.reshape(-1) for g in grads])
-        if dist.get_backend(self.group) == "nccl":
-            dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=self.group)       # mean inside the collective
-        else:
-            dist.all_reduce(flat, group=self.group)
-            flat.div_(self.world)
-        torch._foreach_copy_([g.reshape(-1) for g in grads], list(torch.split(flat, [g.numel() for g in grads])))
+        bases = {}
+        for p in self._params:
+            g = p.grad
+            if g is None:
+                continue
+            st = g.untyped_storage()
+            key = st.data_ptr()
+            if key not in bases:
+                # the whole storage as one flat tensor: the arena for SAN / SASRec gradients, the tensor itself otherwise
+                bases[key] = torch.empty(0, dtype=g.dtype, device=g.device).set_(st)
+        nccl = dist.get_backend(self.group) == "nccl"
+        for b in bases.values():
+            if nccl:
+                dist.all_reduce(b, op=dist.ReduceOp.AVG, group=self.group)       # mean inside the collective
+            else:
+                dist.all_reduce(b, group=self.group)
+                b.div_(self.world)
 
     def _snapshot(self):
         params = [p.detach().clone() for p in self._params]
