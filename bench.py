@@ -583,7 +583,13 @@ def run_ours(a):
         roof = hbm_roof("chain", "san_chain2_fwd_kernel (fused layer-select gather + gate fusion + adapter chain, forward)", "fwd")
         roof_bwd = hbm_roof("chain_bwd", "chain backward kernel (fused data/gate/bias gradients of the chain)", "bwd")
     else:
-        roof = hbm_roof("stream", "mix kernels (layer-select gather + gate fusion fwd, gate-grad re-stream bwd), summed", None)
+        # layered path (group layer-drop / dim alignment): the hidden states are streamed by the mix kernels, once in the forward
+        # and once in the backward; all their launches of a step are summed against 2 x the algorithmic bytes
+        st_ms = classes["stream"]["ms_per_step"]
+        roof = {"bound": "hbm", "kernel": "mix kernels (layer-select gather + gate fusion forward, gate-gradient re-stream backward), all launches of a step",
+                "achieved": 2 * alg_bytes / (st_ms / 1e3) / 1e9 if st_ms > 0 else None, "peak": hbm_peak, "unit": "GB/s", "traffic": None,
+                "traffic_source": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": 2 * alg_bytes, "ms_per_launch": st_ms}
+        roof["frac"] = (roof["achieved"] / hbm_peak) if roof["achieved"] else None
         roof_bwd = None
     gemm_ms = classes["gemm"]["ms_per_step"] + classes["chain"]["ms_per_step"] + classes["chain_bwd"]["ms_per_step"]
     # forward GEMM FLOPs of the SAN per item: adapters (down + up per active tower and stage), dim-alignment GEMMs, heads

@@ -340,9 +340,17 @@ static int san_forward_bf16_t(const iisan_san_desc* D, const iisan_san_params* P
     // ---- all stages of all three towers in one launch (san_chain.cu) ----
     ChainArgs ca{};
     ca.n_items = N; ca.n_pad = chain_n_pad(N); ca.d = D->d_mm; ca.n_stages = D->n_stages; ca.pf = g_chain_pf_fwd;
-    IISAN_TRY(chain_fill_tower(&ca.tower[0], 0, text, N, (int64_t)D->layers_text * D->d_text, nullptr, 0, L.wd_pack[0], L.wu_pack[0], L.x_t[0], L.last_t[0], L.z_t[0], D->n_stages, D->d_text));
-    IISAN_TRY(chain_fill_tower(&ca.tower[1], 0, image, N, (int64_t)D->layers_img * D->d_img, nullptr, 0, L.wd_pack[1], L.wu_pack[1], L.x_i[0], L.last_i[0], L.z_i[0], D->n_stages, D->d_img));
-    IISAN_TRY(chain_fill_tower(&ca.tower[2], 1, image, N, (int64_t)D->layers_img * D->d_img, text, (int64_t)D->layers_text * D->d_text, L.wd_pack[2], L.wu_pack[2], L.x_m[0], L.last_m[0], L.z_m[0], D->n_stages, D->d_mm));
+    bool gen2 = g_chain_gen.load(std::memory_order_relaxed) >= 2 && chain2_shape_supported(D->d_mm);
+    for (int s = 0; gen2 && s < D->n_stages; ++s) {      // the bias vectors are staged by 16-byte bulk copies
+      const uintptr_t al = reinterpret_cast<uintptr_t>(P->text[D->text_adapter[s]].b_up) | reinterpret_cast<uintptr_t>(P->text[D->text_adapter[s]].b_down) |
+                           reinterpret_cast<uintptr_t>(P->img[D->img_adapter[s]].b_up) | reinterpret_cast<uintptr_t>(P->img[D->img_adapter[s]].b_down) |
+                           reinterpret_cast<uintptr_t>(P->mm[D->mm_index[s]].b_up) | reinterpret_cast<uintptr_t>(P->mm[D->mm_index[s]].b_down);
+      if (al & 15) gen2 = false;
+    }
+    ca.rows = gen2 ? chain_tile_rows(N) : 128;
+    IISAN_TRY(chain_fill_tower(&ca.tower[0], 0, text, N, (int64_t)D->layers_text * D->d_text, nullptr, 0, L.wd_pack[0], L.wu_pack[0], L.x_t[0], L.last_t[0], L.z_t[0], D->n_stages, D->d_text, ca.rows));
+    IISAN_TRY(chain_fill_tower(&ca.tower[1], 0, image, N, (int64_t)D->layers_img * D->d_img, nullptr, 0, L.wd_pack[1], L.wu_pack[1], L.x_i[0], L.last_i[0], L.z_i[0], D->n_stages, D->d_img, ca.rows));
+    IISAN_TRY(chain_fill_tower(&ca.tower[2], 1, image, N, (int64_t)D->layers_img * D->d_img, text, (int64_t)D->layers_text * D->d_text, L.wd_pack[2], L.wu_pack[2], L.x_m[0], L.last_m[0], L.z_m[0], D->n_stages, D->d_mm, ca.rows));
     // only last_{A-1} (the operand of the heads) is written: the backward recovers h_s - last_{s-1} of the intra-modal towers
     // from the x_s stash, and the inter-modal gate gradient only needs the raw states
     ca.tower[0].store_last = 0; ca.tower[1].store_last = 0; ca.tower[2].store_last = 0;
@@ -353,7 +361,7 @@ static int san_forward_bf16_t(const iisan_san_desc* D, const iisan_san_params* P
       t1.layer[s] = D->img_layer[s]; t1.gate[s] = P->gate_img[ia]; t1.b_down[s] = P->img[ia].b_down; t1.b_up[s] = P->img[ia].b_up;
       t2.layer[s] = D->img_layer[s]; t2.layer2[s] = D->text_layer[s]; t2.gate[s] = P->gate_mm[mi]; t2.b_down[s] = P->mm[mi].b_down; t2.b_up[s] = P->mm[mi].b_up;
     }
-    if (g_chain_gen.load(std::memory_order_relaxed) >= 2) IISAN_TRY(launch_san_chain2_fwd(ca, 3, st));
+    if (gen2) IISAN_TRY(launch_san_chain2_fwd(ca, 3, st));
     else IISAN_TRY(launch_san_chain_fwd(ca, 3, st));
     last_t = L.last_t[D->n_stages - 1]; last_i = L.last_i[D->n_stages - 1]; last_m = L.last_m[D->n_stages - 1];
   }
@@ -509,9 +517,11 @@ static int san_backward_bf16_t(const iisan_san_desc* D, const iisan_san_params* 
     // ---- data / gate / bias gradients of all stages and towers in one launch (san_chain.cu) ----
     ChainBwdArgs ca{};
     ca.n_items = N; ca.n_pad = chain_n_pad(N); ca.d = D->d_mm; ca.n_stages = D->n_stages; ca.pf = g_chain_pf_bwd;
-    IISAN_TRY(chain_fill_bwd_tower(&ca.tower[0], 0, text, N, (int64_t)D->layers_text * D->d_text, nullptr, 0, L.wd_pack[0], L.wu_pack[0], L.dys[0], L.x_t[0], L.dzs[0][0], D->n_stages, D->d_text));
-    IISAN_TRY(chain_fill_bwd_tower(&ca.tower[1], 0, image, N, (int64_t)D->layers_img * D->d_img, nullptr, 0, L.wd_pack[1], L.wu_pack[1], L.dys[1], L.x_i[0], L.dzs[1][0], D->n_stages, D->d_img));
-    IISAN_TRY(chain_fill_bwd_tower(&ca.tower[2], 1, image, N, (int64_t)D->layers_img * D->d_img, text, (int64_t)D->layers_text * D->d_text, L.wd_pack[2], L.wu_pack[2], L.dys[2], L.x_m[0], L.dzs[2][0], D->n_stages, D->d_mm));
+    const bool gen2 = g_chain_gen.load(std::memory_order_relaxed) >= 2 && chain2_shape_supported(D->d_mm);
+    ca.rows = gen2 ? chain_tile_rows(N) : 128;
+    IISAN_TRY(chain_fill_bwd_tower(&ca.tower[0], 0, text, N, (int64_t)D->layers_text * D->d_text, nullptr, 0, L.wd_pack[0], L.wu_pack[0], L.dys[0], L.x_t[0], L.dzs[0][0], D->n_stages, D->d_text, ca.rows));
+    IISAN_TRY(chain_fill_bwd_tower(&ca.tower[1], 0, image, N, (int64_t)D->layers_img * D->d_img, nullptr, 0, L.wd_pack[1], L.wu_pack[1], L.dys[1], L.x_i[0], L.dzs[1][0], D->n_stages, D->d_img, ca.rows));
+    IISAN_TRY(chain_fill_bwd_tower(&ca.tower[2], 1, image, N, (int64_t)D->layers_img * D->d_img, text, (int64_t)D->layers_text * D->d_text, L.wd_pack[2], L.wu_pack[2], L.dys[2], L.x_m[0], L.dzs[2][0], D->n_stages, D->d_mm, ca.rows));
     ca.tower[0].z_stash = L.z_t[0]; ca.tower[1].z_stash = L.z_i[0]; ca.tower[2].z_stash = L.z_m[0];
     for (int s = 0; s < D->n_stages; ++s) {
       const int ta = D->text_adapter[s], ia = D->img_adapter[s], mi = D->mm_index[s];
@@ -520,7 +530,7 @@ static int san_backward_bf16_t(const iisan_san_desc* D, const iisan_san_params* 
       t1.layer[s] = D->img_layer[s]; t1.gate[s] = P->gate_img[ia]; t1.g_gate[s] = G->gate_img[ia]; t1.g_b_down[s] = G->img[ia].b_down; t1.g_b_up[s] = G->img[ia].b_up;
       t2.layer[s] = D->img_layer[s]; t2.layer2[s] = D->text_layer[s]; t2.gate[s] = P->gate_mm[mi]; t2.g_gate[s] = G->gate_mm[mi]; t2.g_b_down[s] = G->mm[mi].b_down; t2.g_b_up[s] = G->mm[mi].b_up;
     }
-    if (g_chain_gen.load(std::memory_order_relaxed) >= 2) IISAN_TRY(launch_san_chain2_bwd(ca, 3, st));
+    if (gen2) IISAN_TRY(launch_san_chain2_bwd(ca, 3, st));
     else IISAN_TRY(launch_san_chain_bwd(ca, 3, st));
     // ---- weight gradients: reductions over all items; the 6 x A split-K GEMMs over the stashes share ONE launch ----
     {

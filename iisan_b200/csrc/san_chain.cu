@@ -25,6 +25,8 @@
 // whose depth of ~2 chunks is far below the 12 chunks between a write and its re-read).
 //
 // warp roles: 0 weight TMA producer | 1 TMEM allocator + MMA issuer + TMA stores | 2 data TMA producer | 3..10 epilogue
+#include <cstdlib>
+
 #include "common.cuh"
 #include "launch.cuh"
 #include "san_chain.cuh"
@@ -683,7 +685,23 @@ __global__ void __launch_bounds__(CH_THREADS, 1) san_chain_bwd_kernel(const __gr
 // ================================================================================================================
 int make_tensor_map_bf16(CUtensorMap* out, const void* ptr, int64_t rows, int64_t cols, int64_t pitch, int box_inner, int box_outer);
 
-int chain_n_pad(int n_items) { return (n_items + CH_ROWS - 1) / CH_ROWS * CH_ROWS; }
+// Row tiles.  The first-generation kernels use 128-row tiles.  The second generation shrinks the tile so that the three towers
+// fill the chip in ONE wave (148 SMs / 3 towers = 49 tiles per tower: 115 rows at the benchmark's 5632 items instead of 44 tiles
+// of 128 rows on 132 SMs); the MMAs keep M = 128, the surplus TMEM lanes idle.  The stash matrices are addressed by row
+// (stage s starts at row s * n_pad), so both generations can read what either wrote.
+int chain_tile_rows(int n_items) {
+  static const int forced = [] { const char* e = getenv("IISAN_B200_CHAIN_ROWS"); return e ? atoi(e) : 0; }();      // measurement switch
+  if (forced >= 16 && forced <= CH_ROWS) return forced;
+  constexpr int kTilesPerTower = 148 / 3;
+  if (n_items <= kTilesPerTower * 64 || n_items > kTilesPerTower * CH_ROWS) return CH_ROWS;
+  return (n_items + kTilesPerTower - 1) / kTilesPerTower;
+}
+int chain_n_pad(int n_items) {
+  const int p128 = (n_items + CH_ROWS - 1) / CH_ROWS * CH_ROWS;
+  const int r = chain_tile_rows(n_items);
+  const int pr = (n_items + r - 1) / r * r;
+  return p128 > pr ? p128 : pr;
+}
 
 static int fill_common(CUtensorMap* map_wd, CUtensorMap* map_wu, const bf16* wd_pack, const bf16* wu_pack, int n_stages, int d) {
   IISAN_TRY(make_tensor_map_bf16(map_wd, wd_pack, (int64_t)n_stages * CH_R, d, d, CH_CW, CH_R));
@@ -693,7 +711,8 @@ static int fill_common(CUtensorMap* map_wd, CUtensorMap* map_wu, const bf16* wd_
 
 int chain_fill_tower(ChainTower* T, int mode, const void* h, int64_t n_items, int64_t h_pitch_cols, const void* h2, int64_t h2_pitch_cols,
                      const bf16* wd_pack, const bf16* wu_pack, const bf16* x_all, const bf16* last_all, const bf16* z_all, int n_stages,
-                     int d) {
+                     int d, int box_rows) {
+  const int CH_ROWS = box_rows;          // rows of the TMA boxes (= the row tile of the generation that will run)
   const int64_t np = chain_n_pad((int)n_items);
   T->mode = mode;
   IISAN_TRY(make_tensor_map_bf16(&T->map_h, h, n_items, h_pitch_cols, h_pitch_cols, CH_CW, CH_ROWS));
@@ -708,7 +727,8 @@ int chain_fill_tower(ChainTower* T, int mode, const void* h, int64_t n_items, in
 
 int chain_fill_bwd_tower(ChainBwdTower* T, int mode, const void* h, int64_t n_items, int64_t h_pitch_cols, const void* h2,
                          int64_t h2_pitch_cols, const bf16* wd_pack, const bf16* wu_pack, const bf16* dy_all, const bf16* x_all,
-                         const bf16* dz_all, int n_stages, int d) {
+                         const bf16* dz_all, int n_stages, int d, int box_rows) {
+  const int CH_ROWS = box_rows;
   const int64_t np = chain_n_pad((int)n_items);
   T->mode = mode;
   IISAN_TRY(make_tensor_map_bf16(&T->map_h, h, n_items, h_pitch_cols, h_pitch_cols, CH_CW, CH_ROWS));

@@ -31,6 +31,7 @@ struct ChainArgs {
   ChainTower tower[3];
   int n_items, n_pad, d, n_stages;
   int pf;                   // second generation: hidden-state tiles are requested into L2 this many chunks ahead (0: off)
+  int rows;                 // second generation: rows per tile (TMA box rows), <= 128
 };
 
 struct ChainBwdTower {
@@ -53,18 +54,21 @@ struct ChainBwdArgs {
   ChainBwdTower tower[3];
   int n_items, n_pad, d, n_stages;
   int pf;
+  int rows;
 };
 
 int chain_n_pad(int n_items);
+int chain_tile_rows(int n_items);          // row tile of the second-generation kernels (the first generation: 128)
 int chain_fill_tower(ChainTower* T, int mode, const void* h, int64_t n_items, int64_t h_pitch_cols, const void* h2, int64_t h2_pitch_cols,
                      const __nv_bfloat16* wd_pack, const __nv_bfloat16* wu_pack, const __nv_bfloat16* x_all, const __nv_bfloat16* last_all,
-                     const __nv_bfloat16* z_all, int n_stages, int d);
+                     const __nv_bfloat16* z_all, int n_stages, int d, int box_rows = 128);
 int chain_fill_bwd_tower(ChainBwdTower* T, int mode, const void* h, int64_t n_items, int64_t h_pitch_cols, const void* h2,
                          int64_t h2_pitch_cols, const __nv_bfloat16* wd_pack, const __nv_bfloat16* wu_pack, const __nv_bfloat16* dy_all,
-                         const __nv_bfloat16* last_all, const __nv_bfloat16* dz_all, int n_stages, int d);
+                         const __nv_bfloat16* last_all, const __nv_bfloat16* dz_all, int n_stages, int d, int box_rows = 128);
 int launch_san_chain_fwd(const ChainArgs& args, int n_towers, cudaStream_t st);
-int launch_san_chain2_fwd(const ChainArgs& args, int n_towers, cudaStream_t st);   // san_chain2.cu (falls back to generation 1 for shapes it does not cover)
-int launch_san_chain2_bwd(const ChainBwdArgs& args, int n_towers, cudaStream_t st);   // san_chain2_bwd.cu (same)
+bool chain2_shape_supported(int d);                                                  // widths the second generation covers
+int launch_san_chain2_fwd(const ChainArgs& args, int n_towers, cudaStream_t st);   // san_chain2.cu
+int launch_san_chain2_bwd(const ChainBwdArgs& args, int n_towers, cudaStream_t st);   // san_chain2_bwd.cu
 int launch_san_chain_bwd(const ChainBwdArgs& args, int n_towers, cudaStream_t st);
 
 }  // namespace iisan

@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(THREADS, 1) san_chain2_fwd_kernel(const __grid
   const bool is_mm = (T.mode == 1);
   const int NC = a.d / CW;
   const int A = a.n_stages;
-  const int m0 = blockIdx.x * ROWS;
+  const int m0 = blockIdx.x * a.rows;            // a.rows <= 128 rows per tile: the TMA boxes carry a.rows rows, TMEM lanes beyond idle
   const int NP = a.n_pad;
 
   extern __shared__ uint8_t smem_raw[];
@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(THREADS, 1) san_chain2_fwd_kernel(const __grid
         const int slot = par * NDR + (n & (NDR - 1));
         TR(0, mbar_wait_park(bar0 + Smem::bDEmpty + 8 * slot, ((uint32_t)(n / NDR) & 1u) ^ 1u));
         const uint32_t bar = bar0 + Smem::bDFull + 8 * slot;
-        mbar_expect_tx_a(bar, TILE_BYTES);
+        mbar_expect_tx_a(bar, (uint32_t)(a.rows * CW * 2));
         tma_load_2d_a(sbase + Smem::kD + slot * TILE_BYTES, m, bar, col, row);
         ++n;
       };
@@ -410,9 +410,11 @@ __global__ void __launch_bounds__(THREADS, 1) san_chain2_fwd_kernel(const __grid
         __syncwarp();
         if (lane == 0) mbar_arrive_a(bar0 + Smem::bZReady);
         // stash (backward: ReLU mask and the operand of dWu); rows past the item count are never read
-        uint4* zs = reinterpret_cast<uint4*>(T.z_out + ((int64_t)s * NP + grow) * R + grp * 16);
-        zs[0] = make_uint4(zo[0], zo[1], zo[2], zo[3]);
-        zs[1] = make_uint4(zo[4], zo[5], zo[6], zo[7]);
+        if (m < a.rows) {                               // (rows of the tile, not of the neighbouring one)
+          uint4* zs = reinterpret_cast<uint4*>(T.z_out + ((int64_t)s * NP + grow) * R + grp * 16);
+          zs[0] = make_uint4(zo[0], zo[1], zo[2], zo[3]);
+          zs[1] = make_uint4(zo[4], zo[5], zo[6], zo[7]);
+        }
       }
       if (is_mm) { if (more) stage_chunks(BoolTag<true>{}, BoolTag<true>{}, s); else stage_chunks(BoolTag<true>{}, BoolTag<false>{}, s); }
       else { if (more) stage_chunks(BoolTag<false>{}, BoolTag<true>{}, s); else stage_chunks(BoolTag<false>{}, BoolTag<false>{}, s); }
@@ -424,24 +426,22 @@ __global__ void __launch_bounds__(THREADS, 1) san_chain2_fwd_kernel(const __grid
   if (warp == 1) tmem_dealloc(tmem_base, T_COLS);
 }
 
-// What this generation covers; everything else stays with the first generation (san_chain.cu).
-static bool chain2_supported(const ChainArgs& args, int n_towers) {
-  if (args.d % 128 != 0 || args.d < 256 || args.d > MAX_D) return false;      // even chunk count (per-parity rings), bias staging buffer
-  for (int t = 0; t < n_towers; ++t)
-    for (int s = 0; s < args.n_stages; ++s)                                    // bulk copies of the biases need 16-byte aligned sources
-      if ((reinterpret_cast<uintptr_t>(args.tower[t].b_up[s]) | reinterpret_cast<uintptr_t>(args.tower[t].b_down[s])) & 15) return false;
-  return true;
-}
+// What this generation covers; everything else stays with the first generation (san_chain.cu): an even number of 64-column
+// chunks (per-parity rings), the bias staging buffer, 16-byte aligned bias vectors (bulk copies).
+bool chain2_shape_supported(int d) { return d % 128 == 0 && d >= 256 && d <= MAX_D; }
 
 int launch_san_chain2_fwd(const ChainArgs& args, int n_towers, cudaStream_t st) {
-  if (!chain2_supported(args, n_towers)) return launch_san_chain_fwd(args, n_towers, st);
+  if (!chain2_shape_supported(args.d) || args.rows < 1 || args.rows > ROWS) return IISAN_EINVAL;
+  for (int t = 0; t < n_towers; ++t)
+    for (int s = 0; s < args.n_stages; ++s)
+      if ((reinterpret_cast<uintptr_t>(args.tower[t].b_up[s]) | reinterpret_cast<uintptr_t>(args.tower[t].b_down[s])) & 15) return IISAN_EINVAL;
   static std::atomic<uint64_t> attr_done{0};      // devices on which the attribute has been set
   const uint64_t dev_bit = device_bit();
   if (!(attr_done.load(std::memory_order_acquire) & dev_bit)) {
     IISAN_CUDA_OK(cudaFuncSetAttribute(san_chain2_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::kTotal));
     attr_done.fetch_or(dev_bit, std::memory_order_release);
   }
-  const int tiles = (args.n_items + ROWS - 1) / ROWS;
+  const int tiles = (args.n_items + args.rows - 1) / args.rows;
   { LaunchScope ls_(IISAN_K_CHAIN, st); san_chain2_fwd_kernel<<<dim3(tiles, n_towers), THREADS, Smem::kTotal, st>>>(args); }
   IISAN_LAUNCH_OK();
   return IISAN_OK;

@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(THREADS, 1) san_chain2_bwd_kernel(const __grid
   const bool is_mm = (T.mode == 1);
   const int NC = a.d / CW;
   const int A = a.n_stages;
-  const int m0 = blockIdx.x * ROWS;
+  const int m0 = blockIdx.x * a.rows;            // a.rows <= 128 rows per tile (see chain_tile_rows)
   const int NP = a.n_pad;
 
   extern __shared__ uint8_t smem_raw[];
@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(THREADS, 1) san_chain2_bwd_kernel(const __grid
         const int slot = par * NDR + (n & (NDR - 1));
         TR(0, mbar_wait_park(bar0 + S::bDEmpty + 8 * slot, ((uint32_t)(n / NDR) & 1u) ^ 1u));
         const uint32_t bar = bar0 + S::bDFull + 8 * slot;
-        mbar_expect_tx_a(bar, TILE_BYTES);
+        mbar_expect_tx_a(bar, (uint32_t)(a.rows * CW * 2));
         tma_load_2d_a(sbase + S::kD + slot * TILE_BYTES, m, bar, col, row);
         ++n;
       };
@@ -297,7 +297,7 @@ __global__ void __launch_bounds__(THREADS, 1) san_chain2_bwd_kernel(const __grid
 #pragma unroll
     for (int q = 0; q < 4; ++q) offq[q] = sw_row + (uint32_t)(((half * 4 + q) ^ (m & 7)) << 4);
     const int64_t grow = (int64_t)m0 + m;
-    const bool row_ok = grow < a.n_items;
+    const bool row_ok = m < a.rows && grow < a.n_items;     // TMEM lanes beyond the tile's rows, rows beyond the batch
     const uint32_t rmask = row_ok ? 0xFFFFFFFFu : 0u;       // rows past the item count: dy is whatever the workspace held
     const uint32_t bar_d_full = bar0 + S::bDFull + par * NDR * 8, bar_d_empty = bar0 + S::bDEmpty + par * NDR * 8;
     const uint32_t bar_x_full = bar0 + S::bXFull + par * 8, bar_x_empty = bar0 + S::bXEmpty + par * 8;
@@ -398,7 +398,7 @@ __global__ void __launch_bounds__(THREADS, 1) san_chain2_bwd_kernel(const __grid
       // ---- dz_s = dz_acc * (z_s > 0): packed bf16 into the TMEM operand of the dx MMAs, to the stash (weight-gradient operand),
       //      db_down.  Warp (quad, grp) takes columns [grp*16, +16) of its 32 rows ----
       {
-        const uint4* zs = reinterpret_cast<const uint4*>(T.z_stash + ((int64_t)s * NP + grow) * R + grp * 16);
+        const uint4* zs = reinterpret_cast<const uint4*>(T.z_stash + ((int64_t)s * NP + (row_ok ? grow : (int64_t)m0)) * R + grp * 16);
         const uint4 z0 = __ldg(zs), z1 = __ldg(zs + 1);              // issued before the wait
         TR(2, mbar_wait_a(bar0 + S::bZFull, (uint32_t)q & 1u));
         tc_fence_after();
@@ -421,9 +421,11 @@ __global__ void __launch_bounds__(THREADS, 1) san_chain2_bwd_kernel(const __grid
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_a(bar0 + S::bZReady);
-        uint4* dzs = reinterpret_cast<uint4*>(T.dz_out + ((int64_t)s * NP + grow) * R + grp * 16);
-        dzs[0] = make_uint4(zo[0], zo[1], zo[2], zo[3]);
-        dzs[1] = make_uint4(zo[4], zo[5], zo[6], zo[7]);
+        if (m < a.rows) {
+          uint4* dzs = reinterpret_cast<uint4*>(T.dz_out + ((int64_t)s * NP + grow) * R + grp * 16);
+          dzs[0] = make_uint4(zo[0], zo[1], zo[2], zo[3]);
+          dzs[1] = make_uint4(zo[4], zo[5], zo[6], zo[7]);
+        }
         // db_down: sum over the 32 rows of this warp for each of its 16 columns -> lanes 0..15 (15 + 16 shuffles)
 #pragma unroll
         for (int k = 0; k < 16; ++k) dzv[k] += __shfl_xor_sync(0xffffffffu, dzv[k], 16);
@@ -456,20 +458,15 @@ __global__ void __launch_bounds__(THREADS, 1) san_chain2_bwd_kernel(const __grid
   if (warp == 1) tmem_dealloc(tmem_base, c2b::T_COLS);
 }
 
-// What this generation covers; everything else stays with the first generation (san_chain.cu).
-static bool chain2_bwd_supported(const ChainBwdArgs& args) {
-  return args.d % 128 == 0 && args.d >= 256;      // even chunk count (per-parity rings), at least two chunks per parity
-}
-
 int launch_san_chain2_bwd(const ChainBwdArgs& args, int n_towers, cudaStream_t st) {
-  if (!chain2_bwd_supported(args)) return launch_san_chain_bwd(args, n_towers, st);
+  if (!chain2_shape_supported(args.d) || args.rows < 1 || args.rows > ROWS) return IISAN_EINVAL;
   static std::atomic<uint64_t> attr_done{0};      // devices on which the attribute has been set
   const uint64_t dev_bit = device_bit();
   if (!(attr_done.load(std::memory_order_acquire) & dev_bit)) {
     IISAN_CUDA_OK(cudaFuncSetAttribute(san_chain2_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c2b::Smem::kTotal));
     attr_done.fetch_or(dev_bit, std::memory_order_release);
   }
-  const int tiles = (args.n_items + ROWS - 1) / ROWS;
+  const int tiles = (args.n_items + args.rows - 1) / args.rows;
   { LaunchScope ls_(IISAN_K_CHAIN_BWD, st); san_chain2_bwd_kernel<<<dim3(tiles, n_towers), THREADS, c2b::Smem::kTotal, st>>>(args); }
   IISAN_LAUNCH_OK();
   return IISAN_OK;

@@ -87,12 +87,19 @@ def test_padded_slots_do_not_influence_loss_or_gradients():
     # gradients: equal up to the reduction order of the atomics (split-K, per-CTA partial sums); the 21 scalar gate gradients are
     # cancellation-heavy sums over N*d terms and get a looser bound
     worst = 0.0
+    sa, sb = [], []
     for n in res[0][1]:
         a, b = res[0][1][n].double(), res[1][1][n].double()
+        if a.numel() == 1:                       # the 21 scalar gate gradients are compared pooled into one vector (as in test_gpu_parity)
+            sa.append(a.reshape(1)); sb.append(b.reshape(1))
+            continue
         rel = float((a - b).norm() / (a.norm() + 1e-30))
         worst = max(worst, rel)
-        assert rel <= (5e-2 if a.numel() == 1 else 1e-3), (n, rel)
-    print(f"worst relative L2 difference of a gradient tensor: {worst:.2e}")
+        assert rel <= 1e-3, (n, rel)
+    sa, sb = torch.cat(sa), torch.cat(sb)
+    rel_gates = float((sa - sb).norm() / (sa.norm() + 1e-30))
+    assert rel_gates <= 5e-2, rel_gates
+    print(f"worst relative L2 difference of a gradient tensor: {worst:.2e}; pooled gate gradients: {rel_gates:.2e}")
 
 
 def test_loss_invariant_under_user_permutation():
