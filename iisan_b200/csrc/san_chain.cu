@@ -685,16 +685,16 @@ __global__ void __launch_bounds__(CH_THREADS, 1) san_chain_bwd_kernel(const __gr
 // ================================================================================================================
 int make_tensor_map_bf16(CUtensorMap* out, const void* ptr, int64_t rows, int64_t cols, int64_t pitch, int box_inner, int box_outer);
 
-// Row tiles.  The first-generation kernels use 128-row tiles.  The second generation shrinks the tile so that the three towers
-// fill the chip in ONE wave (148 SMs / 3 towers = 49 tiles per tower: 115 rows at the benchmark's 5632 items instead of 44 tiles
-// of 128 rows on 132 SMs); the MMAs keep M = 128, the surplus TMEM lanes idle.  The stash matrices are addressed by row
-// (stage s starts at row s * n_pad), so both generations can read what either wrote.
+// Row tiles.  The first-generation kernels use 128-row tiles.  The second generation takes the tile height as a launch parameter
+// (IISAN_B200_CHAIN_ROWS, e.g. 115 rows = 49 tiles per tower = one wave of 147 CTAs); the MMAs keep M = 128, surplus TMEM lanes
+// idle.  The stash matrices are addressed by row (stage s starts at row s * n_pad), so both generations can read what either wrote.
 int chain_tile_rows(int n_items) {
   static const int forced = [] { const char* e = getenv("IISAN_B200_CHAIN_ROWS"); return e ? atoi(e) : 0; }();      // measurement switch
   if (forced >= 16 && forced <= CH_ROWS) return forced;
-  constexpr int kTilesPerTower = 148 / 3;
-  if (n_items <= kTilesPerTower * 64 || n_items > kTilesPerTower * CH_ROWS) return CH_ROWS;
-  return (n_items + kTilesPerTower - 1) / kTilesPerTower;
+  // Measured on B200 (B = 512): 147 CTAs x 115 rows run exactly as long as 132 CTAs x 128 rows -- the kernels are bound by the
+  // per-chunk latency chain inside a CTA, not by the rows it owns -- so the default stays at full tiles.
+  (void)n_items;
+  return CH_ROWS;
 }
 int chain_n_pad(int n_items) {
   const int p128 = (n_items + CH_ROWS - 1) / CH_ROWS * CH_ROWS;
