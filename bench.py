@@ -455,7 +455,14 @@ def run_ours(a):
             runners[i % n_rot].replay()
         nms, _, _, _, _ = timed(a.steps, lambda i: runners[i % n_rot].replay(), max(3, a.reps // 2))
         local_ms = (ms if a.negatives == "local" else other["ms_per_step"] * a.steps) / a.steps
+        # the bare collective: one fp32 all-reduce of the size of the gradient arena, back to back
+        n_par = sum(p.numel() for p in model.parameters() if p.requires_grad)
+        probe = torch.zeros(n_par, dtype=torch.float32, device=device)
+        for _ in range(5):
+            dist.all_reduce(probe, op=dist.ReduceOp.AVG)
+        ar_ms, _, _, _, _ = timed(20, lambda i: dist.all_reduce(probe, op=dist.ReduceOp.AVG))
         exposed = {"ms_per_step_no_collectives": nms / a.steps, "ms_per_step_local_negatives": local_ms,
+                   "bare_allreduce_ms": ar_ms / 20, "allreduce_bytes": n_par * 4,
                    "exposed_comm_ms": local_ms - nms / a.steps,
                    "note": "local in-batch negatives: captured step with the gradient all-reduce minus the same step without any collective"}
         runners = None

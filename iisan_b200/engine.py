@@ -37,16 +37,29 @@ class TrainStep:
         self.static_in = None
         self.static_loss = None
         self._params = [p for p in model.parameters() if p.requires_grad]
+        self._grad_arena = None
 
     # ------------------------------------------------------------------------------------------------------------
+    def _arena(self, device):
+        """Gradient arena of the data-parallel step (ops.GradArena): every parameter gradient of the step is a slice of one buffer."""
+        if self.world == 1:
+            return None
+        if self._grad_arena is None:
+            from .ops import GradArena
+            n = sum((p.numel() + 63) // 64 * 64 for p in self._params) + 64 * 64
+            self._grad_arena = GradArena(n, device)
+        return self._grad_arena
+
     def _allreduce(self):
-        """Mean of the gradients over the ranks, in place and without staging copies: the gradients of the SAN (146 tensors) and of
-        the SASRec encoder are views of ONE flat buffer each (ops.SanFn / ops.UserEncoderFn hand views of their zero-initialised
-        gradient arena to autograd, which adopts them as ``.grad``), so all-reducing the distinct base buffers covers every
-        parameter with a handful of collectives."""
+        """Mean of the gradients over the ranks, in place and without staging copies.  With the gradient arena active (the
+        normal case) this is ONE collective over the used part of the arena; gradients that live elsewhere (a foreign autograd
+        function) are reduced through their own storage."""
         if self.world == 1:
             return
         bases = {}
+        arena = self._grad_arena
+        if arena is not None and arena.off > 0:
+            bases[arena.buf.untyped_storage().data_ptr()] = arena.used()
         for p in self._params:
             g = p.grad
             if g is None:
@@ -54,7 +67,7 @@ class TrainStep:
             st = g.untyped_storage()
             key = st.data_ptr()
             if key not in bases:
-                # the whole storage as one flat tensor: the arena for SAN / SASRec gradients, the tensor itself otherwise
+                # the whole storage as one flat tensor: the arena of SAN / SASRec gradients, the tensor itself otherwise
                 bases[key] = torch.empty(0, dtype=g.dtype, device=g.device).set_(st)
         nccl = dist.get_backend(self.group) == "nccl"
         for b in bases.values():
@@ -93,13 +106,21 @@ class TrainStep:
                         v.zero_()            # the state did not exist before the warm-up: back to its initial value
 
     def _eager(self, ids, image, text, log_mask):
+        from .ops import GradArena
         self.opt.zero_grad(set_to_none=True)
-        if self.store is not None:
-            image, text = self.store.gather(ids)
-            loss = self.model(ids, image, text, log_mask, ids.device, packed=True)
-        else:
-            loss = self.model(ids, image, text, log_mask, ids.device)
-        loss.backward()
+        arena = self._arena(ids.device)
+        if arena is not None:
+            arena.reset()
+        prev, GradArena.active = GradArena.active, arena
+        try:
+            if self.store is not None:
+                image, text = self.store.gather(ids)
+                loss = self.model(ids, image, text, log_mask, ids.device, packed=True)
+            else:
+                loss = self.model(ids, image, text, log_mask, ids.device)
+            loss.backward()
+        finally:
+            GradArena.active = prev
         self._allreduce()
         self.opt.step()
         return loss.detach()

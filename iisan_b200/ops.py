@@ -25,6 +25,41 @@ def _workspace(nbytes: int, device):
     return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
 
 
+class GradArena:
+    """One persistent fp32 buffer that the backward functions carve their zero-initialised parameter gradients from (instead of a
+    fresh torch.zeros each): the data-parallel step then averages ALL gradients with ONE collective over ``used()``.  Activated by
+    iisan_b200.engine.TrainStep for N > 1; without an active arena the functions allocate as before."""
+
+    active = None
+
+    def __init__(self, numel, device):
+        self.buf = torch.zeros(int(numel), dtype=torch.float32, device=device)
+        self.off = 0
+
+    def reset(self):
+        self.buf.zero_()                    # one memset per step (stream-ordered, capturable)
+        self.off = 0
+
+    def take(self, numel):
+        n = (int(numel) + 63) // 64 * 64    # 256-byte aligned slices
+        if self.off + n > self.buf.numel():
+            raise L.IisanLibraryError("gradient arena too small")
+        v = self.buf[self.off:self.off + int(numel)]
+        self.off += n
+        return v
+
+    def used(self):
+        return self.buf[:self.off]
+
+
+def grad_zeros(numel, device):
+    """Zero-initialised flat fp32 gradient buffer: a slice of the active arena, else a fresh tensor."""
+    a = GradArena.active
+    if a is not None and a.buf.device == torch.device(device):
+        return a.take(numel)
+    return torch.zeros(max(int(numel), 1), dtype=torch.float32, device=device)
+
+
 # --------------------------------------------------------------------------------------------------
 # dense layer (com_dense)
 # --------------------------------------------------------------------------------------------------
@@ -61,8 +96,8 @@ class LinearFn(torch.autograd.Function):
         if dy2.stride(-1) != 1 or dy2.dtype != torch.float32:
             dy2 = dy2.contiguous().float()
         dx = torch.empty(rows, k, dtype=torch.float32, device=dy.device) if ctx.needs_input_grad[0] else None
-        dw = torch.zeros_like(weight) if ctx.needs_input_grad[1] else None
-        db = torch.zeros(n, dtype=torch.float32, device=dy.device) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+        dw = grad_zeros(weight.numel(), dy.device).view(weight.shape) if ctx.needs_input_grad[1] else None
+        db = grad_zeros(n, dy.device)[:n] if (ctx.has_bias and ctx.needs_input_grad[2]) else None
         L.check(lib.iisan_linear_backward(rows, n, k, _p(x2), x2.stride(0), _p(weight), _p(dy2), dy2.stride(0), _p(dx), k,
                                           _p(dw), _p(db), ctx.compute, _stream()), "iisan_linear_backward")
         return (None if dx is None else dx.view(*ctx.lead, k)), dw, db, None

@@ -198,7 +198,8 @@ class SanBinder(_BinderBase):
         offs, tot = [], 0
         for s in sizes:
             offs.append(tot); tot += (s + 63) // 64 * 64
-        flat = torch.zeros(max(tot, 1), dtype=torch.float32, device=device)
+        from .ops import grad_zeros
+        flat = grad_zeros(max(tot, 1), device)
         t = L.SanParams()
         views = []
         base = flat.data_ptr()
@@ -296,7 +297,8 @@ class UserEncoderBinder(_BinderBase):
         offs, tot = [], 0
         for p in params:
             offs.append(tot); tot += (p.numel() + 63) // 64 * 64
-        flat = torch.zeros(tot, dtype=torch.float32, device=device)
+        from .ops import grad_zeros
+        flat = grad_zeros(tot, device)
         t = L.UeParams()
         views = []
         base = flat.data_ptr()
