@@ -20,7 +20,8 @@ LIBDIR = os.path.join(HERE, "lib")
 # with wait-time accounting (-DIISAN_CHAIN_TRACE, san_chain.cu) into lib/libiisan_b200_trace.so; load it with
 # IISAN_B200_LIB=<path> (iisan_b200/_lib.py), see scripts/chain_trace.py.
 VARIANT = os.environ.get("IISAN_B200_BUILD_VARIANT", "")
-VARIANT_FLAGS = {"": [], "trace": ["-DIISAN_CHAIN_TRACE"]}[VARIANT]
+# any other variant name: the flags come from IISAN_B200_EXTRA_FLAGS (A/B builds of kernel parameters, e.g. "-DC3_NT=5 -DC3_NW=4")
+VARIANT_FLAGS = {"": [], "trace": ["-DIISAN_CHAIN_TRACE"]}.get(VARIANT, os.environ.get("IISAN_B200_EXTRA_FLAGS", "").split())
 OBJDIR = os.path.join(HERE, "build" + ("_" + VARIANT if VARIANT else ""))
 LIB = os.path.join(LIBDIR, "libiisan_b200" + ("_" + VARIANT if VARIANT else "") + ".so")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")

@@ -18,6 +18,7 @@
 #include "gemm_simt.cuh"
 #include "launch.cuh"
 #include "san_layout.cuh"
+#include "san_lr.cuh"
 #include "san_chain.cuh"
 #include "san_mix.cuh"
 #include "umma_gemm.cuh"
@@ -129,6 +130,7 @@ struct SanLayoutBf16 {
   bf16 *wd_pack[3], *wu_pack[3];          // fused chain: per tower (text, img, mm) all stages' weights, contiguous
   bf16* dys[3];                           // fused chain backward: d last_s of all stages [A, N, d] per tower
   bf16* dzs[3][IISAN_MAX_STAGES];         //                        dz_s [N, r]
+  void* lr_ws;                            // third generation (san_lr.cu): its own block of the workspace
   size_t bytes;
 
   static WCopy takew(Arena& a, size_t n) { WCopy c; c.w = a.take<bf16>(n); c.wt = a.take<bf16>(n); return c; }
@@ -198,14 +200,20 @@ struct SanLayoutBf16 {
         for (int s = 0; s < D.n_stages; ++s) dzs[t][s] = dz + (size_t)s * NP * D.r_mm;
       }
     }
+    lr_ws = nullptr;
+    if (san_chain_eligible(D) && san_lr_eligible(D)) {
+      lr_ws = a.base + a.off;
+      a.off += align_up(san_lr_workspace_bytes(D), 256);
+    }
     bytes = a.off;
   }
 };
 
-// test / profiling switches: IISAN_B200_NO_CHAIN=1 forces the layered path, IISAN_B200_CHAIN_GEN=1 the first-generation chain
-// forward (A/B measurements; the default is the second generation wherever it applies: d a multiple of 128)
+// test / profiling switches: IISAN_B200_NO_CHAIN=1 forces the layered path, IISAN_B200_CHAIN_GEN=1 | 2 an older generation of the
+// fused chain (A/B measurements; the default is the newest generation that covers the shape: 3 = resident-state forward +
+// low-rank adjoint backward (san_lr.cu) for d <= 768, 2 for the other multiples of 128)
 static const bool g_disable_chain = [] { const char* e = getenv("IISAN_B200_NO_CHAIN"); return e && e[0] == '1'; }();
-static std::atomic<int> g_chain_gen{[] { const char* e = getenv("IISAN_B200_CHAIN_GEN"); return (e && e[0] == '1') ? 1 : 2; }()};
+static std::atomic<int> g_chain_gen{[] { const char* e = getenv("IISAN_B200_CHAIN_GEN"); return (e && e[0] >= '1' && e[0] <= '3') ? e[0] - '0' : 3; }()};
 int set_chain_generation(int gen) { return g_chain_gen.exchange(gen); }
 // L2 prefetch distance (chunks) of the second-generation chain kernels; IISAN_B200_CHAIN_PF overrides (measurement switch)
 static const int g_chain_pf_fwd = [] { const char* e = getenv("IISAN_B200_CHAIN_PF"); return e ? atoi(e) : 0; }();
@@ -305,6 +313,8 @@ static int san_forward_bf16_t(const iisan_san_desc* D, const iisan_san_params* P
   const int dwide = text_wide ? D->d_text : D->d_img;
   const int ft = D->asym ? E : D->d_text, fi = D->asym ? E : D->d_img, fm = D->d_mm;
   const bool chain = san_chain_eligible(*D) && !g_disable_chain;
+  if (chain && L.lr_ws && g_chain_gen.load(std::memory_order_relaxed) >= 3 && san_lr_usable(*D, *P))
+    return san_lr_forward(D, P, image, text, L.lr_ws, out, st);
   // ---- bf16 weight copies (the fp32 nn.Parameters stay the source of truth) ----
   {
     CastList c(st);
@@ -463,6 +473,8 @@ static int san_backward_bf16_t(const iisan_san_desc* D, const iisan_san_params* 
   }
   if (ls_t < 0 || ls_i < 0 || ls_m < 0) return IISAN_EINVAL;
   const bool chain = san_chain_eligible(*D) && !g_disable_chain;
+  if (chain && L.lr_ws && g_chain_gen.load(std::memory_order_relaxed) >= 3 && san_lr_usable(*D, *P))
+    return san_lr_backward(D, P, G, image, text, L.lr_ws, d_out, st);
   // ---- bf16 operand copy of d_out ----
   {
     MixBatch cb{}; cb.n = 1;

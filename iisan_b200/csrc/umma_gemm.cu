@@ -551,4 +551,20 @@ int launch_umma_gemm_big(const UmmaBatchBig& b, cudaStream_t st) {
   return launch_cfg<64, true, true, kUmmaBigProbs>(b.p, b.n, st);
 }
 
+int launch_umma_gemm_many(const UmmaBatchBig& b, cudaStream_t st) {
+  if (b.n <= 0) return IISAN_OK;
+  if (b.n > kUmmaBigProbs) return IISAN_EINVAL;
+  const bool a_mn = b.p[0].a_mn_major != 0, b_mn = b.p[0].b_mn_major != 0;
+  int maxN = 0;
+  for (int i = 0; i < b.n; ++i) {
+    if ((b.p[i].a_mn_major != 0) != a_mn || (b.p[i].b_mn_major != 0) != b_mn) return IISAN_EINVAL;
+    if (b.p[i].N > maxN) maxN = b.p[i].N;
+  }
+  if (a_mn && !b_mn) return IISAN_EUNSUPPORTED;
+  const bool wide = maxN > 64;
+  if (a_mn) return wide ? launch_cfg<256, true, true, kUmmaBigProbs>(b.p, b.n, st) : launch_cfg<64, true, true, kUmmaBigProbs>(b.p, b.n, st);
+  if (b_mn) return wide ? launch_cfg<256, false, true, kUmmaBigProbs>(b.p, b.n, st) : launch_cfg<64, false, true, kUmmaBigProbs>(b.p, b.n, st);
+  return wide ? launch_cfg<256, false, false, kUmmaBigProbs>(b.p, b.n, st) : launch_cfg<64, false, false, kUmmaBigProbs>(b.p, b.n, st);
+}
+
 }  // namespace iisan

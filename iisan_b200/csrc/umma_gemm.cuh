@@ -57,5 +57,8 @@ struct UmmaBatchBig {
   int n;
 };
 int launch_umma_gemm_big(const UmmaBatchBig& batch, cudaStream_t st);
+// Many problems of ONE operand-major combination (K/K, K/MN or MN/MN) in one launch; 64-wide column tiles when every N <= 64,
+// else 256-wide.  The low-rank adjoint path (san_lr.cu): weight products, G = dz^T h, Gram blocks, combine GEMMs.
+int launch_umma_gemm_many(const UmmaBatchBig& batch, cudaStream_t st);
 
 }  // namespace iisan
