@@ -18,7 +18,8 @@
 //   x_{s+1}   = fuse(h_{s+1}, last_s)                              (mm tower: last_s + g h_cv + (1-g) h_text)
 //   y         = pre_fc(fc(last_{A-1}))                             CC/model/model.py:340-347
 //
-// warp roles: 0 weight TMA producer | 1 TMEM allocator + MMA issuer | 2 hidden-state TMA producer | 3 idle | 4..19 epilogue
+// warp roles: 0 weight TMA producer | 1 TMEM allocator + MMA issuer (down-projections) | 2 hidden-state TMA producer |
+//             3 MMA issuer (up-projections) | 4..19 epilogue
 #include "san_chain3.cuh"
 
 #include "san_chain2.cuh"
@@ -164,44 +165,56 @@ __global__ void __launch_bounds__(THREADS, 1) san_chain3_fwd_kernel(const __grid
           if (is_mm) load(c & 1, &T.map_h2, T.layer2[p] * a.d + c * CW);
         }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
+  } else if (warp == 1 || warp == 3) {
+    // ===================== MMA issuers: warp 1 the down-projections, warp 3 the up-projections =====================
+    // Two threads, because a chunk costs an issuing thread two barrier waits and two or three tcgen05.commit of ~100 cycles each
+    // even when nothing has to be waited for: one thread would pace the whole CTA at ~900 cycles per chunk.  Both consume the ONE
+    // weight ring; unit indices in the producer's order: the NC units Wd(0, c), then per stage s the interleaving
+    // i = 0 .. NC + LOOK3 - 1 : [i < NC] Wu(s, i) , [i >= LOOK3] Wd(s + 1, i - LOOK3).
     if (elect_one()) {
       constexpr uint32_t idesc = instr_desc_bf16(ROWS, 64, 0, 0);   // [128 x 64] (+)= A x B^T (K-major), K = 64
-      int nw = 0;
-      auto wait_w = [&]() -> uint32_t {
-        const int slot = nw % NW3;
-        mbar_wait_park(bar0 + Smem3::bWFull + 8 * slot, (uint32_t)(nw / NW3) & 1u);
+      auto unit_u = [&](int s, int i) { return NC + s * 2 * NC + i + (i > LOOK3 ? i - LOOK3 : 0); };
+      auto unit_d = [&](int k, int c) {          // k == 0: the prologue units ; else stage s = k - 1, loop index i = c + LOOK3
+        if (k == 0) return c;
+        const int i = c + LOOK3;
+        return NC + (k - 1) * 2 * NC + (i < NC ? i + 1 : NC) + c;
+      };
+      auto wait_w = [&](int n) -> uint32_t {
+        const int slot = n % NW3;
+        mbar_wait_park(bar0 + Smem3::bWFull + 8 * slot, (uint32_t)(n / NW3) & 1u);
         return sbase + Smem3::kW + slot * W_BYTES;
       };
-      auto free_w = [&]() { mma_commit_a(bar0 + Smem3::bWEmpty + 8 * (nw % NW3)); ++nw; };
-      // z_acc (+)= x_k[c] Wd_k[c]^T : the chunk is resident in tensor memory (c < NT3) or in shared memory
-      auto down = [&](int k, int c) {
-        const uint32_t sw = wait_w();
-        mbar_wait_park(bar0 + Smem3::bXFull + 8 * c, (uint32_t)k & 1u);
-        tc_fence_after();
-        if (c < NT3) {
+      auto free_w = [&](int n) { mma_commit_a(bar0 + Smem3::bWEmpty + 8 * (n % NW3)); };
+      if (warp == 1) {
+        // z_acc (+)= x_k[c] Wd_k[c]^T : the chunk is resident in tensor memory (c < NT3) or in shared memory
+        for (int k = 0; k <= A; ++k)
+          for (int c = 0; c < NC; ++c) {
+            const int n = unit_d(k, c);
+            const uint32_t sw = wait_w(n);
+            mbar_wait_park(bar0 + Smem3::bXFull + 8 * c, (uint32_t)k & 1u);
+            tc_fence_after();
+            if (c < NT3) {
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk)
-            mma_bf16_ts(tmem_base + T3_ZACC, tmem_base + T3_X + c * 32 + kk * 8, smem_desc_sw128(sw + kk * 32, 16, 1024), idesc,
-                        (c > 0 || kk > 0) ? 1u : 0u);
-        } else {
-          const uint32_t xs = sbase + Smem3::kXs + (c - NT3) * TILE_BYTES;
+              for (int kk = 0; kk < 4; ++kk)
+                mma_bf16_ts(tmem_base + T3_ZACC, tmem_base + T3_X + c * 32 + kk * 8, smem_desc_sw128(sw + kk * 32, 16, 1024), idesc,
+                            (c > 0 || kk > 0) ? 1u : 0u);
+            } else {
+              const uint32_t xs = sbase + Smem3::kXs + (c - NT3) * TILE_BYTES;
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk)
-            mma_bf16_ss(tmem_base + T3_ZACC, smem_desc_sw128(xs + kk * 32, 16, 1024), smem_desc_sw128(sw + kk * 32, 16, 1024), idesc,
-                        (c > 0 || kk > 0) ? 1u : 0u);
-        }
-        if (c == NC - 1) mma_commit_a(bar0 + Smem3::bZFull);
-        free_w();
-      };
-      for (int c = 0; c < NC; ++c) down(0, c);
-      for (int s = 0; s < A; ++s) {
-        mbar_wait_park(bar0 + Smem3::bZReady, (uint32_t)s & 1u);
-        tc_fence_after();
-        for (int i = 0; i < NC + LOOK3; ++i) {
-          if (i < NC) {
-            const uint32_t sw = wait_w();
+              for (int kk = 0; kk < 4; ++kk)
+                mma_bf16_ss(tmem_base + T3_ZACC, smem_desc_sw128(xs + kk * 32, 16, 1024), smem_desc_sw128(sw + kk * 32, 16, 1024), idesc,
+                            (c > 0 || kk > 0) ? 1u : 0u);
+            }
+            if (c == NC - 1) mma_commit_a(bar0 + Smem3::bZFull);
+            free_w(n);
+          }
+      } else {
+        for (int s = 0; s < A; ++s) {
+          mbar_wait_park(bar0 + Smem3::bZReady, (uint32_t)s & 1u);
+          tc_fence_after();
+          for (int i = 0; i < NC; ++i) {
+            const int n = unit_u(s, i);
+            const uint32_t sw = wait_w(n);
             const int nu = s * NC + i, ub = nu & 1;
             mbar_wait_park(bar0 + Smem3::bUEmpty + 8 * ub, ((uint32_t)(nu >> 1) & 1u) ^ 1u);
             tc_fence_after();
@@ -209,9 +222,8 @@ __global__ void __launch_bounds__(THREADS, 1) san_chain3_fwd_kernel(const __grid
             for (int kk = 0; kk < 4; ++kk)
               mma_bf16_ts(tmem_base + T3_UACC + ub * 64, tmem_base + T3_ZOP + kk * 8, smem_desc_sw128(sw + kk * 32, 16, 1024), idesc, kk > 0 ? 1u : 0u);
             mma_commit_a(bar0 + Smem3::bUFull + 8 * ub);
-            free_w();
+            free_w(n);
           }
-          if (i >= LOOK3) down(s + 1, i - LOOK3);
         }
       }
     }

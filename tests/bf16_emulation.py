@@ -53,9 +53,16 @@ def user_encoder_forward_emul(P, embs, log_mask, cfg, prefix="user_encoder.trans
     return x
 
 
+def lr_path(cfg, fused_chain):
+    """True where the third-generation path runs (san_lr_eligible, san_lr.cu): symmetric chain, d a multiple of 128 in
+    [256, 768], E == 64, CC heads."""
+    return bool(fused_chain and not cfg.asym and cfg.d_text % 128 == 0 and 256 <= cfg.d_text <= 768 and cfg.embedding_dim == 64)
+
+
 def san_forward_emul(P, image, text, cfg, prefix="mm_encoder.", fused_chain=False):
     """``fused_chain``: the fused chain kernel keeps last_s in fp32 registers when it fuses the next stage (only the stash
-    and the final stage, which feeds the heads, are rounded)."""
+    and the final stage, which feeds the heads, are rounded).  On the third-generation path (``lr_path``) the two head layers
+    are applied as ONE matrix M = bf16(bf16(W_pre) bf16(W_fc)) with the bias W_pre b_fc + b_pre in fp32."""
     h_cv = image.reshape(-1, image.shape[-2], image.shape[-1]).float()
     h_tx = text.reshape(-1, text.shape[-2], text.shape[-1]).float()
     N = h_cv.shape[0]
@@ -95,6 +102,12 @@ def san_forward_emul(P, image, text, cfg, prefix="mm_encoder.", fused_chain=Fals
             g = O._gate(P[f"{prefix}side_gate_params_mm.{mi}"])
             x_mm = rb(last_mm + g * mm_cv + (1 - g) * mm_tx)
             last_mm = adapter(f"{prefix}mm_adapter_list.{mi}", x_mm, final)
+    if lr_path(cfg, fused_chain):
+        def head(fc, pre, last):
+            M = rb(rb(P[f"{prefix}{pre}.weight"]) @ rb(P[f"{prefix}{fc}.weight"]))
+            c = P[f"{prefix}{pre}.weight"] @ P[f"{prefix}{fc}.bias"] + P[f"{prefix}{pre}.bias"]
+            return last @ M.T + c
+        return head("fc_cv", "cv_pre_fc", last_cv), head("fc_bert", "bert_pre_fc", last_tx), head("fc_mm", "fc_mm_down", last_mm)
     lin = lambda n, x: _lin(x, P[f"{prefix}{n}.weight"], P[f"{prefix}{n}.bias"])
     e_tx = lin("bert_pre_fc", rb(lin("fc_bert", last_tx)))
     e_cv = lin("cv_pre_fc", rb(lin("fc_cv", last_cv)))
