@@ -3,10 +3,13 @@
 // matrix; what changed is where the running state lives:
 //
 //   * x_s (128 x d bf16) is RESIDENT on the SM for the whole kernel: chunks 0..8 as packed bf16 in tensor memory (288 columns),
-//     chunks 9.. in shared memory (128-byte swizzled tiles).  An epilogue thread owns the same cells in every stage: it reads
-//     the residual x_s[c] from them and overwrites them with x_{s+1}[c], which is then the A operand of the next down-projection
-//     (tcgen05.mma with A in TMEM, or an SS-mode MMA for the shared-memory chunks).  No stash store, no residual re-read, no
-//     store warp, no x-slot hand-back: per chunk the only hand-overs left are U (MMA -> epilogue) and x (epilogue -> MMA);
+//     chunks 9.. in shared memory (128-byte swizzled tiles).  An epilogue thread owns the same cells in every stage and
+//     overwrites x_s[c] with x_{s+1}[c], which is the A operand of the next down-projection (tcgen05.mma with A in TMEM, or an
+//     SS-mode MMA for the shared-memory chunks) AND of the residual: the up-projection accumulator is started as x_s[c] I
+//     (an MMA with a 64 x 64 identity tile: bf16 values times 1.0, exact), so the epilogue reads  x_s + relu(z_s) Wu_s^T  in ONE
+//     tcgen05.ld and never unpacks the residual.  No stash store, no residual re-read, no store warp, no x-slot hand-back;
+//   * the up-projection bias arrives pre-multiplied by the gate factor of the next fusion ((1 - g_{s+1}) b_up, prepared with the
+//     weight casts), so a column costs the epilogue two fused multiply-adds, one bf16 unpack and one pack;
 //   * the only global traffic of width d is the hidden-state stream itself (the algorithmic bytes); the backward needs
 //     relu(z_s) [N, 64] per stage and nothing else (san_lr.cu);
 //   * stage A is the merged head: y = last_{A-1} M^T + c with M = W_pre W_fc, one more down-projection of the same loop.
@@ -19,7 +22,7 @@
 //   y         = pre_fc(fc(last_{A-1}))                             CC/model/model.py:340-347
 //
 // warp roles: 0 weight TMA producer | 1 TMEM allocator + MMA issuer (down-projections) | 2 hidden-state TMA producer |
-//             3 MMA issuer (up-projections) | 4..19 epilogue
+//             3 / 20 MMA issuers (up-projections of the even / odd chunks) | 4..19 epilogue
 #include "san_chain3.cuh"
 
 #include "san_chain2.cuh"
@@ -29,17 +32,28 @@ namespace iisan {
 using bf16 = __nv_bfloat16;
 
 namespace c3 {
-#ifndef C3_NW
-#define C3_NW 6
+// Ring sizes per tower kind (same 160 KB in total): an intra-modal tower reads ONE hidden-state tile per chunk and is bound by
+// its weight stream, the inter-modal tower reads two and starves on a shallow hidden-state ring (measured: 600 cycles per chunk
+// at 3 tiles per parity).
+#ifndef C3_NW_INTRA
+#define C3_NW_INTRA 8
 #endif
-#ifndef C3_NDR
-#define C3_NDR 3
+#ifndef C3_NDR_INTRA
+#define C3_NDR_INTRA 3
+#endif
+#ifndef C3_NW_MM
+#define C3_NW_MM 4
+#endif
+#ifndef C3_NDR_MM
+#define C3_NDR_MM 4
 #endif
 #ifndef C3_NT
 #define C3_NT 9
 #endif
-constexpr int NW3 = C3_NW;                  // weight ring (8 KB units in the MMA thread's consumption order)
-constexpr int NDR3 = C3_NDR;                // hidden-state ring depth PER CHUNK PARITY (16 KB tiles)
+constexpr int NW3_MAX = C3_NW_INTRA > C3_NW_MM ? C3_NW_INTRA : C3_NW_MM;         // weight ring (8 KB units in consumption order)
+constexpr int NDR3_MAX = C3_NDR_INTRA > C3_NDR_MM ? C3_NDR_INTRA : C3_NDR_MM;   // hidden-state ring depth PER CHUNK PARITY (16 KB tiles)
+constexpr int RING3_BYTES = (C3_NW_INTRA * W_BYTES + 2 * C3_NDR_INTRA * TILE_BYTES) > (C3_NW_MM * W_BYTES + 2 * C3_NDR_MM * TILE_BYTES)
+                                ? (C3_NW_INTRA * W_BYTES + 2 * C3_NDR_INTRA * TILE_BYTES) : (C3_NW_MM * W_BYTES + 2 * C3_NDR_MM * TILE_BYTES);
 constexpr int NT3 = C3_NT;                  // x chunks resident in tensor memory
 constexpr int NS3 = 12 - C3_NT;             // x chunks resident in shared memory
 constexpr int NU3 = 2;                      // one U accumulator per chunk parity
@@ -50,14 +64,14 @@ constexpr int T3_ZACC = 0, T3_ZOP = 64, T3_UACC = 96, T3_X = T3_UACC + NU3 * 64;
 static_assert(T3_X + NT3 * 32 <= 512, "tensor memory budget");
 
 struct Smem3 {
-  static constexpr int kW = 0;
-  static constexpr int kD = kW + NW3 * W_BYTES;                 // [parity][NDR3] tiles
-  static constexpr int kXs = kD + 2 * NDR3 * TILE_BYTES;        // resident x chunks NT3..
-  static constexpr int kBias = kXs + NS3 * TILE_BYTES;          // two stages
+  static constexpr int kW = 0;                                  // weight ring, then the hidden-state ring [parity][NDR] (runtime split)
+  static constexpr int kXs = kW + RING3_BYTES;                  // resident x chunks NT3..
+  static constexpr int kIdent = kXs + NS3 * TILE_BYTES;         // [64 x 64] bf16 identity (K-major, swizzled): B operand of the residual MMAs
+  static constexpr int kBias = kIdent + W_BYTES;                // two stages
   static constexpr int kBar = kBias + 2 * BIAS3;
   static constexpr int kTotal = kBar + 1024 + 1024;             // barriers + alignment slack
-  static constexpr int bWFull = 0, bWEmpty = bWFull + 8 * NW3, bDFull = bWEmpty + 8 * NW3, bDEmpty = bDFull + 16 * NDR3;
-  static constexpr int bXFull = bDEmpty + 16 * NDR3, bUFull = bXFull + 8 * (NT3 + NS3), bUEmpty = bUFull + 8 * NU3;
+  static constexpr int bWFull = 0, bWEmpty = bWFull + 8 * NW3_MAX, bDFull = bWEmpty + 8 * NW3_MAX, bDEmpty = bDFull + 16 * NDR3_MAX;
+  static constexpr int bXFull = bDEmpty + 16 * NDR3_MAX, bUFull = bXFull + 8 * (NT3 + NS3), bUEmpty = bUFull + 8 * NU3;
   static constexpr int bZFull = bUEmpty + 8 * NU3, bZReady = bZFull + 8, bBias = bZReady + 8, bTmem = bBias + 16;
   static constexpr int bGates = bTmem + 8;                      // kChainMaxStages floats
 };
@@ -66,9 +80,25 @@ static_assert(Smem3::kTotal <= 232448, "shared memory budget");
 }  // namespace c3
 using namespace c3;
 
-__global__ void __launch_bounds__(THREADS, 1) san_chain3_fwd_kernel(const __grid_constant__ Chain3Args a) {
+// optional wait-time accounting (build variant "trace"; scripts/chain3_trace.py): lap timers per role, middle CTA of each tower
+#ifdef IISAN_CHAIN_TRACE
+__device__ unsigned int g_c3_trace[3][8][8];      // [tower][role][site] ; site 7 = lifetime of the role
+#undef C2_TRACE_BUF
+#define C2_TRACE_BUF g_c3_trace
+#define T3_MARK() unsigned int tr_lap = clock()
+#define T3_LAP(site) do { const unsigned int now_ = clock(); tr_acc[site] += now_ - tr_lap; tr_lap = now_; } while (0)
+#else
+#define T3_MARK() do {} while (0)
+#define T3_LAP(site) do {} while (0)
+#endif
+
+constexpr int THREADS3 = THREADS + 32;        // + warp 20: the second up-projection issuer
+
+__global__ void __launch_bounds__(THREADS3, 1) san_chain3_fwd_kernel(const __grid_constant__ Chain3Args a) {
   const Chain3Tower& T = a.tower[blockIdx.y];
   const bool is_mm = (T.mode == 1);
+  const int NW3 = is_mm ? C3_NW_MM : C3_NW_INTRA, NDR3 = is_mm ? C3_NDR_MM : C3_NDR_INTRA;
+  const int kD = Smem3::kW + NW3 * W_BYTES;      // start of the hidden-state ring
   const int NC = a.d / CW;                       // even, <= 12
   const int NCh = NC >> 1;
   const int A = a.n_stages;
@@ -81,8 +111,8 @@ __global__ void __launch_bounds__(THREADS, 1) san_chain3_fwd_kernel(const __grid
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&T.map_wd); tma_prefetch_desc(&T.map_wu); tma_prefetch_desc(&T.map_h);
     if (is_mm) tma_prefetch_desc(&T.map_h2);
-    for (int i = 0; i < NW3; ++i) { mbar_init_a(bar0 + Smem3::bWFull + 8 * i, 1); mbar_init_a(bar0 + Smem3::bWEmpty + 8 * i, 1); }
-    for (int i = 0; i < 2 * NDR3; ++i) { mbar_init_a(bar0 + Smem3::bDFull + 8 * i, 1); mbar_init_a(bar0 + Smem3::bDEmpty + 8 * i, 8); }   // 8 warps read a tile
+    for (int i = 0; i < NW3_MAX; ++i) { mbar_init_a(bar0 + Smem3::bWFull + 8 * i, 1); mbar_init_a(bar0 + Smem3::bWEmpty + 8 * i, 1); }
+    for (int i = 0; i < 2 * NDR3_MAX; ++i) { mbar_init_a(bar0 + Smem3::bDFull + 8 * i, 1); mbar_init_a(bar0 + Smem3::bDEmpty + 8 * i, 8); }   // 8 warps read a tile
     for (int i = 0; i < NT3 + NS3; ++i) mbar_init_a(bar0 + Smem3::bXFull + 8 * i, 8);                                                   // 8 warps write a chunk
     for (int i = 0; i < NU3; ++i) { mbar_init_a(bar0 + Smem3::bUFull + 8 * i, 1); mbar_init_a(bar0 + Smem3::bUEmpty + 8 * i, 8); }
     mbar_init_a(bar0 + Smem3::bZFull, 1); mbar_init_a(bar0 + Smem3::bZReady, EPI_WARPS);
@@ -92,6 +122,18 @@ __global__ void __launch_bounds__(THREADS, 1) san_chain3_fwd_kernel(const __grid
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(bar0 + Smem3::bTmem), "r"(512u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (warp == 3) {           // identity tile: row n = 128 bytes, 16-byte groups swizzled by (n & 7)
+    for (int n = lane; n < 64; n += 32) {
+      const uint32_t row = sbase + Smem3::kIdent + (uint32_t)((n >> 3) * 1024 + (n & 7) * 128);
+#pragma unroll
+      for (int gq = 0; gq < 8; ++gq) {
+        uint32_t w[4] = {0u, 0u, 0u, 0u};
+        if (gq == (n >> 3)) w[(n & 7) >> 1] = (n & 1) ? 0x3F800000u : 0x00003F80u;      // bf16 1.0 at column n
+        sts128(row + (uint32_t)((gq ^ (n & 7)) << 4), w[0], w[1], w[2], w[3]);
+      }
+    }
+    fence_proxy_async_smem();
   }
   if (warp == 2 && lane < A) {
     const float gv = gate_value(T.gate[lane]);
@@ -108,9 +150,10 @@ __global__ void __launch_bounds__(THREADS, 1) san_chain3_fwd_kernel(const __grid
     // ===================== weight + bias producer: 8 KB units in the MMA thread's consumption order =====================
     if (elect_one()) {
       int n = 0;
+      TR_DECL();
       auto put = [&](bool up, int s, int c) {
         const int slot = n % NW3;
-        mbar_wait_park(bar0 + Smem3::bWEmpty + 8 * slot, ((uint32_t)(n / NW3) & 1u) ^ 1u);
+        TR(0, mbar_wait_park(bar0 + Smem3::bWEmpty + 8 * slot, ((uint32_t)(n / NW3) & 1u) ^ 1u));
         const uint32_t dst = sbase + Smem3::kW + slot * W_BYTES, bar = bar0 + Smem3::bWFull + 8 * slot;
         mbar_expect_tx_a(bar, W_BYTES);
         if (up) tma_load_2d_a(dst, &T.map_wu, bar, 0, s * a.d + c * CW);      // Wu_s rows [c*64, +64), all r : [64 x r]
@@ -145,18 +188,20 @@ __global__ void __launch_bounds__(THREADS, 1) san_chain3_fwd_kernel(const __grid
           put_bias(s + 1);
         }
       }
+      TR_FLUSH(0);
     }
   } else if (warp == 2) {
     // ===================== hidden-state producer: per chunk parity, tiles in the epilogue's consumption order =====================
     if (elect_one()) {
       int n0 = 0, n1 = 0;
+      TR_DECL();
       auto load = [&](int par, const CUtensorMap* m, int col) {
         int& n = par ? n1 : n0;
         const int slot = par * NDR3 + (n % NDR3);
-        mbar_wait_park(bar0 + Smem3::bDEmpty + 8 * slot, ((uint32_t)(n / NDR3) & 1u) ^ 1u);
+        TR(0, mbar_wait_park(bar0 + Smem3::bDEmpty + 8 * slot, ((uint32_t)(n / NDR3) & 1u) ^ 1u));
         const uint32_t bar = bar0 + Smem3::bDFull + 8 * slot;
         mbar_expect_tx_a(bar, (uint32_t)TILE_BYTES);
-        tma_load_2d_a(sbase + Smem3::kD + slot * TILE_BYTES, m, bar, col, m0);
+        tma_load_2d_a(sbase + kD + slot * TILE_BYTES, m, bar, col, m0);
         ++n;
       };
       for (int p = 0; p < A; ++p)
@@ -164,11 +209,13 @@ __global__ void __launch_bounds__(THREADS, 1) san_chain3_fwd_kernel(const __grid
           load(c & 1, &T.map_h, T.layer[p] * a.d + c * CW);
           if (is_mm) load(c & 1, &T.map_h2, T.layer2[p] * a.d + c * CW);
         }
+      TR_FLUSH(2);
     }
-  } else if (warp == 1 || warp == 3) {
-    // ===================== MMA issuers: warp 1 the down-projections, warp 3 the up-projections =====================
-    // Two threads, because a chunk costs an issuing thread two barrier waits and two or three tcgen05.commit of ~100 cycles each
-    // even when nothing has to be waited for: one thread would pace the whole CTA at ~900 cycles per chunk.  Both consume the ONE
+  } else if (warp == 1 || warp == 3 || warp == 20) {
+    // ===================== MMA issuers: warp 1 the down-projections, warps 3 / 20 the up-projections of the even / odd chunks =====================
+    // Three threads, because a chunk costs an issuing thread two barrier waits, its MMAs and two or three tcgen05.commit of ~100
+    // cycles each even when nothing has to be waited for (measured: ~570 cycles per up-projection): one thread paces the whole
+    // CTA at ~1000 cycles per chunk.  All consume the ONE
     // weight ring; unit indices in the producer's order: the NC units Wd(0, c), then per stage s the interleaving
     // i = 0 .. NC + LOOK3 - 1 : [i < NC] Wu(s, i) , [i >= LOOK3] Wd(s + 1, i - LOOK3).
     if (elect_one()) {
@@ -179,9 +226,10 @@ __global__ void __launch_bounds__(THREADS, 1) san_chain3_fwd_kernel(const __grid
         const int i = c + LOOK3;
         return NC + (k - 1) * 2 * NC + (i < NC ? i + 1 : NC) + c;
       };
+      TR_DECL();
       auto wait_w = [&](int n) -> uint32_t {
         const int slot = n % NW3;
-        mbar_wait_park(bar0 + Smem3::bWFull + 8 * slot, (uint32_t)(n / NW3) & 1u);
+        TR(0, mbar_wait_park(bar0 + Smem3::bWFull + 8 * slot, (uint32_t)(n / NW3) & 1u));
         return sbase + Smem3::kW + slot * W_BYTES;
       };
       auto free_w = [&](int n) { mma_commit_a(bar0 + Smem3::bWEmpty + 8 * (n % NW3)); };
@@ -191,7 +239,8 @@ __global__ void __launch_bounds__(THREADS, 1) san_chain3_fwd_kernel(const __grid
           for (int c = 0; c < NC; ++c) {
             const int n = unit_d(k, c);
             const uint32_t sw = wait_w(n);
-            mbar_wait_park(bar0 + Smem3::bXFull + 8 * c, (uint32_t)k & 1u);
+            TR(1, mbar_wait_park(bar0 + Smem3::bXFull + 8 * c, (uint32_t)k & 1u));
+            T3_MARK();
             tc_fence_after();
             if (c < NT3) {
 #pragma unroll
@@ -207,27 +256,46 @@ __global__ void __launch_bounds__(THREADS, 1) san_chain3_fwd_kernel(const __grid
             }
             if (c == NC - 1) mma_commit_a(bar0 + Smem3::bZFull);
             free_w(n);
+            T3_LAP(2);
           }
+        TR_FLUSH(1);
       } else {
         for (int s = 0; s < A; ++s) {
-          mbar_wait_park(bar0 + Smem3::bZReady, (uint32_t)s & 1u);
-          tc_fence_after();
-          for (int i = 0; i < NC; ++i) {
+          bool z_seen = false;             // the residual MMAs of the first chunk do not need z_s: they are issued ahead of z_ready
+          for (int i = (warp == 3 ? 0 : 1); i < NC; i += 2) {
             const int n = unit_u(s, i);
-            const uint32_t sw = wait_w(n);
             const int nu = s * NC + i, ub = nu & 1;
-            mbar_wait_park(bar0 + Smem3::bUEmpty + 8 * ub, ((uint32_t)(nu >> 1) & 1u) ^ 1u);
+            TR(1, mbar_wait_park(bar0 + Smem3::bUEmpty + 8 * ub, ((uint32_t)(nu >> 1) & 1u) ^ 1u));
+            if (!z_seen) mbar_wait_park(bar0 + Smem3::bXFull + 8 * i, (uint32_t)s & 1u);      // ahead of z_ready: x_s[i] itself must be final
+            T3_MARK();
             tc_fence_after();
+            // acc = x_s[i] I  (exact: bf16 values times 1.0, fp32 accumulation) ...
+            const uint32_t ident = sbase + Smem3::kIdent;
+            if (i < NT3) {
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk)
+                mma_bf16_ts(tmem_base + T3_UACC + ub * 64, tmem_base + T3_X + i * 32 + kk * 8, smem_desc_sw128(ident + kk * 32, 16, 1024), idesc, kk > 0 ? 1u : 0u);
+            } else {
+              const uint32_t xs = sbase + Smem3::kXs + (i - NT3) * TILE_BYTES;
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk)
+                mma_bf16_ss(tmem_base + T3_UACC + ub * 64, smem_desc_sw128(xs + kk * 32, 16, 1024), smem_desc_sw128(ident + kk * 32, 16, 1024), idesc, kk > 0 ? 1u : 0u);
+            }
+            // ... + relu(z_s) Wu_s[i]^T
+            if (!z_seen) { TR(3, mbar_wait_park(bar0 + Smem3::bZReady, (uint32_t)s & 1u)); tc_fence_after(); z_seen = true; }
+            const uint32_t sw = wait_w(n);
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk)
-              mma_bf16_ts(tmem_base + T3_UACC + ub * 64, tmem_base + T3_ZOP + kk * 8, smem_desc_sw128(sw + kk * 32, 16, 1024), idesc, kk > 0 ? 1u : 0u);
+              mma_bf16_ts(tmem_base + T3_UACC + ub * 64, tmem_base + T3_ZOP + kk * 8, smem_desc_sw128(sw + kk * 32, 16, 1024), idesc, 1u);
             mma_commit_a(bar0 + Smem3::bUFull + 8 * ub);
             free_w(n);
+            T3_LAP(2);
           }
         }
+        if (warp == 3) TR_FLUSH(3);
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && warp < 20) {
     // ===================== epilogue warps =====================
     const int ew = warp - 4;                  // 0..15
     const int quad = warp & 3;                // TMEM lane quadrant (warp % 4)
@@ -242,21 +310,15 @@ __global__ void __launch_bounds__(THREADS, 1) san_chain3_fwd_kernel(const __grid
     for (int q = 0; q < 4; ++q) offq[q] = sw_row + (uint32_t)(((half * 4 + q) ^ (m & 7)) << 4);
     const int64_t grow = (int64_t)m0 + m;
     const uint32_t bar_d_full = bar0 + Smem3::bDFull + par * NDR3 * 8, bar_d_empty = bar0 + Smem3::bDEmpty + par * NDR3 * 8;
-    const uint32_t d_base = sbase + Smem3::kD + par * NDR3 * TILE_BYTES;
+    const uint32_t d_base = sbase + kD + par * NDR3 * TILE_BYTES;
+    TR_DECL();
 
-    auto d_tile = [&](int t) -> uint32_t { return d_base + (uint32_t)(t % NDR3) * TILE_BYTES; };
-    auto d_wait = [&](int t) { mbar_wait_a(bar_d_full + (t % NDR3) * 8, (uint32_t)(t / NDR3) & 1u); };
-    auto d_release = [&](int t) { if (lane == 0) mbar_arrive_a(bar_d_empty + (t % NDR3) * 8); };
-    // this thread's 32 columns of the resident chunk c: read (residual) / overwrite (next state), then publish the chunk
-    auto x_read = [&](int c, uint32_t (&r)[16]) {
-      if (c < NT3) {
-        tmem_ld_32x16(tmem_base + lane_addr + (uint32_t)(T3_X + c * 32 + half * 16), r);
-      } else {
-        const uint32_t xs = sbase + Smem3::kXs + (uint32_t)(c - NT3) * TILE_BYTES;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) { const uint4 v = lds128(xs + offq[q]); r[4 * q] = v.x; r[4 * q + 1] = v.y; r[4 * q + 2] = v.z; r[4 * q + 3] = v.w; }
-      }
-    };
+    auto d_slot = [&](int t) -> int { return is_mm ? t % C3_NDR_MM : t % C3_NDR_INTRA; };
+    auto d_phase = [&](int t) -> uint32_t { return (uint32_t)(is_mm ? t / C3_NDR_MM : t / C3_NDR_INTRA) & 1u; };
+    auto d_tile = [&](int t) -> uint32_t { return d_base + (uint32_t)d_slot(t) * TILE_BYTES; };
+    auto d_wait = [&](int t) { mbar_wait_a(bar_d_full + d_slot(t) * 8, d_phase(t)); };
+    auto d_release = [&](int t) { if (lane == 0) mbar_arrive_a(bar_d_empty + d_slot(t) * 8); };
+    // overwrite this thread's 32 columns of the resident chunk c with the next state, then publish the chunk
     auto x_write = [&](int c, const uint32_t (&o)[16]) {
       if (c < NT3) {
         tmem_st_32x16(tmem_base + lane_addr + (uint32_t)(T3_X + c * 32 + half * 16), o);
@@ -315,31 +377,28 @@ __global__ void __launch_bounds__(THREADS, 1) san_chain3_fwd_kernel(const __grid
       for (int c = par; c < NC; c += 2) {
         const int t0 = ((s + 1) * NCh + (c >> 1)) * (MM ? 2 : 1);       // hidden states of stage s + 1 (MORE only)
         const int nu = s * NC + c;
+        T3_MARK();
         mbar_wait_a(bar0 + Smem3::bUFull + 8 * par, (uint32_t)(nu >> 1) & 1u);
+        T3_LAP(0);
         tc_fence_after();
-        uint32_t raw[32], rx[16];
-        tmem_ld_32x32(tmem_base + lane_addr + (uint32_t)(T3_UACC + par * 64 + half * 32), raw);
-        x_read(c, rx);
+        uint32_t raw[32];
+        tmem_ld_32x32(tmem_base + lane_addr + (uint32_t)(T3_UACC + par * 64 + half * 32), raw);      // x_s[c] + relu(z_s) Wu_s[c]^T
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_a(bar0 + Smem3::bUEmpty + 8 * par);
-        uint64_t uv[16];                           // U + bias, two columns per register pair
-        const uint32_t bc = bias + c * (CW * 4);
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const uint4 b = lds128(bc + q * 16);
-          uv[2 * q] = fadd2(u2pack(raw[4 * q], raw[4 * q + 1]), u2pack(b.x, b.y));
-          uv[2 * q + 1] = fadd2(u2pack(raw[4 * q + 2], raw[4 * q + 3]), u2pack(b.z, b.w));
-        }
+        T3_LAP(1);
+        const uint32_t bc = bias + c * (CW * 4);        // intra-modal, MORE: (1 - g_{s+1}) b_up ; else b_up  (prepared by lr_prep_fwd_kernel)
+        T3_LAP(2);
         if (MORE) { d_wait(t0); if (MM) d_wait(t0 + 1); }
+        T3_LAP(3);
         const uint32_t tb1 = d_tile(t0), tb2 = d_tile(t0 + 1);
         uint32_t o[16];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
+          const uint4 b0 = lds128(bc + q * 32), b1 = lds128(bc + q * 32 + 16);
+          const uint64_t bb[4] = {u2pack(b0.x, b0.y), u2pack(b0.z, b0.w), u2pack(b1.x, b1.y), u2pack(b1.z, b1.w)};
           uint64_t lv[4];
-#pragma unroll
-          for (int k = 0; k < 4; ++k) lv[k] = fadd2(uv[4 * q + k], bf2(rx[4 * q + k]));
           if (MORE) {
             const uint4 hq = lds128(tb1 + offq[q]);
             const uint32_t hw[4] = {hq.x, hq.y, hq.z, hq.w};
@@ -347,11 +406,16 @@ __global__ void __launch_bounds__(THREADS, 1) san_chain3_fwd_kernel(const __grid
               const uint4 h2q = lds128(tb2 + offq[q]);
               const uint32_t h2w[4] = {h2q.x, h2q.y, h2q.z, h2q.w};
 #pragma unroll
-              for (int k = 0; k < 4; ++k) lv[k] = ffma2(omg2, bf2(h2w[k]), ffma2(g2, bf2(hw[k]), lv[k]));
+              for (int k = 0; k < 4; ++k)
+                lv[k] = ffma2(g2, bf2(hw[k]), ffma2(omg2, bf2(h2w[k]), fadd2(u2pack(raw[8 * q + 2 * k], raw[8 * q + 2 * k + 1]), bb[k])));
             } else {
 #pragma unroll
-              for (int k = 0; k < 4; ++k) lv[k] = ffma2(g2, bf2(hw[k]), fmul2(omg2, lv[k]));
+              for (int k = 0; k < 4; ++k)
+                lv[k] = ffma2(g2, bf2(hw[k]), ffma2(omg2, u2pack(raw[8 * q + 2 * k], raw[8 * q + 2 * k + 1]), bb[k]));
             }
+          } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) lv[k] = fadd2(u2pack(raw[8 * q + 2 * k], raw[8 * q + 2 * k + 1]), bb[k]);
           }
 #pragma unroll
           for (int k = 0; k < 4; ++k) o[4 * q + k] = pack2x(lv[k]);
@@ -361,11 +425,14 @@ __global__ void __launch_bounds__(THREADS, 1) san_chain3_fwd_kernel(const __grid
           d_release(t0);
           if (MM) d_release(t0 + 1);
         }
+        T3_LAP(4);
         x_write(c, o);
+        T3_LAP(5);
       }
     };
 
     for (int s = 0; s <= A; ++s) {
+      T3_MARK();
       // ---- z_s = relu(zacc + bd): packed bf16 into the TMEM operand of the U MMAs and into the backward's stash; stage A:
       //      y = zacc + c, fp32, straight to the output.  All 16 warps: warp (quad, grp) takes columns [grp*16, +16) ----
       mbar_wait_a(bar0 + Smem3::bBias + 8 * (s & 1), (uint32_t)(s >> 1) & 1u);      // this stage's biases have landed
@@ -411,10 +478,12 @@ __global__ void __launch_bounds__(THREADS, 1) san_chain3_fwd_kernel(const __grid
           zs2[1] = make_uint4(zo[4], zo[5], zo[6], zo[7]);
         }
       }
+      T3_LAP(6);
       const bool more = s + 1 < A;
       if (is_mm) { if (more) stage_chunks(BoolTag<true>{}, BoolTag<true>{}, s); else stage_chunks(BoolTag<true>{}, BoolTag<false>{}, s); }
       else { if (more) stage_chunks(BoolTag<false>{}, BoolTag<true>{}, s); else stage_chunks(BoolTag<false>{}, BoolTag<false>{}, s); }
     }
+    if (quad == 0 && lane == 0) TR_FLUSH(4 + grp);
   }
   tc_fence_before();
   __syncthreads();
@@ -440,9 +509,20 @@ int launch_san_chain3_fwd(const Chain3Args& args, int n_towers, cudaStream_t st)
     attr_done.fetch_or(dev_bit, std::memory_order_release);
   }
   const int tiles = (args.n_items + ROWS - 1) / ROWS;
-  { LaunchScope ls_(IISAN_K_CHAIN, st); san_chain3_fwd_kernel<<<dim3(tiles, n_towers), THREADS, Smem3::kTotal, st>>>(args); }
+  { LaunchScope ls_(IISAN_K_CHAIN, st); san_chain3_fwd_kernel<<<dim3(tiles, n_towers), THREADS3, Smem3::kTotal, st>>>(args); }
   IISAN_LAUNCH_OK();
   return IISAN_OK;
 }
 
 }  // namespace iisan
+
+#ifdef IISAN_CHAIN_TRACE
+// trace build only: [tower][role][site] cycle sums of the last chain3 forward launch (scripts/chain3_trace.py)
+extern "C" int iisan_debug_chain3_trace_read(unsigned int* host_out) {
+  using namespace iisan;
+  if (!host_out) return IISAN_EINVAL;
+  IISAN_CUDA_OK(cudaDeviceSynchronize());
+  IISAN_CUDA_OK(cudaMemcpyFromSymbol(host_out, g_c3_trace, sizeof(g_c3_trace)));
+  return IISAN_OK;
+}
+#endif

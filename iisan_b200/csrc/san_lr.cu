@@ -61,7 +61,7 @@ bool san_lr_usable(const iisan_san_desc& D, const iisan_san_params& P) {
 
 struct LrLayout {
   bf16 *wd_pack[3], *wu_pack[3], *wu_rows[3], *fcb[3], *preb[3];
-  float *M32[3], *hb[3];
+  float *M32[3], *hb[3], *bsc[3];     // bsc: up-projection biases times the gate factor of the next fusion [A, d]
   bf16 *Rst[2], *Dst[2];
   float* KK[3];
   bf16* KB[3];                   // rank-space B operands: [32 A (A+1), 64] per tower
@@ -81,7 +81,7 @@ struct LrLayout {
     for (int t = 0; t < 3; ++t) {
       wd_pack[t] = a.take<bf16>((A + 1) * LE * d); wu_pack[t] = a.take<bf16>(A * d * LE); wu_rows[t] = a.take<bf16>(d * A * LE);
       fcb[t] = a.take<bf16>(f * d); preb[t] = a.take<bf16>(LE * f);
-      M32[t] = a.take<float>(LE * d); hb[t] = a.take<float>(LE);
+      M32[t] = a.take<float>(LE * d); hb[t] = a.take<float>(LE); bsc[t] = a.take<float>(A * d);
     }
     for (int x = 0; x < 2; ++x) { Rst[x] = a.take<bf16>(N * A * 128); Dst[x] = a.take<bf16>(N * (A + 1) * 128); }
     for (int t = 0; t < 3; ++t) KK[t] = a.take<float>((A + 1) * LE * A * LE);
@@ -151,9 +151,17 @@ constexpr int kLrCastJobs = 72;
 struct LrPrepArgs {
   LrCastJob j[kLrCastJobs]; int n;
   const float* w_pre[3]; const float* b_fc[3]; const float* b_pre[3]; float* hb[3]; int f;
+  const float* gate[3][LMAXA]; const float* bu[3][LMAXA]; float* bsc[3]; int A, d;
 };
 
 __global__ void __launch_bounds__(256) lr_prep_fwd_kernel(const __grid_constant__ LrPrepArgs a) {
+  if ((int)blockIdx.y >= a.n + 3) {          // (1 - g_{s+1}) b_up_s for the intra-modal towers (the fusion that consumes last_s), else b_up_s
+    const int i = blockIdx.y - a.n - 3, t = i / a.A, s = i % a.A;
+    if (blockIdx.x != 0) return;
+    const float coef = (t < 2 && s + 1 < a.A) ? 1.0f - gate_value(a.gate[t][s + 1]) : 1.0f;
+    for (int k = threadIdx.x; k < a.d; k += 256) a.bsc[t][(size_t)s * a.d + k] = coef * a.bu[t][s][k];
+    return;
+  }
   if ((int)blockIdx.y >= a.n) {              // merged head bias  c = W_pre b_fc + b_pre  (blocks 0..7 of a tower, one warp per output)
     const int t = blockIdx.y - a.n;
     if (blockIdx.x >= LE / 8) return;
@@ -197,9 +205,12 @@ int san_lr_forward(const iisan_san_desc* D, const iisan_san_params* P, const voi
     pa.j[pa.n++] = LrCastJob{tp[t].w_fc, L.fcb[t], f, d, d};
     pa.j[pa.n++] = LrCastJob{tp[t].w_pre, L.preb[t], E, f, f};
     pa.w_pre[t] = tp[t].w_pre; pa.b_fc[t] = tp[t].b_fc; pa.b_pre[t] = tp[t].b_pre; pa.hb[t] = L.hb[t];
+    for (int s = 0; s < A; ++s) { pa.gate[t][s] = tp[t].gate[s]; pa.bu[t][s] = tp[t].bu[s]; }
+    pa.bsc[t] = L.bsc[t];
   }
+  pa.A = A; pa.d = d;
   if (pa.n > kLrCastJobs) return IISAN_EINVAL;
-  { LaunchScope ls_(IISAN_K_MISC, st); lr_prep_fwd_kernel<<<dim3(48, pa.n + 3), 256, 0, st>>>(pa); }
+  { LaunchScope ls_(IISAN_K_MISC, st); lr_prep_fwd_kernel<<<dim3(48, pa.n + 3 + 3 * A), 256, 0, st>>>(pa); }
   IISAN_LAUNCH_OK();
   // ---- merged head  M = W_pre W_fc  (bf16 operands, fp32 accumulation): fp32 copy for the backward, bf16 as stage A of wd_pack ----
   {
@@ -231,7 +242,7 @@ int san_lr_forward(const iisan_san_desc* D, const iisan_san_params* P, const voi
       const iisan_adapter_ptrs& ad = tower_adapter(*D, *P, t, s);
       T.layer[s] = t == 0 ? D->text_layer[s] : D->img_layer[s];
       T.layer2[s] = D->text_layer[s];
-      T.gate[s] = tp[t].gate[s]; T.b_down[s] = ad.b_down; T.b_up[s] = ad.b_up;
+      T.gate[s] = tp[t].gate[s]; T.b_down[s] = ad.b_down; T.b_up[s] = L.bsc[t] + (size_t)s * d;
     }
     T.b_down[A] = L.hb[t];
     T.r_out = L.Rst[t == 0 ? 0 : 1]; T.r_out2 = t == 2 ? L.Rst[0] : nullptr; T.r_slot = t == 2 ? 1 : 0;
