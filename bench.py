@@ -586,7 +586,25 @@ def run_ours(a):
         r["frac"] = (r["achieved"] / hbm_peak) if r["achieved"] else None
         return r
 
-    if classes["chain"]["launches_per_step"] > 0:
+    gen3 = classes.get("wgrad_stream", {}).get("launches_per_step", 0) > 0          # third generation: san_chain3.cu + san_lr.cu
+    if classes["chain"]["launches_per_step"] > 0 and gen3:
+        roof = hbm_roof("chain", "san_chain3_fwd_kernel (resident-state chain: layer-select gather + gate fusion + 3 x 7 adapters + merged "
+                                 "heads, forward; writes only relu(z) [N,64] per stage and the E outputs)", "fwd")
+        # The backward reads the hidden states exactly once more, inside ONE tensor-core GEMM launch (G = dz^T h for every tower,
+        # stage pair and layer, plus the Gram blocks dz^T relu(z)): tensor bound.  FLOPs: 2 * N * d * 64 per (layer j, stage s >= j)
+        # block, 36 blocks per intra-modal tower and 2 x 36 for the inter-modal one, + the 28 needed Gram blocks per tower.
+        A_st = len(plan.stages)
+        n_items = B * 11
+        g_flop = 2.0 * n_items * plan.d_mm * 64 * ((A_st + 1) * (A_st + 2) / 2 - 1) * 4 + 2.0 * n_items * 64 * 64 * (A_st * (A_st + 1) / 2) * 3
+        wg = classes["wgrad_stream"]
+        wg_ms = wg["ms_per_step"] / wg["launches_per_step"]
+        roof_bwd = {"bound": "tensor", "kernel": "umma_gemm_kernel<256, MN, MN> (the backward's one pass over the hidden states: G = dz^T h, + Gram blocks dz^T relu(z))",
+                    "achieved": g_flop / (wg_ms / 1e3) / 1e12, "peak": tf_peak, "unit": "TFLOP/s", "peak_source": peak_src,
+                    "useful_flop_per_launch": g_flop, "ms_per_launch": wg_ms, "algorithmic_bytes_per_launch": alg_bytes,
+                    "hbm_gbs_of_the_algorithmic_bytes": alg_bytes / (wg_ms / 1e3) / 1e9, "traffic": traffic.get("wgrad"), "traffic_source": traffic_src,
+                    "rank_space_chain_ms": classes["chain_bwd"]["ms_per_step"]}
+        roof_bwd["frac"] = roof_bwd["achieved"] / tf_peak
+    elif classes["chain"]["launches_per_step"] > 0:
         roof = hbm_roof("chain", "san_chain2_fwd_kernel (fused layer-select gather + gate fusion + adapter chain, forward)", "fwd")
         roof_bwd = hbm_roof("chain_bwd", "chain backward kernel (fused data/gate/bias gradients of the chain)", "bwd")
     else:
@@ -598,7 +616,8 @@ def run_ours(a):
                 "traffic_source": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": 2 * alg_bytes, "ms_per_launch": st_ms}
         roof["frac"] = (roof["achieved"] / hbm_peak) if roof["achieved"] else None
         roof_bwd = None
-    gemm_ms = classes["gemm"]["ms_per_step"] + classes["chain"]["ms_per_step"] + classes["chain_bwd"]["ms_per_step"]
+    gemm_ms = (classes["gemm"]["ms_per_step"] + classes["chain"]["ms_per_step"] + classes["chain_bwd"]["ms_per_step"] +
+               classes.get("wgrad_stream", {}).get("ms_per_step", 0.0))
     # forward GEMM FLOPs of the SAN per item: adapters (down + up per active tower and stage), dim-alignment GEMMs, heads
     E = plan.emb
     f_item = 0

@@ -14,7 +14,7 @@ ABI_VERSION = 2
 
 F32, BF16, F16 = 0, 1, 2
 K_STREAM, K_GEMM, K_USER, K_CE, K_MISC, K_CHAIN, K_CHAIN_BWD = range(7)
-KERNEL_CLASSES = ("stream", "gemm", "user", "ce", "misc", "chain", "chain_bwd")
+KERNEL_CLASSES = ("stream", "gemm", "user", "ce", "misc", "chain", "chain_bwd", "wgrad_stream")
 COMPUTE_FP32, COMPUTE_BF16 = 0, 1
 
 # IISAN_B200_LIB: load an instrumented build variant instead (iisan_b200/build.py; debugging aid, same ABI)

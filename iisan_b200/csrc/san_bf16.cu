@@ -214,7 +214,7 @@ struct SanLayoutBf16 {
 // low-rank adjoint backward (san_lr.cu) for d <= 768, 2 for the other multiples of 128)
 static const bool g_disable_chain = [] { const char* e = getenv("IISAN_B200_NO_CHAIN"); return e && e[0] == '1'; }();
 static std::atomic<int> g_chain_gen{[] { const char* e = getenv("IISAN_B200_CHAIN_GEN"); return (e && e[0] >= '1' && e[0] <= '3') ? e[0] - '0' : 3; }()};
-int set_chain_generation(int gen) { return g_chain_gen.exchange(gen); }
+int set_chain_generation(int gen) { return gen >= 1 ? g_chain_gen.exchange(gen) : g_chain_gen.load(); }      // gen < 1: query only
 // L2 prefetch distance (chunks) of the second-generation chain kernels; IISAN_B200_CHAIN_PF overrides (measurement switch)
 static const int g_chain_pf_fwd = [] { const char* e = getenv("IISAN_B200_CHAIN_PF"); return e ? atoi(e) : 0; }();
 static const int g_chain_pf_bwd = [] { const char* e = getenv("IISAN_B200_CHAIN_PF_BWD"); return e ? atoi(e) : 0; }();

@@ -468,15 +468,9 @@ __global__ void __launch_bounds__(THREADS3, 1) san_chain3_fwd_kernel(const __gri
       __syncwarp();
       if (lane == 0) mbar_arrive_a(bar0 + Smem3::bZReady);
       if (grow < a.n_items) {
-        const int64_t off = ((grow * A + s) * 2 + T.r_slot) * R + grp * 16;
-        uint4* zs = reinterpret_cast<uint4*>(T.r_out + off);
+        uint4* zs = reinterpret_cast<uint4*>(T.r_out + (grow * A + s) * R + grp * 16);
         zs[0] = make_uint4(zo[0], zo[1], zo[2], zo[3]);
         zs[1] = make_uint4(zo[4], zo[5], zo[6], zo[7]);
-        if (T.r_out2) {
-          uint4* zs2 = reinterpret_cast<uint4*>(T.r_out2 + off);
-          zs2[0] = make_uint4(zo[0], zo[1], zo[2], zo[3]);
-          zs2[1] = make_uint4(zo[4], zo[5], zo[6], zo[7]);
-        }
       }
       T3_LAP(6);
       const bool more = s + 1 < A;

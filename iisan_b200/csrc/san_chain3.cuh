@@ -24,9 +24,7 @@ struct Chain3Tower {
   const float* gate[kChainMaxStages];
   const float* b_down[kChainMaxStages + 1];   // [A]: merged head bias  W_pre b_fc + b_pre
   const float* b_up[kChainMaxStages];
-  __nv_bfloat16* r_out;     // relu(z_s) stash [n_pad, A, 2, 64] of this tower's modality; this tower writes slot r_slot
-  __nv_bfloat16* r_out2;    // inter-modal tower: the same values into the other modality's stash (null otherwise)
-  int r_slot;
+  __nv_bfloat16* r_out;     // relu(z_s) stash of this tower [N, A, 64]
   int out_col;              // first column of this tower's E = 64 outputs
 };
 

@@ -15,11 +15,11 @@
 // the reduction) plus rank-space work; no x_s / last_s / d last_s stash exists.  The algebra is restated in torch and checked
 // against autograd of the oracle in float64: tests/lowrank_reference.py, tests/test_lowrank_adjoint_cpu.py.
 //
-// Buffers (workspace).  Modality X = 0 text, 1 image; slot 0 = the modality's own tower, slot 1 = the inter-modal tower (written
-// into both modalities' buffers so that one GEMM over a modality's hidden states serves both towers that read them):
-//   R_X [N, A, 2, 64]     relu(z_s)                       (forward)
-//   D_X [N, A+1, 2, 64]   dz_s ; stage A = dL/dy          (backward)
-//   GT_X[j] [(A+1-j)*128, d] = D_X[:, j..A]^T h^X_{layer j} ;  Pg_X [(A+1)*128, A*128] = D_X^T R_X  (fp32)
+// Buffers (workspace).  Per tower t (0 text, 1 image, 2 inter-modal), compact:  Rc_t [N, A, 64] relu(z_s) (forward),
+// Dc_t [N, A+1, 64] dz_s with stage A = dL/dy (backward).  Per modality X (0 text, 1 image), interleaved: D_X [N, A+1, 2, 64] with
+// slot 0 = the modality's own tower and slot 1 = the inter-modal tower (written into both modalities' buffers), so that ONE GEMM
+// over a modality's hidden states serves both towers that read them:
+//   GT_X[j] [(A+1-j)*128, d] = D_X[:, j..A]^T h^X_{layer j} ;   Pc_t [(A+1)*64, A*64] = Dc_t^T Rc_t   (fp32)
 #include "san_lr.cuh"
 
 #include "gemm_simt.cuh"
@@ -34,6 +34,7 @@ using bf16 = __nv_bfloat16;
 constexpr int LE = 64;                    // rank of every bottleneck handled here (adapters and merged head)
 constexpr int LMAXA = kChainMaxStages;    // 8
 
+extern thread_local int g_umma_launch_class;
 int make_tensor_map_bf16(CUtensorMap* out, const void* ptr, int64_t rows, int64_t cols, int64_t pitch, int box_inner, int box_outer);
 
 
@@ -62,13 +63,12 @@ bool san_lr_usable(const iisan_san_desc& D, const iisan_san_params& P) {
 struct LrLayout {
   bf16 *wd_pack[3], *wu_pack[3], *wu_rows[3], *fcb[3], *preb[3];
   float *M32[3], *hb[3], *bsc[3];     // bsc: up-projection biases times the gate factor of the next fusion [A, d]
-  bf16 *Rst[2], *Dst[2];
+  bf16 *Rc[3], *Dc[3], *Dst[2];   // relu(z) [N, A, 64] and dz [N, A+1, 64] per tower (compact) ; dz interleaved per modality [N, A+1, 2, 64]
   float* KK[3];
   bf16* KB[3];                   // rank-space B operands: [32 A (A+1), 64] per tower
   float* tab;                    // GateTab
-  float *part, *part2;           // per-block partial sums of the scalar reductions
   float* zero_begin;
-  float *GT[2], *Pg[2], *cs[2], *dWd[3], *dWu[3];
+  float *GT[2], *Pc[3], *cs[2], *dWd[3], *dWu[3], *scal;
   size_t zero_bytes;
   bf16 *Pd[3], *Pu[3], *dMb[3];
   size_t gt_off[LMAXA];          // element offset of GT_X[j] inside GT[X]
@@ -83,18 +83,19 @@ struct LrLayout {
       fcb[t] = a.take<bf16>(f * d); preb[t] = a.take<bf16>(LE * f);
       M32[t] = a.take<float>(LE * d); hb[t] = a.take<float>(LE); bsc[t] = a.take<float>(A * d);
     }
-    for (int x = 0; x < 2; ++x) { Rst[x] = a.take<bf16>(N * A * 128); Dst[x] = a.take<bf16>(N * (A + 1) * 128); }
+    for (int t = 0; t < 3; ++t) { Rc[t] = a.take<bf16>(N * A * LE); Dc[t] = a.take<bf16>(N * (A + 1) * LE); }
+    for (int x = 0; x < 2; ++x) Dst[x] = a.take<bf16>(N * (A + 1) * 128);
     for (int t = 0; t < 3; ++t) KK[t] = a.take<float>((A + 1) * LE * A * LE);
     size_t gt = 0;
     for (size_t s = 0; s < A; ++s) { gt_off[s] = gt; gt += 128 * (A + 1 - s) * d; }
     for (int t = 0; t < 3; ++t) KB[t] = a.take<bf16>(32 * A * (A + 1) * LE);
     tab = a.take<float>(512);
-    part = a.take<float>(3 * (A + 1) * (d / 64) * 4 * (1 + 2 * LMAXA));
     const size_t z0 = a.off;
     zero_begin = reinterpret_cast<float*>(a.base + a.off);
-    for (int x = 0; x < 2; ++x) { GT[x] = a.take<float>(gt); Pg[x] = a.take<float>((A + 1) * 128 * A * 128); cs[x] = a.take<float>((A + 1) * 128); }
+    for (int x = 0; x < 2; ++x) { GT[x] = a.take<float>(gt); cs[x] = a.take<float>((A + 1) * 128); }
+    for (int t = 0; t < 3; ++t) Pc[t] = a.take<float>((A + 1) * LE * A * LE);
     for (int t = 0; t < 3; ++t) { dWd[t] = a.take<float>((A + 1) * LE * d); dWu[t] = a.take<float>(A * d * LE); }
-    part2 = a.take<float>(3 * A * (12 + d / 64) * 2);      // (zeroed: every block writes only its own half of a row)
+    scal = a.take<float>(256);
     zero_bytes = a.off - z0;
     for (int t = 0; t < 3; ++t) { Pd[t] = a.take<bf16>((A + 1) * LE * A * LE); Pu[t] = a.take<bf16>(A * (A + 1) * LE * LE); dMb[t] = a.take<bf16>(LE * d); }
     bytes = a.off;
@@ -245,7 +246,7 @@ int san_lr_forward(const iisan_san_desc* D, const iisan_san_params* P, const voi
       T.gate[s] = tp[t].gate[s]; T.b_down[s] = ad.b_down; T.b_up[s] = L.bsc[t] + (size_t)s * d;
     }
     T.b_down[A] = L.hb[t];
-    T.r_out = L.Rst[t == 0 ? 0 : 1]; T.r_out2 = t == 2 ? L.Rst[0] : nullptr; T.r_slot = t == 2 ? 1 : 0;
+    T.r_out = L.Rc[t];
     T.out_col = tower_out_col(t, E);
   }
   return launch_san_chain3_fwd(ca, 3, st);
@@ -300,7 +301,7 @@ __global__ void __launch_bounds__(256) lr_kb_kernel(const __grid_constant__ LrKb
 struct LrRankArgs {
   CUtensorMap map_kb[3];            // KB_t as a [32 A (A+1), 64] bf16 matrix, boxes of 64 x 64
   const float* d_out; int64_t ld_out; int out_col[3];
-  const bf16* R[3]; bf16* D[3]; bf16* D2; int slot[3];
+  const bf16* R[3]; bf16* Dc[3]; bf16* D[3]; bf16* D2; int slot[3];     // R / Dc: compact per tower ; D (+ D2 for the inter-modal tower): interleaved per modality
   int n_items, A;
 };
 constexpr int RK_THREADS = 320;
@@ -386,7 +387,21 @@ __global__ void __launch_bounds__(RK_THREADS, 1) lr_rank_kernel(const __grid_con
 #pragma unroll
     for (int q = 0; q < 4; ++q) offq[q] = sw_row + (uint32_t)(((half * 4 + q) ^ (m & 7)) << 4);
     const int slot = a.slot[t];
-    const int64_t ldD = (int64_t)(A + 1) * 128, ldR = (int64_t)A * 128;
+    const int64_t ldD = (int64_t)(A + 1) * 128, ldR = (int64_t)A * 64, ldC = (int64_t)(A + 1) * 64;
+    // this thread's 32 columns of dz_s -> global: interleaved per modality (operand of the G GEMM) and compact per tower (Gram GEMM)
+    auto stash = [&](int s, const uint32_t (&o)[16]) {
+      if (!live) return;
+      const int64_t off = grow * ldD + s * 128 + slot * 64 + half * 32;
+      uint4* p = reinterpret_cast<uint4*>(a.D[t] + off);
+      uint4* pc = reinterpret_cast<uint4*>(a.Dc[t] + grow * ldC + s * 64 + half * 32);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { const uint4 v = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]); p[q] = v; pc[q] = v; }
+      if (t == 2) {
+        uint4* p2 = reinterpret_cast<uint4*>(a.D2 + off);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) p2[q] = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+      }
+    };
     // publish this thread's 32 columns of dz_s: shared-memory operand of step `n` and the global stash
     auto publish = [&](int s, int n, const uint32_t (&o)[16]) {
       const uint32_t dstA = sA + (n & 1) * RK_A_BYTES;
@@ -395,17 +410,7 @@ __global__ void __launch_bounds__(RK_THREADS, 1) lr_rank_kernel(const __grid_con
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) c2::mbar_arrive_a(bAFull + 8 * (n & 1));
-      if (live) {
-        const int64_t off = grow * ldD + s * 128 + slot * 64 + half * 32;
-        uint4* p = reinterpret_cast<uint4*>(a.D[t] + off);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) p[q] = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
-        if (t == 2) {
-          uint4* p2 = reinterpret_cast<uint4*>(a.D2 + off);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) p2[q] = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
-        }
-      }
+      stash(s, o);
     };
     {   // dz_A = dL/dy
       uint32_t o[16];
@@ -423,7 +428,7 @@ __global__ void __launch_bounds__(RK_THREADS, 1) lr_rank_kernel(const __grid_con
       const int s = j - 1;
       uint4 rm[4];                                               // relu(z_s) of this thread's 32 columns (the ReLU mask)
       if (live) {
-        const uint4* rp = reinterpret_cast<const uint4*>(a.R[t] + grow * ldR + s * 128 + slot * 64 + half * 32);
+        const uint4* rp = reinterpret_cast<const uint4*>(a.R[t] + grow * ldR + s * 64 + half * 32);
 #pragma unroll
         for (int q = 0; q < 4; ++q) rm[q] = rp[q];
       } else {
@@ -445,17 +450,7 @@ __global__ void __launch_bounds__(RK_THREADS, 1) lr_rank_kernel(const __grid_con
         o[q] = c2::pack2(lo, hi);
       }
       if (s > 0) publish(s, n + 1, o);
-      else if (live) {                                           // dz_0: only the stash
-        const int64_t off = grow * ldD + slot * 64 + half * 32;
-        uint4* p = reinterpret_cast<uint4*>(a.D[t] + off);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) p[q] = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
-        if (t == 2) {
-          uint4* p2 = reinterpret_cast<uint4*>(a.D2 + off);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) p2[q] = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
-        }
-      }
+      else stash(0, o);                                          // dz_0: only the stash
     }
   }
   tc_fence_before();
@@ -464,14 +459,13 @@ __global__ void __launch_bounds__(RK_THREADS, 1) lr_rank_kernel(const __grid_con
 }
 
 // pi-scaled bf16 copies of the Gram blocks: Pd[t][s][a, (j, b)] = pi(s, j) P_t[(s, a), (j, b)]  (j < s, else 0) ;
-// Pu[t][s][(j - s - 1, a), b] = pi(j, s) P_t[(j, a), (s, b)]  (j > s).  P_t lives in Pg_X at slot-strided positions.
-struct LrScaleArgs { const GateTab* tab; const float* Pg[2]; bf16* Pd[3]; bf16* Pu[3]; int A; };
+// Pu[t][s][(j - s - 1, a), b] = pi(j, s) P_t[(j, a), (s, b)]  (j > s).
+struct LrScaleArgs { const GateTab* tab; const float* Pc[3]; bf16* Pd[3]; bf16* Pu[3]; int A; };
 __global__ void __launch_bounds__(256) lr_scale_kernel(const __grid_constant__ LrScaleArgs a) {
   const int A = a.A, t = blockIdx.z;
-  const int x = t == 1 ? 1 : 0, slot = t == 2 ? 1 : 0;
-  const float* Pg = a.Pg[x];
-  const int ldP = A * 128;
-  auto P = [&](int j, int aa, int s, int b) { return Pg[(size_t)((j * 2 + slot) * 64 + aa) * ldP + (s * 2 + slot) * 64 + b]; };
+  const float* Pc = a.Pc[t];                // [(A+1)*64, A*64]: P_t[(j, a), (s, b)] = sum_n dz_j[n, a] relu(z_s)[n, b]
+  const int ldP = A * LE;
+  auto P = [&](int j, int aa, int s, int b) { return Pc[(size_t)(j * LE + aa) * ldP + s * LE + b]; };
   const int s = blockIdx.y;               // 0..A
   const int AL = A * LE;
   for (int i = blockIdx.x * 256 + threadIdx.x; i < LE * AL; i += gridDim.x * 256) {          // Pd block s: [64, A*64]
@@ -489,8 +483,9 @@ __global__ void __launch_bounds__(256) lr_scale_kernel(const __grid_constant__ L
 }
 
 // ------------------------------------------------------------------------------------------------
-// combine.  Partial sums of the scalar reductions go to `part` (one row of LR_NPART floats per block, no atomics); the gate
-// kernel adds them up.  Row layout: [0] <dWd_s, Wd_s>, [1 + j] Q_j partial, [1 + 8 + j] Q2_j partial (inter-modal: text states)
+// combine.  The scalar reductions are added (one red.add per block and scalar) into `scal` (zeroed per backward), t stride 64:
+//   [0..7] Q_j (inter-modal: from the image states), [8..15] Q2_j (inter-modal: text states), [16..23] <dWd_s, Wd_s>,
+//   [24..31] <dWu_s, Wu_s>, [32..39] <dbu_s, bu_s>
 // ------------------------------------------------------------------------------------------------
 constexpr int LR_NPART = 1 + 2 * LMAXA;
 struct LrCombineArgs {
@@ -499,8 +494,7 @@ struct LrCombineArgs {
   const float* GT[2]; size_t gt_off[LMAXA];
   const float* cs[2];
   float* dWd[3]; const float* dWu[3]; const float* M32[3]; bf16* dMb[3];
-  float* part;            // combine partials: [3][A+1][d/64][4][LR_NPART]
-  float* part2;           // wu / bias partials: [3][A][LR_WU_BLOCKS + d/64][2]
+  float* scal;
   int d, f, A;
 };
 
@@ -527,8 +521,9 @@ __global__ void __launch_bounds__(256) lr_combine_kernel(const __grid_constant__
   }
   const float* cs_s = a.cs[xo] + (s * 2 + slot) * 64;
   const float* GTo = a.GT[xo]; const float* GT0 = a.GT[0]; const float* GT1 = a.GT[1];
+  float accv[4], oldg[4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < 4; ++i) {             // every load of the four rows first (the gradient stores below may alias as far as the compiler knows)
     const int aa = a0 + i;
     const float w = Wd_s[(size_t)aa * d + k];
     float v1[LMAXA], v2[LMAXA];
@@ -542,17 +537,20 @@ __global__ void __launch_bounds__(256) lr_combine_kernel(const __grid_constant__
       }
     }
     float acc = a.dWd[t][(size_t)(s * LE + aa) * d + k] + cs_s[aa] * bsum;
+    oldg[i] = s < A ? a.G[t].wd[s][(size_t)aa * d + k] : 0.f;
 #pragma unroll
     for (int j = 0; j < LMAXA; ++j) {
       if (t < 2) { acc += pij[j] * gj[j] * v1[j]; q1[j] += pij[j] * v1[j] * w; }
       else { acc += pij[j] * (gj[j] * v1[j] + (1.0f - gj[j]) * v2[j]); q1[j] += pij[j] * v1[j] * w; q2[j] += pij[j] * v2[j] * w; }
     }
-    if (s < A) {
-      a.G[t].wd[s][(size_t)aa * d + k] += acc;
-      ipd += acc * w;
-    } else {
-      a.dMb[t][(size_t)aa * d + k] = __float2bfloat16_rn(acc);
-    }
+    accv[i] = acc;
+    if (s < A) ipd += acc * w;
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int aa = a0 + i;
+    if (s < A) a.G[t].wd[s][(size_t)aa * d + k] = oldg[i] + accv[i];
+    else a.dMb[t][(size_t)aa * d + k] = __float2bfloat16_rn(accv[i]);
   }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   ipd = warp_sum(ipd);
@@ -566,8 +564,10 @@ __global__ void __launch_bounds__(256) lr_combine_kernel(const __grid_constant__
   if (threadIdx.x < LR_NPART) {
     float v = 0.f;
     for (int w = 0; w < 8; ++w) v += red[w][threadIdx.x];
-    const size_t blk = (((size_t)t * (A + 1) + s) * gridDim.x + blockIdx.x) * 4 + rq;
-    a.part[blk * LR_NPART + threadIdx.x] = v;
+    float* sc = a.scal + t * 64;
+    if (threadIdx.x == 0) { if (s < A) atomicAdd(sc + 16 + s, v); }
+    else if (threadIdx.x <= LMAXA) { const int j = threadIdx.x - 1; if (j <= jmax) atomicAdd(sc + j, v); }
+    else { const int j = threadIdx.x - 1 - LMAXA; if (t == 2 && j <= jmax) atomicAdd(sc + 8 + j, v); }
   }
 }
 
@@ -592,68 +592,60 @@ __global__ void __launch_bounds__(256) lr_wu_kernel(const __grid_constant__ LrCo
   if (threadIdx.x == 0) {
     float v = 0.f;
     for (int w = 0; w < 8; ++w) v += red[w];
-    const int nb = LR_WU_BLOCKS + a.d / 64;
-    a.part2[(((size_t)t * A + s) * nb + blockIdx.x) * 2] = v;
+    atomicAdd(a.scal + t * 64 + 24 + s, v);
   }
 }
 
-// Bias-sized pieces.  grid (d / 64, 3), 256 threads = 64 columns x 4 row groups.  v_j[k] = colsum(dz_j) . Wd_j[:, k]  (j = 1..A),
-// dbu_s[k] = sum_{j > s} pi(j, s) v_j[k] -> grad bu_s, partial <dbu_s, bu_s> ; block x == 0 also adds colsum(dz_s) to grad bd_s,
-// colsum(e) to db_pre ; every block: db_fc[k] += W_pre[:, k] . colsum(e), dW_pre[:, k] += colsum(e) b_fc[k].
+// Bias-sized pieces.  grid (d / 32, 3), 256 threads = 32 columns x 8 row groups of 8.  v_j[k] = colsum(dz_j) . Wd_j[:, k] (j = 1..A),
+// dbu_s[k] = sum_{j > s} pi(j, s) v_j[k] -> grad bu_s (row group s), <dbu_s, bu_s> ; db_fc[k] += W_pre[:, k] . colsum(e) ;
+// dW_pre[:, k] += colsum(e) b_fc[k] ; block x == 0 also adds colsum(dz_s) to grad bd_s and colsum(e) to db_pre.
 __global__ void __launch_bounds__(256) lr_bias_kernel(const __grid_constant__ LrCombineArgs a) {
   __shared__ float csj[(LMAXA + 1) * LE];
-  __shared__ float vpart[4][LMAXA + 1][64];
-  __shared__ float red[2][LMAXA];
+  __shared__ float vpart[8][LMAXA + 1][32];
   const int A = a.A, d = a.d, t = blockIdx.y;
   const int xo = t == 1 ? 1 : 0, slot = t == 2 ? 1 : 0;
   const GateTab& tab = *a.tab;
   for (int i = threadIdx.x; i < (A + 1) * LE; i += 256) csj[i] = a.cs[xo][((i >> 6) * 2 + slot) * 64 + (i & 63)];
   __syncthreads();
-  const int kc = threadIdx.x & 63, ag = threadIdx.x >> 6, k = blockIdx.x * 64 + kc;
+  const int kc = threadIdx.x & 31, ag = threadIdx.x >> 5, k = blockIdx.x * 32 + kc;
   for (int j = 1; j <= A; ++j) {
     const float* W = j < A ? a.P[t].wd[j] : a.M32[t];
     float v = 0.f;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) { const int aa = ag * 16 + i; v += csj[j * LE + aa] * W[(size_t)aa * d + k]; }
+    for (int i = 0; i < 8; ++i) { const int aa = ag * 8 + i; v += csj[j * LE + aa] * W[(size_t)aa * d + k]; }
     vpart[ag][j][kc] = v;
   }
-  // head pieces on the same thread layout: partial over this thread's 16 rows e of W_pre[e, k] colsum(e)[e]   (f == d)
-  float hb = 0.f;
+  float hb = 0.f;                      // head: partial over this thread's 8 rows e of W_pre[e, k] colsum(e)[e]   (f == d)
 #pragma unroll
-  for (int i = 0; i < 16; ++i) { const int e = ag * 16 + i; hb += a.P[t].w_pre[(size_t)e * a.f + k] * csj[A * LE + e]; }
+  for (int i = 0; i < 8; ++i) { const int e = ag * 8 + i; hb += a.P[t].w_pre[(size_t)e * a.f + k] * csj[A * LE + e]; }
   vpart[ag][0][kc] = hb;
   __syncthreads();
-  if (threadIdx.x < 2 * LMAXA) red[threadIdx.x / LMAXA][threadIdx.x % LMAXA] = 0.f;
-  __syncthreads();
-  float vj[LMAXA + 1];
+  if (ag < A) {                        // row group ag: stage s = ag of dbu (one warp: the inner product reduces with one warp_sum)
+    const int s = ag;
+    float dbu = 0.f;
+    for (int j = s + 1; j <= A; ++j) {
+      float vj = 0.f;
 #pragma unroll
-  for (int j = 0; j <= LMAXA; ++j) vj[j] = (j <= A) ? vpart[0][j][kc] + vpart[1][j][kc] + vpart[2][j][kc] + vpart[3][j][kc] : 0.f;
-  // row group ag: stages s = ag, ag + 4 of dbu ; the 16 rows e = ag*16.. of the rank-1 term of dW_pre ; ag == 0: db_fc
-#pragma unroll
-  for (int r = 0; r < 2; ++r) {
-    const int s = ag + 4 * r;
-    if (s < A) {
-      float dbu = 0.f;
-#pragma unroll
-      for (int j = 1; j <= LMAXA; ++j) if (j > s && j <= A) dbu += tab.pi[t][j][s] * vj[j];
-      a.G[t].bu[s][k] += dbu;
-      const float ipb = warp_sum(dbu * a.P[t].bu[s][k]);
-      if ((threadIdx.x & 31) == 0) atomicAdd(&red[1][s], ipb);
+      for (int g8 = 0; g8 < 8; ++g8) vj += vpart[g8][j][kc];
+      dbu += tab.pi[t][j][s] * vj;
     }
+    a.G[t].bu[s][k] += dbu;
+    const float ipb = warp_sum(dbu * a.P[t].bu[s][k]);
+    if (kc == 0) atomicAdd(a.scal + t * 64 + 32 + s, ipb);
   }
-  if (ag == 0) a.G[t].b_fc[k] += vj[0];
+  if (ag == 7) {
+    float v0 = 0.f;
+#pragma unroll
+    for (int g8 = 0; g8 < 8; ++g8) v0 += vpart[g8][0][kc];
+    a.G[t].b_fc[k] += v0;
+  }
   {
     const float bf = a.P[t].b_fc[k];
-    float old[16];
+    float old[8];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) old[i] = a.G[t].w_pre[(size_t)(ag * 16 + i) * a.f + k];
+    for (int i = 0; i < 8; ++i) old[i] = a.G[t].w_pre[(size_t)(ag * 8 + i) * a.f + k];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) a.G[t].w_pre[(size_t)(ag * 16 + i) * a.f + k] = old[i] + csj[A * LE + ag * 16 + i] * bf;
-  }
-  __syncthreads();
-  if (threadIdx.x < A) {
-    const int nb = LR_WU_BLOCKS + d / 64;
-    a.part2[(((size_t)t * A + threadIdx.x) * nb + LR_WU_BLOCKS + blockIdx.x) * 2 + 1] = red[1][threadIdx.x];
+    for (int i = 0; i < 8; ++i) a.G[t].w_pre[(size_t)(ag * 8 + i) * a.f + k] = old[i] + csj[A * LE + ag * 8 + i] * bf;
   }
   if (blockIdx.x == 0 && threadIdx.x < LE) {
     float old[LMAXA + 1];
@@ -666,44 +658,22 @@ __global__ void __launch_bounds__(256) lr_bias_kernel(const __grid_constant__ Lr
   }
 }
 
-// gate gradients from the partial sums (one block)
-struct LrGateArgs { const GateTab* tab; float* g_gate[3][LMAXA]; const float* part; const float* part2; int A, kt; };
-__global__ void __launch_bounds__(256) lr_gate_kernel(const __grid_constant__ LrGateArgs a) {
-  __shared__ float sc[3][5][LMAXA];            // Q, Q2, <dWd,Wd>, <dWu,Wu>, <dbu,bu>
-  const int A = a.A;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int i = warp; i < 3 * 5 * LMAXA; i += 8) {               // one warp per sum
-    const int t = i / (5 * LMAXA), q = (i / LMAXA) % 5, j = i % LMAXA;
-    float v = 0.f;
-    if (j < A) {
-      if (q < 2) {            // Q_j: every block of tower t (all s, column tiles, row quarters)
-        const float* p = a.part + (size_t)t * (A + 1) * a.kt * 4 * LR_NPART + 1 + q * LMAXA + j;
-        for (int b = lane; b < (A + 1) * a.kt * 4; b += 32) v += p[(size_t)b * LR_NPART];
-      } else if (q == 2) {    // <dWd_j, Wd_j>: blocks of stage j
-        const float* p = a.part + ((size_t)t * (A + 1) + j) * a.kt * 4 * LR_NPART;
-        for (int b = lane; b < a.kt * 4; b += 32) v += p[(size_t)b * LR_NPART];
-      } else {
-        const int nb = LR_WU_BLOCKS + a.kt;
-        const float* p = a.part2 + ((size_t)t * A + j) * nb * 2 + (q - 3);
-        for (int b = lane; b < nb; b += 32) v += p[(size_t)b * 2];
-      }
-    }
-    v = warp_sum(v);
-    if (lane == 0) sc[t][q][j] = v;
-  }
-  __syncthreads();
-  const int t = threadIdx.x;
+// gate gradients from the reduced scalars (one warp)
+struct LrGateArgs { const GateTab* tab; float* g_gate[3][LMAXA]; const float* scal; int A; };
+__global__ void lr_gate_kernel(const __grid_constant__ LrGateArgs a) {
+  const int A = a.A, t = threadIdx.x;
   if (t >= 3) return;
   const GateTab& tab = *a.tab;
+  const float* sc = a.scal + t * 64;
   if (t == 2) {
-    for (int s = 0; s < A; ++s) { const float g = tab.g[2][s]; atomicAdd(a.g_gate[2][s], g * (1.0f - g) / 0.1f * (sc[2][0][s] - sc[2][1][s])); }
+    for (int s = 0; s < A; ++s) { const float g = tab.g[2][s]; atomicAdd(a.g_gate[2][s], g * (1.0f - g) / 0.1f * (sc[s] - sc[8 + s])); }
     return;
   }
   float R = 0.f;
   for (int s = 0; s < A; ++s) {
-    const float g = tab.g[t][s], Q = sc[t][0][s];
+    const float g = tab.g[t][s], Q = sc[s];
     atomicAdd(a.g_gate[t][s], (g / 0.1f) * ((1.0f - g) * Q - R));
-    R += g * Q - sc[t][2][s] + sc[t][3][s] + sc[t][4][s];
+    R += g * Q - sc[16 + s] + sc[24 + s] + sc[32 + s];
   }
 }
 
@@ -718,13 +688,17 @@ static UmmaProblem lr_linear(const bf16* x, int64_t ldx, const bf16* w, int64_t 
   p.M = M; p.N = N; p.K = K; p.splitk = 1;
   return p;
 }
+// Split-K factor of a persistent launch over 148 SMs: the one that minimises (rounds of tiles per SM) / split, i.e. the length
+// of the longest SM's work list (ties: the smaller split, fewer red.add epilogues).
 static int lr_pick_split(int K, int tiles_launch) {
   const int kb = (K + 63) / 64;
-  int s = (2 * 148 + tiles_launch - 1) / tiles_launch;
-  if (s > kb / 2) s = kb / 2;
-  if (s < 1) s = 1;
-  if (s > 64) s = 64;
-  return s;
+  int best = 1; double best_cost = 1e30;
+  for (int s = 1; s <= 6 && s <= kb / 8; ++s) {
+    const int rounds = (tiles_launch * s + 147) / 148;
+    const double cost = (double)rounds / s + 0.02 * s;
+    if (cost < best_cost - 1e-9) { best_cost = cost; best = s; }
+  }
+  return best;
 }
 // out[m, n] (+)= y[rows, m]^T x[rows, n]   (MN-major operands; the larger of m, n becomes the UMMA M dimension)
 static UmmaProblem lr_wgrad(const bf16* y, int64_t ldy, int m, const bf16* x, int64_t ldx, int n, int rows, float* out, int split) {
@@ -747,7 +721,7 @@ int san_lr_backward(const iisan_san_desc* D, const iisan_san_params* P, const ii
                     void* lr_ws, const float* d_out, cudaStream_t st) {
   LrLayout L(*D, lr_ws);
   const int N = D->n_items, A = D->n_stages, d = D->d_mm, E = D->emb, f = D->d_mm;
-  const int64_t ldD = (int64_t)(A + 1) * 128, ldR = (int64_t)A * 128;
+  const int64_t ldD = (int64_t)(A + 1) * 128;
   GateTab* tab = reinterpret_cast<GateTab*>(L.tab);
   GatePtrs gp{}; gp.A = A;
   static thread_local LrCombineArgs ca;
@@ -788,7 +762,7 @@ int san_lr_backward(const iisan_san_desc* D, const iisan_san_params* P, const ii
     for (int t = 0; t < 3; ++t) {
       IISAN_TRY(make_tensor_map_bf16(&ra.map_kb[t], L.KB[t], (int64_t)32 * A * (A + 1), LE, LE, 64, 64));
       ra.out_col[t] = tower_out_col(t, E);
-      ra.R[t] = L.Rst[t == 1 ? 1 : 0]; ra.D[t] = L.Dst[t == 1 ? 1 : 0]; ra.slot[t] = t == 2 ? 1 : 0;
+      ra.R[t] = L.Rc[t]; ra.Dc[t] = L.Dc[t]; ra.D[t] = L.Dst[t == 1 ? 1 : 0]; ra.slot[t] = t == 2 ? 1 : 0;
     }
     ra.D2 = L.Dst[1];
     ra.d_out = d_out; ra.ld_out = D->out_ld; ra.n_items = N; ra.A = A;
@@ -814,7 +788,7 @@ int san_lr_backward(const iisan_san_desc* D, const iisan_san_params* P, const ii
     gb.n = 0;
     int tiles = 0;
     for (int j = 0; j < A; ++j) tiles += 2 * ((d + 127) / 128) * ((128 * (A + 1 - j) + 255) / 256);
-    tiles += 2 * (((A + 1) * 128 + 127) / 128) * ((A * 128 + 255) / 256);
+    tiles += 3 * (((A + 1) * LE + 127) / 128) * ((A * LE + 255) / 256);
     const int split = lr_pick_split(N, tiles);
     for (int x = 0; x < 2; ++x) {
       const bf16* h = reinterpret_cast<const bf16*>(x == 0 ? text : image);
@@ -823,15 +797,18 @@ int san_lr_backward(const iisan_san_desc* D, const iisan_san_params* P, const ii
         const int layer = x == 0 ? D->text_layer[j] : D->img_layer[j];
         gb.p[gb.n++] = lr_wgrad(L.Dst[x] + (size_t)j * 128, ldD, 128 * (A + 1 - j), h + (size_t)layer * d, pitch, d, N, L.GT[x] + L.gt_off[j], split);
       }
-      gb.p[gb.n++] = lr_wgrad(L.Dst[x], ldD, (A + 1) * 128, L.Rst[x], ldR, A * 128, N, L.Pg[x], split);
     }
-    IISAN_TRY(launch_umma_gemm_many(gb, st));
+    for (int t = 0; t < 3; ++t)
+      gb.p[gb.n++] = lr_wgrad(L.Dc[t], (int64_t)(A + 1) * LE, (A + 1) * LE, L.Rc[t], (int64_t)A * LE, A * LE, N, L.Pc[t], split);
+    g_umma_launch_class = IISAN_K_WGRAD_STREAM;
+    const int gst = launch_umma_gemm_many(gb, st);
+    g_umma_launch_class = IISAN_K_GEMM;
+    IISAN_TRY(gst);
   }
   // ---- low-rank terms of dWd / dWu ----
   {
     LrScaleArgs sa{}; sa.tab = tab; sa.A = A;
-    for (int x = 0; x < 2; ++x) sa.Pg[x] = L.Pg[x];
-    for (int t = 0; t < 3; ++t) { sa.Pd[t] = L.Pd[t]; sa.Pu[t] = L.Pu[t]; }
+    for (int t = 0; t < 3; ++t) { sa.Pc[t] = L.Pc[t]; sa.Pd[t] = L.Pd[t]; sa.Pu[t] = L.Pu[t]; }
     LaunchScope ls_(IISAN_K_MISC, st);
     lr_scale_kernel<<<dim3(16, A + 1, 3), 256, 0, st>>>(sa);
   }
@@ -858,12 +835,12 @@ int san_lr_backward(const iisan_san_desc* D, const iisan_san_params* P, const ii
   for (int x = 0; x < 2; ++x) { ca.GT[x] = L.GT[x]; ca.cs[x] = L.cs[x]; }
   for (int j = 0; j < A; ++j) ca.gt_off[j] = L.gt_off[j];
   for (int t = 0; t < 3; ++t) { ca.dWd[t] = L.dWd[t]; ca.dWu[t] = L.dWu[t]; ca.M32[t] = L.M32[t]; ca.dMb[t] = L.dMb[t]; }
-  ca.part = L.part; ca.part2 = L.part2; ca.d = d; ca.f = f;
+  ca.scal = L.scal; ca.d = d; ca.f = f;
   { LaunchScope ls_(IISAN_K_MISC, st); lr_combine_kernel<<<dim3(d / 64, A + 1, 12), 256, 0, st>>>(ca); }
   IISAN_LAUNCH_OK();
   { LaunchScope ls_(IISAN_K_MISC, st); lr_wu_kernel<<<dim3(LR_WU_BLOCKS, A, 3), 256, 0, st>>>(ca); }
   IISAN_LAUNCH_OK();
-  { LaunchScope ls_(IISAN_K_MISC, st); lr_bias_kernel<<<dim3(d / 64, 3), 256, 0, st>>>(ca); }
+  { LaunchScope ls_(IISAN_K_MISC, st); lr_bias_kernel<<<dim3(d / 32, 3), 256, 0, st>>>(ca); }
   IISAN_LAUNCH_OK();
   // ---- heads:  dW_pre += dM W_fc^T ,  dW_fc += W_pre^T dM   (bf16 operands) ----
   {
@@ -878,10 +855,10 @@ int san_lr_backward(const iisan_san_desc* D, const iisan_san_params* P, const ii
     IISAN_TRY(launch_umma_gemm(hf, st));
   }
   {
-    LrGateArgs ga{}; ga.tab = tab; ga.part = L.part; ga.part2 = L.part2; ga.A = A; ga.kt = d / 64;
+    LrGateArgs ga{}; ga.tab = tab; ga.scal = L.scal; ga.A = A;
     for (int t = 0; t < 3; ++t) for (int s = 0; s < A; ++s) ga.g_gate[t][s] = ca.G[t].gate[s];
     LaunchScope ls_(IISAN_K_MISC, st);
-    lr_gate_kernel<<<1, 256, 0, st>>>(ga);
+    lr_gate_kernel<<<1, 32, 0, st>>>(ga);
   }
   IISAN_LAUNCH_OK();
   return IISAN_OK;

@@ -440,6 +440,9 @@ int make_tensor_map_bf16(CUtensorMap* out, const void* ptr, int64_t rows, int64_
   return IISAN_OK;
 }
 
+// kernel class the next launches are accounted under (san_lr.cu times its hidden-state GEMM pass separately)
+thread_local int g_umma_launch_class = IISAN_K_GEMM;
+
 static const bool g_no_multicast = [] { const char* e = getenv("IISAN_B200_NO_MULTICAST"); return e && e[0] == '1'; }();
 
 template <int BN, bool A_MN, bool B_MN, int NP, bool MC = false>
@@ -492,12 +495,12 @@ static int launch_cfg(const UmmaProblem* probs, int n_probs, cudaStream_t st) {
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    { LaunchScope ls_(IISAN_K_GEMM, st); IISAN_CUDA_OK(cudaLaunchKernelEx(&cfg, umma_gemm_kernel<BN, A_MN, B_MN, NP, MC>, dev)); }
+    { LaunchScope ls_(g_umma_launch_class, st); IISAN_CUDA_OK(cudaLaunchKernelEx(&cfg, umma_gemm_kernel<BN, A_MN, B_MN, NP, MC>, dev)); }
     IISAN_LAUNCH_OK();
     return IISAN_OK;
   }
   const int grid = total_tiles < n_sm ? total_tiles : n_sm;
-  { LaunchScope ls_(IISAN_K_GEMM, st); umma_gemm_kernel<BN, A_MN, B_MN, NP, MC><<<grid, UTHREADS, UmmaSmem<BN>::total(dev.stages), st>>>(dev); }
+  { LaunchScope ls_(g_umma_launch_class, st); umma_gemm_kernel<BN, A_MN, B_MN, NP, MC><<<grid, UTHREADS, UmmaSmem<BN>::total(dev.stages), st>>>(dev); }
   IISAN_LAUNCH_OK();
   return IISAN_OK;
 }

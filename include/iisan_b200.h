@@ -68,8 +68,9 @@ enum iisan_kernel_class {
   IISAN_K_CE = 3,     /* fused in-batch cross-entropy */
   IISAN_K_MISC = 4,   /* reductions, gathers, optimizer */
   IISAN_K_CHAIN = 5,  /* fused tcgen05 adapter-chain kernel, forward */
-  IISAN_K_CHAIN_BWD = 6, /* fused tcgen05 adapter-chain kernel, backward */
-  IISAN_K_COUNT = 7
+  IISAN_K_CHAIN_BWD = 6, /* fused tcgen05 adapter-chain kernel, backward (third generation: the rank-space chain) */
+  IISAN_K_WGRAD_STREAM = 7, /* third generation: the backward's one GEMM pass over the cached hidden states (G = dz^T h) + Gram blocks */
+  IISAN_K_COUNT = 8
 };
 /* total kernels launched by this process through the library, per class (kclass < 0: all classes) */
 int64_t iisan_launch_count(int kclass);
@@ -325,7 +326,8 @@ int iisan_probe_tile_stream(const void* base, int64_t n_rows, int32_t layers, in
                             int32_t slots, int32_t repeat, int32_t contiguous, void* sink, iisan_stream_t stream);
 
 /* Measurement switch (not on the product path; scripts/chain_ab.py): generation of the fused chain kernels used from now on
- * (1 = first generation, 2 = second generation, the default wherever it applies).  Returns the previous value. */
+ * (1 = first, 2 = second generation, 3 = resident-state forward + low-rank adjoint backward: the default wherever it applies;
+ * the newest generation that covers a shape is used).  Returns the previous value; gen < 1 only queries. */
 int iisan_debug_chain_generation(int32_t gen);
 
 #ifdef __cplusplus

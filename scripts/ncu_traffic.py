@@ -12,7 +12,7 @@ res = {"source": rep.split("/")[-1]}
 for r in rows[2:]:
     d = dict(zip(hdr, r)); u = dict(zip(hdr, units))
     name = d.get("Kernel Name", "")
-    key = "bwd" if "bwd" in name else ("fwd" if "chain" in name else None)
+    key = "bwd" if "bwd" in name else ("fwd" if "chain" in name else ("rank" if "lr_rank" in name else ("wgrad" if "umma_gemm_kernel<256, 1, 1, 48" in name else None)))
     if key is None or key in res:
         continue
     tot = 0.0
