@@ -39,7 +39,9 @@ int make_tensor_map_bf16(CUtensorMap* out, const void* ptr, int64_t rows, int64_
 
 
 bool san_lr_eligible(const iisan_san_desc& D) {
-  if (D.d_text != D.d_img || !chain3_shape_supported(D.d_text, D.emb)) return false;
+  // d == 768: the only width the Code_Cached tree (the non-asym heads this path merges) can have (CC/model/model.py:260,301-302);
+  // the kernels themselves take any even number of 64-column chunks up to 12, which nothing reachable exercises
+  if (D.d_text != D.d_img || D.d_text != 768 || !chain3_shape_supported(D.d_text, D.emb)) return false;
   if (D.r_text != 64 || D.r_img != 64 || D.r_mm != 64 || D.asym) return false;
   if (D.state_dtype != IISAN_BF16 || D.remove_first || D.n_stages > kChainMaxStages || D.n_stages < 1) return false;
   for (int s = 0; s < D.n_stages; ++s)

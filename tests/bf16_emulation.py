@@ -54,9 +54,8 @@ def user_encoder_forward_emul(P, embs, log_mask, cfg, prefix="user_encoder.trans
 
 
 def lr_path(cfg, fused_chain):
-    """True where the third-generation path runs (san_lr_eligible, san_lr.cu): symmetric chain, d a multiple of 128 in
-    [256, 768], E == 64, CC heads."""
-    return bool(fused_chain and not cfg.asym and cfg.d_text % 128 == 0 and 256 <= cfg.d_text <= 768 and cfg.embedding_dim == 64)
+    """True where the third-generation path runs (san_lr_eligible, san_lr.cu): symmetric chain, d == 768, E == 64, CC heads."""
+    return bool(fused_chain and not cfg.asym and cfg.d_text == 768 and cfg.embedding_dim == 64)
 
 
 def san_forward_emul(P, image, text, cfg, prefix="mm_encoder.", fused_chain=False):
