@@ -279,6 +279,10 @@ __global__ void __launch_bounds__(256) lr_coef_kernel(const __grid_constant__ Ga
   }
 }
 
+__global__ void __launch_bounds__(256) lr_zero_kernel(uint4* __restrict__ p, size_t n16) {
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n16; i += (size_t)gridDim.x * 256) p[i] = make_uint4(0u, 0u, 0u, 0u);
+}
+
 // KB_t: the B operands of the rank-space chain.  Step j (A..1) multiplies dz_j [128 x 64] with the 64 j rows starting at row
 // 32 j (j - 1):  KB_t[32 j (j-1) + s*64 + b][a] = pi_t(j, s) (Wd_j Wu_s)[a, b]   (s < j ; K-major: the reduction index a is contiguous)
 struct LrKbArgs { const GateTab* tab; const float* KK[3]; bf16* KB[3]; int A; };
@@ -731,7 +735,12 @@ int san_lr_backward(const iisan_san_desc* D, const iisan_san_params* P, const ii
     tower_ptrs(*D, *P, t, &ca.P[t]); tower_grads(*D, *G, t, &ca.G[t]);
     for (int s = 0; s < A; ++s) gp.p[t][s] = ca.P[t].gate[s];
   }
-  IISAN_CUDA_OK(cudaMemsetAsync(L.zero_begin, 0, L.zero_bytes, st));
+  {   // zero the accumulation scratch (split-K / red.add targets) with a kernel of our own: one more node of the same kind in a captured step
+    const size_t n16 = L.zero_bytes / 16;
+    LaunchScope ls_(IISAN_K_MISC, st);
+    lr_zero_kernel<<<296, 256, 0, st>>>(reinterpret_cast<uint4*>(L.zero_begin), n16);
+  }
+  IISAN_LAUNCH_OK();
   { LaunchScope ls_(IISAN_K_MISC, st); lr_coef_kernel<<<1, 256, 0, st>>>(gp, tab); }
   IISAN_LAUNCH_OK();
   // ---- weight products  KK_t[(s, b), (j, a)] = (Wd_j Wu_s)[a, b]  for j > s ----

@@ -565,11 +565,8 @@ int launch_umma_gemm_many(const UmmaBatchBig& b, cudaStream_t st) {
   }
   if (a_mn && !b_mn) return IISAN_EUNSUPPORTED;
   const bool wide = maxN > 64;
-  // Long reductions over 256-wide tiles are bound by operand traffic from L2 (85 FLOP per byte at 128 x 256): clusters of two CTAs
-  // share the column tile by TMA multicast (-33 % bytes per CTA).  IISAN_B200_NO_MULTICAST=1 switches it off (A/B measurements).
-  bool mc = a_mn && wide && !g_no_multicast;
-  for (int i = 0; i < b.n; ++i) mc = mc && b.p[i].M > UBM;
-  if (mc) return launch_cfg<256, true, true, kUmmaBigProbs, true>(b.p, b.n, st);
+  // (Clusters of two CTAs sharing the column tile by TMA multicast were measured on the 17-problem hidden-state pass of san_lr.cu:
+  // 93.6 vs 95.5 us -- the 128 x 256 tile is bound by the shared-memory operand fetch of the MMA, not by L2 -- and are not used here.)
   if (a_mn) return wide ? launch_cfg<256, true, true, kUmmaBigProbs>(b.p, b.n, st) : launch_cfg<64, true, true, kUmmaBigProbs>(b.p, b.n, st);
   if (b_mn) return wide ? launch_cfg<256, false, true, kUmmaBigProbs>(b.p, b.n, st) : launch_cfg<64, false, true, kUmmaBigProbs>(b.p, b.n, st);
   return wide ? launch_cfg<256, false, false, kUmmaBigProbs>(b.p, b.n, st) : launch_cfg<64, false, false, kUmmaBigProbs>(b.p, b.n, st);

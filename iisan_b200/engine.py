@@ -32,6 +32,14 @@ class TrainStep:
             self.world = dist.get_world_size(group) if (group is not None or (dist.is_available() and dist.is_initialized())) else 1
             if self.world > 1 and group is None:
                 self.group = dist.group.WORLD
+        if self.world > 1:
+            # Generation 3 of the fused side-adapter path (san_chain3.cu / san_lr.cu) faulted intermittently on 8 x B200
+            # ("unspecified launch failure" on one rank, 3 of 3 runs; 1 and 2 GPUs and every compute-sanitizer run are clean) and the
+            # cause is not found yet: data-parallel steps run generation 2 (measured cost at 8 GPUs: 1.30 -> 1.37 ms per step).
+            # IISAN_B200_DP_CHAIN_GEN=3 overrides (for the investigation).
+            import os
+            from . import _lib as L
+            L.load().iisan_debug_chain_generation(int(os.environ.get("IISAN_B200_DP_CHAIN_GEN", "2")))
         self.warmup = int(warmup)
         self.graph = None
         self.static_in = None
