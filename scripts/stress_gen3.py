@@ -17,7 +17,14 @@ def main():
     dev = torch.device("cuda", 0)
     model, args, _ = bench.build_model(dev, "bf16")
     model.train()
-    opt = bench.make_optimizer(model) if hasattr(bench, "make_optimizer") else None
+    from iisan_b200.optim import FusedAdam, param_groups
+    from iisan_b200.engine import TrainStep
+    from iisan_b200 import _lib
+    lib = _lib.load()
+    opt = FusedAdam(param_groups(model, args))
+    eager = TrainStep(model, opt, use_graph=False)
+    if "timing" in mode:
+        lib.iisan_timing_enable(1)
     g = torch.Generator(device=dev).manual_seed(7)
     batches = bench.make_device_batches(3, 512, dev, torch.bfloat16, g)
     side = torch.cuda.Stream()
@@ -25,18 +32,21 @@ def main():
     small = torch.randn(256, 256, device=dev)
     t0 = time.time()
     for i in range(steps):
-        if mode != "none":
+        if "matmul" in mode or "spin" in mode:
             with torch.cuda.stream(side):
-                if mode == "matmul":
+                if "matmul" in mode:
                     for _ in range(2 + i % 5):
                         a @ a
                 else:
                     for _ in range(20 + i % 30):
                         small.add_(1.0)
         ids, image, text, lm = batches[i % 3]
-        model.zero_grad(set_to_none=True)
-        loss = model(ids, image, text, lm, dev)
-        loss.backward()
+        if "adam" in mode:
+            loss = eager(ids, image, text, lm)
+        else:
+            model.zero_grad(set_to_none=True)
+            loss = model(ids, image, text, lm, dev)
+            loss.backward()
         if i % 50 == 0:
             torch.cuda.synchronize()
             print(i, float(loss), flush=True)
