@@ -68,7 +68,7 @@ struct Smem3 {
   static constexpr int kXs = kW + RING3_BYTES;                  // resident x chunks NT3..
   static constexpr int kIdent = kXs + NS3 * TILE_BYTES;         // [64 x 64] bf16 identity (K-major, swizzled): B operand of the residual MMAs
   static constexpr int kBias = kIdent + W_BYTES;                // two stages
-  static constexpr int kBar = kBias + 2 * BIAS3;
+  static constexpr int kBar = kBias + 2 * BIAS3 + 256;          // (a gap between the bulk-copy destination and the barriers: see lr_rank_kernel)
   static constexpr int kTotal = kBar + 1024 + 1024;             // barriers + alignment slack
   static constexpr int bWFull = 0, bWEmpty = bWFull + 8 * NW3_MAX, bDFull = bWEmpty + 8 * NW3_MAX, bDEmpty = bDFull + 16 * NDR3_MAX;
   static constexpr int bXFull = bDEmpty + 16 * NDR3_MAX, bUFull = bXFull + 8 * (NT3 + NS3), bUEmpty = bUFull + 8 * NU3;

@@ -321,7 +321,9 @@ __global__ void __launch_bounds__(RK_THREADS, 1) lr_rank_kernel(const __grid_con
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sA = sbase, sB = sbase + 2 * RK_A_BYTES, bar0 = sB + 2 * RK_B_BYTES;
   // barriers: aFull[2] (8 epilogue warps), bFull[2] (tx), bEmpty[2] (commit), accFull (commit), tmem slot
-  const uint32_t bAFull = bar0, bBFull = bar0 + 16, bBEmpty = bar0 + 32, bAcc = bar0 + 48, bTmem = bar0 + 64;
+  // The barriers do NOT start right behind the TMA destination buffers: with aFull at bar0 + 0 compute-sanitizer's synccheck reports
+  // "Missing init" for it and the kernel faults under the tool (and, rarely, without it: DESIGN 4.8); 128 bytes further on both are clean.
+  const uint32_t bAFull = bar0 + 256, bBFull = bar0 + 128, bBEmpty = bar0 + 384, bAcc = bar0 + 512, bTmem = bar0 + 640;
   const int t = blockIdx.y, A = a.A;
   const int m0 = blockIdx.x * 128;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
