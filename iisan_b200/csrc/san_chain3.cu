@@ -233,64 +233,78 @@ __global__ void __launch_bounds__(THREADS3, 1) san_chain3_fwd_kernel(const __gri
         return sbase + Smem3::kW + slot * W_BYTES;
       };
       auto free_w = [&](int n) { mma_commit_a(bar0 + Smem3::bWEmpty + 8 * (n % NW3)); };
-      if (warp == 1) {
-        // z_acc (+)= x_k[c] Wd_k[c]^T : the chunk is resident in tensor memory (c < NT3) or in shared memory
-        for (int k = 0; k <= A; ++k)
-          for (int c = 0; c < NC; ++c) {
-            const int n = unit_d(k, c);
-            const uint32_t sw = wait_w(n);
-            TR(1, mbar_wait_park(bar0 + Smem3::bXFull + 8 * c, (uint32_t)k & 1u));
-            T3_MARK();
-            tc_fence_after();
-            if (c < NT3) {
+      // z_acc (+)= x_k[c] Wd_k[c]^T : the chunk is resident in tensor memory (c < NT3) or in shared memory
+      auto down = [&](int k, int c) {
+        const int n = unit_d(k, c);
+        const uint32_t sw = wait_w(n);
+        TR(1, mbar_wait_park(bar0 + Smem3::bXFull + 8 * c, (uint32_t)k & 1u));
+        T3_MARK();
+        tc_fence_after();
+        if (c < NT3) {
 #pragma unroll
-              for (int kk = 0; kk < 4; ++kk)
-                mma_bf16_ts(tmem_base + T3_ZACC, tmem_base + T3_X + c * 32 + kk * 8, smem_desc_sw128(sw + kk * 32, 16, 1024), idesc,
-                            (c > 0 || kk > 0) ? 1u : 0u);
-            } else {
-              const uint32_t xs = sbase + Smem3::kXs + (c - NT3) * TILE_BYTES;
+          for (int kk = 0; kk < 4; ++kk)
+            mma_bf16_ts(tmem_base + T3_ZACC, tmem_base + T3_X + c * 32 + kk * 8, smem_desc_sw128(sw + kk * 32, 16, 1024), idesc,
+                        (c > 0 || kk > 0) ? 1u : 0u);
+        } else {
+          const uint32_t xs = sbase + Smem3::kXs + (c - NT3) * TILE_BYTES;
 #pragma unroll
-              for (int kk = 0; kk < 4; ++kk)
-                mma_bf16_ss(tmem_base + T3_ZACC, smem_desc_sw128(xs + kk * 32, 16, 1024), smem_desc_sw128(sw + kk * 32, 16, 1024), idesc,
-                            (c > 0 || kk > 0) ? 1u : 0u);
+          for (int kk = 0; kk < 4; ++kk)
+            mma_bf16_ss(tmem_base + T3_ZACC, smem_desc_sw128(xs + kk * 32, 16, 1024), smem_desc_sw128(sw + kk * 32, 16, 1024), idesc,
+                        (c > 0 || kk > 0) ? 1u : 0u);
+        }
+        if (c == NC - 1) mma_commit_a(bar0 + Smem3::bZFull);
+        free_w(n);
+        T3_LAP(2);
+      };
+      // U accumulator of chunk i of stage s: x_s[i] I (exact) + relu(z_s) Wu_s[i]^T ; the residual part is issued ahead of z_ready
+      auto up = [&](int s, int i, bool& z_seen) {
+        const int n = unit_u(s, i);
+        const int nu = s * NC + i, ub = nu & 1;
+        TR(1, mbar_wait_park(bar0 + Smem3::bUEmpty + 8 * ub, ((uint32_t)(nu >> 1) & 1u) ^ 1u));
+        if (!z_seen) mbar_wait_park(bar0 + Smem3::bXFull + 8 * i, (uint32_t)s & 1u);      // ahead of z_ready: x_s[i] itself must be final
+        T3_MARK();
+        tc_fence_after();
+        const uint32_t ident = sbase + Smem3::kIdent;
+        if (i < NT3) {
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            mma_bf16_ts(tmem_base + T3_UACC + ub * 64, tmem_base + T3_X + i * 32 + kk * 8, smem_desc_sw128(ident + kk * 32, 16, 1024), idesc, kk > 0 ? 1u : 0u);
+        } else {
+          const uint32_t xs = sbase + Smem3::kXs + (i - NT3) * TILE_BYTES;
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            mma_bf16_ss(tmem_base + T3_UACC + ub * 64, smem_desc_sw128(xs + kk * 32, 16, 1024), smem_desc_sw128(ident + kk * 32, 16, 1024), idesc, kk > 0 ? 1u : 0u);
+        }
+        if (!z_seen) { TR(3, mbar_wait_park(bar0 + Smem3::bZReady, (uint32_t)s & 1u)); tc_fence_after(); z_seen = true; }
+        const uint32_t sw = wait_w(n);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+          mma_bf16_ts(tmem_base + T3_UACC + ub * 64, tmem_base + T3_ZOP + kk * 8, smem_desc_sw128(sw + kk * 32, 16, 1024), idesc, 1u);
+        mma_commit_a(bar0 + Smem3::bUFull + 8 * ub);
+        free_w(n);
+        T3_LAP(2);
+      };
+      if (a.one_issuer) {
+        // every MMA of the CTA from ONE thread, in the weight ring's order (U(i) ahead of the down-projection of chunk i - LOOK3)
+        if (warp == 1) {
+          for (int c = 0; c < NC; ++c) down(0, c);
+          for (int s = 0; s < A; ++s) {
+            bool z_seen = false;
+            for (int i = 0; i < NC + LOOK3; ++i) {
+              if (i < NC) up(s, i, z_seen);
+              if (i >= LOOK3) down(s + 1, i - LOOK3);
             }
-            if (c == NC - 1) mma_commit_a(bar0 + Smem3::bZFull);
-            free_w(n);
-            T3_LAP(2);
           }
+          TR_FLUSH(1);
+        }
+      } else if (warp == 1) {
+        for (int k = 0; k <= A; ++k)
+          for (int c = 0; c < NC; ++c) down(k, c);
         TR_FLUSH(1);
       } else {
         for (int s = 0; s < A; ++s) {
-          bool z_seen = false;             // the residual MMAs of the first chunk do not need z_s: they are issued ahead of z_ready
-          for (int i = (warp == 3 ? 0 : 1); i < NC; i += 2) {
-            const int n = unit_u(s, i);
-            const int nu = s * NC + i, ub = nu & 1;
-            TR(1, mbar_wait_park(bar0 + Smem3::bUEmpty + 8 * ub, ((uint32_t)(nu >> 1) & 1u) ^ 1u));
-            if (!z_seen) mbar_wait_park(bar0 + Smem3::bXFull + 8 * i, (uint32_t)s & 1u);      // ahead of z_ready: x_s[i] itself must be final
-            T3_MARK();
-            tc_fence_after();
-            // acc = x_s[i] I  (exact: bf16 values times 1.0, fp32 accumulation) ...
-            const uint32_t ident = sbase + Smem3::kIdent;
-            if (i < NT3) {
-#pragma unroll
-              for (int kk = 0; kk < 4; ++kk)
-                mma_bf16_ts(tmem_base + T3_UACC + ub * 64, tmem_base + T3_X + i * 32 + kk * 8, smem_desc_sw128(ident + kk * 32, 16, 1024), idesc, kk > 0 ? 1u : 0u);
-            } else {
-              const uint32_t xs = sbase + Smem3::kXs + (i - NT3) * TILE_BYTES;
-#pragma unroll
-              for (int kk = 0; kk < 4; ++kk)
-                mma_bf16_ss(tmem_base + T3_UACC + ub * 64, smem_desc_sw128(xs + kk * 32, 16, 1024), smem_desc_sw128(ident + kk * 32, 16, 1024), idesc, kk > 0 ? 1u : 0u);
-            }
-            // ... + relu(z_s) Wu_s[i]^T
-            if (!z_seen) { TR(3, mbar_wait_park(bar0 + Smem3::bZReady, (uint32_t)s & 1u)); tc_fence_after(); z_seen = true; }
-            const uint32_t sw = wait_w(n);
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk)
-              mma_bf16_ts(tmem_base + T3_UACC + ub * 64, tmem_base + T3_ZOP + kk * 8, smem_desc_sw128(sw + kk * 32, 16, 1024), idesc, 1u);
-            mma_commit_a(bar0 + Smem3::bUFull + 8 * ub);
-            free_w(n);
-            T3_LAP(2);
-          }
+          bool z_seen = false;
+          for (int i = (warp == 3 ? 0 : 1); i < NC; i += 2) up(s, i, z_seen);
         }
         if (warp == 3) TR_FLUSH(3);
       }

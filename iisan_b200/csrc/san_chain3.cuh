@@ -33,6 +33,7 @@ struct Chain3Args {
   float* out;               // [N, out_ld] fp32
   int out_ld;
   int n_items, d, n_stages;
+  int one_issuer;           // 1: every tcgen05.mma of a CTA from ONE thread (measurement / fault-hunt switch IISAN_B200_C3_ONE_ISSUER)
 };
 
 bool chain3_shape_supported(int d, int emb);

@@ -22,6 +22,8 @@
 //   GT_X[j] [(A+1-j)*128, d] = D_X[:, j..A]^T h^X_{layer j} ;   Pc_t [(A+1)*64, A*64] = Dc_t^T Rc_t   (fp32)
 #include "san_lr.cuh"
 
+#include <cstdlib>
+
 #include "gemm_simt.cuh"
 #include "launch.cuh"
 #include "san_chain2.cuh"
@@ -231,6 +233,12 @@ int san_lr_forward(const iisan_san_desc* D, const iisan_san_params* P, const voi
   // ---- all stages of all three towers + the heads in one launch ----
   Chain3Args ca{};
   ca.out = out; ca.out_ld = D->out_ld; ca.n_items = N; ca.d = d; ca.n_stages = A;
+  // ONE MMA-issuing thread per CTA by default.  Issuing tcgen05.mma from three threads of a CTA (down-projections, up-projections
+  // of the even / odd chunks) is 12 us faster (76 vs 88 us) but produced an intermittent device fault: 4 of 4 data-parallel runs on
+  // 8 x B200 and 1 of ~17 single-GPU bench processes failed with it, the same 8-GPU run passed with one issuer
+  // (profiles/r02_8gpu_gen3_fault.md).  IISAN_B200_C3_ONE_ISSUER=0 selects the three-issuer schedule for measurements.
+  static const int one_issuer = [] { const char* e = getenv("IISAN_B200_C3_ONE_ISSUER"); return (e && e[0] == '0') ? 0 : 1; }();
+  ca.one_issuer = one_issuer;
   for (int t = 0; t < 3; ++t) {
     Chain3Tower& T = ca.tower[t];
     T.mode = t == 2 ? 1 : 0;
