@@ -138,7 +138,7 @@ def load():
     v = lib.iisan_abi_version()
     if v != ABI_VERSION:
         raise IisanLibraryError(f"ABI version mismatch: library {v}, binding {ABI_VERSION}")
-    for which, st in enumerate((SanDesc, SanParams, UeDesc, UeParams, CeDesc)):
+    for which, st in enumerate((SanDesc, SanParams, UeDesc, UeParams, CeDesc, AdamTensor)):
         if lib.iisan_sizeof(which) != C.sizeof(st):
             raise IisanLibraryError(f"struct layout mismatch for {st.__name__}: C {lib.iisan_sizeof(which)} vs ctypes {C.sizeof(st)}")
     _lib = lib

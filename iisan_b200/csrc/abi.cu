@@ -112,6 +112,7 @@ extern "C" size_t iisan_sizeof(int which) {
     case 2: return sizeof(iisan_ue_desc);
     case 3: return sizeof(iisan_ue_params);
     case 4: return sizeof(iisan_ce_desc);
+    case 5: return sizeof(iisan_adam_tensor);
   }
   return 0;
 }

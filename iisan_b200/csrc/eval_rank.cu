@@ -52,7 +52,10 @@ __global__ void __launch_bounds__(ER_THREADS) eval_rank_kernel(const float* __re
   __syncthreads();
   if (threadIdx.x < ER_UPC) {
     const int q = threadIdx.x;
-    s_t[q] = (u0 + q < users) ? er_dot1(items + targets[u0 + q] * E, su[q], E) : INFINITY;
+    // a target outside [0, n_items1) cannot be scored: +inf makes no item beat it -- the host side rejects such inputs
+    // (iisan_b200/eval.py), this only keeps the kernel inside the table
+    const int64_t tg = (u0 + q < users) ? targets[u0 + q] : -1;
+    s_t[q] = (tg >= 0 && tg < n_items1) ? er_dot1(items + tg * E, su[q], E) : INFINITY;
   }
   __syncthreads();
   float st[ER_UPC];

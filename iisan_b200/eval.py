@@ -18,7 +18,12 @@ from . import _lib as L
 
 def eval_ranks(prec, item_embs, targets, history=None):
     """1-based rank [U] (int32) of ``targets`` among ids 1..item_num for the user vectors ``prec`` [U, E] against
-    ``item_embs`` [item_num + 1, E]; ``history`` [U, H] int64 padded with 0: ids that do not compete (metrics.py:217-219)."""
+    ``item_embs`` [item_num + 1, E]; ``history`` [U, H] int64 padded with 0: ids that do not compete (metrics.py:217-219).
+
+    Edge cases against the reference's argsort (metrics.py:212-222): exact score ties resolve to the BEST rank here (strict
+    ``>`` count) instead of argsort order; a target that also appears in the user's history is ranked normally here, while the
+    reference masks it to -inf (its rank is then item_num) -- the reference's data pipeline never produces such a pair (the
+    history is the sequence without its last item).  A target outside [0, item_num] is a caller error (the kernel scores it +inf)."""
     lib = L.load()
     L.require_cuda(prec, "prec_emb")
     prec = prec.contiguous().float()

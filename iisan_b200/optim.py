@@ -118,6 +118,11 @@ class FusedAdam(torch.optim.Optimizer):
         if self._step_dev is None:
             self._step_dev = torch.zeros(1, dtype=torch.float32, device=dev)
         b1, b2 = self.param_groups[0]["betas"]
+        for g in self.param_groups:          # ONE launch for every group: only the learning rate may differ between groups
+            if tuple(g["betas"]) != (b1, b2) or g["eps"] != self.param_groups[0]["eps"]:
+                raise ValueError("FusedAdam: all parameter groups must share betas and eps (only lr is per group)")
+            if g.get("weight_decay", 0) or g.get("amsgrad", False) or g.get("maximize", False):
+                raise ValueError("FusedAdam implements plain Adam: weight_decay, amsgrad and maximize are not supported")
         L.check(lib.iisan_adam_step(self._table, n, b1, b2, self.param_groups[0]["eps"], C.c_void_p(self._step_dev.data_ptr()), 1,
                                     C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), "iisan_adam_step")
         return None

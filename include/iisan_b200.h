@@ -56,7 +56,7 @@ const char* iisan_status_string(int status);
 int iisan_last_cuda_error(void);
 const char* iisan_last_cuda_error_string(void);
 /* sizeof() of the POD structs as compiled, so that a foreign-language binding can verify its mirror:
- * which = 0 iisan_san_desc, 1 iisan_san_params, 2 iisan_ue_desc, 3 iisan_ue_params, 4 iisan_ce_desc. */
+ * which = 0 iisan_san_desc, 1 iisan_san_params, 2 iisan_ue_desc, 3 iisan_ue_params, 4 iisan_ce_desc, 5 iisan_adam_tensor. */
 size_t iisan_sizeof(int which);
 
 /* Launch accounting and live kernel timing (used by bench.py for the roofline numbers).
