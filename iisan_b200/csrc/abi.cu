@@ -50,21 +50,32 @@ void launch_scope_end(int slot, cudaStream_t st) {
 // over the host link): the access pattern is identical.
 //   restates Build_MM_Dataset.__getitem__ (CC/data_utils/dataset.py:65-92): per-item load of the
 //   cached [layers, d] tensor, left padding with zeros, stacking into the batch.
-template <int BYTES_PER_ELT>
-__global__ void __launch_bounds__(256) gather_states_kernel(const uint4* __restrict__ table, int64_t n_table_items, int layers, int d,
+// One WARP per (row, selected layer) pair: the pair's 2*d (4*d) bytes are one contiguous run in the table and in the batch, moved
+// as 128-bit words, up to four in flight per lane; the (row, layer) split costs one 32-bit division per pair instead of four
+// 64-bit div/mod per 16 bytes.
+__global__ void __launch_bounds__(256) gather_states_kernel(const uint4* __restrict__ table, int64_t n_table_items, int layers, int vec_per_row,
                                                             const int64_t* __restrict__ ids, int n, const int* __restrict__ sel, int n_sel,
                                                             uint4* __restrict__ out) {
-  const int vec_per_row = d * BYTES_PER_ELT / 16;
-  const int64_t total = (int64_t)n * n_sel * vec_per_row;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int v = (int)(i % vec_per_row);
-    const int64_t ra = i / vec_per_row;
-    const int a = (int)(ra % n_sel);
-    const int64_t r = ra / n_sel;
+  const int lane = threadIdx.x & 31;
+  const unsigned pairs = (unsigned)n * (unsigned)n_sel;
+  const unsigned warps = (gridDim.x * blockDim.x) >> 5;
+  for (unsigned p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; p < pairs; p += warps) {
+    const unsigned r = p / (unsigned)n_sel, a = p - r * (unsigned)n_sel;
     const int64_t id = ids[r];
-    uint4 val = make_uint4(0u, 0u, 0u, 0u);
-    if (id > 0 && id < n_table_items) val = ld_stream_128(table + ((id * layers + sel[a]) * (int64_t)vec_per_row + v));
-    out[i] = val;
+    const bool live = id > 0 && id < n_table_items;
+    const uint4* src = table + (id * layers + sel[a]) * (int64_t)vec_per_row;
+    uint4* dst = out + (int64_t)p * vec_per_row;
+    for (int v0 = lane; v0 < vec_per_row; v0 += 128) {
+      uint4 val[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        val[k] = make_uint4(0u, 0u, 0u, 0u);
+        if (live && v0 + 32 * k < vec_per_row) val[k] = ld_stream_128(src + v0 + 32 * k);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (v0 + 32 * k < vec_per_row) dst[v0 + 32 * k] = val[k];
+    }
   }
 }
 }  // namespace iisan
@@ -162,13 +173,11 @@ extern "C" int iisan_gather_states(const void* table, int32_t dtype, int64_t n_t
   if (!table || !ids || !sel || !out || n <= 0 || n_sel <= 0 || layers <= 0 || d <= 0 || n_table_items <= 0) return IISAN_EINVAL;
   const int bpe = (int)dtype_size(dtype);
   if ((d * bpe) % 16) return IISAN_EINVAL;
-  const int64_t total = (int64_t)n * n_sel * (d * bpe / 16);
-  const int blocks = (int)imin64((total + 255) / 256, 148 * 16);
+  if ((int64_t)n * n_sel >= ((int64_t)1 << 31)) return IISAN_EINVAL;
+  const int64_t pairs = (int64_t)n * n_sel;
+  const int blocks = (int)imin64((pairs + 7) / 8, 148 * 8);      // 8 warps per block, 64 warps per SM resident
   cudaStream_t st = as_stream(stream);
-  if (bpe == 4)
-    { LaunchScope ls_(IISAN_K_MISC, st); gather_states_kernel<4><<<blocks, 256, 0, st>>>((const uint4*)table, n_table_items, layers, d, ids, n, sel, n_sel, (uint4*)out); }
-  else
-    { LaunchScope ls_(IISAN_K_MISC, st); gather_states_kernel<2><<<blocks, 256, 0, st>>>((const uint4*)table, n_table_items, layers, d, ids, n, sel, n_sel, (uint4*)out); }
+  { LaunchScope ls_(IISAN_K_MISC, st); gather_states_kernel<<<blocks, 256, 0, st>>>((const uint4*)table, n_table_items, layers, d * bpe / 16, ids, n, sel, n_sel, (uint4*)out); }
   IISAN_LAUNCH_OK();
   return IISAN_OK;
 }

@@ -582,14 +582,36 @@ struct CeFastLayout {
   }
 };
 
-// One CTA per SM (512 TMEM columns, 129 KB smem): pick the split count so that owner_tiles * splits stays within ONE wave of
-// 148 CTAs (a 160-CTA grid would run a second, almost empty wave).
+// One CTA per SM (512 TMEM columns, 129 KB smem).  Short column pools: the split count keeps owner_tiles * splits within ONE
+// wave of 148 CTAs (a 160-CTA grid would run a second, almost empty wave).  Long pools (the global negative pool of a
+// data-parallel step: W times the columns): one wave of 40 x 3 = 120 CTAs leaves 28 SMs idle for the whole kernel, so the pool
+// is cut into k waves' worth of splits when the modelled time -- waves x (tiles per CTA + one tile-equivalent of CTA prologue:
+// barrier init, tensor-memory allocation, owner-tile load) -- drops by at least 8 %.
 int ce_fast_splits(int owner_tiles, int stream_tiles) {
-  int s = 148 / owner_tiles;
-  if (s > stream_tiles) s = stream_tiles;
-  if (s < 1) s = 1;
-  const int per = (stream_tiles + s - 1) / s;
-  return (stream_tiles + per - 1) / per;
+  auto shape = [&](int s, int* per_out) {          // effective split count for a requested one
+    if (s > stream_tiles) s = stream_tiles;
+    if (s < 1) s = 1;
+    const int per = (stream_tiles + s - 1) / s;
+    *per_out = per;
+    return (stream_tiles + per - 1) / per;
+  };
+  int per1 = 0;
+  const int s1 = shape(148 / (owner_tiles < 1 ? 1 : owner_tiles), &per1);
+  int best = s1;
+  const int waves1 = (owner_tiles * s1 + 147) / 148;
+  double best_cost = (double)waves1 * (per1 + 1);
+  const double bar = 0.92 * best_cost;
+  const char* env = getenv("IISAN_B200_CE_ONE_WAVE");      // A/B switch, read per call (scripts/ce_gather_bench.py toggles it)
+  const bool one_wave = env && env[0] == '1';
+  for (int k = 2; k <= 8 && !one_wave; ++k) {
+    int per = 0;
+    const int s = shape(k * 148 / (owner_tiles < 1 ? 1 : owner_tiles), &per);
+    if (per < 16) break;                           // measured (scripts/ce_gather_bench.py, W = 2: 168 -> 174 us with 8 tiles per CTA): short CTAs lose to their prologue
+    const int waves = (owner_tiles * s + 147) / 148;
+    const double cost = (double)waves * (per + 1);
+    if (cost < bar && cost < best_cost) { best = s; best_cost = cost; }
+  }
+  return best;
 }
 
 int ce_fast_supported(const iisan_ce_desc& d) {

@@ -20,9 +20,10 @@ import torch.distributed as dist
 
 
 class TrainStep:
-    def __init__(self, model, optimizer, use_graph=True, group=None, warmup=3, autocast_dtype=None, store=None):
+    def __init__(self, model, optimizer, use_graph=True, group=None, warmup=3, autocast_dtype=None, store=None, packed=False):
         self.model = model
         self.store = store            # iisan_b200.store.CachedStateStore: batches are (ids, log_mask) only, states gathered on the device
+        self.packed = bool(packed)    # the image / text tensors hold only the selected layers [N, A, d] (already gathered from a store)
         self.opt = optimizer
         self.use_graph = bool(use_graph)
         self.group = group
@@ -49,9 +50,8 @@ class TrainStep:
 
     # ------------------------------------------------------------------------------------------------------------
     def _arena(self, device):
-        """Gradient arena of the data-parallel step (ops.GradArena): every parameter gradient of the step is a slice of one buffer."""
-        if self.world == 1:
-            return None
+        """Gradient arena of the step (ops.GradArena): every parameter gradient is a slice of one buffer -- ONE memset per step
+        instead of a fill kernel per backward function, and (N > 1) one collective over the used part."""
         if self._grad_arena is None:
             from .ops import GradArena
             n = sum((p.numel() + 63) // 64 * 64 for p in self._params) + 64 * 64
@@ -125,7 +125,7 @@ class TrainStep:
                 image, text = self.store.gather(ids)
                 loss = self.model(ids, image, text, log_mask, ids.device, packed=True)
             else:
-                loss = self.model(ids, image, text, log_mask, ids.device)
+                loss = self.model(ids, image, text, log_mask, ids.device, packed=self.packed)
             loss.backward()
         finally:
             GradArena.active = prev
@@ -217,19 +217,36 @@ class PipelinedTrainStep:
             pipe.submit(nxt)                    # asynchronous H2D of the NEXT batch
             loss = pipe.run()                   # step on the batch submitted before it
         loss = pipe.run()
+
+    ``run()`` returns the loss as a 0-dim DEVICE tensor (reading it with ``.item()`` waits for the step).  ``run_logged()`` is the
+    logging-friendly variant: it also enqueues the device-to-host copy of that loss into pinned memory and returns the VALUE of
+    the step before it (a float; None for the first call), so the host thread never waits for the step it has just launched --
+    the reference logs its loss every 100 steps (Code_Cached/run.py:386-390); here every step's loss reaches the host, one step late.
+    ``last_loss()`` waits for and returns the newest one.
     """
 
-    def __init__(self, model, optimizer, group=None, use_graph=True, depth=2, store=None):
+    def __init__(self, model, optimizer, group=None, use_graph=True, depth=2, store=None, prefetch_gather=True):
         self.model, self.opt, self.group, self.use_graph = model, optimizer, group, use_graph
         self.depth = depth
         self.store = store
-        self.steps = [TrainStep(model, optimizer, use_graph=use_graph, group=group, store=store) for _ in range(depth)]
+        # With a store: the per-item gather of batch i + 1 (HBM-bound: every selected layer read and written once) is issued by
+        # submit() on the copy stream, behind the H2D copy of its ids, and so runs WHILE step i computes (whose kernels are
+        # latency-, not bandwidth-bound); the captured step then consumes the gathered [N, A, d] buffers (packed=True).
+        # prefetch_gather=False keeps the gather inside the captured step (one stream, no overlap).
+        self.prefetch = store is not None and bool(prefetch_gather)
+        if self.prefetch:
+            self.steps = [TrainStep(model, optimizer, use_graph=use_graph, group=group, packed=True) for _ in range(depth)]
+        else:
+            self.steps = [TrainStep(model, optimizer, use_graph=use_graph, group=group, store=store) for _ in range(depth)]
         self.bufs = [None] * depth
         self.copied = [None] * depth
         self.done = [None] * depth
         self.copy_stream = None
         self.n_sub = 0
         self.n_run = 0
+        self._loss_host = None        # pinned [depth] fp32: asynchronous loss read-back of run_logged()
+        self._loss_ev = [None] * depth
+        self._n_logged = 0
         enc = getattr(model, "mm_encoder", None)
         plan = getattr(enc, "plan", None)
         self.sel_img = list(plan.layers_img_read) if plan is not None else None      # incl. layer 0 under remove_first
@@ -246,6 +263,9 @@ class PipelinedTrainStep:
         if self.bufs[k] is None:
             self.bufs[k] = tuple(None if t is None else torch.zeros(t.shape, dtype=t.dtype, device=device)
                                  for t in (ids.reshape(-1), image, text, log_mask))
+            if self.prefetch:
+                gi, gt = self.store.batch_buffers(ids.numel())
+                self.bufs[k] = (self.bufs[k][0], gi, gt, self.bufs[k][3])
             self.copied[k] = torch.cuda.Event()
             self.done[k] = torch.cuda.Event()
             self.done[k].record(torch.cuda.current_stream(device))
@@ -255,8 +275,11 @@ class PipelinedTrainStep:
         with torch.cuda.stream(cs):
             d_ids.copy_(ids.reshape(-1), non_blocking=True)
             d_lm.copy_(log_mask, non_blocking=True)
+            if self.prefetch:
+                self.store.gather(d_ids, out=(d_img, d_txt))
+                image = text = None
             for dst, src, sel in ((d_img, image, self.sel_img), (d_txt, text, self.sel_text)):
-                if dst is None:
+                if dst is None or src is None:
                     continue
                 if (not src.is_cuda) and src.is_pinned() and sel is not None and src.dim() >= 3 and len(sel) < src.shape[-2]:
                     stage_states_h2d(dst, src, sel, cs)
@@ -282,3 +305,25 @@ class PipelinedTrainStep:
         self.done[k].record(cur)
         self.n_run += 1
         return loss
+
+    def run_logged(self):
+        """run() + asynchronous loss read-back; returns the loss value (float) of the PREVIOUS run_logged() step, None at first."""
+        k = self.n_run % self.depth
+        loss = self.run()
+        if self._loss_host is None:
+            self._loss_host = torch.zeros(self.depth, dtype=torch.float32).pin_memory()
+        if self._loss_ev[k] is None:
+            self._loss_ev[k] = torch.cuda.Event()
+        prev = self.last_loss() if self._n_logged > 0 else None        # waits for step i - 1 only: step i is already queued
+        self._loss_host[k:k + 1].copy_(loss.detach().reshape(1), non_blocking=True)
+        self._loss_ev[k].record(torch.cuda.current_stream(loss.device))
+        self._n_logged += 1
+        self._last_k = k
+        return prev
+
+    def last_loss(self):
+        """Value of the newest loss whose read-back was enqueued by run_logged() (waits for that copy)."""
+        if self._n_logged == 0:
+            raise RuntimeError("PipelinedTrainStep.last_loss(): no run_logged() step yet")
+        self._loss_ev[self._last_k].synchronize()
+        return float(self._loss_host[self._last_k])

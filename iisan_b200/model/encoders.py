@@ -30,8 +30,11 @@ class User_Encoder(nn.Module):
             if getattr(module, "bias", None) is not None:
                 constant_(module.bias.data, 0)
 
-    def forward(self, input_embs, log_mask, local_rank=None):
-        return self.transformer_encoder(input_embs, log_mask, None)
+    def forward(self, input_embs, log_mask, local_rank=None, seq_len=None):
+        """Reference call: ``user_encoder(input_embs[:, :-1, :], log_mask, local_rank)`` (CC/model/model.py:76-79).  ``seq_len``
+        (extension): pass the unsliced [B, S, E] block and the number of leading slots to use; same result, the slice and its
+        autograd backward (a zero fill and a strided copy) disappear from the step."""
+        return self.transformer_encoder(input_embs, log_mask, None, seq_len=seq_len)
 
 
 def _off_path(what):

@@ -147,7 +147,7 @@ class ModelMM(nn.Module):
                     deferred = None
                 pool = par.start_pool_gather(score_embs, ids.view(log_mask.shape[0], -1), log_mask, group)
         input_embs = score_embs.view(-1, S, E)
-        prec_vec = self.user_encoder(input_embs[:, :-1, :], log_mask, local_rank).reshape(-1, E)   # model.py:76-79
+        prec_vec = self.user_encoder(input_embs, log_mask, local_rank, seq_len=S - 1).reshape(-1, E)   # model.py:76-79: input_embs[:, :-1, :]
         pop = self._pop(device)
         if self.negatives == "global":
             from ..parallel import global_negative_loss

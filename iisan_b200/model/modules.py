@@ -98,8 +98,9 @@ class TransformerEncoder(nn.Module):
             dev = device if device is not None else next(self.parameters()).device
             self._step_dev = torch.full((1,), int(st["step"]), dtype=torch.int64, device=dev)
 
-    def forward(self, input_embs, log_mask, att_mask=None):
+    def forward(self, input_embs, log_mask, att_mask=None, seq_len=None):
         # att_mask is implied by log_mask (causal + key padding, encoders.py:54-57) and rebuilt in-kernel.
+        # seq_len: input_embs is a whole [B, S, E] block of which only the first seq_len slots are the input (ops.UserEncoderFn).
         params = tuple(self.parameters())
         d_model, n_heads, n_layers, p = self._cfg
         offset, seed = 0, 0
@@ -112,7 +113,7 @@ class TransformerEncoder(nn.Module):
             offset = ctr.clone()
             seed = self.dropout_seed
         return UserEncoderFn.apply(self._bind(), input_embs, log_mask, self.training, seed, offset,
-                                   compute_mode(), *params)
+                                   compute_mode(), seq_len, *params)
 
 
 class AdapterBlock(nn.Module):

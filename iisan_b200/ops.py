@@ -27,17 +27,19 @@ def _workspace(nbytes: int, device):
 
 class GradArena:
     """One persistent fp32 buffer that the backward functions carve their zero-initialised parameter gradients from (instead of a
-    fresh torch.zeros each): the data-parallel step then averages ALL gradients with ONE collective over ``used()``.  Activated by
-    iisan_b200.engine.TrainStep for N > 1; without an active arena the functions allocate as before."""
+    fresh torch.zeros each): one memset per step, and the data-parallel step averages ALL gradients with ONE collective over
+    ``used()``.  Activated by iisan_b200.engine.TrainStep; without an active arena the functions allocate as before."""
 
     active = None
 
     def __init__(self, numel, device):
         self.buf = torch.zeros(int(numel), dtype=torch.float32, device=device)
         self.off = 0
+        self.high = 0                       # high-water mark of the slices handed out so far
 
     def reset(self):
-        self.buf.zero_()                    # one memset per step (stream-ordered, capturable)
+        # one memset per step (stream-ordered, capturable); after the first step only the part the last step used
+        (self.buf if self.high == 0 else self.buf[:self.high]).zero_()
         self.off = 0
 
     def take(self, numel):
@@ -46,6 +48,7 @@ class GradArena:
             raise L.IisanLibraryError("gradient arena too small")
         v = self.buf[self.off:self.off + int(numel)]
         self.off += n
+        self.high = max(self.high, self.off)
         return v
 
     def used(self):
@@ -147,12 +150,20 @@ class SanFn(torch.autograd.Function):
 # --------------------------------------------------------------------------------------------------
 class UserEncoderFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, binder, embs, log_mask, training, seed, offset, compute, *params):
+    def forward(ctx, binder, embs, log_mask, training, seed, offset, compute, use_len, *params):
+        """``use_len``: None, or the number of leading sequence slots of ``embs`` [B, S, E] that form the input (the model
+        passes the whole [B, L+1, E] item-embedding block with use_len = L: the gradient then comes back as ONE [B, S, E]
+        tensor with a zero last slot, instead of through autograd's slice backward = a fill and a strided copy per step)."""
         L.require_cuda(embs, "user-encoder input")
         lib = L.load()
         if embs.dtype != torch.float32 or embs.stride(-1) != 1 or embs.stride(1) != embs.shape[2]:
             embs = embs.float().contiguous()
         b, l, e = embs.shape
+        ctx.full = use_len is not None and int(use_len) < l
+        if ctx.full:
+            if embs.stride(0) != l * e:
+                embs = embs.contiguous()
+            l = int(use_len)
         log_mask = log_mask.to(device=embs.device, dtype=torch.float32).contiguous()
         offset_dev = None
         if torch.is_tensor(offset):                       # device-side step counter (CUDA-graph safe dropout stream)
@@ -184,7 +195,7 @@ class UserEncoderFn(torch.autograd.Function):
                                                 ctx.embs.stride(0), _p(ctx.log_mask), _p(ctx.ws), ctx.ws.numel(), _p(d_out),
                                                 _p(d_embs), _stream()), "iisan_user_encoder_backward")
         ctx.ws = None
-        return (None, d_embs, None, None, None, None, None, *views)
+        return (None, d_full if ctx.full else d_embs, None, None, None, None, None, None, *views)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -232,6 +243,7 @@ class InBatchCeFn(torch.autograd.Function):
         ctx.tensors = (prec, score, ids_rows, ids_cols, lm_rows, lm_cols, pop_prob)
         ctx.n_valid = n_valid
         ctx.mark_non_differentiable(n_valid)
+        ctx.set_materialize_grads(False)          # an unused output (loss_sum or loss) arrives as None, not as a zero-filled tensor
         return res[0], n_valid, res[1]
 
     @staticmethod
@@ -271,15 +283,19 @@ def inbatch_ce_masks(ids_rows, ids_cols, lm_rows, lm_cols, user_offset=0, fast=F
     return out
 
 
-def gather_states(table, ids, sel):
-    """out[n, len(sel), d] = table[ids, sel, :] (zeros for id 0) through iisan_gather_states."""
+def gather_states(table, ids, sel, out=None):
+    """out[n, len(sel), d] = table[ids, sel, :] (zeros for id 0) through iisan_gather_states.  ``out``: write into this buffer
+    (the pipelined runner gathers the next batch into the static inputs of a captured step)."""
     lib = L.load()
     L.require_cuda(ids, "ids")
     n_items, layers, d = table.shape
     ids = ids.contiguous().view(-1)
     # a device int32 tensor is used as is (no H2D copy: legal during CUDA-graph capture)
     sel_t = sel if torch.is_tensor(sel) else torch.as_tensor(sel, dtype=torch.int32, device=ids.device)
-    out = torch.empty(ids.numel(), len(sel), d, dtype=table.dtype, device=ids.device)
+    if out is None:
+        out = torch.empty(ids.numel(), len(sel), d, dtype=table.dtype, device=ids.device)
+    elif out.shape != (ids.numel(), len(sel), d) or out.dtype != table.dtype or not out.is_contiguous() or out.device != table.device:
+        raise ValueError("gather_states: `out` must be a contiguous [n, len(sel), d] tensor of the table's dtype and device")
     L.check(lib.iisan_gather_states(_p(table), L.torch_dtype_code(table.dtype), n_items, layers, d, _p(ids), ids.numel(),
                                     _p(sel_t), len(sel), _p(out), _stream()), "iisan_gather_states")
     return out

@@ -92,6 +92,13 @@ class CachedStateStore:
         out[0].zero_()
         return out
 
-    def gather(self, ids):
-        """ids int64 [n] on the store's device -> (image [n, A_i, d], text [n, A_t, d]); id 0 -> zeros (bit-exact selection)."""
-        return ops.gather_states(self.image, ids, self._all_img), ops.gather_states(self.text, ids, self._all_text)
+    def gather(self, ids, out=None):
+        """ids int64 [n] on the store's device -> (image [n, A_i, d], text [n, A_t, d]); id 0 -> zeros (bit-exact selection).
+        ``out``: (image, text) buffers to fill instead of fresh tensors."""
+        oi, ot = out if out is not None else (None, None)
+        return ops.gather_states(self.image, ids, self._all_img, out=oi), ops.gather_states(self.text, ids, self._all_text, out=ot)
+
+    def batch_buffers(self, n):
+        """Empty (image, text) buffers for ``gather(ids, out=...)`` of n ids."""
+        mk = lambda t: torch.empty(n, t.shape[1], t.shape[2], dtype=t.dtype, device=t.device)
+        return mk(self.image), mk(self.text)

@@ -21,7 +21,9 @@ def _case(B, Bc, off, seed, mode, item_num):
 
 @pytest.mark.parametrize("B,Bc,off,mode,item_num", [(512, 512, 0, "dense", 19246), (512, 512, 0, "realistic", 300),
                                                      (37, 37, 0, "realistic", 50), (13, 13, 0, "dense", 20),
-                                                     (64, 256, 128, "realistic", 200), (128, 1024, 896, "dense", 5000)])
+                                                     (64, 256, 128, "realistic", 200), (128, 1024, 896, "dense", 5000),
+                                                     # a two-rank pool at the benchmark size: the multi-wave column split of ce_fast_splits
+                                                     (512, 1024, 512, "dense", 19246)])
 def test_fast_ce_matches_oracle(B, Bc, off, mode, item_num):
     from iisan_b200 import _lib
     from iisan_b200.ops import InBatchCeFn, inbatch_ce_masks
