@@ -556,6 +556,14 @@ def run_ours(a):
                             "overlaps the step of batch i")
         if e2e is None:
             e2e = dict(e2e_host, path="host batches")
+    # the same with the states as the reference's DataLoader delivers them: fp32 (dataset.py:29-34 loads the fp32 .pt files).  The
+    # copy doubles (242 MB per step); on the device the selected layers are rounded to bf16 once (iisan_pack_states) and take
+    # the same fused kernels.  One GPU only (2 x 0.9 GB of pinned host memory per rank).
+    e2e_host_fp32 = None
+    if e2e_host is not None and world == 1 and a.workload == "instrument" and state_dtype != torch.float32:
+        host32 = [(h[0], h[1].float().pin_memory(), h[2].float().pin_memory(), h[3]) for h in host]
+        e2e_host_fp32 = host_batch_e2e(host32, "float32")
+        host32 = None
 
     def shutdown():
         """Release the captured graphs (they hold NCCL work) before tearing the process group down; a process that still
@@ -674,7 +682,7 @@ def run_ours(a):
                                 f"{B * 11 * (W['layers_img'] * W['d_img'] + W['layers_text'] * W['d_text']) * elt / 1e6:.0f} MB (> 126 MB L2)",
                    "step_runner": "CUDA graph replay (iisan_b200.engine.TrainStep)" if use_graph else "eager",
                    "parallelism": f"dp{world}", "host_numa_binding": numa},
-        "e2e": e2e, "e2e_host_batches": e2e_host,
+        "e2e": e2e, "e2e_host_batches": e2e_host, "e2e_host_batches_fp32": e2e_host_fp32,
         "gpu_launches": int(launches_per_step * n_timed),
         "gpu_launches_per_step": launches_per_step,
         "clocks": clocks,

@@ -10,7 +10,7 @@ import os
 
 MAX_STAGES = 64
 MAX_BLOCKS = 8
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 F32, BF16, F16 = 0, 1, 2
 K_STREAM, K_GEMM, K_USER, K_CE, K_MISC, K_CHAIN, K_CHAIN_BWD = range(7)
@@ -49,7 +49,8 @@ class SanDesc(C.Structure):
                 ("text_adapter", i32 * MAX_STAGES), ("text_layer", i32 * MAX_STAGES),
                 ("img_adapter", i32 * MAX_STAGES), ("img_layer", i32 * MAX_STAGES),
                 ("mm_index", i32 * MAX_STAGES),
-                ("asym", i32), ("remove_first", i32), ("state_dtype", i32), ("compute", i32), ("out_ld", i32)]
+                ("asym", i32), ("remove_first", i32), ("state_dtype", i32), ("compute", i32), ("out_ld", i32),
+                ("activation", i32)]
 
 
 class UeBlockPtrs(C.Structure):
@@ -103,6 +104,8 @@ _SIGNATURES = {
     "iisan_adam_step": (C.c_int, [C.POINTER(AdamTensor), i32, C.c_float, C.c_float, C.c_float, vp, i32, vp]),
     "iisan_stage_states_h2d": (C.c_int, [vp, vp, C.c_int64, i32, i32, i32, C.POINTER(i32), i32, vp]),
     "iisan_gather_states": (C.c_int, [vp, i32, C.c_int64, i32, i32, vp, i32, vp, i32, vp, vp]),
+    "iisan_pack_states": (C.c_int, [vp, i32, C.c_int64, i32, i32, vp, i32, vp, vp]),
+    "iisan_san_fused_eligible": (C.c_int, [C.POINTER(SanDesc)]),
     "iisan_eval_ranks": (C.c_int, [vp, vp, vp, vp, i32, i32, i32, i32, vp, vp]),
     "iisan_probe_tile_stream": (C.c_int, [vp, C.c_int64, i32, i32, C.POINTER(i32), i32, i32, i32, i32, vp, vp]),
     "iisan_debug_chain_generation": (C.c_int, [i32]),

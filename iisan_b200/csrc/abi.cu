@@ -78,6 +78,30 @@ __global__ void __launch_bounds__(256) gather_states_kernel(const uint4* __restr
     }
   }
 }
+
+// ---- layer selection + cast to bf16 (fast mode, states stored in fp32 / fp16) ------------------------
+// out[i, a, :] = bf16_rn(in[i, sel[a], :]).  One warp per (row, selected layer) pair, eight elements per lane and trip: two
+// (fp32) or one (fp16) 128-bit loads, one 128-bit store.  Same rounding as torch's .bfloat16().
+template <typename T>
+__global__ void __launch_bounds__(256) pack_states_kernel(const T* __restrict__ in, int layers, int d, int n, const int* __restrict__ sel, int n_sel,
+                                                          __nv_bfloat16* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const unsigned pairs = (unsigned)n * (unsigned)n_sel;
+  const unsigned warps = (gridDim.x * blockDim.x) >> 5;
+  for (unsigned p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; p < pairs; p += warps) {
+    const unsigned r = p / (unsigned)n_sel, a = p - r * (unsigned)n_sel;
+    const T* src = in + ((int64_t)r * layers + sel[a]) * d;
+    __nv_bfloat16* dst = out + (int64_t)p * d;
+    for (int c = lane * 8; c < d; c += 256) {
+      const float4 lo = load4<T>(src + c), hi = load4<T>(src + c + 4);
+      uint4 pk;
+      __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&pk);
+      h2[0] = __floats2bfloat162_rn(lo.x, lo.y); h2[1] = __floats2bfloat162_rn(lo.z, lo.w);
+      h2[2] = __floats2bfloat162_rn(hi.x, hi.y); h2[3] = __floats2bfloat162_rn(hi.z, hi.w);
+      *reinterpret_cast<uint4*>(dst + c) = pk;
+    }
+  }
+}
 }  // namespace iisan
 
 using namespace iisan;
@@ -178,6 +202,27 @@ extern "C" int iisan_gather_states(const void* table, int32_t dtype, int64_t n_t
   const int blocks = (int)imin64((pairs + 7) / 8, 148 * 8);      // 8 warps per block, 64 warps per SM resident
   cudaStream_t st = as_stream(stream);
   { LaunchScope ls_(IISAN_K_MISC, st); gather_states_kernel<<<blocks, 256, 0, st>>>((const uint4*)table, n_table_items, layers, d * bpe / 16, ids, n, sel, n_sel, (uint4*)out); }
+  IISAN_LAUNCH_OK();
+  return IISAN_OK;
+}
+
+extern "C" int iisan_pack_states(const void* states, int32_t dtype, int64_t n, int32_t layers, int32_t d, const int32_t* sel,
+                                 int32_t n_sel, void* out_bf16, iisan_stream_t stream) {
+  if (!states || !sel || !out_bf16 || n <= 0 || n_sel <= 0 || layers <= 0 || d <= 0 || (d % 8)) return IISAN_EINVAL;
+  if (n * n_sel >= ((int64_t)1 << 31)) return IISAN_EINVAL;
+  if ((reinterpret_cast<uintptr_t>(states) | reinterpret_cast<uintptr_t>(out_bf16)) & 15) return IISAN_EINVAL;
+  if (dtype != IISAN_F32 && dtype != IISAN_F16 && dtype != IISAN_BF16) return IISAN_EINVAL;
+  const int64_t pairs = n * n_sel;
+  const int blocks = (int)imin64((pairs + 7) / 8, 148 * 8);
+  cudaStream_t st = as_stream(stream);
+  __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(out_bf16);
+  LaunchScope ls_(IISAN_K_MISC, st);
+  switch (dtype) {
+    case IISAN_F32: pack_states_kernel<float><<<blocks, 256, 0, st>>>((const float*)states, layers, d, (int)n, sel, n_sel, out); break;
+    case IISAN_F16: pack_states_kernel<__half><<<blocks, 256, 0, st>>>((const __half*)states, layers, d, (int)n, sel, n_sel, out); break;
+    case IISAN_BF16: pack_states_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)states, layers, d, (int)n, sel, n_sel, out); break;
+    default: break;
+  }
   IISAN_LAUNCH_OK();
   return IISAN_OK;
 }

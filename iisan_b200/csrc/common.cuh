@@ -77,6 +77,12 @@ __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return
 template <>
 __device__ __forceinline__ float to_f32<__half>(__half v) { return __half2float(v); }
 
+// exact GELU, torch's nn.GELU() default (CC/model/modules.py:104-105):  x Phi(x)  and its derivative  Phi(x) + x phi(x)
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float gelu_erf_grad(float x) {
+  return 0.5f * (1.f + erff(x * 0.70710678118654752f)) + x * 0.39894228040143268f * expf(-0.5f * x * x);
+}
+
 // 128-bit read-only streaming load (L1 no-allocate): hidden states are read once per pass.
 __device__ __forceinline__ uint4 ld_stream_128(const void* p) {
   uint4 r;

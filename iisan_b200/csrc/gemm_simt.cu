@@ -110,8 +110,12 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmBatch batch) {
         atomicAdd(P.C + (int64_t)gm * P.ldc + gn, v);
       } else {
         if (P.bias) v += __ldg(P.bias + gn);
-        if (P.relu) v = fmaxf(v, 0.f);
-        if (P.mask) v = (__ldg(P.mask + (int64_t)gm * P.ldm + gn) > 0.f) ? v : 0.f;
+        if (P.relu == 1) v = fmaxf(v, 0.f);
+        else if (P.relu == 2) { if (P.pre) P.pre[(int64_t)gm * P.ldp + gn] = v; v = gelu_erf(v); }
+        if (P.mask) {
+          const float mk = __ldg(P.mask + (int64_t)gm * P.ldm + gn);
+          v = P.mask_gelu ? v * gelu_erf_grad(mk) : (mk > 0.f ? v : 0.f);
+        }
         if (P.resid) v += __ldg(P.resid + (int64_t)gm * P.ldr + gn);
         float* c = P.C + (int64_t)gm * P.ldc + gn;
         if (P.accumulate) v += *c;

@@ -16,9 +16,11 @@ struct GemmProb {
   float* C; int64_t ldc;                // C[m*ldc + n]
   const float* bias;                    // [N] or null
   const float* resid; int64_t ldr;      // added after bias/relu/mask, or null
-  const float* mask; int64_t ldm;       // multiply by (mask[m,n] > 0), or null
+  const float* mask; int64_t ldm;       // multiply by (mask[m,n] > 0) -- or, mask_gelu, by gelu'(mask[m,n]) -- or null
+  float* pre; int64_t ldp;              // relu == 2: the pre-activation (bias added) is stored here as well (GELU backward), or null
   int M, N, K;
-  int relu;
+  int relu;                             // 0 none, 1 ReLU, 2 exact (erf) GELU
+  int mask_gelu;
   int splitk;                           // >1: K is split over blockIdx.y and C is atomically accumulated
   int accumulate;                       // 1 (with splitk==1): C += result
 };
@@ -46,11 +48,11 @@ inline GemmProb prob_linear(const float* x, int64_t ldx, const float* w, const f
 // dx[M,K] = dy[M,N] W[N,K]  (* (mask>0)) (+ resid)
 inline GemmProb prob_dgrad(const float* dy, int64_t lddy, const float* w, float* dx, int64_t lddx,
                            int M, int N, int K, const float* mask = nullptr, int64_t ldm = 0,
-                           const float* resid = nullptr, int64_t ldr = 0) {
+                           const float* resid = nullptr, int64_t ldr = 0, int mask_gelu = 0) {
   GemmProb p{};
   p.A = dy; p.a_rs = lddy; p.a_cs = 1;
   p.B = w; p.b_rs = K; p.b_cs = 1;
-  p.C = dx; p.ldc = lddx; p.mask = mask; p.ldm = ldm; p.resid = resid; p.ldr = ldr;
+  p.C = dx; p.ldc = lddx; p.mask = mask; p.ldm = ldm; p.resid = resid; p.ldr = ldr; p.mask_gelu = mask_gelu;
   p.M = M; p.N = K; p.K = N; p.splitk = 1;
   return p;
 }

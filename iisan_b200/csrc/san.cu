@@ -29,6 +29,7 @@ int san_validate(const iisan_san_desc* d) {
   if (d->out_ld < 3 * d->emb) return IISAN_EINVAL;
   if (d->state_dtype < IISAN_F32 || d->state_dtype > IISAN_F16) return IISAN_EINVAL;
   if (d->compute != IISAN_COMPUTE_FP32 && d->compute != IISAN_COMPUTE_BF16) return IISAN_EINVAL;
+  if (d->activation != IISAN_ACT_RELU && d->activation != IISAN_ACT_GELU) return IISAN_EINVAL;
   for (int s = 0; s < d->n_stages; ++s) {
     if (d->text_adapter[s] >= 0 && (d->text_layer[s] < 0 || d->text_layer[s] >= d->layers_text)) return IISAN_EINVAL;
     if (d->img_adapter[s] >= 0 && (d->img_layer[s] < 0 || d->img_layer[s] >= d->layers_img)) return IISAN_EINVAL;
@@ -44,6 +45,7 @@ static int san_forward_fp32(const iisan_san_desc* D, const iisan_san_params* P, 
   const int N = D->n_items;
   const float* last_t = nullptr; const float* last_i = nullptr; const float* last_m = nullptr;
   bool first_t = true, first_i = true;
+  const int act = D->activation == IISAN_ACT_GELU ? 2 : 1;      // epilogue of the down-projection (GELU also stores the pre-activation)
   for (int s = 0; s < D->n_stages; ++s) {
     const int ta = D->text_adapter[s], ia = D->img_adapter[s], mi = D->mm_index[s];
     // ---- optional dim alignment GEMM (CA/model/model.py:406-411) ----
@@ -70,7 +72,8 @@ static int san_forward_fp32(const iisan_san_desc* D, const iisan_san_params* P, 
       if (first_t && D->remove_first) m.R = state_src<T>(text, D->layers_text, D->d_text, 0);
       else m.R = dense_src(last_t, D->d_text);
       m.gate = P->gate_text[ta]; m.mode = 0; m.X = L.x_t[s]; m.N = N; m.d = D->d_text;
-      down.p[down.n++] = prob_linear(L.x_t[s], D->d_text, P->text[ta].w_down, P->text[ta].b_down, L.z_t[s], D->r_text, N, D->r_text, D->d_text, 1);
+      down.p[down.n] = prob_linear(L.x_t[s], D->d_text, P->text[ta].w_down, P->text[ta].b_down, L.z_t[s], D->r_text, N, D->r_text, D->d_text, act);
+      down.p[down.n].pre = L.a_t[s]; down.p[down.n++].ldp = D->r_text;
       up.p[up.n++] = prob_linear(L.z_t[s], D->r_text, P->text[ta].w_up, P->text[ta].b_up, L.last_t[s], D->d_text, N, D->d_text, D->r_text, 0, L.x_t[s], D->d_text);
     }
     if (ia >= 0) {
@@ -79,7 +82,8 @@ static int san_forward_fp32(const iisan_san_desc* D, const iisan_san_params* P, 
       if (first_i && D->remove_first) m.R = state_src<T>(image, D->layers_img, D->d_img, 0);
       else m.R = dense_src(last_i, D->d_img);
       m.gate = P->gate_img[ia]; m.mode = 0; m.X = L.x_i[s]; m.N = N; m.d = D->d_img;
-      down.p[down.n++] = prob_linear(L.x_i[s], D->d_img, P->img[ia].w_down, P->img[ia].b_down, L.z_i[s], D->r_img, N, D->r_img, D->d_img, 1);
+      down.p[down.n] = prob_linear(L.x_i[s], D->d_img, P->img[ia].w_down, P->img[ia].b_down, L.z_i[s], D->r_img, N, D->r_img, D->d_img, act);
+      down.p[down.n].pre = L.a_i[s]; down.p[down.n++].ldp = D->r_img;
       up.p[up.n++] = prob_linear(L.z_i[s], D->r_img, P->img[ia].w_up, P->img[ia].b_up, L.last_i[s], D->d_img, N, D->d_img, D->r_img, 0, L.x_i[s], D->d_img);
     }
     if (mi >= 0) {
@@ -88,7 +92,8 @@ static int san_forward_fp32(const iisan_san_desc* D, const iisan_san_params* P, 
       m.Q = (dp && D->d_text > D->d_img) ? dense_src(dp, D->d_mm) : state_src<T>(text, D->layers_text, D->d_text, D->text_layer[s]);
       m.R = dense_src(last_m, D->d_mm);
       m.gate = P->gate_mm[mi]; m.mode = 1; m.X = L.x_m[s]; m.N = N; m.d = D->d_mm;
-      down.p[down.n++] = prob_linear(L.x_m[s], D->d_mm, P->mm[mi].w_down, P->mm[mi].b_down, L.z_m[s], D->r_mm, N, D->r_mm, D->d_mm, 1);
+      down.p[down.n] = prob_linear(L.x_m[s], D->d_mm, P->mm[mi].w_down, P->mm[mi].b_down, L.z_m[s], D->r_mm, N, D->r_mm, D->d_mm, act);
+      down.p[down.n].pre = L.a_m[s]; down.p[down.n++].ldp = D->r_mm;
       up.p[up.n++] = prob_linear(L.z_m[s], D->r_mm, P->mm[mi].w_up, P->mm[mi].b_up, L.last_m[s], D->d_mm, N, D->d_mm, D->r_mm, 0, L.x_m[s], D->d_mm);
     }
     IISAN_TRY(launch_mix<T>(mb, st));
@@ -178,18 +183,19 @@ static int san_backward_fp32(const iisan_san_desc* D, const iisan_san_params* P,
     }
     GemmBatch wu{}, dz{}, wd{}, dx{}; ColsumBatch cu{}, cd{};
     MixBwdBatch mb{};
-    auto add = [&](const iisan_adapter_ptrs& p, const iisan_adapter_ptrs& g, const float* x, const float* z,
+    auto add = [&](const iisan_adapter_ptrs& p, const iisan_adapter_ptrs& g, const float* x, const float* z, const float* pre,
                    float* dz_buf, const float* dy, float* dxb, int d, int r) {
       wu.p[wu.n++] = prob_wgrad(dy, d, z, r, g.w_up, N, d, r);                 // dWu += dy^T z
       cu.p[cu.n++] = {dy, d, N, d, g.b_up};
-      dz.p[dz.n++] = prob_dgrad(dy, d, p.w_up, dz_buf, r, N, d, r, z, r);       // dz = (dy Wu) * (z>0)
+      if (pre) dz.p[dz.n++] = prob_dgrad(dy, d, p.w_up, dz_buf, r, N, d, r, pre, r, nullptr, 0, 1);   // GELU: dz = (dy Wu) * gelu'(pre)
+      else dz.p[dz.n++] = prob_dgrad(dy, d, p.w_up, dz_buf, r, N, d, r, z, r);  // ReLU: dz = (dy Wu) * (z>0)
       wd.p[wd.n++] = prob_wgrad(dz_buf, r, x, d, g.w_down, N, r, d);            // dWd += dz^T x
       cd.p[cd.n++] = {dz_buf, r, N, r, g.b_down};
       dx.p[dx.n++] = prob_dgrad(dz_buf, r, p.w_down, dxb, d, N, r, d, nullptr, 0, dy, d);  // dx = dy + dz Wd
     };
-    if (ta >= 0) add(P->text[ta], G->text[ta], L.x_t[s], L.z_t[s], L.dz_t, dy_t, dx_t, D->d_text, D->r_text);
-    if (ia >= 0) add(P->img[ia], G->img[ia], L.x_i[s], L.z_i[s], L.dz_i, dy_i, dx_i, D->d_img, D->r_img);
-    if (mi >= 0) add(P->mm[mi], G->mm[mi], L.x_m[s], L.z_m[s], L.dz_m, dy_m, dx_m, D->d_mm, D->r_mm);
+    if (ta >= 0) add(P->text[ta], G->text[ta], L.x_t[s], L.z_t[s], L.a_t[s], L.dz_t, dy_t, dx_t, D->d_text, D->r_text);
+    if (ia >= 0) add(P->img[ia], G->img[ia], L.x_i[s], L.z_i[s], L.a_i[s], L.dz_i, dy_i, dx_i, D->d_img, D->r_img);
+    if (mi >= 0) add(P->mm[mi], G->mm[mi], L.x_m[s], L.z_m[s], L.a_m[s], L.dz_m, dy_m, dx_m, D->d_mm, D->r_mm);
     IISAN_TRY(launch_gemm(wu, st));
     IISAN_TRY(launch_colsum(cu, st));
     IISAN_TRY(launch_gemm(dz, st));
@@ -256,6 +262,11 @@ extern "C" size_t iisan_san_workspace_bytes(const iisan_san_desc* desc) {
   if (desc->compute == IISAN_COMPUTE_BF16) return san_bf16_supported(*desc) ? san_bf16_workspace_bytes(*desc) : 0;
   SanLayout L(*desc, nullptr);
   return L.bytes;
+}
+
+extern "C" int iisan_san_fused_eligible(const iisan_san_desc* desc) {
+  if (san_validate(desc) != IISAN_OK || desc->compute != IISAN_COMPUTE_BF16 || !san_bf16_supported(*desc)) return 0;
+  return san_chain_eligible_if_bf16(*desc);
 }
 
 extern "C" int iisan_san_forward(const iisan_san_desc* desc, const iisan_san_params* params, const void* image,

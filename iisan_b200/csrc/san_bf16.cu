@@ -104,9 +104,18 @@ struct CastList {
 static bool san_chain_eligible(const iisan_san_desc& D) {
   if (D.d_text != D.d_img || D.d_text % 64 || D.d_text < 640 || D.r_text != 64 || D.r_img != 64 || D.r_mm != 64) return false;
   if (D.state_dtype != IISAN_BF16 || D.remove_first || D.n_stages > kChainMaxStages) return false;
+  if (D.activation != IISAN_ACT_RELU) return false;          // the chain kernels and the low-rank adjoint are built on ReLU (mask = relu(z) > 0)
   for (int s = 0; s < D.n_stages; ++s)
     if (D.text_adapter[s] < 0 || D.img_adapter[s] < 0 || D.mm_index[s] < 0) return false;
   return true;
+}
+
+// Would this configuration take the fused chain if its states were stored in bf16?  (The host packs + casts fp32 / fp16 states
+// once per step -- iisan_pack_states -- when the answer is yes: ops.SanFn.)
+int san_chain_eligible_if_bf16(const iisan_san_desc& D) {
+  iisan_san_desc B = D;
+  B.state_dtype = IISAN_BF16;
+  return san_chain_eligible(B) ? 1 : 0;
 }
 
 struct WCopy { bf16* w; bf16* wt; };
@@ -119,6 +128,7 @@ struct SanLayoutBf16 {
   bf16 *x_i[IISAN_MAX_STAGES], *z_i[IISAN_MAX_STAGES], *last_i[IISAN_MAX_STAGES];
   bf16 *x_m[IISAN_MAX_STAGES], *z_m[IISAN_MAX_STAGES], *last_m[IISAN_MAX_STAGES];
   float* dpo[IISAN_MAX_STAGES];          // down_project output [N, d_mm] (Versa)
+  float *a_t[IISAN_MAX_STAGES], *a_i[IISAN_MAX_STAGES], *a_m[IISAN_MAX_STAGES];      // GELU: fp32 pre-activations [N, r] (null for ReLU)
   bf16 *head_t, *head_i, *head_m;
   bf16* wide_b;                          // [N, max d] bf16 copy of one wide layer when the states are not bf16
   // backward scratch
@@ -146,9 +156,15 @@ struct SanLayoutBf16 {
       t_down[s] = t_up[s] = i_down[s] = i_up[s] = m_down[s] = m_up[s] = dpw[s] = WCopy{nullptr, nullptr};
       x_t[s] = z_t[s] = last_t[s] = x_i[s] = z_i[s] = last_i[s] = x_m[s] = z_m[s] = last_m[s] = nullptr;
       dpo[s] = nullptr;
+      a_t[s] = a_i[s] = a_m[s] = nullptr;
     }
     for (int s = 0; s < D.n_stages; ++s) {
       const int ta = D.text_adapter[s], ia = D.img_adapter[s], mi = D.mm_index[s];
+      if (D.activation == IISAN_ACT_GELU) {
+        if (ta >= 0) a_t[s] = a.take<float>(N * D.r_text);
+        if (ia >= 0) a_i[s] = a.take<float>(N * D.r_img);
+        if (mi >= 0) a_m[s] = a.take<float>(N * D.r_mm);
+      }
       if (ta >= 0) {
         t_down[ta] = takew(a, (size_t)D.r_text * D.d_text); t_up[ta] = takew(a, (size_t)D.r_text * D.d_text);
       }
@@ -391,10 +407,12 @@ static int san_forward_bf16_t(const iisan_san_desc* D, const iisan_san_params* P
       dp = L.dpo[s];
     }
     MixBatch mb{}; UmmaBatch down{}, up{};
-    auto tower = [&](const iisan_adapter_ptrs& p, const WCopy& wd, const WCopy& wu, bf16* x, bf16* z, bf16* last, int d, int r) {
+    auto tower = [&](const iisan_adapter_ptrs& p, const WCopy& wd, const WCopy& wu, bf16* x, bf16* z, float* pre, bf16* last, int d, int r) {
       UmmaProblem& dn = down.p[down.n++];
       dn = mk_linear(x, d, wd.w, N, r, d);
-      dn.epi.bias = p.b_down; dn.epi.relu = 1; dn.epi.out_bf16 = z; dn.epi.ld_bf16 = r;
+      dn.epi.bias = p.b_down; dn.epi.out_bf16 = z; dn.epi.ld_bf16 = r;
+      if (pre) { dn.epi.gelu = 1; dn.epi.out_f32 = pre; dn.epi.ld_f32 = r; }      // GELU: z = gelu(pre), pre kept for the backward
+      else dn.epi.relu = 1;
       UmmaProblem& u = up.p[up.n++];
       u = mk_linear(z, r, wu.w, N, d, r);
       u.epi.bias = p.b_up; u.epi.resid_bf16 = x; u.epi.ld_resid_bf16 = d; u.epi.out_bf16 = last; u.epi.ld_bf16 = d;
@@ -406,7 +424,7 @@ static int san_forward_bf16_t(const iisan_san_desc* D, const iisan_san_params* P
       else if (last_t) m.R = dense_bf16_src(last_t, D->d_text);
       else m.R = MixSrc{nullptr, 0, 0};
       m.gate = P->gate_text[ta]; m.mode = 0; m.X = nullptr; m.Xb = L.x_t[s]; m.N = N; m.d = D->d_text;
-      tower(P->text[ta], L.t_down[ta], L.t_up[ta], L.x_t[s], L.z_t[s], L.last_t[s], D->d_text, D->r_text);
+      tower(P->text[ta], L.t_down[ta], L.t_up[ta], L.x_t[s], L.z_t[s], L.a_t[s], L.last_t[s], D->d_text, D->r_text);
     }
     if (ia >= 0) {
       MixProb& m = mb.p[mb.n++];
@@ -415,7 +433,7 @@ static int san_forward_bf16_t(const iisan_san_desc* D, const iisan_san_params* P
       else if (last_i) m.R = dense_bf16_src(last_i, D->d_img);
       else m.R = MixSrc{nullptr, 0, 0};
       m.gate = P->gate_img[ia]; m.mode = 0; m.X = nullptr; m.Xb = L.x_i[s]; m.N = N; m.d = D->d_img;
-      tower(P->img[ia], L.i_down[ia], L.i_up[ia], L.x_i[s], L.z_i[s], L.last_i[s], D->d_img, D->r_img);
+      tower(P->img[ia], L.i_down[ia], L.i_up[ia], L.x_i[s], L.z_i[s], L.a_i[s], L.last_i[s], D->d_img, D->r_img);
     }
     if (mi >= 0) {
       MixProb& m = mb.p[mb.n++];
@@ -423,7 +441,7 @@ static int san_forward_bf16_t(const iisan_san_desc* D, const iisan_san_params* P
       m.Q = (dp && text_wide) ? dense_src(dp, D->d_mm) : state_src<T>(text, D->layers_text, D->d_text, D->text_layer[s]);
       m.R = last_m ? dense_bf16_src(last_m, D->d_mm) : MixSrc{nullptr, 0, 0};
       m.gate = P->gate_mm[mi]; m.mode = 1; m.X = nullptr; m.Xb = L.x_m[s]; m.N = N; m.d = D->d_mm;
-      tower(P->mm[mi], L.m_down[mi], L.m_up[mi], L.x_m[s], L.z_m[s], L.last_m[s], D->d_mm, D->r_mm);
+      tower(P->mm[mi], L.m_down[mi], L.m_up[mi], L.x_m[s], L.z_m[s], L.a_m[s], L.last_m[s], D->d_mm, D->r_mm);
     }
     IISAN_TRY(launch_mix<T>(mb, st));
     IISAN_TRY(launch_umma_gemm(down, st));
@@ -576,22 +594,24 @@ static int san_backward_bf16_t(const iisan_san_desc* D, const iisan_san_params* 
     }
     const int nt = (ta >= 0) + (ia >= 0) + (mi >= 0);
     UmmaBatch wu{}, dz{}, wd{}, dx{}; ColsumBatch cu{}, cd{};
-    auto add = [&](const iisan_adapter_ptrs& g, const WCopy& wdn, const WCopy& wup, const bf16* x, const bf16* z, bf16* dzb,
+    auto add = [&](const iisan_adapter_ptrs& g, const WCopy& wdn, const WCopy& wup, const bf16* x, const bf16* z, const float* pre, bf16* dzb,
                    const float* dy, const bf16* dyb, float* dxo, bf16* dxob, int d, int r) {
       wu.p[wu.n++] = mk_wgrad(dyb, d, d, z, r, r, N, g.w_up, nt);               // dWu[d,r] += dy^T z
       cu.p[cu.n++] = {dy, d, N, d, g.b_up};
       UmmaProblem& q = dz.p[dz.n++];                                             // dz = (dy Wu) * (z > 0)
       q = mk_linear(dyb, d, wup.wt, N, r, d);
-      q.epi.mask = z; q.epi.ld_mask = r; q.epi.out_bf16 = dzb; q.epi.ld_bf16 = r;
+      if (pre) { q.epi.gelu_pre = pre; q.epi.ld_gelu_pre = r; }                  // GELU: dz = (dy Wu) * gelu'(pre)
+      else { q.epi.mask = z; q.epi.ld_mask = r; }
+      q.epi.out_bf16 = dzb; q.epi.ld_bf16 = r;
       wd.p[wd.n++] = mk_wgrad(dzb, r, r, x, d, d, N, g.w_down, nt);             // dWd[r,d] += dz^T x
       cd.p[cd.n++] = {nullptr, r, N, r, g.b_down, dzb};
       UmmaProblem& u = dx.p[dx.n++];                                             // dx = dy + dz Wd
       u = mk_linear(dzb, r, wdn.wt, N, d, r);
       u.epi.resid_f32 = dy; u.epi.ld_resid_f32 = d; u.epi.out_f32 = dxo; u.epi.ld_f32 = d; u.epi.out_bf16 = dxob; u.epi.ld_bf16 = d;
     };
-    if (ta >= 0) add(G->text[ta], L.t_down[ta], L.t_up[ta], L.x_t[s], L.z_t[s], L.dzb_t, dy_t, dyb_t, dx_t, dxb_t, D->d_text, D->r_text);
-    if (ia >= 0) add(G->img[ia], L.i_down[ia], L.i_up[ia], L.x_i[s], L.z_i[s], L.dzb_i, dy_i, dyb_i, dx_i, dxb_i, D->d_img, D->r_img);
-    if (mi >= 0) add(G->mm[mi], L.m_down[mi], L.m_up[mi], L.x_m[s], L.z_m[s], L.dzb_m, dy_m, dyb_m, dx_m, dxb_m, D->d_mm, D->r_mm);
+    if (ta >= 0) add(G->text[ta], L.t_down[ta], L.t_up[ta], L.x_t[s], L.z_t[s], L.a_t[s], L.dzb_t, dy_t, dyb_t, dx_t, dxb_t, D->d_text, D->r_text);
+    if (ia >= 0) add(G->img[ia], L.i_down[ia], L.i_up[ia], L.x_i[s], L.z_i[s], L.a_i[s], L.dzb_i, dy_i, dyb_i, dx_i, dxb_i, D->d_img, D->r_img);
+    if (mi >= 0) add(G->mm[mi], L.m_down[mi], L.m_up[mi], L.x_m[s], L.z_m[s], L.a_m[s], L.dzb_m, dy_m, dyb_m, dx_m, dxb_m, D->d_mm, D->r_mm);
     IISAN_TRY(launch_umma_gemm(wu, st));
     IISAN_TRY(launch_colsum(cu, st));
     IISAN_TRY(launch_umma_gemm(dz, st));

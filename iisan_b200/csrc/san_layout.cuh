@@ -8,6 +8,7 @@ namespace iisan {
 int san_validate(const iisan_san_desc* d);
 // bf16 tensor-core mode (san_bf16.cu)
 size_t san_bf16_workspace_bytes(const iisan_san_desc& D);
+int san_chain_eligible_if_bf16(const iisan_san_desc& D);
 int san_bf16_supported(const iisan_san_desc& D);
 int san_forward_bf16(const iisan_san_desc* D, const iisan_san_params* P, const void* image, const void* text, void* ws,
                      float* out, cudaStream_t st);
@@ -20,6 +21,7 @@ struct SanLayout {
   float* x_i[IISAN_MAX_STAGES]; float* z_i[IISAN_MAX_STAGES]; float* last_i[IISAN_MAX_STAGES];
   float* x_m[IISAN_MAX_STAGES]; float* z_m[IISAN_MAX_STAGES]; float* last_m[IISAN_MAX_STAGES];
   float* dp[IISAN_MAX_STAGES];      // down_project output of the wide modality (Versa)
+  float* a_t[IISAN_MAX_STAGES]; float* a_i[IISAN_MAX_STAGES]; float* a_m[IISAN_MAX_STAGES];   // GELU: pre-activations [N, r] (null for ReLU)
   float *head_t, *head_i, *head_m;  // fc outputs
   // scratch
   float* wide_dense;                // [N, max(d)] fp32 copy of one wide hidden-state layer (Versa)
@@ -34,10 +36,15 @@ struct SanLayout {
     const bool dimdiff = D.d_text != D.d_img;
     for (int s = 0; s < IISAN_MAX_STAGES; ++s) {
       x_t[s] = z_t[s] = last_t[s] = x_i[s] = z_i[s] = last_i[s] = x_m[s] = z_m[s] = last_m[s] = dp[s] = nullptr;
+      a_t[s] = a_i[s] = a_m[s] = nullptr;
     }
+    const bool gelu = D.activation == IISAN_ACT_GELU;
     for (int s = 0; s < D.n_stages; ++s) {
       if (D.text_adapter[s] >= 0) { x_t[s] = a.take<float>(N * D.d_text); z_t[s] = a.take<float>(N * D.r_text); last_t[s] = a.take<float>(N * D.d_text); }
       if (D.img_adapter[s] >= 0) { x_i[s] = a.take<float>(N * D.d_img); z_i[s] = a.take<float>(N * D.r_img); last_i[s] = a.take<float>(N * D.d_img); }
+      if (gelu && D.text_adapter[s] >= 0) a_t[s] = a.take<float>(N * D.r_text);
+      if (gelu && D.img_adapter[s] >= 0) a_i[s] = a.take<float>(N * D.r_img);
+      if (gelu && D.mm_index[s] >= 0) a_m[s] = a.take<float>(N * D.r_mm);
       if (D.mm_index[s] >= 0) {
         x_m[s] = a.take<float>(N * D.d_mm); z_m[s] = a.take<float>(N * D.r_mm); last_m[s] = a.take<float>(N * D.d_mm);
         if (dimdiff) dp[s] = a.take<float>(N * D.d_mm);

@@ -114,7 +114,14 @@ __device__ __noinline__ void epi_block_generic(const UmmaEpilogue& E, const floa
                                                float bias_v, float lo) {
   for (int r = 0; r < nrow; ++r) {
     const int64_t row = row_base + r;
+    if (E.gelu) {          // AdapterBlock down-projection with GELU: the activation feeds the up-projection, the backward needs the pre-activation
+      const float pre = stg[r * 33 + lane] + bias_v;
+      if (E.out_f32) E.out_f32[row * E.ld_f32 + col] = pre;
+      if (E.out_bf16) E.out_bf16[row * E.ld_bf16 + col] = __float2bfloat16_rn(gelu_erf(pre));
+      continue;
+    }
     float v = fmaxf(stg[r * 33 + lane] + bias_v, lo);
+    if (E.gelu_pre) v *= gelu_erf_grad(E.gelu_pre[row * E.ld_gelu_pre + col]);
     if (E.mask) { if (!(__bfloat162float(E.mask[row * E.ld_mask + col]) > 0.f)) v = 0.f; }
     if (E.resid_bf16) v += __bfloat162float(E.resid_bf16[row * E.ld_resid_bf16 + col]);
     if (E.resid_f32) v += E.resid_f32[row * E.ld_resid_f32 + col];
@@ -123,7 +130,7 @@ __device__ __noinline__ void epi_block_generic(const UmmaEpilogue& E, const floa
   }
 }
 
-enum : int { EPI_MASK = 1, EPI_RESB = 2, EPI_RESF = 4, EPI_OUTF = 8, EPI_OUTB = 16, EPI_ATOMIC = 32 };
+enum : int { EPI_MASK = 1, EPI_RESB = 2, EPI_RESF = 4, EPI_OUTF = 8, EPI_OUTB = 16, EPI_ATOMIC = 32, EPI_GELU = 64 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ void cluster_sync_all() {
@@ -266,7 +273,8 @@ __global__ void __launch_bounds__(UTHREADS, 1) umma_gemm_kernel(const __grid_con
       const bool first_split = (t.split == 0);
       const int row_base = m0 + quad * 32;
       const int features = (E.mask ? EPI_MASK : 0) | (E.resid_bf16 ? EPI_RESB : 0) | (E.resid_f32 ? EPI_RESF : 0) | (E.out_f32 ? EPI_OUTF : 0) |
-                           (E.out_bf16 ? EPI_OUTB : 0) | ((E.atomic && E.out_f32) ? EPI_ATOMIC : 0);
+                           (E.out_bf16 ? EPI_OUTB : 0) | ((E.atomic && E.out_f32) ? EPI_ATOMIC : 0) |
+                           ((E.gelu || E.gelu_pre) ? EPI_GELU : 0);      // GELU: the run-time generic block below
 #pragma unroll 1
       for (int c0 = csel * 32; c0 < BN; c0 += 64) {
         if (n0 + c0 >= P.N) break;                   // warp-uniform

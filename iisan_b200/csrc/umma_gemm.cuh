@@ -29,6 +29,8 @@ struct UmmaEpilogue {
   const __nv_bfloat16* resid_bf16; int64_t ld_resid_bf16;   // added last, or null
   const float* resid_f32; int64_t ld_resid_f32;
   int relu;
+  int gelu;                                       // 1: out_bf16 = gelu_erf(acc + bias), out_f32 = the pre-activation acc + bias (AdapterBlock with GELU)
+  const float* gelu_pre; int64_t ld_gelu_pre;     // multiply by gelu_erf'(gelu_pre) or null   (GELU backward)
   int atomic;                                     // 1: red.add into out_f32 (split-K partial sums)
   int transpose_out;                              // 1: out_f32 is addressed [n * ld_f32 + m] (fp32 output only)
 };

@@ -123,14 +123,12 @@ class AdapterBlock(nn.Module):
 
     def __init__(self, args, input_size, down_size, dropout=0.1):
         super().__init__()
-        if getattr(args, "adapter_activation", "RELU") == "GELU":
-            raise NotImplementedError("GELU adapters are not built")
         self.fc_down = nn.Linear(input_size, down_size)
         self.fc_up = nn.Linear(down_size, input_size)
         for lin in (self.fc_down, self.fc_up):
             nn.init.normal_(lin.weight, std=1e-2)
             nn.init.zeros_(lin.bias)
-        self.activate = nn.ReLU()
+        self.activate = nn.GELU() if getattr(args, "adapter_activation", "RELU") == "GELU" else nn.ReLU()     # modules.py:104-107
         self.dropout = nn.Dropout(dropout)
 
     def forward(self, input_embs):

@@ -120,6 +120,16 @@ class SanFn(torch.autograd.Function):
         image = image.contiguous()
         text = text.contiguous()
         desc = binder.desc(image, text, compute, packed)
+        if (compute == L.COMPUTE_BF16 and not packed and image.dtype != torch.bfloat16
+                and lib.iisan_san_fused_eligible(C.byref(desc))):
+            # states stored as the reference writes them (fp32 .pt files; fp16 for the LLaMA / EVA caches): select the layers the
+            # towers read and round them to bf16 ONCE (iisan_pack_states), then run the fused chain kernels on the packed batch
+            # instead of the layered path (which reads the stored dtype in place, three launches per stage)
+            sel_i, sel_t = binder.read_layers_dev(image.device)        # device int32 tensors, made once (no H2D copy under capture)
+            image = pack_states(image, sel_i)
+            text = pack_states(text, sel_t)
+            packed = True
+            desc = binder.desc(image, text, compute, True)
         ptrs = binder.param_table(params)
         n, e = desc.n_items, desc.emb
         out = torch.empty(n, 3 * e, dtype=torch.float32, device=image.device)
@@ -280,6 +290,20 @@ def inbatch_ce_masks(ids_rows, ids_cols, lm_rows, lm_cols, user_offset=0, fast=F
     L.check(lib.iisan_inbatch_ce_masks(C.byref(desc), _p(ids_rows.contiguous().view(-1)), _p(ids_cols.contiguous().view(-1)),
                                        _p(lm_rows.contiguous().float()), _p(lm_cols.contiguous().float()), _p(out), _stream()),
             "iisan_inbatch_ce_masks")
+    return out
+
+
+def pack_states(states, sel):
+    """out[n, len(sel), d] bf16 = round(states[..., sel, :]) through iisan_pack_states (states [..., layers, d], any stored dtype)."""
+    lib = L.load()
+    L.require_cuda(states, "hidden states")
+    states = states.contiguous()
+    layers, d = states.shape[-2], states.shape[-1]
+    n = states.numel() // (layers * d)
+    sel_t = sel if torch.is_tensor(sel) else torch.as_tensor(list(sel), dtype=torch.int32, device=states.device)
+    out = torch.empty(n, len(sel), d, dtype=torch.bfloat16, device=states.device)
+    L.check(lib.iisan_pack_states(_p(states), L.torch_dtype_code(states.dtype), n, layers, d, _p(sel_t), len(sel), _p(out), _stream()),
+            "iisan_pack_states")
     return out
 
 

@@ -42,6 +42,7 @@ class SanPlan:
     n_gate_mm: int
     n_down_project: int
     stages: list          # (text_adapter, text_layer, img_adapter, img_layer, mm_index) with -1 = idle
+    activation: int = 0   # iisan_activation: 0 ReLU, 1 exact GELU (args.adapter_activation, CC/model/modules.py:104-107)
 
     @property
     def d_mm(self):
@@ -67,8 +68,8 @@ def make_plan(args, asym: bool) -> SanPlan:
     if "intra" not in args.modality or "inter" not in args.modality:
         raise NotImplementedError("iisan_b200 builds modality='intra_inter' only (the only configuration the "
                                   "reference Code_Cached forward can run, SURVEY.md Q2)")
-    if getattr(args, "adapter_activation", "RELU") == "GELU":
-        raise NotImplementedError("GELU adapters are not built (reference default and launchers use RELU)")
+    # CC/model/modules.py:104-107: nn.GELU() iff the string is exactly "GELU", nn.ReLU() for anything else
+    activation = 1 if getattr(args, "adapter_activation", "RELU") == "GELU" else 0
     rf = (args.remove_first == "TRUE")
     E = int(args.embedding_dim)
     if asym:
@@ -113,7 +114,7 @@ def make_plan(args, asym: bool) -> SanPlan:
     if len(stages) > L.MAX_STAGES:
         raise NotImplementedError(f"more than {L.MAX_STAGES} stages")
     return SanPlan(asym, rf, d_text, d_img, r_text, r_img, r_mm, E, t_sel, i_sel, n_text, n_img, n_mm,
-                   n_gate_text, n_gate_img, n_gate_mm, n_dp, stages)
+                   n_gate_text, n_gate_img, n_gate_mm, n_dp, stages, activation)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -183,6 +184,15 @@ class SanBinder(_BinderBase):
         self.used = [any(n == u or (u.endswith(".") and n.startswith(u)) for u in used) or n.split(".")[0] in _HEADS
                      for n in self.names]
         self._desc_cache = {}
+        self._sel_dev = {}
+
+    def read_layers_dev(self, device):
+        """(image, text) layer lists the towers read, as int32 tensors on ``device`` (cached: created outside any graph capture)."""
+        key = str(device)
+        if key not in self._sel_dev:
+            self._sel_dev[key] = (torch.as_tensor(self.plan.layers_img_read, dtype=torch.int32, device=device),
+                                  torch.as_tensor(self.plan.layers_text_read, dtype=torch.int32, device=device))
+        return self._sel_dev[key]
 
     def _build(self, params):
         t = L.SanParams()
@@ -246,6 +256,7 @@ class SanBinder(_BinderBase):
                 d.img_adapter[s], d.img_layer[s] = ia, (rank_i[il] if (packed and ia >= 0) else il)
                 d.mm_index[s] = mi
             d.asym, d.remove_first = int(pl.asym), int(pl.remove_first)
+            d.activation = int(pl.activation)
             d.state_dtype = L.torch_dtype_code(image.dtype)
             d.compute = compute
             d.out_ld = 3 * pl.emb

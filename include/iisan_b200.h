@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define IISAN_ABI_VERSION 2
+#define IISAN_ABI_VERSION 3
 #define IISAN_MAX_STAGES 64
 #define IISAN_MAX_BLOCKS 8
 
@@ -109,6 +109,10 @@ typedef struct iisan_san_params {
   iisan_linear_ptrs pre_text, pre_img, mm_down;     /* bert_pre_fc, cv_pre_fc, fc_mm_down */
 } iisan_san_params;
 
+/* AdapterBlock activation (CC/model/modules.py:104-107: nn.GELU() when args.adapter_activation == "GELU", else nn.ReLU()).
+ * GELU is the exact (erf) form, torch's default.  The fused chain kernels are ReLU-only: GELU runs on the layered path. */
+typedef enum iisan_activation { IISAN_ACT_RELU = 0, IISAN_ACT_GELU = 1 } iisan_activation;
+
 typedef struct iisan_san_desc {
   int32_t n_items;                  /* rows N: B*11 for a train batch, b for the eval sweep */
   int32_t d_text, d_img, d_mm;      /* hidden widths; d_mm = min(d_text, d_img) */
@@ -125,6 +129,7 @@ typedef struct iisan_san_desc {
   int32_t state_dtype;  /* iisan_dtype of the cached hidden states */
   int32_t compute;      /* iisan_compute */
   int32_t out_ld;       /* leading dimension of `out` (>= 3*emb) */
+  int32_t activation;   /* iisan_activation of the AdapterBlocks: args.adapter_activation (CC/model/modules.py:104-107) */
 } iisan_san_desc;
 
 size_t iisan_san_workspace_bytes(const iisan_san_desc* desc);
@@ -278,6 +283,19 @@ int iisan_inbatch_ce_masks_fast(const iisan_ce_desc* desc, const int64_t* ids_ro
 int iisan_gather_states(const void* table, int32_t dtype, int64_t n_table_items, int32_t layers,
                         int32_t d, const int64_t* ids, int32_t n, const int32_t* sel, int32_t n_sel,
                         void* out, iisan_stream_t stream);
+
+/* Layer selection + cast of a dense batch of cached states to bf16 (fast mode with states stored as the reference writes them:
+ * fp32 .pt files, CC/preprocess_vectors.py:27-31; fp16 for the LLaMA / EVA-CLIP caches of Code_Cached_Asym):
+ *   out_bf16[i, a, :] = bf16_rn(states[i, sel[a], :]),  states [n, layers, d] of `dtype`, out [n, n_sel, d] bf16.
+ * The result is a "packed" batch (what iisan_gather_states produces from a bf16 store): the fused chain kernels then serve the
+ * reference's on-disk dtype too.  d % 8 == 0, 16-byte aligned pointers. */
+int iisan_pack_states(const void* states, int32_t dtype, int64_t n, int32_t layers, int32_t d, const int32_t* sel,
+                      int32_t n_sel, void* out_bf16, iisan_stream_t stream);
+
+/* 1 if this (fast-mode) configuration runs on the fused side-adapter chain kernels once its states are bf16 (equal widths,
+ * bottleneck 64, every tower active in every stage, towers starting from zero: CC/model/model.py:300-338 as launched by the
+ * reference's scripts), else 0 (it runs on the layered path whatever the stored dtype). */
+int iisan_san_fused_eligible(const iisan_san_desc* desc);
 
 /* ---------------------------------------------------------------------------------------------
  * Optimizer step (CC/run.py:260-307 name-routed LR groups, :383-385 step): fused multi-tensor Adam with torch.optim.Adam's

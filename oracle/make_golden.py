@@ -40,6 +40,11 @@ CASES = {
     "asym_equal": ("Code_Cached_Asym", dict(asym=True, d_text=64, d_img=64, layers_text=7, layers_img=7,
                                             bert_list="1,3,5", vit_list="1,3,5", r_cv=16, r_bert=16,
                                             embedding_dim=32, item_num=500), 5, "dense", 606),
+    # --- args.adapter_activation == "GELU" (CC/model/modules.py:104-107; parameters.py:72 defaults to RELU), both trees ---
+    "cc_gelu_b6": ("Code_Cached", {"adapter_activation": "GELU"}, 6, "realistic", 909),
+    "asym_gelu_text_wide": ("Code_Cached_Asym", dict(asym=True, d_text=96, d_img=64, layers_text=9, layers_img=5,
+                                                     bert_list="1,3,5,7", vit_list="1,3", r_cv=16, r_bert=24, embedding_dim=32,
+                                                     item_num=500, adapter_activation="GELU"), 5, "realistic", 919),
     # --- BASELINE.json configs[3] / configs[4] at their REAL widths and layer counts (small B: the widths, layer pitches,
     #     stage plans and the dim-alignment GEMM are what these cases pin; tests/test_gpu_versa_shapes.py) ---
     # BERT-large text + ViT-large image, group layer-drop 13 text vs 7 image adapters: 6 text-only stages, then 7 paired

@@ -75,8 +75,10 @@ def san_forward_emul(P, image, text, cfg, prefix="mm_encoder.", fused_chain=Fals
 
     plan = O.stage_plan(cfg)
 
+    act = F.gelu if getattr(cfg, "adapter_activation", "RELU") == "GELU" else F.relu      # GELU: exact erf form on the fp32 pre-activation
+
     def adapter(pfx, x, final):
-        z = rb(F.relu(_lin(x, P[pfx + ".fc_down.weight"], P[pfx + ".fc_down.bias"])))
+        z = rb(act(_lin(x, P[pfx + ".fc_down.weight"], P[pfx + ".fc_down.bias"])))
         y = _lin(z, P[pfx + ".fc_up.weight"], P[pfx + ".fc_up.bias"]) + x
         return y if (fused_chain and not final) else rb(y)
 

@@ -37,3 +37,20 @@ def run_step(model, batch, device="cuda", dtype=torch.float32):
     loss.backward()
     grads = {n: (None if p.grad is None else p.grad.detach().float().cpu().numpy()) for n, p in model.named_parameters()}
     return loss.detach().float().cpu().numpy(), grads
+
+
+def fused_chain_route(cfg, plan):
+    """Mirror of san_chain_eligible (iisan_b200/csrc/san_bf16.cu) WITHOUT the stored dtype: fp32 / fp16 states of such a
+    configuration are packed and rounded to bf16 once (ops.SanFn -> iisan_pack_states) and take the same fused kernels."""
+    return bool(cfg.d_text == cfg.d_img and cfg.d_text % 64 == 0 and cfg.d_text >= 640 and cfg.r_cv == 64 and cfg.r_bert == 64 and
+                cfg.remove_first != "TRUE" and len(plan) <= 8 and all(None not in st for st in plan) and
+                getattr(cfg, "adapter_activation", "RELU") != "GELU")
+
+
+def emulation_batch(batch, fused, stored_dtype):
+    """What the rounding-point emulation must see: on the fused route the product rounds the stored states to bf16 first."""
+    import torch
+    if not fused or stored_dtype == torch.bfloat16:
+        return batch
+    r = lambda a: torch.from_numpy(a).bfloat16().float().numpy()
+    return dict(batch, image=r(batch["image"]), text=r(batch["text"]))

@@ -19,7 +19,7 @@ import pytest
 import torch
 
 from golden_util import VERSA_CASES, check_grads, golden_masked, load_case, rebuild_inputs
-from product_util import build_product, run_step
+from product_util import emulation_batch, fused_chain_route, build_product, run_step
 
 pytestmark = pytest.mark.gpu
 
@@ -153,9 +153,8 @@ def test_versa_bf16_mode(name, state_dtype):
         batch = dict(batch, image=_round_to(batch["image"], dt), text=_round_to(batch["text"], dt))
     ref_out, ref_grads = O.train_step_grads(params, batch, pop, cfg)
     plan = O.stage_plan(cfg)
-    fused = (dt == torch.bfloat16 and cfg.d_text == cfg.d_img and cfg.d_text % 64 == 0 and cfg.r_cv == 64 and cfg.r_bert == 64 and
-             cfg.remove_first != "TRUE" and len(plan) <= 8 and all(None not in st for st in plan))       # san_chain_eligible
-    emu_out, emu_grads = train_step_grads_emul(params, batch, pop, cfg, ce_bf16=(cfg.embedding_dim == 64), fused_chain=fused)
+    fused = fused_chain_route(cfg, plan)          # whatever the stored dtype: fp32 / fp16 states are packed to bf16 first (ops.SanFn)
+    emu_out, emu_grads = train_step_grads_emul(params, emulation_batch(batch, fused, dt), pop, cfg, ce_bf16=(cfg.embedding_dim == 64), fused_chain=fused)
     set_compute_mode("bf16")
     try:
         model = build_product(cfg, params, pop).eval()
