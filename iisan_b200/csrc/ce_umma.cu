@@ -606,7 +606,10 @@ int ce_fast_splits(int owner_tiles, int stream_tiles) {
   for (int k = 2; k <= 8 && !one_wave; ++k) {
     int per = 0;
     const int s = shape(k * 148 / (owner_tiles < 1 ? 1 : owner_tiles), &per);
-    if (per < 16) break;                           // measured (scripts/ce_gather_bench.py, W = 2: 168 -> 174 us with 8 tiles per CTA): short CTAs lose to their prologue
+    // measured (scripts/ce_gather_bench.py; W = 2: 168 -> 174 us with 8 tiles per CTA, W = 4: 269 -> 262 us with 16, W = 8: 480 -> 447 us
+    // with 32): short CTAs lose to their prologue.  IISAN_B200_CE_MIN_TILES lowers the bar (tests force the multi-wave grid at W = 2).
+    const char* mt = getenv("IISAN_B200_CE_MIN_TILES");
+    if (per < (mt ? atoi(mt) : 16)) break;
     const int waves = (owner_tiles * s + 147) / 148;
     const double cost = (double)waves * (per + 1);
     if (cost < bar && cost < best_cost) { best = s; best_cost = cost; }

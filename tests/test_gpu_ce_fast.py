@@ -24,7 +24,10 @@ def _case(B, Bc, off, seed, mode, item_num):
                                                      (64, 256, 128, "realistic", 200), (128, 1024, 896, "dense", 5000),
                                                      # a two-rank pool at the benchmark size: the multi-wave column split of ce_fast_splits
                                                      (512, 1024, 512, "dense", 19246)])
-def test_fast_ce_matches_oracle(B, Bc, off, mode, item_num):
+def test_fast_ce_matches_oracle(B, Bc, off, mode, item_num, monkeypatch):
+    # (512, 1024): 40 owner tiles x 88 column tiles.  The production policy keeps ONE wave of 40 x 3 CTAs there (the multi-wave
+    # grid pays from 16 tiles per CTA, i.e. pools of >= 4 ranks); the override makes this case run 40 x 11 CTAs in three waves
+    monkeypatch.setenv("IISAN_B200_CE_MIN_TILES", "4")
     from iisan_b200 import _lib
     from iisan_b200.ops import InBatchCeFn, inbatch_ce_masks
     from oracle import iisan_oracle as O
