@@ -98,6 +98,67 @@ def test_unsupported_configs_rejected_at_construction():
         make_plan(a, False)
 
 
+def test_gelu_activation_plan_descriptor_and_routing():
+    """args.adapter_activation: nn.GELU() iff the string is exactly "GELU" (CC/model/modules.py:104-107).  The plan carries it
+    into the descriptor; a GELU configuration is never routed to the ReLU-only fused chain kernels; the workspace grows by
+    the pre-activation stash the GELU backward needs.  Host-side checks only (no kernel is launched)."""
+    import torch
+    from oracle.synthetic import PathConfig, make_args
+    from iisan_b200 import _lib
+    from iisan_b200.model.modules import AdapterBlock
+    from iisan_b200.plan import SanBinder, make_plan
+    lib = _lib.load()
+    out = {}
+    for act in ("RELU", "GELU", "gelu"):
+        cfg = PathConfig(adapter_activation=act)
+        args = make_args(cfg)
+        plan = make_plan(args, False)
+        assert plan.activation == (1 if act == "GELU" else 0)
+        assert isinstance(AdapterBlock(args, 768, 64).activate, nn.GELU if act == "GELU" else nn.ReLU)
+        binder = SanBinder(plan, [])
+        img = torch.empty(2, 11, 13, 768, dtype=torch.float32); txt = torch.empty(2, 11, 13, 768, dtype=torch.float32)
+        d = binder.desc(img, txt, _lib.COMPUTE_BF16, False)
+        assert d.activation == plan.activation
+        out[act] = (lib.iisan_san_fused_eligible(ctypes.byref(d)), lib.iisan_san_workspace_bytes(ctypes.byref(d)))
+        d32 = binder.desc(img, txt, _lib.COMPUTE_FP32, False)
+        out[act + "/fp32"] = lib.iisan_san_workspace_bytes(ctypes.byref(d32))
+        d.activation = 7
+        assert lib.iisan_san_workspace_bytes(ctypes.byref(d)) == 0           # unknown activation code rejected
+        d.activation = plan.activation
+    assert out["RELU"][0] == 1 and out["gelu"][0] == 1 and out["GELU"][0] == 0
+    n, r, stages, towers = 22, 64, 7, 3
+    assert out["GELU"][1] > out["RELU"][1] - 1 and out["GELU/fp32"] - out["RELU/fp32"] >= n * r * 4 * stages * towers
+
+
+def test_grad_arena_hands_out_zeroed_aligned_slices():
+    """ops.GradArena (one memset per step instead of a fill per backward function): slices are 256-byte aligned, disjoint, zero
+    after reset(), and reset() clears exactly what the previous step used."""
+    import torch
+    from iisan_b200.ops import GradArena, grad_zeros
+    a = GradArena(1024, "cpu")
+    x = a.take(10); y = a.take(100)
+    assert x.numel() == 10 and y.numel() == 100 and (y.data_ptr() - x.data_ptr()) == 64 * 4 and a.used().numel() == 192
+    x.fill_(1.0); y.fill_(2.0)
+    a.reset()
+    assert a.off == 0 and float(a.buf.abs().sum()) == 0.0
+    z = a.take(5)
+    assert z.data_ptr() == x.data_ptr() and float(z.abs().sum()) == 0.0
+    with pytest.raises(_lib_error()):
+        a.take(2048)
+    prev, GradArena.active = GradArena.active, a
+    try:
+        g = grad_zeros(7, "cpu")
+        assert g.untyped_storage().data_ptr() == a.buf.untyped_storage().data_ptr()
+    finally:
+        GradArena.active = prev
+    assert grad_zeros(7, "cpu").untyped_storage().data_ptr() != a.buf.untyped_storage().data_ptr()
+
+
+def _lib_error():
+    from iisan_b200._lib import IisanLibraryError
+    return IisanLibraryError
+
+
 def test_stage_plan_matches_oracle_plan():
     from oracle.iisan_oracle import stage_plan
     from oracle.synthetic import PathConfig, make_args
