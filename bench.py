@@ -712,7 +712,11 @@ def supervised(a):
     notes = []
     for attempt, gen in enumerate((os.environ.get("IISAN_B200_CHAIN_GEN", "3"), "2")):
         env = dict(os.environ, IISAN_B200_CHAIN_GEN=gen)
-        r = subprocess.run(base, env=env, stdout=subprocess.PIPE, text=True)
+        try:      # a child that hangs is killed (subprocess.run does that on timeout) and counts as failed
+            r = subprocess.run(base, env=env, stdout=subprocess.PIPE, text=True, timeout=float(os.environ.get("IISAN_BENCH_CHILD_TIMEOUT", "1500")))
+        except subprocess.TimeoutExpired as e:
+            out = e.stdout.decode() if isinstance(e.stdout, bytes) else (e.stdout or "")
+            r = subprocess.CompletedProcess(base, returncode=-9, stdout=out)
         lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
         if r.returncode == 0 and lines:
             line = json.loads(lines[-1])
