@@ -45,6 +45,15 @@ CASES = {
     "asym_gelu_text_wide": ("Code_Cached_Asym", dict(asym=True, d_text=96, d_img=64, layers_text=9, layers_img=5,
                                                      bert_list="1,3,5,7", vit_list="1,3", r_cv=16, r_bert=24, embedding_dim=32,
                                                      item_num=500, adapter_activation="GELU"), 5, "realistic", 919),
+    # --- remove_first == "TRUE" (CC/model/model.py:264-265, 305-308: the towers start from cached layer 0 and -- quirk Q1 -- the
+    #     cv layer list is read from side_adapter_bert_list; CA/model/model.py:265-270 reads each modality's own string).  The
+    #     "oracle_" prefix keeps these out of the GPU case lists (tests/golden_util.py): they pin the ORACLE's restatement of the
+    #     option; the product is compared with the oracle on it in tests/test_gpu_store.py ---
+    "oracle_cc_remove_first": ("Code_Cached", {"remove_first": "TRUE", "bert_list": "0,2,4,6,8,10", "vit_list": "1,3,5,7,9,11"},
+                               5, "realistic", 929),
+    "oracle_asym_remove_first": ("Code_Cached_Asym", dict(asym=True, remove_first="TRUE", d_text=96, d_img=64, layers_text=9, layers_img=5,
+                                                          bert_list="1,3,5,7", vit_list="0,2", r_cv=16, r_bert=24, embedding_dim=32,
+                                                          item_num=500), 5, "realistic", 939),
     # --- BASELINE.json configs[3] / configs[4] at their REAL widths and layer counts (small B: the widths, layer pitches,
     #     stage plans and the dim-alignment GEMM are what these cases pin; tests/test_gpu_versa_shapes.py) ---
     # BERT-large text + ViT-large image, group layer-drop 13 text vs 7 image adapters: 6 text-only stages, then 7 paired

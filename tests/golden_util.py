@@ -7,6 +7,8 @@ import numpy as np
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 _ALL = sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz") and not f.startswith(("eval_", "data_")))   # eval_*: tests/test_eval.py, data_*: tests/test_store_cpu.py
+ORACLE_ONLY_CASES = [c for c in _ALL if c.startswith("oracle_")]  # pin the oracle only (CPU suite): options whose product parity is tested against the oracle
+_ALL = [c for c in _ALL if not c.startswith("oracle_")]
 CASES = [c for c in _ALL if not c.startswith("versa_")]          # small widths: every parity test runs on all of them
 VERSA_CASES = [c for c in _ALL if c.startswith("versa_")]         # BASELINE configs[3]/[4] at their real widths / layer counts
 

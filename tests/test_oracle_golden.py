@@ -3,10 +3,10 @@ tests/golden (fp32, CPU): loss, embeddings, bit-exact masks/labels, and every pa
 import numpy as np
 import pytest
 
-from golden_util import CASES, VERSA_CASES, check_grads, golden_masked, load_case, rebuild_inputs
+from golden_util import CASES, ORACLE_ONLY_CASES, VERSA_CASES, check_grads, golden_masked, load_case, rebuild_inputs
 
 
-@pytest.mark.parametrize("name", CASES + VERSA_CASES)
+@pytest.mark.parametrize("name", CASES + VERSA_CASES + ORACLE_ONLY_CASES)
 def test_oracle_matches_reference_fixture(name):
     from oracle import iisan_oracle as O
     z, meta = load_case(name)
