@@ -221,7 +221,8 @@ class PipelinedTrainStep:
     ``run()`` returns the loss as a 0-dim DEVICE tensor (reading it with ``.item()`` waits for the step).  ``run_logged()`` is the
     logging-friendly variant: it also enqueues the device-to-host copy of that loss into pinned memory and returns the VALUE of
     the step before it (a float; None for the first call), so the host thread never waits for the step it has just launched --
-    the reference logs its loss every 100 steps (Code_Cached/run.py:386-390); here every step's loss reaches the host, one step late.
+    the reference accumulates the loss on the device and logs it every ``steps_for_log`` batches (Code_Cached/run.py:382, 390-392; its
+    per-step ``torch.isnan`` test at :387 is what synchronises its loop); here every step's loss reaches the host, one step late.
     ``last_loss()`` waits for and returns the newest one.
     """
 
