@@ -79,7 +79,8 @@ def parse():
     ap.add_argument("--batch", type=int, default=0, help="users per GPU (default: the workload's, 512)")
     ap.add_argument("--compute", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--cpu-batch", type=int, default=0, help="users per CPU-arm step (default: the workload's bounded sample)")
-    ap.add_argument("--cpu-steps", type=int, default=3)
+    ap.add_argument("--cpu-steps", type=int, default=3, help="cpu_baseline: at least this many timed steps of the CPU arm ...")
+    ap.add_argument("--cpu-seconds", type=float, default=10.0, help="... and at least this much timed CPU work (at most 64 steps)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--child", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--no-store", action="store_true", help="skip the HBM-resident store e2e measurement")
@@ -116,8 +117,9 @@ def oracle_config(wname, item_num):
                       layers_img=w["layers_img"], vit_list=w["vit"], bert_list=w["bert"])
 
 
-def cpu_reference_steps(batch, steps, warmup, wname="instrument"):
-    """fwd + bwd + Adam of the oracle restatement (fp32, all host threads).  Returns (samples/s, s/step, cores)."""
+def cpu_reference_steps(batch, steps, warmup, wname="instrument", min_seconds=0.0, max_steps=64):
+    """fwd + bwd + Adam of the oracle restatement (fp32, all host threads).  Returns (samples/s, s/step, cores, last loss, steps timed).
+    ``min_seconds``: keep stepping past ``steps`` until that much CPU work has been timed (at most ``max_steps`` steps)."""
     import numpy as np
     import torch
     from oracle import iisan_oracle as O
@@ -135,7 +137,8 @@ def cpu_reference_steps(batch, steps, warmup, wname="instrument"):
     P = O.params_to_torch(make_params(cfg, SEED, perturb=False))
     opt = torch.optim.Adam(list(P.values()), lr=LRS["lr"])
     times = []
-    for it in range(warmup + steps):
+    it = 0
+    while len(times) < steps or (sum(times) < min_seconds and len(times) < max_steps):
         t0 = time.perf_counter()
         opt.zero_grad(set_to_none=True)
         out = O.model_forward(P, b, pop, cfg)
@@ -144,8 +147,9 @@ def cpu_reference_steps(batch, steps, warmup, wname="instrument"):
         dt = time.perf_counter() - t0
         if it >= warmup:
             times.append(dt)
+        it += 1
     sps = batch * len(times) / sum(times)
-    return sps, sum(times) / len(times), cores, float(out["loss"].item())
+    return sps, sum(times) / len(times), cores, float(out["loss"].item()), len(times)
 
 
 def workload_name(batch, stored, item_num=ITEM_NUM, wname="instrument"):
@@ -165,7 +169,7 @@ def run_reference_arm(a):
         return
     cpu_batch = a.cpu_batch or WORKLOADS[a.workload]["cpu_batch"]
     a.cpu_batch = cpu_batch
-    sps, sec, cores, loss = cpu_reference_steps(cpu_batch, a.steps, a.warmup, a.workload)
+    sps, sec, cores, loss, _n = cpu_reference_steps(cpu_batch, a.steps, a.warmup, a.workload)
     sample = (f"{a.steps} full train steps (fwd+bwd+Adam) of B={a.cpu_batch} dense users, fp32, torch CPU, oracle port of the reference "
               f"algorithm (its negative masks are vectorised; the reference's own per-user Python mask loop, Code_Cached/model/model.py:92-100, "
               f"is slower: SURVEY 8a row a6)")
@@ -662,9 +666,10 @@ def run_ours(a):
     loss_ref_step0 = None
     if world == 1 and not a.no_cpu_baseline:
         a.cpu_batch = a.cpu_batch or W["cpu_batch"]
-        sps, sec, cores, _ = cpu_reference_steps(a.cpu_batch, a.cpu_steps, 1, a.workload)
+        # a bounded sample of the same workload: at least --cpu-steps steps and ~10 s of CPU work (at most 64 steps)
+        sps, sec, cores, _, n_cpu = cpu_reference_steps(a.cpu_batch, a.cpu_steps, 1, a.workload, min_seconds=a.cpu_seconds)
         cpu = {"value": sps, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"{a.cpu_steps} full train steps of B={a.cpu_batch} dense users (fp32, torch CPU, oracle port of the reference "
+               "sample": f"{n_cpu} full train steps of B={a.cpu_batch} dense users (fp32, torch CPU, oracle port of the reference "
                          f"algorithm with vectorised negative masks -- faster than the reference's per-user Python mask loop; {sec:.2f} s/step)"}
         if selfcheck is not None:
             loss_ref_step0 = cpu_reference_loss(selfcheck["params"], selfcheck["batch"], selfcheck["pop"], item_num, a.workload)
